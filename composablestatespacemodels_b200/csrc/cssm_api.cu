@@ -1,0 +1,937 @@
+// cssm_api.cu -- host side of libcssm_gpu.so: the C ABI of include/cssm.h over the kernels of
+// cssm_kernels.cuh.  One CUDA stream per filter handle, no global mutable state, no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "cssm_kernels.cuh"
+
+using namespace cssm;
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? CSSM_ERR_NOMEM : CSSM_ERR_CUDA,                \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+  } while (0)
+
+struct HostLeaf {
+  int sde_kind, dim, f_kind, period, harmonics;
+  std::vector<double> m0, c0, phi, mu, sigma;
+};
+struct HostModel {
+  std::vector<HostLeaf> leaves;
+  int obs_kind, has_scale, step_mode, lgcp_precision, d;
+  double scale;
+};
+
+int copy_model(const cssm_model_desc_t* m, HostModel& out) {
+  if (!m || m->n_leaves <= 0 || !m->leaves) return fail(CSSM_ERR_INVALID, "model descriptor: no leaves");
+  if (m->obs_kind < CSSM_OBS_POISSON || m->obs_kind > CSSM_OBS_LGCP) return fail(CSSM_ERR_INVALID, "model descriptor: unknown obs_kind");
+  if (m->step_mode != CSSM_STEP_EXACT && m->step_mode != CSSM_STEP_EULER) return fail(CSSM_ERR_INVALID, "model descriptor: unknown step_mode");
+  if ((m->obs_kind == CSSM_OBS_NEGBIN || m->obs_kind == CSSM_OBS_NORMAL) && !m->has_scale)
+    return fail(CSSM_ERR_INVALID, m->obs_kind == CSSM_OBS_NEGBIN ? "No scale parameter provided to Negativebinomial Model"
+                                                                 : "Must provide SD parameter for LinearModel");
+  out.leaves.clear();
+  out.d = 0;
+  for (int l = 0; l < m->n_leaves; ++l) {
+    const cssm_leaf_t& L = m->leaves[l];
+    HostLeaf h;
+    h.sde_kind = L.sde_kind; h.dim = L.dim; h.f_kind = L.f_kind; h.period = L.period; h.harmonics = L.harmonics;
+    if (L.dim <= 0) return fail(CSSM_ERR_INVALID, "model descriptor: leaf dimension must be positive");
+    if (L.sde_kind < CSSM_SDE_BROWNIAN || L.sde_kind > CSSM_SDE_OU) return fail(CSSM_ERR_INVALID, "model descriptor: unknown sde_kind");
+    if (L.f_kind == CSSM_F_SEASONAL && (L.dim != 2 * L.harmonics || L.period <= 0))
+      return fail(CSSM_ERR_INVALID, "model descriptor: seasonal leaf needs dim == 2*harmonics and period > 0");
+    if (!L.m0 || !L.c0 || !L.sigma) return fail(CSSM_ERR_INVALID, "model descriptor: m0/c0/sigma missing");
+    if (L.sde_kind != CSSM_SDE_BROWNIAN && !L.mu) return fail(CSSM_ERR_INVALID, "model descriptor: mu missing");
+    if (L.sde_kind == CSSM_SDE_OU && !L.phi) return fail(CSSM_ERR_INVALID, "model descriptor: phi missing");
+    h.m0.assign(L.m0, L.m0 + L.dim);
+    h.c0.assign(L.c0, L.c0 + L.dim);
+    h.sigma.assign(L.sigma, L.sigma + L.dim);
+    if (L.mu) h.mu.assign(L.mu, L.mu + L.dim);
+    if (L.phi) h.phi.assign(L.phi, L.phi + L.dim);
+    out.d += L.dim;
+    out.leaves.push_back(h);
+  }
+  if (out.d > MAXD) return fail(CSSM_ERR_UNSUPPORTED, "total latent dimension exceeds 32");
+  out.obs_kind = m->obs_kind; out.has_scale = m->has_scale; out.scale = m->scale;
+  out.step_mode = m->step_mode; out.lgcp_precision = m->lgcp_precision;
+  return CSSM_OK;
+}
+
+// f-coefficients at time t: gamma = sum_k C[k] x[k]   (model/Model.scala:184,217-225)
+void f_coeffs(const HostModel& m, double t, double* C) {
+  int k = 0;
+  for (const HostLeaf& L : m.leaves) {
+    for (int c = 0; c < L.dim; ++c) C[k + c] = 0.0;
+    if (L.f_kind == CSSM_F_SEASONAL) {
+      double frequency = 2 * M_PI / L.period;
+      for (int a = 1; a <= L.harmonics; ++a) {
+        C[k + 2 * (a - 1)] = std::cos(frequency * a * t);
+        C[k + 2 * (a - 1) + 1] = std::sin(frequency * a * t);
+      }
+    } else {
+      C[k] = 1.0;
+    }
+    k += L.dim;
+  }
+}
+
+// per-step constants in fp64 (see StepArgs in cssm_kernels.cuh for the transition forms)
+struct StepHost {
+  double A[MAXD], M[MAXD], D[MAXD], S[MAXD], C[MAXD];
+  double y, k0, k1, k2, k3;
+  int has_obs;
+};
+void transition_consts(const HostModel& m, double dt, StepHost& s) {
+  int k = 0;
+  for (const HostLeaf& L : m.leaves)
+    for (int c = 0; c < L.dim; ++c, ++k) {
+      double A = 1.0, M = 0.0, D = 0.0, S;
+      if (m.step_mode == CSSM_STEP_EXACT) {
+        switch (L.sde_kind) {
+          case CSSM_SDE_BROWNIAN: S = std::sqrt(L.sigma[c] * dt); break;                       // model/Sde.scala:114-123
+          case CSSM_SDE_GEN_BROWNIAN: D = L.mu[c] * dt; S = std::sqrt(L.sigma[c] * dt); break;  // :86-95
+          default: {                                                                            // :139-150
+            double phi = L.phi[c], sigma = L.sigma[c];
+            A = std::exp(-phi * dt);
+            M = L.mu[c];
+            S = std::sqrt((sigma * sigma / (phi * 2.0)) * (1.0 - std::exp(phi * -2.0 * dt)));
+          }
+        }
+      } else {  // Euler-Maruyama, model/Sde.scala:30-43 with :82-84,:110-112,:158-162
+        S = L.sigma[c] * std::sqrt(dt);
+        switch (L.sde_kind) {
+          case CSSM_SDE_BROWNIAN: D = 1.0 * dt; break;
+          case CSSM_SDE_GEN_BROWNIAN: D = L.mu[c] * dt; break;
+          default: A = 1.0 - L.phi[c] * dt; M = L.mu[c];
+        }
+      }
+      s.A[k] = A; s.M[k] = M; s.D[k] = D; s.S[k] = S;
+    }
+}
+void obs_consts(const HostModel& m, int has_obs, double y, StepHost& s) {
+  s.y = y; s.has_obs = has_obs; s.k0 = s.k1 = s.k2 = s.k3 = 0.0;
+  if (!has_obs) return;
+  switch (m.obs_kind) {
+    case CSSM_OBS_POISSON: { int k = (int)y; s.k0 = k; s.k1 = std::lgamma(k + 1.0); break; }
+    case CSSM_OBS_NEGBIN: {
+      int k = (int)y;
+      double size = std::exp(m.scale);
+      s.k0 = k; s.k1 = size;
+      s.k2 = std::lgamma(size + k) - std::lgamma(k + 1.0) - std::lgamma(size);
+      s.k3 = std::log(size);
+      break;
+    }
+    case CSSM_OBS_NORMAL: { double v = std::exp(m.scale); s.k0 = v; s.k1 = std::log(std::sqrt(2 * M_PI)) + std::log(v); break; }
+    case CSSM_OBS_BERNOULLI: s.k0 = (y == 1.0) ? 1.0 : 0.0; break;
+    default: break;
+  }
+}
+template <typename real>
+void to_args(const HostModel& m, const StepHost& h, StepArgs<real>& a) {
+  std::memset(&a, 0, sizeof(a));
+  for (int k = 0; k < m.d; ++k) {
+    a.A[k] = (real)h.A[k]; a.M[k] = (real)h.M[k]; a.D[k] = (real)h.D[k]; a.S[k] = (real)h.S[k]; a.C[k] = (real)h.C[k];
+  }
+  a.y = (real)h.y; a.k0 = (real)h.k0; a.k1 = (real)h.k1; a.k2 = (real)h.k2; a.k3 = (real)h.k3;
+  a.d = m.d; a.obs_kind = m.obs_kind; a.has_obs = h.has_obs;
+}
+
+uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct SeriesStep {
+  double t, dt;
+  StepHost h;       // transition for dt (for LGCP: for one sub-step delta), C at time t
+  long long n_sub;  // LGCP sub-steps (1 otherwise)
+  size_t ctab_off;  // offset into the LGCP coefficient table (elements)
+};
+
+}  // namespace
+
+struct cssm_filter {
+  int device = 0, dtype = CSSM_F32, resample_kind = 0;
+  long long N = 0, Ns = 0;
+  int d = 0, nt = 0;
+  HostModel model;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void *xa = nullptr, *xb = nullptr, *logw = nullptr;  // x_cur = xa after every swap
+  int32_t* anc = nullptr;
+  bool anc_valid = false, initialised = false;
+  Scalars* sc = nullptr;
+  u128 *tile_sum = nullptr, *tile_excl = nullptr;
+  double* cend = nullptr;
+  double* ubuf = nullptr;   // N uniforms (stratified / multinomial, injected)
+  double* cdf = nullptr;    // N cumulative values (multinomial)
+  double* scratch = nullptr;  // grow-only fp64 scratch (injected noise, read-back staging)
+  size_t scratch_n = 0;
+  void* ctab = nullptr;  // LGCP per-sub-step f coefficients (filter dtype)
+  size_t ctab_n = 0;
+  double *ll_steps = nullptr; int* ess_steps = nullptr; double* states = nullptr; size_t steps_cap = 0;
+  std::vector<SeriesStep> series;
+  std::vector<double> ctab_host;
+  double t0_series = 0.0;
+  double t_cur = 0.0;
+  uint64_t seed = 0, stream_id = 0, epoch = 0;
+  uint32_t key0 = 0, key1 = 0;
+  uint32_t step_ctr = 0;
+  unsigned long long slot0 = 0;  // global slot of local particle 0 (sharded filters)
+  int shard_rank = 0, shard_world = 1;
+  float last_ms = 0.f;
+  long long last_launches = 0, launches = 0;
+};
+
+namespace {
+
+void rekey(cssm_filter* f) {
+  uint64_t k = splitmix64(f->seed ^ splitmix64(f->stream_id + 0x632BE59BD9B4E019ull) ^ splitmix64(f->epoch * 0xD1B54A32D192ED03ull + 1));
+  f->key0 = (uint32_t)k;
+  f->key1 = (uint32_t)(k >> 32);
+}
+
+int ensure_scratch(cssm_filter* f, size_t n) {
+  if (n <= f->scratch_n) return CSSM_OK;
+  if (f->scratch) cudaFree(f->scratch);
+  f->scratch = nullptr; f->scratch_n = 0;
+  CU(cudaMalloc(&f->scratch, n * sizeof(double)));
+  f->scratch_n = n;
+  return CSSM_OK;
+}
+
+inline int nblk(long long n, int per) { return (int)((n + per - 1) / per); }
+
+template <typename real>
+int launch_init(cssm_filter* f, const double* zinj_dev, const double* x0) {
+  StepArgs<real> a;
+  std::memset(&a, 0, sizeof(a));
+  a.d = f->d;
+  int k = 0;
+  for (const HostLeaf& L : f->model.leaves)
+    for (int c = 0; c < L.dim; ++c, ++k) {
+      a.S[k] = (real)std::sqrt(L.c0[c]);
+      a.M[k] = (real)(x0 ? x0[k] : L.m0[c]);
+    }
+  if (x0)
+    k_fill_particles<real><<<nblk(f->N, 256), 256, 0, f->stream>>>(a, (real*)f->xa, f->N, f->Ns);
+  else
+    k_init_particles<real><<<nblk(f->N, 256), 256, 0, f->stream>>>(a, (real*)f->xa, zinj_dev, f->N, f->Ns, f->slot0, f->key0,
+                                                                    f->key1, (uint32_t)f->epoch);
+  f->launches++;
+  CU(cudaGetLastError());
+  return CSSM_OK;
+}
+
+int do_init(cssm_filter* f, double t0, const double* zinj_dev, const double* x0) {
+  f->epoch++;
+  rekey(f);
+  f->step_ctr = 0;
+  Scalars z;
+  std::memset(&z, 0, sizeof(z));
+  z.ess = (int)std::min<long long>(f->N * (long long)f->shard_world, 2147483647LL);
+  z.qb = 96;
+  CU(cudaMemcpyAsync(f->sc, &z, sizeof(z), cudaMemcpyHostToDevice, f->stream));
+  int rc = (f->dtype == CSSM_F32) ? launch_init<float>(f, zinj_dev, x0) : launch_init<double>(f, zinj_dev, x0);
+  if (rc) return rc;
+  f->anc_valid = false;
+  f->initialised = true;
+  f->t_cur = t0;
+  return CSSM_OK;
+}
+
+struct StepIO {
+  const double* zinj = nullptr;   // device, [n_sub][d][N]
+  const double* uarr = nullptr;   // device, N uniforms (stratified / multinomial)
+  int use_u_inj = 0;              // systematic uniform taken from sc->u_inj
+  double* ll_steps = nullptr;     // device
+  int* ess_steps = nullptr;       // device
+  long long step_slot = 0;
+};
+
+// one stepFilter on the device; no host synchronisation
+template <typename real>
+int launch_step(cssm_filter* f, const StepHost& h, long long n_sub, const void* ctab, double delta, const StepIO& io) {
+  StepArgs<real> a;
+  to_args<real>(f->model, h, a);
+  const int32_t* anc = f->anc_valid ? f->anc : nullptr;
+  const uint32_t step = f->step_ctr++;
+  real* xsrc = (real*)f->xa;
+  real* xdst = (real*)f->xb;
+  if (f->model.obs_kind == CSSM_OBS_LGCP) {
+    const int g = nblk(f->N, 256);
+#define LGCP_CASE(DP)                                                                                              \
+  k_lgcp_weight<real, DP><<<g, 256, 0, f->stream>>>(a, xsrc, xdst, anc, (real*)f->logw, io.zinj, (const real*)ctab, n_sub, \
+                                                     (real)delta, f->N, f->Ns, f->slot0, f->key0, f->key1, step, f->sc)
+    if (f->d <= 1) LGCP_CASE(1);
+    else if (f->d <= 2) LGCP_CASE(2);
+    else if (f->d <= 4) LGCP_CASE(4);
+    else if (f->d <= 8) LGCP_CASE(8);
+    else if (f->d <= 16) LGCP_CASE(16);
+    else LGCP_CASE(32);
+#undef LGCP_CASE
+  } else {
+    constexpr int PPT = VecOf<real>::PPT;
+    k_propagate_weight<real><<<nblk(f->N, 256 * PPT), 256, 0, f->stream>>>(a, xsrc, xdst, anc, (real*)f->logw, io.zinj, f->N, f->Ns,
+                                                                           f->slot0, f->key0, f->key1, step, f->sc);
+  }
+  f->launches++;
+  std::swap(f->xa, f->xb);
+  f->anc_valid = false;
+  if (!h.has_obs) { CU(cudaGetLastError()); return CSSM_OK; }
+  const int normalise = (f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ? 0 : 1;
+  const real* lw = (const real*)f->logw;
+  k_weight_total<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, f->sc);
+  k_tile_sums<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, normalise, f->sc, f->tile_sum);
+  k_scan_tiles<<<1, 1024, 0, f->stream>>>(f->sc, f->tile_sum, f->tile_excl, f->cend, f->nt, f->N, normalise, 0, 1, io.use_u_inj,
+                                          f->key0, f->key1, step, io.ll_steps, io.ess_steps, io.step_slot);
+  if (normalise) {
+    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 1, f->sc, f->tile_excl, f->cend, f->nt, f->resample_kind,
+                                                               io.uarr, f->key0, f->key1, step, f->anc, nullptr, &f->sc->flags);
+    f->launches += 4;
+  } else {
+    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 0, f->sc, f->tile_excl, f->cend, f->nt, f->resample_kind,
+                                                               nullptr, f->key0, f->key1, step, nullptr, f->cdf, &f->sc->flags);
+    k_multinomial_search<<<nblk(f->N, 256), 256, 0, f->stream>>>(f->cdf, f->N, io.uarr, f->key0, f->key1, step, f->anc, &f->sc->flags);
+    f->launches += 5;
+  }
+  f->anc_valid = true;
+  CU(cudaGetLastError());
+  return CSSM_OK;
+}
+
+int step_consts(cssm_filter* f, double t_prev, double t, int has_obs, double y, StepHost& h, long long& n_sub, double& delta) {
+  const HostModel& m = f->model;
+  double dt = t - t_prev;
+  n_sub = 1;
+  delta = 0.0;
+  if (m.obs_kind == CSSM_OBS_LGCP) {
+    delta = std::pow(10, -m.lgcp_precision);
+    n_sub = (dt == 0) ? 0 : (long long)(int)std::ceil(dt / delta);  // model/ParticleFilter.scala:190
+    if (n_sub >= (1 << 22)) return fail(CSSM_ERR_UNSUPPORTED, "LGCP: more than 2^22 sub-steps in one increment");
+    transition_consts(m, delta, h);
+    has_obs = 1;  // every datum is an event; FilterLgcp always weights and resamples (:217-225)
+  } else {
+    transition_consts(m, dt, h);
+  }
+  f_coeffs(m, t, h.C);
+  obs_consts(m, has_obs, y, h);
+  h.has_obs = has_obs;
+  return CSSM_OK;
+}
+
+bool has_seasonal(const HostModel& m) {
+  for (const HostLeaf& L : m.leaves)
+    if (L.f_kind == CSSM_F_SEASONAL) return true;
+  return false;
+}
+
+// LGCP with a time-dependent f: coefficients at the sub-step times t_i = t + i*delta (accumulated,
+// the stream starts at the observation time, model/ParticleFilter.scala:194,215)
+void lgcp_ctab_host(const HostModel& m, double t, long long n_sub, double delta, std::vector<double>& out) {
+  double time = t;
+  size_t o = out.size();
+  out.resize(o + (size_t)n_sub * m.d);
+  for (long long s = 0; s < n_sub; ++s) {
+    time = time + delta;
+    f_coeffs(m, time, out.data() + o + (size_t)s * m.d);
+  }
+}
+
+int upload_ctab(cssm_filter* f, const std::vector<double>& host) {
+  if (host.empty()) return CSSM_OK;
+  size_t esz = (f->dtype == CSSM_F32) ? 4 : 8;
+  if (host.size() > f->ctab_n) {
+    if (f->ctab) cudaFree(f->ctab);
+    f->ctab = nullptr; f->ctab_n = 0;
+    CU(cudaMalloc(&f->ctab, host.size() * esz));
+    f->ctab_n = host.size();
+  }
+  if (f->dtype == CSSM_F32) {
+    std::vector<float> tmp(host.begin(), host.end());
+    CU(cudaMemcpyAsync(f->ctab, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+  } else {
+    CU(cudaMemcpyAsync(f->ctab, host.data(), host.size() * 8, cudaMemcpyHostToDevice, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+  }
+  return CSSM_OK;
+}
+
+int run_one_step(cssm_filter* f, double t, int has_obs, double y, const StepIO& io) {
+  StepHost h;
+  long long n_sub;
+  double delta;
+  int rc = step_consts(f, f->t_cur, t, has_obs, y, h, n_sub, delta);
+  if (rc) return rc;
+  const void* ctab = nullptr;
+  if (f->model.obs_kind == CSSM_OBS_LGCP && has_seasonal(f->model) && n_sub > 0) {
+    std::vector<double> host;
+    lgcp_ctab_host(f->model, t, n_sub, delta, host);
+    rc = upload_ctab(f, host);
+    if (rc) return rc;
+    ctab = f->ctab;
+  }
+  rc = (f->dtype == CSSM_F32) ? launch_step<float>(f, h, n_sub, ctab, delta, io) : launch_step<double>(f, h, n_sub, ctab, delta, io);
+  if (rc) return rc;
+  f->t_cur = t;
+  return CSSM_OK;
+}
+
+int read_ll(cssm_filter* f, double* ll, int32_t* ess) {
+  Scalars s;
+  CU(cudaMemcpyAsync(&s, f->sc, sizeof(s), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  if (ll) *ll = s.ll;
+  if (ess) *ess = s.ess;
+  return CSSM_OK;
+}
+
+int enter(const cssm_filter* f) {
+  if (!f) return fail(CSSM_ERR_INVALID, "null filter handle");
+  CU(cudaSetDevice(f->device));
+  return CSSM_OK;
+}
+
+int ensure_steps_cap(cssm_filter* f, size_t T) {
+  if (T + 1 <= f->steps_cap) return CSSM_OK;
+  if (f->ll_steps) cudaFree(f->ll_steps);
+  if (f->ess_steps) cudaFree(f->ess_steps);
+  if (f->states) cudaFree(f->states);
+  f->ll_steps = nullptr; f->ess_steps = nullptr; f->states = nullptr; f->steps_cap = 0;
+  CU(cudaMalloc(&f->ll_steps, (T + 1) * sizeof(double)));
+  CU(cudaMalloc(&f->ess_steps, (T + 1) * sizeof(int)));
+  CU(cudaMalloc(&f->states, (T + 1) * (size_t)f->d * sizeof(double)));
+  f->steps_cap = T + 1;
+  return CSSM_OK;
+}
+
+template <typename real>
+void launch_sample_one(cssm_filter* f, double* out_dev, uint32_t tag) {
+  k_sample_one<real><<<1, 32, 0, f->stream>>>((const real*)f->xa, f->anc_valid ? f->anc : nullptr, out_dev, f->d, f->N, f->Ns, f->key0,
+                                              f->key1, tag);
+  f->launches++;
+}
+
+// init + T steps on the loaded series; optionally one sampled particle per time (filter, :152-158)
+int run_series(cssm_filter* f, bool sample_states) {
+  const size_t T = f->series.size();
+  int rc = ensure_steps_cap(f, T);
+  if (rc) return rc;
+  f->launches = 0;
+  CU(cudaEventRecord(f->ev0, f->stream));
+  rc = do_init(f, f->t0_series, nullptr, nullptr);
+  if (rc) return rc;
+  if (sample_states) {
+    if (f->dtype == CSSM_F32) launch_sample_one<float>(f, f->states, 0x80000000u);
+    else launch_sample_one<double>(f, f->states, 0x80000000u);
+  }
+  for (size_t s = 0; s < T; ++s) {
+    const SeriesStep& st = f->series[s];
+    StepIO io;
+    io.ll_steps = f->ll_steps;
+    io.ess_steps = f->ess_steps;
+    io.step_slot = (long long)s;
+    const void* ctab = nullptr;
+    if (f->ctab && st.n_sub > 0 && !f->ctab_host.empty())
+      ctab = (const char*)f->ctab + st.ctab_off * ((f->dtype == CSSM_F32) ? 4 : 8);
+    double delta = (f->model.obs_kind == CSSM_OBS_LGCP) ? std::pow(10, -f->model.lgcp_precision) : 0.0;
+    rc = (f->dtype == CSSM_F32) ? launch_step<float>(f, st.h, st.n_sub, ctab, delta, io)
+                                : launch_step<double>(f, st.h, st.n_sub, ctab, delta, io);
+    if (rc) return rc;
+    if (!st.h.has_obs) {
+      // ll/ess unchanged on an unobserved step: carry the previous values into the per-step arrays
+      // (done on the host side when reading back, see cssm_filter_ll_resident)
+    }
+    f->t_cur = st.t;
+    if (sample_states) {
+      if (f->dtype == CSSM_F32) launch_sample_one<float>(f, f->states + (s + 1) * f->d, 0x80000001u + (uint32_t)s);
+      else launch_sample_one<double>(f, f->states + (s + 1) * f->d, 0x80000001u + (uint32_t)s);
+    }
+  }
+  CU(cudaEventRecord(f->ev1, f->stream));
+  return CSSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cssm_version(void) { return CSSM_VERSION; }
+const char* cssm_last_error(void) { return g_err.c_str(); }
+
+int cssm_device_count(int* n_out) {
+  if (!n_out) return fail(CSSM_ERR_INVALID, "null output");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *n_out = 0;
+    return fail(CSSM_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *n_out = n;
+  return CSSM_OK;
+}
+
+int cssm_filter_create(const cssm_model_desc_t* model, int64_t n_particles, int resample_kind, int dtype, int device,
+                       uint64_t seed, uint64_t stream_id, cssm_filter_t** out) {
+  if (!out) return fail(CSSM_ERR_INVALID, "null output handle");
+  *out = nullptr;
+  if (n_particles <= 0 || n_particles > 2147483647LL) return fail(CSSM_ERR_INVALID, "n_particles must be in [1, 2^31-1]");
+  if (resample_kind < 0 || resample_kind > 2) return fail(CSSM_ERR_INVALID, "unknown resample_kind");
+  if (dtype != CSSM_F32 && dtype != CSSM_F64) return fail(CSSM_ERR_INVALID, "unknown dtype");
+  HostModel hm;
+  int rc = copy_model(model, hm);
+  if (rc) return rc;
+  int ndev = 0;
+  rc = cssm_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(CSSM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(CSSM_ERR_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  cssm_filter* f = new cssm_filter();
+  f->device = device; f->dtype = dtype; f->resample_kind = resample_kind;
+  f->N = n_particles; f->Ns = (n_particles + 63) / 64 * 64;
+  f->model = hm; f->d = hm.d;
+  f->nt = nblk(f->N, TILE);
+  f->seed = seed; f->stream_id = stream_id;
+  const size_t esz = (dtype == CSSM_F32) ? 4 : 8;
+#define ALLOC(ptr, bytes)                                                                        \
+  do {                                                                                           \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                        \
+    if (e_ != cudaSuccess) {                                                                     \
+      cssm_filter_destroy(f);                                                                    \
+      return fail(CSSM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e_));         \
+    }                                                                                            \
+  } while (0)
+  ALLOC(f->xa, (size_t)f->d * f->Ns * esz);
+  ALLOC(f->xb, (size_t)f->d * f->Ns * esz);
+  ALLOC(f->logw, (size_t)(f->Ns + TILE) * esz);
+  ALLOC(f->anc, (size_t)f->Ns * sizeof(int32_t));
+  ALLOC(f->sc, sizeof(Scalars));
+  ALLOC(f->tile_sum, (size_t)(f->nt + 1) * sizeof(u128));
+  ALLOC(f->tile_excl, (size_t)(f->nt + 1) * sizeof(u128));
+  ALLOC(f->cend, (size_t)(f->nt + 1) * sizeof(double));
+  if (resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ALLOC(f->cdf, (size_t)f->Ns * sizeof(double));
+#undef ALLOC
+  cudaMemset(f->xa, 0, (size_t)f->d * f->Ns * esz);
+  cudaMemset(f->xb, 0, (size_t)f->d * f->Ns * esz);
+  cudaMemset(f->logw, 0, (size_t)(f->Ns + TILE) * esz);
+  cudaMemset(f->sc, 0, sizeof(Scalars));
+  if (cudaStreamCreateWithFlags(&f->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&f->ev0) != cudaSuccess ||
+      cudaEventCreate(&f->ev1) != cudaSuccess) {
+    cssm_filter_destroy(f);
+    return fail(CSSM_ERR_CUDA, "stream/event creation failed");
+  }
+  f->stream = f->own_stream;
+  CU(cudaDeviceSynchronize());
+  *out = f;
+  return CSSM_OK;
+}
+
+int cssm_filter_set_params(cssm_filter_t* f, const cssm_model_desc_t* model) {
+  int rc = enter(f);
+  if (rc) return rc;
+  HostModel hm;
+  rc = copy_model(model, hm);
+  if (rc) return rc;
+  if (hm.d != f->d || hm.leaves.size() != f->model.leaves.size() || hm.obs_kind != f->model.obs_kind)
+    return fail(CSSM_ERR_INVALID, "set_params: model shape differs from the one the filter was created with");
+  for (size_t l = 0; l < hm.leaves.size(); ++l)
+    if (hm.leaves[l].dim != f->model.leaves[l].dim || hm.leaves[l].sde_kind != f->model.leaves[l].sde_kind ||
+        hm.leaves[l].f_kind != f->model.leaves[l].f_kind)
+      return fail(CSSM_ERR_INVALID, "set_params: leaf shape differs");
+  f->model = hm;
+  // the constants of a loaded series depend on the parameters: rebuild them
+  if (!f->series.empty()) {
+    std::vector<double> t, y;
+    std::vector<uint8_t> ho;
+    for (const SeriesStep& s : f->series) { t.push_back(s.t); y.push_back(s.h.y); ho.push_back((uint8_t)s.h.has_obs); }
+    return cssm_filter_load_series(f, t.data(), y.data(), ho.data(), (int64_t)t.size());
+  }
+  return CSSM_OK;
+}
+
+int cssm_filter_reseed(cssm_filter_t* f, uint64_t seed, uint64_t stream_id) {
+  if (!f) return fail(CSSM_ERR_INVALID, "null filter handle");
+  f->seed = seed; f->stream_id = stream_id; f->epoch = 0;
+  return CSSM_OK;
+}
+
+int cssm_filter_set_stream(cssm_filter_t* f, void* cuda_stream) {
+  int rc = enter(f);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(f->stream));
+  f->stream = cuda_stream ? (cudaStream_t)cuda_stream : f->own_stream;
+  return CSSM_OK;
+}
+
+int cssm_filter_destroy(cssm_filter_t* f) {
+  if (!f) return CSSM_OK;
+  cudaSetDevice(f->device);
+  if (f->own_stream) cudaStreamSynchronize(f->own_stream);
+  void* ptrs[] = {f->xa, f->xb, f->logw, f->anc, f->sc, f->tile_sum, f->tile_excl, f->cend, f->ubuf, f->cdf,
+                  f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (f->ev0) cudaEventDestroy(f->ev0);
+  if (f->ev1) cudaEventDestroy(f->ev1);
+  if (f->own_stream) cudaStreamDestroy(f->own_stream);
+  delete f;
+  return CSSM_OK;
+}
+
+int cssm_filter_dim(const cssm_filter_t* f, int32_t* d_out) {
+  if (!f || !d_out) return fail(CSSM_ERR_INVALID, "null argument");
+  *d_out = f->d;
+  return CSSM_OK;
+}
+int cssm_filter_n_particles(const cssm_filter_t* f, int64_t* n_out) {
+  if (!f || !n_out) return fail(CSSM_ERR_INVALID, "null argument");
+  *n_out = f->N;
+  return CSSM_OK;
+}
+
+int cssm_filter_init(cssm_filter_t* f, double t0) {
+  int rc = enter(f);
+  if (rc) return rc;
+  f->launches = 0;
+  rc = do_init(f, t0, nullptr, nullptr);
+  f->last_launches = f->launches;
+  return rc;
+}
+
+int cssm_filter_init_state(cssm_filter_t* f, double t0, const double* x0) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!x0) return fail(CSSM_ERR_INVALID, "null initial state");
+  f->launches = 0;
+  rc = do_init(f, t0, nullptr, x0);
+  f->last_launches = f->launches;
+  return rc;
+}
+
+int cssm_filter_init_injected(cssm_filter_t* f, double t0, const double* z0) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!z0) return fail(CSSM_ERR_INVALID, "null noise");
+  size_t n = (size_t)f->d * f->N;
+  rc = ensure_scratch(f, n);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(f->scratch, z0, n * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  f->launches = 0;
+  rc = do_init(f, t0, f->scratch, nullptr);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(f->stream));
+  f->last_launches = f->launches;
+  return CSSM_OK;
+}
+
+int cssm_filter_step(cssm_filter_t* f, double t, int has_obs, double y, double* ll_out, int32_t* ess_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "stepFilter before initialiseState");
+  f->launches = 0;
+  StepIO io;
+  rc = run_one_step(f, t, has_obs, y, io);
+  if (rc) return rc;
+  f->last_launches = f->launches;
+  return read_ll(f, ll_out, ess_out);
+}
+
+int cssm_filter_n_substeps(const cssm_filter_t* f, double dt, int64_t* n_out) {
+  if (!f || !n_out) return fail(CSSM_ERR_INVALID, "null argument");
+  if (f->model.obs_kind != CSSM_OBS_LGCP) { *n_out = 1; return CSSM_OK; }
+  *n_out = (dt == 0) ? 0 : (int64_t)(int)std::ceil(dt / std::pow(10, -f->model.lgcp_precision));
+  return CSSM_OK;
+}
+
+int cssm_filter_step_injected(cssm_filter_t* f, double t, int has_obs, double y, const double* z, const double* u,
+                              double* x_prop_out, double* logw_out, double* w1_out, int32_t* anc_out, double* ll_out,
+                              int32_t* ess_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "stepFilter before initialiseState");
+  int64_t n_sub = 1;
+  cssm_filter_n_substeps(f, t - f->t_cur, &n_sub);
+  const bool lgcp = f->model.obs_kind == CSSM_OBS_LGCP;
+  const bool weighted = lgcp || has_obs;
+  if (n_sub > 0 && !z) return fail(CSSM_ERR_INVALID, "null noise");
+  if (weighted && !u) return fail(CSSM_ERR_INVALID, "null uniforms");
+  const size_t nz = (size_t)std::max<int64_t>(n_sub, 1) * f->d * f->N;
+  rc = ensure_scratch(f, nz + (size_t)f->d * f->N);
+  if (rc) return rc;
+  if (n_sub > 0) CU(cudaMemcpyAsync(f->scratch, z, (size_t)n_sub * f->d * f->N * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  StepIO io;
+  io.zinj = f->scratch;
+  if (weighted) {
+    if (f->resample_kind == CSSM_RESAMPLE_SYSTEMATIC) {
+      CU(cudaMemcpyAsync(&f->sc->u_inj, u, sizeof(double), cudaMemcpyHostToDevice, f->stream));
+      io.use_u_inj = 1;
+    } else {
+      if (!f->ubuf) CU(cudaMalloc(&f->ubuf, (size_t)f->N * sizeof(double)));
+      CU(cudaMemcpyAsync(f->ubuf, u, (size_t)f->N * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+      io.uarr = f->ubuf;
+    }
+  }
+  f->launches = 0;
+  rc = run_one_step(f, t, has_obs, y, io);
+  if (rc) return rc;
+  double* stage = f->scratch + nz;  // d*N doubles
+  const int g = nblk(f->N, 256);
+  if (x_prop_out) {
+    if (f->dtype == CSSM_F32) k_gather<float, double><<<g, 256, 0, f->stream>>>((const float*)f->xa, nullptr, stage, f->d, f->N, f->Ns, f->N);
+    else k_gather<double, double><<<g, 256, 0, f->stream>>>((const double*)f->xa, nullptr, stage, f->d, f->N, f->Ns, f->N);
+    CU(cudaMemcpyAsync(x_prop_out, stage, (size_t)f->d * f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+  }
+  if (weighted) {
+    if (logw_out) {
+      if (f->dtype == CSSM_F32) k_to_double<float><<<g, 256, 0, f->stream>>>((const float*)f->logw, stage, f->N);
+      else k_to_double<double><<<g, 256, 0, f->stream>>>((const double*)f->logw, stage, f->N);
+      CU(cudaMemcpyAsync(logw_out, stage, (size_t)f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+      CU(cudaStreamSynchronize(f->stream));
+    }
+    if (w1_out) {
+      if (f->dtype == CSSM_F32) k_w1_out<float><<<g, 256, 0, f->stream>>>((const float*)f->logw, f->sc, stage, f->N);
+      else k_w1_out<double><<<g, 256, 0, f->stream>>>((const double*)f->logw, f->sc, stage, f->N);
+      CU(cudaMemcpyAsync(w1_out, stage, (size_t)f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+      CU(cudaStreamSynchronize(f->stream));
+    }
+    if (anc_out) CU(cudaMemcpyAsync(anc_out, f->anc, (size_t)f->N * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+  }
+  f->last_launches = f->launches;
+  return read_ll(f, ll_out, ess_out);
+}
+
+int cssm_filter_load_series(cssm_filter_t* f, const double* t, const double* y, const uint8_t* has_obs, int64_t T) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (T <= 0 || !t || !y) return fail(CSSM_ERR_INVALID, "empty series");
+  std::vector<SeriesStep> series((size_t)T);
+  std::vector<double> ctab_host;
+  double t0 = t[0];
+  for (int64_t s = 1; s < T; ++s) t0 = std::min(t0, t[s]);  // data.minBy(_.t).t, model/ParticleFilter.scala:138
+  double tp = t0;
+  const bool lgcp = f->model.obs_kind == CSSM_OBS_LGCP;
+  const bool seas = lgcp && has_seasonal(f->model);
+  for (int64_t s = 0; s < T; ++s) {
+    SeriesStep& st = series[(size_t)s];
+    st.t = t[s];
+    st.dt = t[s] - tp;
+    double delta;
+    rc = step_consts(f, tp, t[s], has_obs ? (int)has_obs[s] : 1, y[s], st.h, st.n_sub, delta);
+    if (rc) return rc;
+    st.ctab_off = ctab_host.size();
+    if (seas && st.n_sub > 0) lgcp_ctab_host(f->model, t[s], st.n_sub, delta, ctab_host);
+    tp = t[s];
+  }
+  rc = upload_ctab(f, ctab_host);
+  if (rc) return rc;
+  f->series.swap(series);
+  f->ctab_host.swap(ctab_host);
+  f->t0_series = t0;
+  return CSSM_OK;
+}
+
+int cssm_filter_ll_resident(cssm_filter_t* f, double* ll_out, double* ll_steps_out, int32_t* ess_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (f->series.empty()) return fail(CSSM_ERR_STATE, "no series loaded");
+  rc = run_series(f, false);
+  if (rc) return rc;
+  double ll;
+  int32_t ess;
+  rc = read_ll(f, &ll, &ess);
+  if (rc) return rc;
+  CU(cudaEventElapsedTime(&f->last_ms, f->ev0, f->ev1));
+  f->last_launches = f->launches;
+  if (ll_out) *ll_out = ll;
+  const size_t T = f->series.size();
+  if (ll_steps_out || ess_out) {
+    std::vector<double> lls(T);
+    std::vector<int> esss(T);
+    CU(cudaMemcpy(lls.data(), f->ll_steps, T * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(esss.data(), f->ess_steps, T * sizeof(int), cudaMemcpyDeviceToHost));
+    double pl = 0.0;
+    int pe = (int)std::min<long long>(f->N, 2147483647LL);
+    for (size_t s = 0; s < T; ++s) {
+      if (f->series[s].h.has_obs) { pl = lls[s]; pe = esss[s]; }  // unobserved step: ll, ess unchanged (:121)
+      if (ll_steps_out) ll_steps_out[s] = pl;
+      if (ess_out) ess_out[s] = pe;
+    }
+  }
+  return CSSM_OK;
+}
+
+int cssm_filter_ll(cssm_filter_t* f, const double* t, const double* y, const uint8_t* has_obs, int64_t T, double* ll_out) {
+  int rc = cssm_filter_load_series(f, t, y, has_obs, T);
+  if (rc) return rc;
+  return cssm_filter_ll_resident(f, ll_out, nullptr, nullptr);
+}
+
+int cssm_filter_run(cssm_filter_t* f, const double* t, const double* y, const uint8_t* has_obs, int64_t T, double* ll_out,
+                    double* states_out) {
+  int rc = cssm_filter_load_series(f, t, y, has_obs, T);
+  if (rc) return rc;
+  rc = run_series(f, states_out != nullptr);
+  if (rc) return rc;
+  double ll;
+  rc = read_ll(f, &ll, nullptr);
+  if (rc) return rc;
+  CU(cudaEventElapsedTime(&f->last_ms, f->ev0, f->ev1));
+  f->last_launches = f->launches;
+  if (ll_out) *ll_out = ll;
+  if (states_out) CU(cudaMemcpy(states_out, f->states, (size_t)(T + 1) * f->d * sizeof(double), cudaMemcpyDeviceToHost));
+  return CSSM_OK;
+}
+
+int cssm_filter_last_elapsed_ms(const cssm_filter_t* f, float* ms_out) {
+  if (!f || !ms_out) return fail(CSSM_ERR_INVALID, "null argument");
+  *ms_out = f->last_ms;
+  return CSSM_OK;
+}
+int cssm_filter_last_launches(const cssm_filter_t* f, int64_t* n_out) {
+  if (!f || !n_out) return fail(CSSM_ERR_INVALID, "null argument");
+  *n_out = f->last_launches;
+  return CSSM_OK;
+}
+
+int cssm_filter_get_particles(cssm_filter_t* f, double* x_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "no particles yet");
+  if (!x_out) return fail(CSSM_ERR_INVALID, "null output");
+  size_t n = (size_t)f->d * f->N;
+  rc = ensure_scratch(f, n);
+  if (rc) return rc;
+  const int g = nblk(f->N, 256);
+  const int32_t* anc = f->anc_valid ? f->anc : nullptr;
+  if (f->dtype == CSSM_F32) k_gather<float, double><<<g, 256, 0, f->stream>>>((const float*)f->xa, anc, f->scratch, f->d, f->N, f->Ns, f->N);
+  else k_gather<double, double><<<g, 256, 0, f->stream>>>((const double*)f->xa, anc, f->scratch, f->d, f->N, f->Ns, f->N);
+  CU(cudaMemcpyAsync(x_out, f->scratch, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  return CSSM_OK;
+}
+
+int cssm_filter_sample_one(cssm_filter_t* f, double* x_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "no particles yet");
+  if (!x_out) return fail(CSSM_ERR_INVALID, "null output");
+  rc = ensure_scratch(f, (size_t)f->d);
+  if (rc) return rc;
+  uint32_t tag = 0x40000000u + f->step_ctr++;
+  if (f->dtype == CSSM_F32) launch_sample_one<float>(f, f->scratch, tag);
+  else launch_sample_one<double>(f, f->scratch, tag);
+  CU(cudaMemcpyAsync(x_out, f->scratch, (size_t)f->d * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  return CSSM_OK;
+}
+
+int cssm_filter_get_ll(cssm_filter_t* f, double* ll_out, int32_t* ess_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  return read_ll(f, ll_out, ess_out);
+}
+
+int cssm_filter_mean_state(cssm_filter_t* f, double* mean_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "no particles yet");
+  if (!mean_out) return fail(CSSM_ERR_INVALID, "null output");
+  rc = ensure_scratch(f, (size_t)f->d);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(f->scratch, 0, (size_t)f->d * sizeof(double), f->stream));
+  dim3 grid((unsigned)std::min<long long>(nblk(f->N, 256), 1184), (unsigned)f->d);
+  const int32_t* anc = f->anc_valid ? f->anc : nullptr;
+  if (f->dtype == CSSM_F32) k_mean_state<float><<<grid, 256, 0, f->stream>>>((const float*)f->xa, anc, f->scratch, f->d, f->N, f->Ns);
+  else k_mean_state<double><<<grid, 256, 0, f->stream>>>((const double*)f->xa, anc, f->scratch, f->d, f->N, f->Ns);
+  CU(cudaMemcpyAsync(mean_out, f->scratch, (size_t)f->d * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  return CSSM_OK;
+}
+
+int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t n_u, int32_t* ancestors_out, int device) {
+  if (kind < 0 || kind > 2) return fail(CSSM_ERR_INVALID, "unknown resample kind");
+  if (!w || !u || !ancestors_out || n <= 0 || n > 2147483647LL) return fail(CSSM_ERR_INVALID, "bad resample arguments");
+  if (n_u < ((kind == CSSM_RESAMPLE_SYSTEMATIC) ? 1 : n)) return fail(CSSM_ERR_INVALID, "not enough uniforms");
+  int ndev = 0;
+  int rc = cssm_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(CSSM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(CSSM_ERR_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  const long long N = n;
+  const int nt = nblk(N, TILE);
+  double *dw = nullptr, *du = nullptr, *dcend = nullptr, *dcdf = nullptr;
+  int32_t* danc = nullptr;
+  Scalars* sc = nullptr;
+  u128 *ts = nullptr, *te = nullptr;
+  cudaStream_t st = nullptr;
+  int status = CSSM_OK;
+#define RCU(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess && status == CSSM_OK)                                                    \
+      status = fail(CSSM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+  RCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  RCU(cudaMalloc(&dw, (size_t)(N + TILE) * sizeof(double)));
+  RCU(cudaMalloc(&du, (size_t)std::max<int64_t>(n_u, 1) * sizeof(double)));
+  RCU(cudaMalloc(&danc, (size_t)N * sizeof(int32_t)));
+  RCU(cudaMalloc(&sc, sizeof(Scalars)));
+  RCU(cudaMalloc(&ts, (size_t)(nt + 1) * sizeof(u128)));
+  RCU(cudaMalloc(&te, (size_t)(nt + 1) * sizeof(u128)));
+  RCU(cudaMalloc(&dcend, (size_t)(nt + 1) * sizeof(double)));
+  if (kind == CSSM_RESAMPLE_MULTINOMIAL) RCU(cudaMalloc(&dcdf, (size_t)N * sizeof(double)));
+  if (status == CSSM_OK) {
+    Scalars z;
+    std::memset(&z, 0, sizeof(z));
+    z.qb = 96;
+    if (kind == CSSM_RESAMPLE_SYSTEMATIC) z.u_inj = u[0];
+    RCU(cudaMemsetAsync(dw, 0, (size_t)(N + TILE) * sizeof(double), st));
+    RCU(cudaMemcpyAsync(dw, w, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
+    RCU(cudaMemcpyAsync(du, u, (size_t)((kind == CSSM_RESAMPLE_SYSTEMATIC) ? 1 : N) * sizeof(double), cudaMemcpyHostToDevice, st));
+    RCU(cudaMemcpyAsync(sc, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+    const int normalise = (kind == CSSM_RESAMPLE_MULTINOMIAL) ? 0 : 1;
+    k_max_direct<<<std::min(nblk(N, 256), 1184), 256, 0, st>>>(dw, N, sc);
+    k_weight_total<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc);
+    k_tile_sums<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, normalise, sc, ts);
+    k_scan_tiles<<<1, 1024, 0, st>>>(sc, ts, te, dcend, nt, N, normalise, 1, 0, 1, 0u, 0u, 0u, nullptr, nullptr, 0);
+    if (normalise) {
+      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 1, sc, te, dcend, nt, kind,
+                                                         (kind == CSSM_RESAMPLE_STRATIFIED) ? du : nullptr, 0u, 0u, 0u, danc, nullptr, &sc->flags);
+    } else {
+      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 0, sc, te, dcend, nt, kind, nullptr, 0u, 0u, 0u, nullptr, dcdf, &sc->flags);
+      k_multinomial_search<<<nblk(N, 256), 256, 0, st>>>(dcdf, N, du, 0u, 0u, 0u, danc, &sc->flags);
+    }
+    RCU(cudaGetLastError());
+    RCU(cudaMemcpyAsync(ancestors_out, danc, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RCU(cudaStreamSynchronize(st));
+  }
+#undef RCU
+  void* ptrs[] = {dw, du, danc, sc, ts, te, dcend, dcdf};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (st) cudaStreamDestroy(st);
+  return status;
+}
+
+}  // extern "C"

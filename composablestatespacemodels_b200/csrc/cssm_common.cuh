@@ -1,0 +1,232 @@
+// cssm_common.cuh -- device-side building blocks shared by all kernels of libcssm_gpu.so
+// (sm_100a only).  No reference code is involved here: 128-bit fixed point, the deterministic
+// exp, Philox4x32-10 and warp/block helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cssm {
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit unsigned fixed point (value * 2^-q).  Integer addition is associative, so any scan /
+// reduction order -- any tile size, grid size or GPU count -- gives the same bits.
+// ---------------------------------------------------------------------------------------------
+struct u128 {
+  unsigned long long lo, hi;
+};
+__host__ __device__ __forceinline__ u128 make_u128(unsigned long long lo, unsigned long long hi) {
+  u128 r;
+  r.lo = lo;
+  r.hi = hi;
+  return r;
+}
+__host__ __device__ __forceinline__ u128 add128(u128 a, u128 b) {
+  u128 r;
+  r.lo = a.lo + b.lo;
+  r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+  return r;
+}
+__host__ __device__ __forceinline__ bool is_zero128(u128 a) { return (a.lo | a.hi) == 0ull; }
+
+// floor(x * 2^q), x >= 0 finite with x * 2^q < 2^100 (callers keep x <= 1, q <= 96);
+// zero / negative / NaN / subnormal -> 0
+__host__ __device__ __forceinline__ u128 fixq(double x, int q) {
+  if (!(x > 0.0)) return make_u128(0, 0);
+#ifdef __CUDA_ARCH__
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+#else
+  unsigned long long b;
+  memcpy(&b, &x, 8);
+#endif
+  int ef = (int)((b >> 52) & 0x7ff);
+  if (ef == 0) return make_u128(0, 0);
+  unsigned long long mant = (b & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+  int sh = ef - 1075 + q;
+  if (sh >= 0) {
+    if (sh == 0) return make_u128(mant, 0);
+    if (sh < 64) return make_u128(mant << sh, mant >> (64 - sh));
+    return make_u128(0, mant << (sh - 64));
+  }
+  if (sh <= -53) return make_u128(0, 0);
+  return make_u128(mant >> (-sh), 0);
+}
+
+// round-to-nearest-even of e * 2^-q  (q in [32, 128))
+__host__ __device__ __forceinline__ double unfixq(u128 e, int q) {
+  if (is_zero128(e)) return 0.0;
+  int p;
+#ifdef __CUDA_ARCH__
+  p = e.hi ? 127 - __clzll((long long)e.hi) : 63 - __clzll((long long)e.lo);
+#else
+  p = e.hi ? 127 - __builtin_clzll(e.hi) : 63 - __builtin_clzll(e.lo);
+#endif
+  unsigned long long mant;
+  int s = 0;
+  if (p <= 52) {
+    mant = e.lo;
+  } else {
+    s = p - 52;  // 1..75
+    unsigned long long rem_hi, rem_lo, half_hi, half_lo;
+    if (s < 64) {
+      mant = (e.lo >> s) | (e.hi << (64 - s));  // s >= 1 so the shift is < 64; e.hi < 2^(p-63)
+      rem_hi = 0;
+      rem_lo = e.lo & ((1ull << s) - 1ull);
+      half_hi = 0;
+      half_lo = 1ull << (s - 1);
+    } else {
+      int s2 = s - 64;  // 0..11
+      mant = e.hi >> s2;
+      rem_hi = s2 ? (e.hi & ((1ull << s2) - 1ull)) : 0ull;
+      rem_lo = e.lo;
+      half_hi = s2 ? (1ull << (s2 - 1)) : 0ull;
+      half_lo = s2 ? 0ull : (1ull << 63);
+    }
+    bool gt = (rem_hi > half_hi) || (rem_hi == half_hi && rem_lo > half_lo);
+    bool eq = (rem_hi == half_hi) && (rem_lo == half_lo);
+    if (gt || (eq && (mant & 1ull))) mant += 1ull;
+  }
+  // (double)mant is exact (mant <= 2^53); the power of two is normal: s - q in [-127, 43]
+  unsigned long long sb = (unsigned long long)(s - q + 1023) << 52;
+#ifdef __CUDA_ARCH__
+  return __dmul_rn((double)mant, __longlong_as_double((long long)sb));
+#else
+  double sc;
+  memcpy(&sc, &sb, 8);
+  return (double)mant * sc;
+#endif
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// Deterministic exp: the same fma/mul/add sequence as oracle/cssm_oracle.cpp orc_exp_det, so the
+// weights w1 = exp(logw - max) have identical bits on the device and in the checker.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exp_det(double x) {
+  if (x != x) return x;
+  if (x < -745.5) return 0.0;
+  const double LOG2E = 1.4426950408889634074;
+  const double LN2_HI = 6.93147180369123816490e-01;
+  const double LN2_LO = 1.90821492927058770002e-10;
+  double kf = rint(__dmul_rn(x, LOG2E));
+  double r = __fma_rn(kf, -LN2_HI, x);
+  r = __fma_rn(kf, -LN2_LO, r);
+  double p = 1.0 / 6227020800.0;
+  p = __fma_rn(p, r, 1.0 / 479001600.0);
+  p = __fma_rn(p, r, 1.0 / 39916800.0);
+  p = __fma_rn(p, r, 1.0 / 3628800.0);
+  p = __fma_rn(p, r, 1.0 / 362880.0);
+  p = __fma_rn(p, r, 1.0 / 40320.0);
+  p = __fma_rn(p, r, 1.0 / 5040.0);
+  p = __fma_rn(p, r, 1.0 / 720.0);
+  p = __fma_rn(p, r, 1.0 / 120.0);
+  p = __fma_rn(p, r, 1.0 / 24.0);
+  p = __fma_rn(p, r, 1.0 / 6.0);
+  p = __fma_rn(p, r, 0.5);
+  p = __fma_rn(p, r, 1.0);
+  p = __fma_rn(p, r, 1.0);
+  int k = (int)kf;
+  int k1 = k / 2, k2 = k - k1;
+  double s1 = __longlong_as_double((long long)(k1 + 1023) << 52);
+  double s2 = __longlong_as_double((long long)(k2 + 1023) << 52);
+  return __dmul_rn(__dmul_rn(p, s1), s2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based, all state in registers.
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += W0;
+    k1 += W1;
+  }
+  return c;
+}
+
+// what a counter block is used for (upper byte of counter word 3)
+enum : uint32_t { RNG_INIT = 1u << 24, RNG_STEP = 2u << 24, RNG_RESAMPLE = 3u << 24, RNG_SAMPLE_ONE = 4u << 24 };
+
+__device__ __forceinline__ double u64_to_unit_double(uint32_t a, uint32_t b) {
+  unsigned long long v = ((unsigned long long)a << 32) | b;
+  return (double)(v >> 11) * (1.0 / 9007199254740992.0);  // [0, 1)
+}
+
+// two uint32 -> two N(0,1) floats (Box-Muller on the SFU)
+__device__ __forceinline__ void box_muller_f(uint32_t a, uint32_t b, float& z0, float& z1) {
+  float u1 = fmaf(__uint2float_rz(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1)
+  float u2 = __uint2float_rz(b) * 2.3283064365386963e-10f;                                 // [0,1)
+  float r = sqrtf(-1.3862943611198906f * __log2f(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+// four uint32 -> two N(0,1) doubles
+__device__ __forceinline__ void box_muller_d(uint4 v, double& z0, double& z1) {
+  double u1 = u64_to_unit_double(v.x, v.y);
+  double u2 = u64_to_unit_double(v.z, v.w);
+  u1 = 1.0 - u1;  // (0, 1]
+  double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ordered-integer view of a double so that max can be taken with one integer atomic
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long ord_key(double v) {
+#ifdef __CUDA_ARCH__
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+#else
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+#endif
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double ord_unkey(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)b);
+#else
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+#endif
+}
+
+__device__ __forceinline__ u128 shfl_xor128(u128 v, int m) {
+  u128 r;
+  r.lo = __shfl_xor_sync(0xffffffffu, v.lo, m);
+  r.hi = __shfl_xor_sync(0xffffffffu, v.hi, m);
+  return r;
+}
+__device__ __forceinline__ u128 shfl_up128(u128 v, int d) {
+  u128 r;
+  r.lo = __shfl_up_sync(0xffffffffu, v.lo, d);
+  r.hi = __shfl_up_sync(0xffffffffu, v.hi, d);
+  return r;
+}
+__device__ __forceinline__ u128 warp_sum128(u128 v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = add128(v, shfl_xor128(v, m));
+  return v;
+}
+// exact 128-bit atomic add built from two 64-bit atomics; commutative, so the final value does
+// not depend on the order in which blocks arrive
+__device__ __forceinline__ void atomic_add128(u128* dst, u128 v) {
+  unsigned long long old = atomicAdd(&dst->lo, v.lo);
+  unsigned long long carry = (old + v.lo < old) ? 1ull : 0ull;
+  if (v.hi | carry) atomicAdd(&dst->hi, v.hi + carry);
+}
+#endif  // __CUDACC__
+
+}  // namespace cssm

@@ -1,0 +1,317 @@
+"""The particle filter behind the reference's API (reference: model/ParticleFilter.scala).
+
+`Filter`, `FilterLgcp`, `FilterInit` and the `ParticleFilter` constructors keep the reference's
+names and argument meaning; every particle operation runs in libcssm_gpu.so on the GPU.  A
+`PfState` does not hold the cloud on the host: `particles` copies it out of device memory on
+demand, `ll` and `ess` are plain numbers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .resampling import Resampling
+
+
+class Data:
+    """model/Data.scala: anything with a time and an optional observation."""
+
+    def __init__(self, t, observation):
+        self.t = float(t)
+        self.observation = None if observation is None else float(observation)
+
+
+TimedObservation = Data
+
+
+class StateSpace:
+    """model/Sde.scala:170: a state at a time."""
+
+    def __init__(self, time, state):
+        self.time, self.state = time, state
+
+
+class PfState:
+    """model/ParticleFilter.scala:32-37.  `particles` is read from the device when asked for."""
+
+    def __init__(self, t, observation, handle, ll, ess):
+        self.t, self.observation, self.ll, self.ess = t, observation, ll, ess
+        self._handle = handle
+
+    @property
+    def particles(self):
+        """The resampled cloud as an array [N, d] (particle-major, like Vector[State])."""
+        return self._handle.get_particles().T.copy()
+
+
+class GpuFilterHandle:
+    """Owner of one cssm_filter_t (AutoCloseable on the JVM side)."""
+
+    def __init__(self, mod, resample_kind, n, dtype=_abi.F32, device=0, seed=0, stream_id=0):
+        self._lib = _abi.lib()
+        self._h = C.c_void_p()
+        self.mod, self.n, self.d = mod, int(n), mod.dimension
+        desc, keep = mod.desc()
+        _abi.check(self._lib.cssm_filter_create(C.byref(desc), self.n, resample_kind, dtype, device, seed, stream_id,
+                                                C.byref(self._h)))
+        self.resample_kind, self.dtype = resample_kind, dtype
+
+    def close(self):
+        if self._h:
+            self._lib.cssm_filter_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- life cycle -------------------------------------------------------------------------
+    def set_params(self, mod):
+        desc, keep = mod.desc()
+        _abi.check(self._lib.cssm_filter_set_params(self._h, C.byref(desc)))
+        self.mod = mod
+
+    def reseed(self, seed, stream_id=0):
+        _abi.check(self._lib.cssm_filter_reseed(self._h, seed, stream_id))
+
+    def set_stream(self, cuda_stream):
+        _abi.check(self._lib.cssm_filter_set_stream(self._h, cuda_stream))
+
+    # ---- stepping ---------------------------------------------------------------------------
+    def init(self, t0):
+        _abi.check(self._lib.cssm_filter_init(self._h, float(t0)))
+
+    def init_state(self, t0, x0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        _abi.check(self._lib.cssm_filter_init_state(self._h, float(t0), _abi.dptr(x0)))
+
+    def init_injected(self, t0, z0):
+        z0 = np.ascontiguousarray(z0, dtype=np.float64)
+        assert z0.shape == (self.d, self.n)
+        _abi.check(self._lib.cssm_filter_init_injected(self._h, float(t0), _abi.dptr(z0)))
+
+    def step(self, t, observation):
+        ll, ess = C.c_double(), C.c_int32()
+        has = 0 if observation is None else 1
+        _abi.check(self._lib.cssm_filter_step(self._h, float(t), has, 0.0 if observation is None else float(observation),
+                                              C.byref(ll), C.byref(ess)))
+        return ll.value, ess.value
+
+    def n_substeps(self, dt):
+        n = C.c_int64()
+        _abi.check(self._lib.cssm_filter_n_substeps(self._h, float(dt), C.byref(n)))
+        return n.value
+
+    def step_injected(self, t, observation, z, u, want=("x_prop", "logw", "w1", "anc")):
+        """One stepFilter with caller-provided noise; returns a dict of the device's results."""
+        has = 0 if observation is None else 1
+        z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        u = None if u is None else np.ascontiguousarray(np.atleast_1d(u), dtype=np.float64)
+        out = {}
+        xp = np.empty((self.d, self.n)) if "x_prop" in want else None
+        lw = np.empty(self.n) if "logw" in want else None
+        w1 = np.empty(self.n) if "w1" in want else None
+        anc = np.empty(self.n, dtype=np.int32) if "anc" in want else None
+        ll, ess = C.c_double(), C.c_int32()
+        _abi.check(self._lib.cssm_filter_step_injected(
+            self._h, float(t), has, 0.0 if observation is None else float(observation), _abi.dptr(z), _abi.dptr(u),
+            _abi.dptr(xp), _abi.dptr(lw), _abi.dptr(w1),
+            None if anc is None else anc.ctypes.data_as(_abi.c_int32_p), C.byref(ll), C.byref(ess)))
+        out.update(x_prop=xp, logw=lw, w1=w1, anc=anc, ll=ll.value, ess=ess.value)
+        return out
+
+    # ---- whole series -----------------------------------------------------------------------
+    @staticmethod
+    def _series(data):
+        t = np.ascontiguousarray([d.t for d in data], dtype=np.float64)
+        y = np.ascontiguousarray([0.0 if d.observation is None else d.observation for d in data], dtype=np.float64)
+        h = np.ascontiguousarray([0 if d.observation is None else 1 for d in data], dtype=np.uint8)
+        return t, y, h
+
+    def ll_arrays(self, t, y, has_obs=None):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        h = None if has_obs is None else np.ascontiguousarray(has_obs, dtype=np.uint8)
+        ll = C.c_double()
+        _abi.check(self._lib.cssm_filter_ll(self._h, _abi.dptr(t), _abi.dptr(y),
+                                            None if h is None else h.ctypes.data_as(_abi.c_uint8_p), t.size, C.byref(ll)))
+        return ll.value
+
+    def load_series(self, t, y, has_obs=None):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        h = None if has_obs is None else np.ascontiguousarray(has_obs, dtype=np.uint8)
+        _abi.check(self._lib.cssm_filter_load_series(self._h, _abi.dptr(t), _abi.dptr(y),
+                                                     None if h is None else h.ctypes.data_as(_abi.c_uint8_p), t.size))
+        self._T = t.size
+
+    def ll_resident(self, steps=False):
+        ll = C.c_double()
+        if not steps:
+            _abi.check(self._lib.cssm_filter_ll_resident(self._h, C.byref(ll), None, None))
+            return ll.value
+        lls, ess = np.empty(self._T), np.empty(self._T, dtype=np.int32)
+        _abi.check(self._lib.cssm_filter_ll_resident(self._h, C.byref(ll), _abi.dptr(lls), ess.ctypes.data_as(_abi.c_int32_p)))
+        return ll.value, lls, ess
+
+    def run_arrays(self, t, y, has_obs=None):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        h = None if has_obs is None else np.ascontiguousarray(has_obs, dtype=np.uint8)
+        ll = C.c_double()
+        states = np.empty((t.size + 1, self.d))
+        _abi.check(self._lib.cssm_filter_run(self._h, _abi.dptr(t), _abi.dptr(y),
+                                             None if h is None else h.ctypes.data_as(_abi.c_uint8_p), t.size, C.byref(ll),
+                                             _abi.dptr(states)))
+        return ll.value, states
+
+    def last_elapsed_ms(self):
+        ms = C.c_float()
+        _abi.check(self._lib.cssm_filter_last_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def last_launches(self):
+        n = C.c_int64()
+        _abi.check(self._lib.cssm_filter_last_launches(self._h, C.byref(n)))
+        return n.value
+
+    # ---- reading the cloud ------------------------------------------------------------------
+    def get_particles(self):
+        x = np.empty((self.d, self.n))
+        _abi.check(self._lib.cssm_filter_get_particles(self._h, _abi.dptr(x)))
+        return x
+
+    def sample_one(self):
+        x = np.empty(self.d)
+        _abi.check(self._lib.cssm_filter_sample_one(self._h, _abi.dptr(x)))
+        return x
+
+    def get_ll(self):
+        ll, ess = C.c_double(), C.c_int32()
+        _abi.check(self._lib.cssm_filter_get_ll(self._h, C.byref(ll), C.byref(ess)))
+        return ll.value, ess.value
+
+    def mean_state(self):
+        m = np.empty(self.d)
+        _abi.check(self._lib.cssm_filter_mean_state(self._h, _abi.dptr(m)))
+        return m
+
+
+class _ParticleFilterBase:
+    """trait ParticleFilter[S], model/ParticleFilter.scala:96-167, on the GPU."""
+
+    def __init__(self, mod, resample, dtype=_abi.F32, device=0, seed=0, stream_id=0):
+        self.mod = mod
+        self.resample = resample
+        self.resample_kind = Resampling.kind_of(resample)
+        self.dtype, self.device, self.seed, self.stream_id = dtype, device, seed, stream_id
+        self._handle = None
+
+    def _get(self, n):
+        if self._handle is None or self._handle.n != n:
+            if self._handle is not None:
+                self._handle.close()
+            self._handle = GpuFilterHandle(self.mod, self.resample_kind, n, self.dtype, self.device, self.seed, self.stream_id)
+        return self._handle
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
+    def initialiseState(self, particles, t0):
+        """model/ParticleFilter.scala:105-108"""
+        h = self._get(particles)
+        h.init(t0)
+        return PfState(t0, None, h, 0.0, particles)
+
+    def stepFilter(self, s, y):
+        """model/ParticleFilter.scala:116-132 (FilterLgcp :210-226).  The cloud lives in the
+        handle, so states must be stepped in order (as foldLeft / scan do)."""
+        h = s._handle
+        ll, ess = h.step(y.t, y.observation)
+        return PfState(y.t, y.observation, h, ll, ess)
+
+    def llFilter(self, data, n):
+        """model/ParticleFilter.scala:137-140"""
+        h = self._get(n)
+        t, y, ho = GpuFilterHandle._series(data)
+        return h.ll_arrays(t, y, ho)
+
+    def filter(self, data, particles):
+        """model/ParticleFilter.scala:152-158: (ll, one sampled particle per time, T+1 of them)"""
+        h = self._get(particles)
+        t, y, ho = GpuFilterHandle._series(data)
+        ll, states = h.run_arrays(t, y, ho)
+        times = [float(t.min())] + [float(v) for v in t]
+        return ll, [StateSpace(tt, st) for tt, st in zip(times, states)]
+
+    def filterStream(self, t0, particles):
+        """model/ParticleFilter.scala:163-166: Flow[Data].scan(init)(stepFilter) as a generator
+        transformer: emits the initial state, then one PfState per datum."""
+        def flow(source):
+            s = self.initialiseState(particles, t0)
+            yield s
+            for y in source:
+                s = self.stepFilter(s, y)
+                yield s
+        return flow
+
+
+class Filter(_ParticleFilterBase):
+    """model/ParticleFilter.scala:233-246"""
+
+
+class FilterLgcp(_ParticleFilterBase):
+    """model/ParticleFilter.scala:169-227: log-Gaussian Cox process, sub-step 10^-precision."""
+
+    def __init__(self, mod, resample, precision, **kw):
+        if mod.obs_kind != _abi.OBS_LGCP:
+            raise Exception("FilterLgcp needs a model built with Model.lgcp")
+        from .model import Model
+        super().__init__(Model(mod.leaves, mod.step_mode, precision), resample, **kw)
+        self.precision = precision
+
+
+class FilterInit(_ParticleFilterBase):
+    """model/ParticleFilter.scala:252-271: every particle starts at a given state."""
+
+    def __init__(self, mod, resample, initState, **kw):
+        super().__init__(mod, resample, **kw)
+        self.initState = np.asarray(initState, dtype=np.float64)
+
+    def initialiseState(self, particles, t0):
+        h = self._get(particles)
+        h.init_state(t0, self.initState)
+        return PfState(t0, None, h, 0.0, particles)
+
+
+class ParticleFilter:
+    """object ParticleFilter, model/ParticleFilter.scala:313-361: Readers from Model."""
+
+    @staticmethod
+    def filter(resample, t0, n, **kw):
+        return lambda mod: Filter(mod, resample, **kw).filterStream(t0, n)
+
+    @staticmethod
+    def filterInit(resample, t0, n, initState, **kw):
+        return lambda mod: FilterInit(mod, resample, initState, **kw).filterStream(t0, n)
+
+    @staticmethod
+    def filterLlState(data, resample, n, **kw):
+        return lambda mod: Filter(mod, resample, **kw).filter(data, n)
+
+    @staticmethod
+    def likelihood(data, resample, n, **kw):
+        return lambda mod: Filter(mod, resample, **kw).llFilter(data, n)
+
+    @staticmethod
+    def effectiveSampleSize(weights):
+        """model/ParticleFilter.scala:431-434 (host helper for small vectors)."""
+        w = np.asarray(weights, dtype=np.float64)
+        wn = w / w.sum()
+        return int(np.floor(1.0 / np.sum(wn * wn)))

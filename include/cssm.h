@@ -1,0 +1,231 @@
+/*
+ * cssm.h -- C ABI of libcssm_gpu.so: the B200 (sm_100a) particle-filter hot path that sits
+ * behind the Scala API of jonnylaw/ComposableStateSpaceModels.
+ *
+ * The reference has no FFI of its own (it is 100 % Scala).  Every entry point below names the
+ * reference interface it replaces; paths are relative to the reference checkout,
+ * "model/X.scala" = src/main/scala/com/github/jonnylaw/model/X.scala.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns an int status: 0 = ok, <0 = error (cssm_status); the message of
+ *     the last error on the calling thread is returned by cssm_last_error().
+ *   - the caller owns every host buffer; the library owns all device memory and streams.
+ *   - a handle is not thread-affine (cudaSetDevice on every entry); one handle must not be used
+ *     from two threads at once; different handles may be used concurrently.
+ *   - there is NO CPU fallback: with no usable CUDA device every compute entry point fails with
+ *     CSSM_ERR_CUDA.
+ *
+ * Particle state layout (host side of the ABI): structure-of-arrays, x[k*N + i] = coordinate k
+ * (leaves in Tree.flatten order, model/Tree.scala:49-53, components in order inside a leaf) of
+ * particle i.  Injected noise uses the same [d][N] layout.
+ */
+#ifndef CSSM_H
+#define CSSM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSSM_VERSION 100 /* 0.1.0 */
+#define CSSM_MAX_DIM 32  /* total latent dimension (sum of leaf dimensions) */
+
+typedef enum {
+  CSSM_OK = 0,
+  CSSM_ERR_INVALID = -1,     /* bad argument / malformed model descriptor                    */
+  CSSM_ERR_CUDA = -2,        /* CUDA runtime error or no device (there is no CPU fallback)   */
+  CSSM_ERR_NOMEM = -3,       /* device or host allocation failed                             */
+  CSSM_ERR_UNSUPPORTED = -4, /* valid request that this build does not implement             */
+  CSSM_ERR_STATE = -5,       /* call order violated (e.g. step before init)                  */
+  CSSM_ERR_COMM = -6         /* multi-GPU communicator failure                               */
+} cssm_status;
+
+/* model/Sde.scala:69-163 */
+typedef enum { CSSM_SDE_BROWNIAN = 0, CSSM_SDE_GEN_BROWNIAN = 1, CSSM_SDE_OU = 2 } cssm_sde_kind;
+/* Model.f: first component (model/Model.scala:184,250,271,328,366) or seasonal (:217-225) */
+typedef enum { CSSM_F_FIRST = 0, CSSM_F_SEASONAL = 1 } cssm_f_kind;
+/* observation model of the LEFT-MOST model of a composition (model/Model.scala:118-132) */
+typedef enum {
+  CSSM_OBS_POISSON = 0,   /* model/Model.scala:266-274 */
+  CSSM_OBS_NEGBIN = 1,    /* :168-196 */
+  CSSM_OBS_NORMAL = 2,    /* LinearModel :241-259 and SeasonalModel :204-234 */
+  CSSM_OBS_BERNOULLI = 3, /* :315-337 */
+  CSSM_OBS_LGCP = 4       /* :363-369 via FilterLgcp, model/ParticleFilter.scala:169-227 */
+} cssm_obs_kind;
+/* exact transition (the stepFunction overrides) or Euler-Maruyama (model/Sde.scala:23-43) */
+typedef enum { CSSM_STEP_EXACT = 0, CSSM_STEP_EULER = 1 } cssm_step_mode;
+/* model/Resampling.scala:63-96 */
+typedef enum { CSSM_RESAMPLE_SYSTEMATIC = 0, CSSM_RESAMPLE_STRATIFIED = 1, CSSM_RESAMPLE_MULTINOMIAL = 2 } cssm_resample_kind;
+typedef enum { CSSM_F32 = 0, CSSM_F64 = 1 } cssm_dtype;
+
+/*
+ * One leaf of the composed model = one (Model, Sde) pair of the reference.
+ * All arrays have length `dim` and hold EFFECTIVE values: already cyclically repeated by
+ * Sde.buildParamRepeat (model/Sde.scala:177-179) and already transformed as the SDE
+ * constructors do (c0, sigma -> exp; phi -> logistic; model/Sde.scala:70-73,99-102,133-137).
+ * Unused arrays (phi for Brownian motion, mu for plain Brownian motion) may be NULL.
+ * A seasonal leaf must have dim == 2*harmonics (model/Model.scala:217-225).
+ */
+typedef struct {
+  int32_t sde_kind; /* cssm_sde_kind */
+  int32_t dim;
+  int32_t f_kind; /* cssm_f_kind */
+  int32_t period; /* seasonal only */
+  int32_t harmonics;
+  const double* m0;
+  const double* c0;
+  const double* phi;
+  const double* mu;
+  const double* sigma;
+} cssm_leaf_t;
+
+/*
+ * A parameterised composed model: what UnparamModel.run(params) returns in the reference
+ * (model/Model.scala:110-136), flattened.  `scale` is the RAW ParamNode.scale of the left-most
+ * leaf (log of the NegBin size, log of the Normal standard deviation).
+ */
+typedef struct {
+  int32_t n_leaves;
+  const cssm_leaf_t* leaves; /* Tree.flatten order */
+  int32_t obs_kind;          /* cssm_obs_kind */
+  int32_t has_scale;
+  double scale;
+  int32_t step_mode;      /* cssm_step_mode */
+  int32_t lgcp_precision; /* FilterLgcp.precision: sub-step = 10^-precision */
+} cssm_model_desc_t;
+
+typedef struct cssm_filter cssm_filter_t;
+
+/* ------------------------------------------------------------------------------------------
+ * library
+ * ---------------------------------------------------------------------------------------- */
+int cssm_version(void);
+const char* cssm_last_error(void); /* thread-local, never NULL */
+int cssm_device_count(int* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * filter life cycle
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces constructing Filter(mod, resample) / FilterLgcp(mod, resample, precision)
+ * (model/ParticleFilter.scala:169-172,233-235) for `n_particles` particles.
+ * `seed`/`stream_id` key the in-register Philox4x32-10 generator; runs with the same
+ * (seed, stream_id) and the same call sequence are reproducible and independent of the
+ * launch geometry. */
+int cssm_filter_create(const cssm_model_desc_t* model, int64_t n_particles, int resample_kind,
+                       int dtype, int device, uint64_t seed, uint64_t stream_id,
+                       cssm_filter_t** out);
+
+/* New parameter values, same shapes: what PMMH does through model.run(p) per iteration
+ * (examples/DetermineParameters.scala:70-72, model/PMMH.scala:71).  No reallocation. */
+int cssm_filter_set_params(cssm_filter_t* f, const cssm_model_desc_t* model);
+
+/* Re-key the generator (a fresh, independent likelihood evaluation). */
+int cssm_filter_reseed(cssm_filter_t* f, uint64_t seed, uint64_t stream_id);
+
+/* Run on a caller-provided CUDA stream (a cudaStream_t passed as void*), e.g. torch's current
+ * stream; NULL restores the filter's own stream. */
+int cssm_filter_set_stream(cssm_filter_t* f, void* cuda_stream);
+
+int cssm_filter_destroy(cssm_filter_t* f);
+
+int cssm_filter_dim(const cssm_filter_t* f, int32_t* d_out);
+int cssm_filter_n_particles(const cssm_filter_t* f, int64_t* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * stepping API  (ParticleFilter.initialiseState / stepFilter)
+ * ---------------------------------------------------------------------------------------- */
+
+/* initialiseState, model/ParticleFilter.scala:105-108: draws every particle from
+ * Sde.initialState (model/Sde.scala:75-80,104-108,152-156,206-209); ll = 0, ess = N. */
+int cssm_filter_init(cssm_filter_t* f, double t0);
+
+/* FilterInit.initialiseState, model/ParticleFilter.scala:257-260: all particles = x0[d]. */
+int cssm_filter_init_state(cssm_filter_t* f, double t0, const double* x0);
+
+/* stepFilter, model/ParticleFilter.scala:116-132 (FilterLgcp: :210-226).
+ * has_obs == 0 is `observation = None`: propagate only, ll and ess unchanged.
+ * *ll_out is the accumulated log-likelihood after the step, *ess_out the ESS. */
+int cssm_filter_step(cssm_filter_t* f, double t, int has_obs, double y, double* ll_out,
+                     int32_t* ess_out);
+
+/* ------------------------------------------------------------------------------------------
+ * whole-series API  (ParticleFilter.llFilter / filter)
+ * ---------------------------------------------------------------------------------------- */
+
+/* llFilter, model/ParticleFilter.scala:137-140: t0 = min(t), initialiseState, fold stepFilter
+ * over the T data, return the log-likelihood.  The whole T-loop runs on the device without a
+ * host round trip.  Host buffers in, one double out (this is the end-to-end entry point). */
+int cssm_filter_ll(cssm_filter_t* f, const double* t, const double* y, const uint8_t* has_obs,
+                   int64_t T, double* ll_out);
+
+/* Split form of cssm_filter_ll for data that stays resident on the device between likelihood
+ * evaluations (PMMH evaluates the same series at many parameter values):
+ *   cssm_filter_load_series  builds and uploads the per-observation constant table,
+ *   cssm_filter_ll_resident  runs init + T steps on it.  ess_out/ll_steps_out may be NULL;
+ *   otherwise they receive the T per-step values (ll accumulated). */
+int cssm_filter_load_series(cssm_filter_t* f, const double* t, const double* y,
+                            const uint8_t* has_obs, int64_t T);
+int cssm_filter_ll_resident(cssm_filter_t* f, double* ll_out, double* ll_steps_out,
+                            int32_t* ess_out);
+
+/* filter, model/ParticleFilter.scala:152-158: as llFilter but also returns, for the initial
+ * state and each of the T steps, ONE particle sampled uniformly from the cloud
+ * (Resampling.sampleOne, model/Resampling.scala:151-154): states_out[(T+1)][d]. */
+int cssm_filter_run(cssm_filter_t* f, const double* t, const double* y, const uint8_t* has_obs,
+                    int64_t T, double* ll_out, double* states_out);
+
+/* device time (ms, CUDA events on the filter's stream) of the last whole-series call */
+int cssm_filter_last_elapsed_ms(const cssm_filter_t* f, float* ms_out);
+/* number of kernels the last whole-series / step call launched */
+int cssm_filter_last_launches(const cssm_filter_t* f, int64_t* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * reading the cloud back  (PfState.particles, model/ParticleFilter.scala:32-37)
+ * ---------------------------------------------------------------------------------------- */
+/* resampled particles after the last step, x_out[d][N] (SoA) */
+int cssm_filter_get_particles(cssm_filter_t* f, double* x_out);
+/* Resampling.sampleOne of the current cloud, x_out[d] */
+int cssm_filter_sample_one(cssm_filter_t* f, double* x_out);
+/* PfState.ll / PfState.ess */
+int cssm_filter_get_ll(cssm_filter_t* f, double* ll_out, int32_t* ess_out);
+/* per-coordinate mean of the current cloud (ParticleFilter.meanState, :477-479), mean_out[d] */
+int cssm_filter_mean_state(cssm_filter_t* f, double* mean_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Resample[A]  (model/package.scala:23; model/Resampling.scala:63-96)
+ * ---------------------------------------------------------------------------------------- */
+/* weights w[n] (unnormalised, >= 0), uniforms u: systematic 1, stratified n, multinomial n.
+ * ancestors_out[n]: the index into the input vector each output position takes. */
+int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t n_u,
+                  int32_t* ancestors_out, int device);
+
+/* ------------------------------------------------------------------------------------------
+ * parity hooks: identical kernels, noise supplied by the caller instead of Philox
+ * ---------------------------------------------------------------------------------------- */
+/* z0[d][N] standard normals (as double; converted to the filter dtype on upload) */
+int cssm_filter_init_injected(cssm_filter_t* f, double t0, const double* z0);
+
+/* One stepFilter with injected noise.
+ *   z   [n_sub][d][N] standard normals; n_sub = 1 except for LGCP (ceil(dt/10^-precision),
+ *       0 when dt == 0) -- see cssm_filter_n_substeps.
+ *   u   uniforms for the resampler (1 / N / N), ignored when has_obs == 0.
+ * Optional outputs (NULL to skip), all as the step computed them on the device:
+ *   x_prop_out[d][N]  propagated particles before resampling   (model/ParticleFilter.scala:118)
+ *   logw_out[N]       log-weights                               (:123)
+ *   w1_out[N]         exp(logw - max)                           (:125)
+ *   anc_out[N]        ancestor indices chosen by the resampler  (:126)
+ */
+int cssm_filter_step_injected(cssm_filter_t* f, double t, int has_obs, double y, const double* z,
+                              const double* u, double* x_prop_out, double* logw_out,
+                              double* w1_out, int32_t* anc_out, double* ll_out,
+                              int32_t* ess_out);
+/* number of sub-steps FilterLgcp.calcWeight takes for time increment dt (:190); 1 otherwise */
+int cssm_filter_n_substeps(const cssm_filter_t* f, double dt, int64_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSSM_H */

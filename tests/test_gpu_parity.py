@@ -1,0 +1,192 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on identical injected
+noise and uniforms.  Tolerances (BASELINE.json north_star): states, log-weights and the
+log-likelihood within 1e-5 relative in fp32 and 1e-12 in fp64; ancestor indices bit-exact."""
+import numpy as np
+import pytest
+
+import composablestatespacemodels_b200 as cs
+from composablestatespacemodels_b200 import _abi
+import oracle
+from configs import ALL, SYS, STRAT, MULTI, c1, c2, c3
+
+pytestmark = pytest.mark.gpu
+
+TOL = {_abi.F64: 1e-12, _abi.F32: 1e-5}
+
+
+def rel_close(a, b, tol, what):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.maximum(np.abs(b), 1.0)
+    err = np.max(np.abs(a - b) / scale)
+    assert err <= tol, f"{what}: max relative error {err:.3e} > {tol:.1e}"
+
+
+def run_steps(mod, N, T, kind, dtype, seed=0, missing=()):
+    """T stepFilters with injected noise on the GPU; each stage checked against the oracle fed
+    with the device's own output of the previous stage (so every comparison is like for like)."""
+    rng = np.random.default_rng(seed)
+    orc = oracle.Oracle(mod)
+    d = mod.dimension
+    t, y, _ = orc.simulate(T, 0.1, seed + 11)
+    h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, seed=3)
+    tol = TOL[dtype]
+    z0 = rng.standard_normal((d, N))
+    h.init_injected(t[0], z0)
+    x = h.get_particles()
+    rel_close(x, orc.init_state(z0), tol, "initial state")
+    tp, ll_ref = t[0], 0.0
+    for s in range(T):
+        obs = None if s in missing else float(y[s])
+        z = rng.standard_normal((d, N))
+        u = rng.random(1 if kind == SYS else N)
+        g = h.step_injected(t[s], obs, z, u)
+        # stage 1: propagate + weight, from the device's own previous cloud
+        o = oracle.Oracle(mod)
+        o.reset(N)
+        r = o.step(x, tp, t[s], obs, z, u, kind, oracle.ORDER_DEVICE)
+        rel_close(g["x_prop"], r["x_prop"], tol, f"step {s} propagated state")
+        if obs is None:
+            x = h.get_particles()
+            np.testing.assert_array_equal(x, g["x_prop"])
+            tp = t[s]
+            continue
+        rel_close(g["logw"], r["logw"], tol, f"step {s} log-weights")
+        # stage 2: from the device's log-weights -> w1, ll increment, ESS, ancestors
+        mx = float(np.max(g["logw"]))
+        w1 = oracle.w1(g["logw"], mx, oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(g["w1"], w1)  # deterministic exp: identical bits
+        incr, ess = oracle.ll_ess(w1, mx, oracle.ORDER_DEVICE)
+        ll_ref += incr
+        assert g["ess"] == ess
+        rel_close(g["ll"], ll_ref, 1e-12, f"step {s} log-likelihood")
+        anc = oracle.resample(kind, w1, u, oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(g["anc"], anc)
+        # the reference-order (sequential fp64) restatement agrees except for last-ulp ties
+        anc_ref = oracle.resample(kind, oracle.w1(g["logw"], mx, oracle.ORDER_REFERENCE), u, oracle.ORDER_REFERENCE)
+        assert np.mean(anc_ref != anc) <= 2e-3
+        # stage 3: gather
+        x = h.get_particles()
+        np.testing.assert_array_equal(x, g["x_prop"][:, anc])
+        tp = t[s]
+    h.close()
+
+
+@pytest.mark.parametrize("name", sorted(ALL))
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+def test_step_parity_systematic(name, dtype):
+    run_steps(ALL[name](), 1000, 6, SYS, dtype, seed=1)
+
+
+@pytest.mark.parametrize("kind", [STRAT, MULTI])
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+def test_step_parity_other_resamplers(kind, dtype):
+    run_steps(c2(), 3000, 4, kind, dtype, seed=2)
+
+
+def test_step_parity_ragged_and_missing():
+    # N not a multiple of anything, observations missing at steps 1 and 2
+    run_steps(c2(), 4099, 5, SYS, _abi.F64, seed=3, missing=(1, 2))
+    run_steps(c1(), 1, 3, SYS, _abi.F64, seed=4)
+    run_steps(c1(), 2049, 3, STRAT, _abi.F32, seed=5)
+
+
+def test_step_parity_euler():
+    run_steps(c2().withStepMode(_abi.STEP_EULER), 1500, 4, SYS, _abi.F64, seed=6)
+    run_steps(ALL["c4"]().withStepMode(_abi.STEP_EULER), 1500, 4, SYS, _abi.F32, seed=7)
+
+
+@pytest.mark.parametrize("kind", [SYS, STRAT, MULTI])
+def test_resample_bit_exact(kind):
+    rng = np.random.default_rng(5)
+    cases = []
+    for n in (1, 2, 7, 2048, 2049, 5000, 70001):
+        cases.append(rng.random(n))                                   # SamplingTest.scala: weights in [0, 1]
+        cases.append(np.exp(rng.normal(0, 2, n)))                     # exp(N(0, 2^2)), may exceed 1
+        w = np.full(n, 1e-30); w[n // 3] = 1.0
+        cases.append(w)                                               # degenerate: one particle carries everything
+        w = rng.random(n); w[rng.random(n) < 0.7] = 0.0
+        if w.sum() == 0: w[0] = 1.0
+        cases.append(w)                                               # runs of exact zeros -> duplicate TreeMap keys
+    cases.append(np.ones(6400))                                       # src/bench/scala/Resampling.scala:17
+    for w in cases:
+        n = w.size
+        u = rng.random(1 if kind == SYS else n)
+        got = cs.resampling.ancestors(kind, w, u)
+        want = oracle.resample(kind, w, u, oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(got, want)
+        assert got.size == n                                          # the reference's only pinned property
+        if kind != MULTI:
+            assert np.all(np.diff(got) >= 0)
+
+
+def test_resample_large_bit_exact():
+    rng = np.random.default_rng(9)
+    n = 1 << 20
+    w = np.exp(rng.normal(0, 3, n))
+    w[100000:400000] = 0.0   # a run of zeros spanning many scan tiles
+    for kind in (SYS, STRAT):
+        u = rng.random(1 if kind == SYS else n)
+        got = cs.resampling.ancestors(kind, w, u)
+        np.testing.assert_array_equal(got, oracle.resample(kind, w, u, oracle.ORDER_DEVICE))
+        ref = oracle.resample(kind, w, u, oracle.ORDER_REFERENCE)
+        assert np.mean(ref != got) < 1e-3
+
+
+def test_lgcp_step_parity():
+    mod = c3(precision=2)
+    for dtype in (_abi.F64, _abi.F32):
+        rng = np.random.default_rng(8)
+        N, d = 1200, 1
+        h = cs.GpuFilterHandle(mod, STRAT, N, dtype=dtype, seed=1)
+        z0 = rng.standard_normal((d, N))
+        h.init_injected(0.0, z0)
+        x = h.get_particles()
+        tp = 0.0
+        for t in (0.0, 0.13, 0.2):
+            n = oracle.lgcp_nsub(t - tp, 2)
+            assert n == h.n_substeps(t - tp)
+            z = rng.standard_normal((max(n, 1), d, N))
+            u = rng.random(N)
+            g = h.step_injected(t, 1.0, z if n > 0 else None, u)
+            o = oracle.Oracle(mod); o.reset(N)
+            r = o.step(x, tp, t, 1.0, z, u, STRAT, oracle.ORDER_DEVICE)
+            rel_close(g["x_prop"], r["x_prop"], TOL[dtype], "lgcp state")
+            np.testing.assert_allclose(g["logw"], r["logw"], rtol=TOL[dtype] * 10, atol=TOL[dtype] * 10)
+            mx = float(np.max(g["logw"]))
+            w1 = oracle.w1(g["logw"], mx)
+            np.testing.assert_array_equal(g["anc"], oracle.resample(STRAT, w1, u))
+            x = h.get_particles()
+            tp = t
+        h.close()
+
+
+def test_full_filter_fp64_matches_oracle_end_to_end():
+    """C1 (1000 particles x 500 observations), every step with injected noise: the accumulated
+    log-likelihood of the GPU equals the oracle's own end-to-end run (no hand-over of device
+    intermediates), reference summation order included."""
+    mod = c1()
+    N, T, d = 1000, 500, 1
+    orc = oracle.Oracle(mod)
+    t, y, _ = orc.simulate(T, 0.1, 1)
+    rng = np.random.default_rng(0)
+    h = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F64, seed=1)
+    z0 = rng.standard_normal((d, N))
+    h.init_injected(t[0], z0)
+    xo = orc.init_state(z0)
+    o_dev, o_ref = oracle.Oracle(mod), oracle.Oracle(mod)
+    o_dev.reset(N); o_ref.reset(N)
+    xr = xo.copy()
+    tp = t[0]
+    n_diff = 0
+    for s in range(T):
+        z, u = rng.standard_normal((d, N)), rng.random(1)
+        g = h.step_injected(t[s], float(y[s]), z, u, want=("anc",))
+        r = o_dev.step(xo, tp, t[s], float(y[s]), z, u, SYS, oracle.ORDER_DEVICE)
+        rr = o_ref.step(xr, tp, t[s], float(y[s]), z, u, SYS, oracle.ORDER_REFERENCE)
+        n_diff += int(np.sum(g["anc"] != r["anc"]))
+        xo, xr, tp = r["x_out"], rr["x_out"], t[s]
+    ll_gpu, _ = h.get_ll()
+    assert n_diff == 0
+    assert abs(ll_gpu - o_dev._ll) <= 1e-12 * abs(o_dev._ll)
+    assert abs(ll_gpu - o_ref._ll) <= 1e-9 * abs(o_ref._ll)
+    h.close()
