@@ -180,6 +180,7 @@ struct cssm_filter {
   Scalars* sc = nullptr;
   u128 *tile_sum = nullptr, *tile_excl = nullptr;
   double* cend = nullptr;
+  double* tile_maxw = nullptr;
   double* ubuf = nullptr;   // N uniforms (stratified / multinomial, injected)
   double* cdf = nullptr;    // N cumulative values (multinomial)
   double* scratch = nullptr;  // grow-only fp64 scratch (injected noise, read-back staging)
@@ -299,15 +300,15 @@ int launch_step(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
   const int normalise = (f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ? 0 : 1;
   const real* lw = (const real*)f->logw;
   k_weight_total<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, f->sc);
-  k_tile_sums<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, normalise, f->sc, f->tile_sum);
+  k_tile_sums<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, normalise, f->sc, f->tile_sum, f->tile_maxw);
   k_scan_tiles<<<1, 1024, 0, f->stream>>>(f->sc, f->tile_sum, f->tile_excl, f->cend, f->nt, f->N, normalise, 0, 1, io.use_u_inj,
                                           f->key0, f->key1, step, io.ll_steps, io.ess_steps, io.step_slot);
   if (normalise) {
-    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 1, f->sc, f->tile_excl, f->cend, f->nt, f->resample_kind,
+    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 1, f->sc, f->tile_excl, f->cend, f->tile_maxw, f->nt, f->resample_kind,
                                                                io.uarr, f->key0, f->key1, step, f->anc, nullptr, &f->sc->flags);
     f->launches += 4;
   } else {
-    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 0, f->sc, f->tile_excl, f->cend, f->nt, f->resample_kind,
+    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 0, f->sc, f->tile_excl, f->cend, f->tile_maxw, f->nt, f->resample_kind,
                                                                nullptr, f->key0, f->key1, step, nullptr, f->cdf, &f->sc->flags);
     k_multinomial_search<<<nblk(f->N, 256), 256, 0, f->stream>>>(f->cdf, f->N, io.uarr, f->key0, f->key1, step, f->anc, &f->sc->flags);
     f->launches += 5;
@@ -528,6 +529,7 @@ int cssm_filter_create(const cssm_model_desc_t* model, int64_t n_particles, int 
   ALLOC(f->tile_sum, (size_t)(f->nt + 1) * sizeof(u128));
   ALLOC(f->tile_excl, (size_t)(f->nt + 1) * sizeof(u128));
   ALLOC(f->cend, (size_t)(f->nt + 1) * sizeof(double));
+  ALLOC(f->tile_maxw, (size_t)(f->nt + 1) * sizeof(double));
   if (resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ALLOC(f->cdf, (size_t)f->Ns * sizeof(double));
 #undef ALLOC
   cudaMemset(f->xa, 0, (size_t)f->d * f->Ns * esz);
@@ -586,7 +588,7 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   if (!f) return CSSM_OK;
   cudaSetDevice(f->device);
   if (f->own_stream) cudaStreamSynchronize(f->own_stream);
-  void* ptrs[] = {f->xa, f->xb, f->logw, f->anc, f->sc, f->tile_sum, f->tile_excl, f->cend, f->ubuf, f->cdf,
+  void* ptrs[] = {f->xa, f->xb, f->logw, f->anc, f->sc, f->tile_sum, f->tile_excl, f->cend, f->tile_maxw, f->ubuf, f->cdf,
                   f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -880,7 +882,7 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
   CU(cudaSetDevice(device));
   const long long N = n;
   const int nt = nblk(N, TILE);
-  double *dw = nullptr, *du = nullptr, *dcend = nullptr, *dcdf = nullptr;
+  double *dw = nullptr, *du = nullptr, *dcend = nullptr, *dcdf = nullptr, *dmaxw = nullptr;
   int32_t* danc = nullptr;
   Scalars* sc = nullptr;
   u128 *ts = nullptr, *te = nullptr;
@@ -900,6 +902,7 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
   RCU(cudaMalloc(&ts, (size_t)(nt + 1) * sizeof(u128)));
   RCU(cudaMalloc(&te, (size_t)(nt + 1) * sizeof(u128)));
   RCU(cudaMalloc(&dcend, (size_t)(nt + 1) * sizeof(double)));
+  RCU(cudaMalloc(&dmaxw, (size_t)(nt + 1) * sizeof(double)));
   if (kind == CSSM_RESAMPLE_MULTINOMIAL) RCU(cudaMalloc(&dcdf, (size_t)N * sizeof(double)));
   if (status == CSSM_OK) {
     Scalars z;
@@ -913,13 +916,13 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
     const int normalise = (kind == CSSM_RESAMPLE_MULTINOMIAL) ? 0 : 1;
     k_max_direct<<<std::min(nblk(N, 256), 1184), 256, 0, st>>>(dw, N, sc);
     k_weight_total<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc);
-    k_tile_sums<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, normalise, sc, ts);
+    k_tile_sums<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, normalise, sc, ts, dmaxw);
     k_scan_tiles<<<1, 1024, 0, st>>>(sc, ts, te, dcend, nt, N, normalise, 1, 0, 1, 0u, 0u, 0u, nullptr, nullptr, 0);
     if (normalise) {
-      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 1, sc, te, dcend, nt, kind,
+      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 1, sc, te, dcend, dmaxw, nt, kind,
                                                          (kind == CSSM_RESAMPLE_STRATIFIED) ? du : nullptr, 0u, 0u, 0u, danc, nullptr, &sc->flags);
     } else {
-      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 0, sc, te, dcend, nt, kind, nullptr, 0u, 0u, 0u, nullptr, dcdf, &sc->flags);
+      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 0, sc, te, dcend, dmaxw, nt, kind, nullptr, 0u, 0u, 0u, nullptr, dcdf, &sc->flags);
       k_multinomial_search<<<nblk(N, 256), 256, 0, st>>>(dcdf, N, du, 0u, 0u, 0u, danc, &sc->flags);
     }
     RCU(cudaGetLastError());
@@ -927,7 +930,7 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
     RCU(cudaStreamSynchronize(st));
   }
 #undef RCU
-  void* ptrs[] = {dw, du, danc, sc, ts, te, dcend, dcdf};
+  void* ptrs[] = {dw, du, danc, sc, ts, te, dcend, dcdf, dmaxw};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (st) cudaStreamDestroy(st);

@@ -453,13 +453,14 @@ k_weight_total(const real* __restrict__ logw, const double* __restrict__ direct,
 template <typename real>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_tile_sums(const real* __restrict__ logw, const double* __restrict__ direct, long long N, int normalise,
-            Scalars* __restrict__ sc, u128* __restrict__ tile_sum) {
+            Scalars* __restrict__ sc, u128* __restrict__ tile_sum, double* __restrict__ tile_maxw) {
   const PreScan ps = pre_scan(sc, direct != nullptr);
   WeightSrc<real> ws{logw, direct, ps.gmax};
   const int qb = ps.qb;
   const double total = unfixq(sc->tot, qb);
   const long long base = (long long)blockIdx.x * TILE;
   u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
+  double mxw = 0.0;
 #pragma unroll
   for (int j = 0; j < TILE_ITEMS; ++j) {
     long long idx = base + j * TILE_THREADS + threadIdx.x;
@@ -468,23 +469,31 @@ k_tile_sums(const real* __restrict__ logw, const double* __restrict__ direct, lo
       double wn = __ddiv_rn(w, total);
       acc = add128(acc, normalise ? fixq(wn, 96) : fixq(w, qb));
       acc2 = add128(acc2, fixq(__dmul_rn(wn, wn), 96));
+      mxw = fmax(mxw, wn);
     }
   }
   acc = warp_sum128(acc);
   acc2 = warp_sum128(acc2);
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
   __shared__ u128 s_acc[TILE_THREADS / 32], s_acc2[TILE_THREADS / 32];
+  __shared__ double s_mxw[TILE_THREADS / 32];
   if ((threadIdx.x & 31) == 0) {
     s_acc[threadIdx.x >> 5] = acc;
     s_acc2[threadIdx.x >> 5] = acc2;
+    s_mxw[threadIdx.x >> 5] = mxw;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     u128 t = s_acc[0], t2 = s_acc2[0];
+    double m2 = s_mxw[0];
     for (int w = 1; w < TILE_THREADS / 32; ++w) {
       t = add128(t, s_acc[w]);
       t2 = add128(t2, s_acc2[w]);
+      m2 = fmax(m2, s_mxw[w]);
     }
     tile_sum[blockIdx.x] = t;
+    tile_maxw[blockIdx.x] = m2;
     atomic_add128(&sc->ess_acc, t2);
   }
 }
@@ -592,7 +601,7 @@ struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stra
 template <typename real>
 __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int normalise, double total, int qb,
                                          const u128* __restrict__ tile_excl, int t, long long N, double* Cs,
-                                         u128* s_warp) {
+                                         double* Ws, u128* s_warp) {
   const long long base = (long long)t * TILE + (long long)threadIdx.x * TILE_ITEMS;
   u128 e[TILE_ITEMS];
   u128 run = make_u128(0, 0);
@@ -600,10 +609,13 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int normalis
   for (int j = 0; j < TILE_ITEMS; ++j) {
     long long idx = base + j;
     u128 q = make_u128(0, 0);
+    double wv = 0.0;
     if (idx < N) {
       double w = ws(idx);
-      q = normalise ? fixq(__ddiv_rn(w, total), 96) : fixq(w, qb);
+      wv = normalise ? __ddiv_rn(w, total) : w;
+      q = normalise ? fixq(wv, 96) : fixq(w, qb);
     }
+    if (Ws) Ws[threadIdx.x * TILE_ITEMS + j] = wv;
     run = add128(run, q);
     e[j] = run;
   }
@@ -629,24 +641,30 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int normalis
   __syncthreads();
 }
 
+// does adding w leave c unchanged?  This is what makes a TreeMap key repeat in the reference
+// (model/Resampling.scala:55-57): the next cumulative sum equals the previous one.
+__device__ __forceinline__ bool vanishes(double c, double w) { return __dadd_rn(c, w) == c; }
+
 // mode 0: search (systematic / stratified), writes anc;  mode 1: write the CDF to cdf_out (multinomial)
 template <typename real>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, int normalise,
               const Scalars* __restrict__ sc, const u128* __restrict__ tile_excl, const double* __restrict__ cend,
-              int nt, int kind, const double* __restrict__ uarr, uint32_t key0, uint32_t key1, uint32_t step,
-              int32_t* __restrict__ anc, double* __restrict__ cdf_out, int* __restrict__ flags_out) {
+              const double* __restrict__ tile_maxw, int nt, int kind, const double* __restrict__ uarr, uint32_t key0,
+              uint32_t key1, uint32_t step, int32_t* __restrict__ anc, double* __restrict__ cdf_out,
+              int* __restrict__ flags_out) {
   __shared__ double Cs[TILE];
+  __shared__ double Ws[TILE];
   __shared__ u128 s_warp[TILE_THREADS / 32];
-  __shared__ long long s_lo, s_hi, s_pend;
-  __shared__ double s_cnext;
-  __shared__ int s_tp, s_lead;
+  __shared__ long long s_lo, s_hi, s_pend, s_jfinal;
+  __shared__ double s_wnext, s_c;
+  __shared__ int s_tp, s_brk;
 
   const int t = blockIdx.x;
   WeightSrc<real> ws{logw, direct, sc->gmax};
   const int qb = sc->qb;
   const double total = sc->total;
-  tile_cdf<real>(ws, normalise, total, qb, tile_excl, t, N, Cs, s_warp);
+  tile_cdf<real>(ws, normalise, total, qb, tile_excl, t, N, Cs, cdf_out ? nullptr : Ws, s_warp);
   const long long tile0 = (long long)t * TILE;
   const int tile_n = (int)min((long long)TILE, N - tile0);
 
@@ -660,19 +678,13 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   if (threadIdx.x == 0) {
     s_lo = (t == 0) ? 0 : kf.count_le(cend[t - 1], N);
     s_hi = (t == nt - 1) ? N : kf.count_le(c_end, N);
-    // does the run of equal CDF values at the end of this tile continue into the next tile?
-    double cn = __longlong_as_double(0x7FF0000000000000ll);
-    if (t < nt - 1) {
-      double w = ws(tile0 + TILE);
-      u128 q = normalise ? fixq(__ddiv_rn(w, total), 96) : fixq(w, qb);
-      cn = unfixq(add128(tile_excl[t + 1], q), normalise ? 96 : qb);
-    }
-    s_cnext = cn;
+    s_wnext = (t < nt - 1) ? __ddiv_rn(ws(tile0 + TILE), total) : 0.0;  // first weight of the next tile
     s_pend = 0x7FFFFFFFFFFFFFFFll;
   }
   __syncthreads();
   const long long lo = s_lo, hi = s_hi;
-  const bool cont = (s_cnext == c_end);
+  // does the run of repeated keys at the end of this tile continue into the next tile?
+  const bool cont = (t < nt - 1) && vanishes(c_end, s_wnext);
   if (t == nt - 1 && threadIdx.x == 0 && kf(N - 1) > c_end) atomicOr(flags_out, FLAG_CLAMPED);  // reference would throw (m.head)
 
   for (long long i = lo + threadIdx.x; i < hi; i += TILE_THREADS) {
@@ -683,40 +695,58 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
       int m = (a + b) >> 1;
       if (Cs[m] >= k) b = m; else a = m + 1;
     }
-    // TreeMap: a duplicated key keeps the last particle inserted (model/Resampling.scala:55-57)
+    // TreeMap: a duplicated key keeps the last particle inserted
     int j = a;
-    double cj = Cs[j];
-    while (j + 1 < tile_n && Cs[j + 1] == cj) ++j;
+    while (j + 1 < tile_n && vanishes(Cs[j], Ws[j + 1])) ++j;
     if (cont && j == tile_n - 1) atomicMin(&s_pend, i);
     anc[i] = (int32_t)(tile0 + j);
   }
   __syncthreads();
   const long long pend = s_pend;
   if (pend >= hi) return;
-  // the selected run of equal keys continues past this tile: its last element is the ancestor
-  if (threadIdx.x == 0) {
-    int a = t + 1, b = nt;  // first tile whose end value exceeds c_end
-    while (a < b) {
-      int m = (a + b) >> 1;
-      if (cend[m] > c_end) b = m; else a = m + 1;
-    }
-    s_tp = a;
-    s_lead = 0;
-  }
+  // The selected run of repeated keys continues past this tile; its last element is the ancestor.
+  // Walk forward: whole tiles are skipped from the tables when every weight in them is strictly
+  // below half an ulp of the running value (same binade), otherwise the tile is recomputed.
+  if (threadIdx.x == 0) { s_tp = t + 1; s_c = c_end; s_jfinal = -1; }
   __syncthreads();
-  const int tp = s_tp;
-  long long jfinal;
-  if (tp >= nt) {
-    jfinal = N - 1;
-  } else {
-    tile_cdf<real>(ws, normalise, total, qb, tile_excl, tp, N, Cs, s_warp);
-    const int tn = (int)min((long long)TILE, N - (long long)tp * TILE);
-    int cnt = 0;
-    for (int j = threadIdx.x; j < tn; j += TILE_THREADS) cnt += (Cs[j] == c_end) ? 1 : 0;
-    if (cnt) atomicAdd(&s_lead, cnt);
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int tp = s_tp;
+      double c = s_c;
+      while (tp < nt) {
+        double ce = cend[tp];
+        // half ulp of c (c > 0 here; a zero running value never skips)
+        long long cb = __double_as_longlong(c), eb = __double_as_longlong(ce);
+        bool same_binade = (cb >> 52) == (eb >> 52) && ((cb >> 52) & 0x7ff) > 54;
+        double half_ulp = same_binade ? __longlong_as_double((((cb >> 52) & 0x7ff) - 53) << 52) : 0.0;
+        if (same_binade && tile_maxw[tp] < half_ulp) { c = ce; ++tp; } else break;
+      }
+      s_tp = tp;
+      s_c = c;
+      s_brk = TILE;
+      if (tp >= nt) s_jfinal = N - 1;
+    }
     __syncthreads();
-    jfinal = (long long)tp * TILE + s_lead - 1;
+    if (s_jfinal >= 0) break;
+    const int tp = s_tp;
+    const double c = s_c;
+    tile_cdf<real>(ws, normalise, total, qb, tile_excl, tp, N, Cs, Ws, s_warp);
+    const int tn = (int)min((long long)TILE, N - (long long)tp * TILE);
+    // first element of tile tp that does NOT vanish against its predecessor's value
+    for (int j = threadIdx.x; j < tn; j += TILE_THREADS) {
+      double prev = (j == 0) ? c : Cs[j - 1];
+      if (!vanishes(prev, Ws[j])) atomicMin(&s_brk, j);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_brk < tn) s_jfinal = (long long)tp * TILE + s_brk - 1;
+      else if (tp == nt - 1) s_jfinal = N - 1;
+      else { s_c = Cs[tn - 1]; s_tp = tp + 1; }
+    }
+    __syncthreads();
+    if (s_jfinal >= 0) break;
   }
+  const long long jfinal = s_jfinal;
   for (long long i = pend + threadIdx.x; i < hi; i += TILE_THREADS) anc[i] = (int32_t)jfinal;
 }
 

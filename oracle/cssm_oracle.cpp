@@ -21,6 +21,8 @@
 //                        EXACTLY as 2^-96 fixed-point integers (any association gives the same
 //                        integer) and each cumulative value is that exact sum rounded once to
 //                        fp64.  Here it is a plain sequential loop over unsigned __int128.
+//                        The TreeMap "duplicate key" rule is applied through the test that
+//                        creates duplicate keys in the reference, fl(C_j + w_{j+1}) == C_j.
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -348,14 +350,15 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
     return 0;
   }
   // cumulative sums of the normalised weights
-  std::vector<double> C(N);
+  std::vector<double> C(N), wn(N);
   double total = orc_total(N, w, order);
+  for (int64_t i = 0; i < N; ++i) wn[i] = w[i] / total;
   if (order == ORC_ORDER_REFERENCE) {
     double c = 0.0;
-    for (int64_t i = 0; i < N; ++i) { c = c + w[i] / total; C[i] = c; }
+    for (int64_t i = 0; i < N; ++i) { c = c + wn[i]; C[i] = c; }
   } else {
     u128 e = 0;
-    for (int64_t i = 0; i < N; ++i) { e += fixq(w[i] / total, 96); C[i] = unfixq(e, 96); }
+    for (int64_t i = 0; i < N; ++i) { e += fixq(wn[i], 96); C[i] = unfixq(e, 96); }
   }
   // TreeMap semantics by a merge over the two sorted sequences
   int64_t j = 0;
@@ -364,8 +367,20 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
     double k = (kind == CSSM_RESAMPLE_SYSTEMATIC) ? (u[0] + (double)i) / n : ((double)i + u[i]) / n;
     while (j < N && C[j] < k) ++j;  // first key >= k
     if (j >= N) { anc[i] = (int32_t)(N - 1); ++clamped; continue; }
+    // duplicate key: last insert wins.  In the reference a key repeats exactly when adding the
+    // next weight does not change the running sum, fl(C_j + wn_{j+1}) == C_j; the device order
+    // applies that same test to its own (exactly accumulated, once-rounded) C_j, so a run of
+    // vanishing weights is skipped as a whole in both orders.
     int64_t jj = j;
-    while (jj + 1 < N && C[jj + 1] == C[jj]) ++jj;  // duplicate key: last insert wins
+    if (order == ORC_ORDER_REFERENCE) {
+      while (jj + 1 < N && C[jj + 1] == C[jj]) ++jj;
+    } else {
+      while (jj + 1 < N) {
+        volatile double nx = C[jj] + wn[jj + 1];
+        if (nx != C[jj]) break;
+        ++jj;
+      }
+    }
     anc[i] = (int32_t)jj;
   }
   if (n_clamped) *n_clamped = clamped;
