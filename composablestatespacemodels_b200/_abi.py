@@ -82,6 +82,8 @@ _SIGNATURES = {
     "cssm_filter_run": [_FILTER, c_double_p, c_double_p, c_uint8_p, C.c_int64, c_double_p, c_double_p],
     "cssm_filter_last_elapsed_ms": [_FILTER, C.POINTER(C.c_float)],
     "cssm_filter_last_launches": [_FILTER, c_int64_p],
+    "cssm_filter_profile": [_FILTER, C.c_int],
+    "cssm_filter_profile_read": [_FILTER, c_double_p, c_int64_p],
     "cssm_filter_get_particles": [_FILTER, c_double_p],
     "cssm_filter_sample_one": [_FILTER, c_double_p],
     "cssm_filter_get_ll": [_FILTER, c_double_p, c_int32_p],

@@ -198,6 +198,13 @@ struct cssm_filter {
   unsigned long long slot0 = 0;  // global slot of local particle 0 (sharded filters)
   int shard_rank = 0, shard_world = 1;
   float last_ms = 0.f;
+  // per-kernel-class device timing (CUDA events on the launching stream), sampled every prof_stride steps
+  int prof_stride = 0;
+  std::vector<cudaEvent_t> prof_ev;  // pairs
+  std::vector<int> prof_cls;
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_step = 0;
   long long last_launches = 0, launches = 0;
 };
 
@@ -258,6 +265,41 @@ int do_init(cssm_filter* f, double t0, const double* zinj_dev, const double* x0)
   return CSSM_OK;
 }
 
+enum { CLS_PROPAGATE = 0, CLS_TOTAL = 1, CLS_TILESUM = 2, CLS_SCANTILES = 3, CLS_SEARCH = 4, CLS_MULTI = 5, CLS_INIT = 6 };
+
+// event pair around one launch when profiling samples this step
+struct ProfScope {
+  cssm_filter* f;
+  bool on;
+  ProfScope(cssm_filter* f_, int cls, bool sampled) : f(f_), on(false) {
+    if (!sampled) return;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    f->prof_ev.push_back(a);
+    f->prof_ev.push_back(b);
+    f->prof_cls.push_back(cls);
+    cudaEventRecord(a, f->stream);
+    on = true;
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(f->prof_ev.back(), f->stream);
+  }
+};
+
+void prof_collect(cssm_filter* f) {
+  for (size_t i = 0; i < f->prof_cls.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, f->prof_ev[2 * i], f->prof_ev[2 * i + 1]) == cudaSuccess) {
+      f->prof_ms[f->prof_cls[i]] += ms;
+      f->prof_n[f->prof_cls[i]] += 1;
+    }
+    cudaEventDestroy(f->prof_ev[2 * i]);
+    cudaEventDestroy(f->prof_ev[2 * i + 1]);
+  }
+  f->prof_ev.clear();
+  f->prof_cls.clear();
+}
+
 struct StepIO {
   const double* zinj = nullptr;   // device, [n_sub][d][N]
   const double* uarr = nullptr;   // device, N uniforms (stratified / multinomial)
@@ -274,8 +316,11 @@ int launch_step(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
   to_args<real>(f->model, h, a);
   const int32_t* anc = f->anc_valid ? f->anc : nullptr;
   const uint32_t step = f->step_ctr++;
+  const bool prof = f->prof_stride > 0 && (f->prof_step++ % f->prof_stride) == 0;
   real* xsrc = (real*)f->xa;
   real* xdst = (real*)f->xb;
+  {
+  ProfScope ps_(f, CLS_PROPAGATE, prof);
   if (f->model.obs_kind == CSSM_OBS_LGCP) {
     const int g = nblk(f->N, 256);
 #define LGCP_CASE(DP)                                                                                              \
@@ -293,23 +338,38 @@ int launch_step(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
     k_propagate_weight<real><<<nblk(f->N, 256 * PPT), 256, 0, f->stream>>>(a, xsrc, xdst, anc, (real*)f->logw, io.zinj, f->N, f->Ns,
                                                                            f->slot0, f->key0, f->key1, step, f->sc);
   }
+  }
   f->launches++;
   std::swap(f->xa, f->xb);
   f->anc_valid = false;
   if (!h.has_obs) { CU(cudaGetLastError()); return CSSM_OK; }
   const int normalise = (f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ? 0 : 1;
   const real* lw = (const real*)f->logw;
-  k_weight_total<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, f->sc);
-  k_tile_sums<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, normalise, f->sc, f->tile_sum, f->tile_maxw);
-  k_scan_tiles<<<1, 1024, 0, f->stream>>>(f->sc, f->tile_sum, f->tile_excl, f->cend, f->nt, f->N, normalise, 0, 1, io.use_u_inj,
-                                          f->key0, f->key1, step, io.ll_steps, io.ess_steps, io.step_slot);
+  {
+    ProfScope ps_(f, CLS_TOTAL, prof);
+    k_weight_total<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, f->sc);
+  }
+  {
+    ProfScope ps_(f, CLS_TILESUM, prof);
+    k_tile_sums<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, normalise, f->sc, f->tile_sum, f->tile_maxw);
+  }
+  {
+    ProfScope ps_(f, CLS_SCANTILES, prof);
+    k_scan_tiles<<<1, 1024, 0, f->stream>>>(f->sc, f->tile_sum, f->tile_excl, f->cend, f->nt, f->N, normalise, 0, 1, io.use_u_inj,
+                                            f->key0, f->key1, step, io.ll_steps, io.ess_steps, io.step_slot);
+  }
   if (normalise) {
+    ProfScope ps_(f, CLS_SEARCH, prof);
     k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 1, f->sc, f->tile_excl, f->cend, f->tile_maxw, f->nt, f->resample_kind,
                                                                io.uarr, f->key0, f->key1, step, f->anc, nullptr, &f->sc->flags);
     f->launches += 4;
   } else {
-    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 0, f->sc, f->tile_excl, f->cend, f->tile_maxw, f->nt, f->resample_kind,
-                                                               nullptr, f->key0, f->key1, step, nullptr, f->cdf, &f->sc->flags);
+    {
+      ProfScope ps_(f, CLS_SEARCH, prof);
+      k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 0, f->sc, f->tile_excl, f->cend, f->tile_maxw, f->nt, f->resample_kind,
+                                                                 nullptr, f->key0, f->key1, step, nullptr, f->cdf, &f->sc->flags);
+    }
+    ProfScope ps_(f, CLS_MULTI, prof);
     k_multinomial_search<<<nblk(f->N, 256), 256, 0, f->stream>>>(f->cdf, f->N, io.uarr, f->key0, f->key1, step, f->anc, &f->sc->flags);
     f->launches += 5;
   }
@@ -400,6 +460,7 @@ int read_ll(cssm_filter* f, double* ll, int32_t* ess) {
   Scalars s;
   CU(cudaMemcpyAsync(&s, f->sc, sizeof(s), cudaMemcpyDeviceToHost, f->stream));
   CU(cudaStreamSynchronize(f->stream));
+  if (!f->prof_cls.empty()) prof_collect(f);
   if (ll) *ll = s.ll;
   if (ess) *ess = s.ess;
   return CSSM_OK;
@@ -812,6 +873,19 @@ int cssm_filter_last_elapsed_ms(const cssm_filter_t* f, float* ms_out) {
 int cssm_filter_last_launches(const cssm_filter_t* f, int64_t* n_out) {
   if (!f || !n_out) return fail(CSSM_ERR_INVALID, "null argument");
   *n_out = f->last_launches;
+  return CSSM_OK;
+}
+
+int cssm_filter_profile(cssm_filter_t* f, int stride) {
+  if (!f) return fail(CSSM_ERR_INVALID, "null filter handle");
+  f->prof_stride = stride > 0 ? stride : 0;
+  f->prof_step = 0;
+  for (int c = 0; c < 8; ++c) { f->prof_ms[c] = 0; f->prof_n[c] = 0; }
+  return CSSM_OK;
+}
+int cssm_filter_profile_read(cssm_filter_t* f, double* ms_sum_out, int64_t* count_out) {
+  if (!f || !ms_sum_out || !count_out) return fail(CSSM_ERR_INVALID, "null argument");
+  for (int c = 0; c < 8; ++c) { ms_sum_out[c] = f->prof_ms[c]; count_out[c] = f->prof_n[c]; }
   return CSSM_OK;
 }
 

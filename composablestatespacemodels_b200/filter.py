@@ -179,6 +179,17 @@ class GpuFilterHandle:
         _abi.check(self._lib.cssm_filter_last_launches(self._h, C.byref(n)))
         return n.value
 
+    KERNEL_CLASSES = ("propagate_weight", "weight_total", "tile_sums", "scan_tiles", "scan_search", "multinomial_search")
+
+    def profile(self, stride):
+        _abi.check(self._lib.cssm_filter_profile(self._h, int(stride)))
+
+    def profile_read(self):
+        """{kernel class: (sum of device ms over the sampled launches, sampled launches)}"""
+        ms, n = np.zeros(8), np.zeros(8, dtype=np.int64)
+        _abi.check(self._lib.cssm_filter_profile_read(self._h, _abi.dptr(ms), n.ctypes.data_as(_abi.c_int64_p)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     # ---- reading the cloud ------------------------------------------------------------------
     def get_particles(self):
         x = np.empty((self.d, self.n))

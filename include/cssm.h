@@ -182,6 +182,13 @@ int cssm_filter_last_elapsed_ms(const cssm_filter_t* f, float* ms_out);
 /* number of kernels the last whole-series / step call launched */
 int cssm_filter_last_launches(const cssm_filter_t* f, int64_t* n_out);
 
+/* Per-kernel device timing for the roofline report: with stride > 0 every stride-th stepFilter
+ * brackets each of its kernels with CUDA events on the launching stream (0 switches it off and
+ * clears the sums).  Classes: 0 propagate+weight, 1 weight total, 2 tile sums, 3 tile scan,
+ * 4 CDF scan + ancestor search, 5 multinomial search.  ms_sum_out[8], count_out[8]. */
+int cssm_filter_profile(cssm_filter_t* f, int stride);
+int cssm_filter_profile_read(cssm_filter_t* f, double* ms_sum_out, int64_t* count_out);
+
 /* ------------------------------------------------------------------------------------------
  * reading the cloud back  (PfState.particles, model/ParticleFilter.scala:32-37)
  * ---------------------------------------------------------------------------------------- */

@@ -1,0 +1,100 @@
+"""CPU tests of the host-side mirror of the reference API: parameters, model composition,
+descriptor building, PMMH chain logic (with a fake bootstrap filter) -- no GPU needed."""
+import math
+
+import numpy as np
+import pytest
+
+import composablestatespacemodels_b200 as cs
+from composablestatespacemodels_b200 import Model, Sde, SdeParameter, Parameters, Leaf, Branch, _abi, flattenParams
+from composablestatespacemodels_b200 import parameters as P
+from configs import c1, c2, c4, c4_params, c4_unparam
+
+
+def test_parameter_transforms_follow_the_reference():
+    # user-facing ouParameter applies log / logistic; OuProcess applies exp / logistic again
+    m = c1()
+    s = m.leaves[0].sde
+    assert s.kind == _abi.SDE_OU and s.dimension == 1
+    assert abs(s.c0[0] - 0.5) < 1e-15 and abs(s.sigma[0] - 0.05) < 1e-15 and s.mu[0] == 1.5 and s.m0[0] == 1.0
+    logistic = lambda x: 1 / (1 + math.exp(-x))
+    assert abs(s.phi[0] - logistic(logistic(0.2))) < 1e-16
+    assert abs(s.phi[0] - 0.6340970762609854) < 1e-15
+
+
+def test_build_param_repeat_and_dimension():
+    m = c2()
+    assert m.dimension == 7 and [l.sde.dimension for l in m.leaves] == [1, 6]
+    np.testing.assert_allclose(m.leaves[1].sde.sigma, np.full(6, 0.5))
+    s8 = Sde.ouProcess(8)(SdeParameter.ouParameter([1.0], [2.0], [0.2], [-4, -4, 0, 0, 0, 0, -0.5, -0.5], [0.3]))
+    np.testing.assert_array_equal(s8.mu, [-4, -4, 0, 0, 0, 0, -0.5, -0.5])   # examples/Simulation.scala:19
+
+
+def test_composition_rules():
+    with pytest.raises(Exception, match="Can't Build composed model from Leaf Parameter"):
+        c4_unparam()(Parameters(1.0, SdeParameter.brownianParameter([0.0], [1.0], [0.01])))
+    with pytest.raises(Exception, match="Can't build model from branch parameter"):
+        Model.poisson(Sde.ouProcess(1))(c4_params())
+    with pytest.raises(Exception, match="Incorrect parameters supplied to OuProcess"):
+        Model.poisson(Sde.ouProcess(1))(Parameters(None, SdeParameter.brownianParameter([0.0], [1.0], [0.01])))
+    m = c4()
+    assert m.obs_kind == _abi.OBS_NEGBIN and m.scale == 2.0           # observation model of the left-most leaf
+    three = (Model.poisson(Sde.brownianMotion(1)) | Model.linear(Sde.brownianMotion(2)) | Model.seasonal(12, 1, Sde.ouProcess(2)))
+    bp = SdeParameter.brownianParameter([0.0], [1.0], [0.1])
+    mm = three((Parameters(None, bp) | Parameters(0.0, bp)) | Parameters(None, SdeParameter.ouParameter([0.0], [1.0], [0.1], [0.0], [0.2])))
+    assert mm.dimension == 5 and len(mm.leaves) == 3
+
+
+def test_descriptor_layout():
+    d, keep = c2().desc()
+    assert d.n_leaves == 2 and d.obs_kind == _abi.OBS_POISSON and d.has_scale == 0
+    assert d.leaves[1].f_kind == _abi.F_SEASONAL and d.leaves[1].period == 24 and d.leaves[1].harmonics == 3 and d.leaves[1].dim == 6
+    assert d.leaves[0].phi[0] == c2().leaves[0].sde.phi[0]
+    bad = Model.seasonal(24, 3, Sde.ouProcess(4))(Parameters(0.0, SdeParameter.ouParameter([0.0], [1.0], [0.1], [0.0], [0.2])))
+    with pytest.raises(Exception, match="seasonal"):
+        bad.desc()
+
+
+def test_flatten_add_perturb():
+    p = c4_params()
+    flat = flattenParams(p)
+    assert flat[0] == 2.0 and len(flat) == 1 + 3 + 4                      # scale first, model/Parameters.scala:88-95
+    q = P.add(p, np.arange(8.0))
+    assert flattenParams(q) == pytest.approx(np.array(flat) + np.arange(8.0))
+    rng = np.random.default_rng(0)
+    prop = P.perturb(0.05, rng)
+    draws = np.array([flattenParams(prop(p)) for _ in range(4000)])
+    assert np.allclose(draws.mean(0), flat, atol=0.02)
+    assert np.allclose(draws.std(0), math.sqrt(0.05), atol=0.02)           # sd sqrt(delta), :65-67
+
+
+def test_pmmh_chain_logic_with_a_fake_filter():
+    """MetropolisHastings.mhStep (model/PMMH.scala:68-81) against a closed-form target: with an exact
+    'filter' returning log N(theta; 1, 0.5^2) the chain must sample that normal."""
+    class FakeP:
+        def __init__(self, v): self.v = v
+    rng = np.random.default_rng(1)
+    pf = lambda p: (-0.5 * ((p.v - 1.0) / 0.5) ** 2, [("state", p.v)])
+    prop = lambda p: FakeP(p.v + 0.8 * rng.standard_normal())
+    mh = cs.ParticleMetropolisHastings(FakeP(5.0), prop, lambda a, b: 0.0, lambda p: 0.0, pf, rng)
+    it = mh.iters()
+    first = next(it)
+    assert first.accepted == 1                                            # init ll = -1e99: first proposal always accepted (:121)
+    xs = np.array([next(it).params.v for _ in range(20000)])[2000:]
+    assert abs(xs.mean() - 1.0) < 0.05 and abs(xs.std() - 0.5) < 0.05
+
+
+def test_resample_kind_mapping():
+    R = cs.Resampling
+    assert R.kind_of(R.systematicResampling) == 0 and R.kind_of(R.stratifiedResampling) == 1 and R.kind_of(R.multinomialResampling) == 2
+    with pytest.raises(Exception):
+        R.kind_of(lambda p, w: p)
+    np.testing.assert_allclose(R.normalise([1, 1, 2]), [0.25, 0.25, 0.5])
+
+
+def test_simulator_is_deterministic_and_shaped():
+    from composablestatespacemodels_b200 import simulate
+    t, y, x = simulate.simRegular(c2(), 0.1, 50, seed=3)
+    t2, y2, _ = simulate.simRegular(c2(), 0.1, 50, seed=3)
+    assert np.array_equal(y, y2) and x.shape == (50, 7) and np.allclose(np.diff(t), 0.1)
+    assert np.all(y >= 0) and np.all(y == np.floor(y))
