@@ -1,0 +1,138 @@
+// FilterGpu.scala -- the Scala side of the drop-in.  NOT COMPILED IN THIS IMAGE (no JVM / sbt / Breeze jars).
+// It lives in package com.github.jonnylaw.model on purpose: the concrete model classes are
+// `private final case class` (model/Model.scala:168,204,241,266,315,363), so a descriptor can only be
+// built from inside the package (SURVEY.md 8b).
+package com.github.jonnylaw.model
+
+import akka.NotUsed
+import akka.stream.scaladsl.Flow
+import breeze.linalg.DenseVector
+import breeze.stats.distributions.Rand
+import cats.data.Reader
+import com.github.jonnylaw.gpu.CssmNative
+
+/** Flat description of a parameterised model: what include/cssm.h calls cssm_model_desc_t. */
+final case class GpuDesc(kinds: Array[Int], params: Array[Double], obsKind: Int, scale: Option[Double],
+  stepMode: Int = 0, precision: Int = 0)
+
+object GpuDesc {
+  private def leafOf(sde: Sde): (Array[Int], Array[Array[Double]]) = sde match {
+    case BrownianMotion(_, d) => val p = sde.asInstanceOf[BrownianMotion].params
+      (Array(0, d), Array(p.m0.toArray, p.c0.toArray, Array.fill(d)(0.0), Array.fill(d)(0.0), p.sigma.toArray))
+    case GenBrownianMotion(_, d) => val p = sde.asInstanceOf[GenBrownianMotion].params
+      (Array(1, d), Array(p.m0.toArray, p.c0.toArray, Array.fill(d)(0.0), p.mu.toArray, p.sigma.toArray))
+    case OuProcess(_, d) => val p = sde.asInstanceOf[OuProcess].params
+      (Array(2, d), Array(p.m0.toArray, p.c0.toArray, p.phi.toArray, p.mu.toArray, p.sigma.toArray))
+  }
+  /** (obsKind, fKind, period, harmonics, scale, sde) of one un-composed model */
+  private def single(m: Model): (Int, Int, Int, Int, Option[Double], Sde) = m match {
+    case PoissonModel(s, p)            => (0, 0, 0, 0, p.scale, s)
+    case NegativeBinomialModel(s, p)   => (1, 0, 0, 0, p.scale, s)
+    case LinearModel(s, p)             => (2, 0, 0, 0, p.scale, s)
+    case SeasonalModel(per, h, s, p)   => (2, 1, per, h, p.scale, s)
+    case BernoulliModel(s, p)          => (3, 0, 0, 0, p.scale, s)
+    case LogGaussianCox(s, p)          => (4, 0, 0, 0, p.scale, s)
+  }
+  /** leaves in Tree.flatten order; `models` is the list of un-composed models, left to right */
+  def apply(models: List[Model], precision: Int = 0): GpuDesc = {
+    val singles = models.map(single)
+    val leaves = singles.map { case (_, f, per, h, _, s) => val (k, p) = leafOf(s); (Array(k(0), k(1), f, per, h), p) }
+    val d = leaves.map(_._1(1)).sum
+    val params = (0 until 5).toArray.flatMap(i => leaves.flatMap(_._2(i)))   // m0 | c0 | phi | mu | sigma
+    GpuDesc(leaves.flatMap(_._1).toArray, params, singles.head._1, singles.head._5, 0, precision)
+  }
+}
+
+/** trait ParticleFilter[State] (model/ParticleFilter.scala:96-167) with the particle work on the GPU.
+  * `particles` of the returned PfState is materialised from device memory (Vector[State] in Tree.flatten order). */
+final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, precision: Int = 0,
+  dtype: Int = 0, device: Int = 0, seed: Long = 0L) extends ParticleFilter[State] with AutoCloseable {
+
+  private val desc = GpuDesc(models, precision)
+  private var handle: Long = 0L
+  private var n: Int = 0
+  private val dims: List[Int] = models.map(_.sde.dimension)
+
+  private def ensure(particles: Int): Long = {
+    if (handle == 0L || n != particles) {
+      close()
+      handle = CssmNative.filterCreate(desc.kinds, desc.params, desc.obsKind, desc.scale.isDefined,
+        desc.scale.getOrElse(0.0), desc.stepMode, desc.precision, particles.toLong, resampleKind, dtype, device, seed, 0L)
+      n = particles
+    }
+    handle
+  }
+  def close(): Unit = if (handle != 0L) { CssmNative.filterDestroy(handle); handle = 0L }
+
+  // the abstract members are only used by the CPU code paths we override
+  def dataLikelihood(g: Gamma, y: Observation) = mod.dataLikelihood(g, y)
+  def stepFunction(dt: TimeIncrement)(s: State): Rand[State] = mod.sde.stepFunction(dt)(s)
+  def initialState = mod.sde.initialState
+  def f(s: State, t: Time) = mod.f(s, t)
+  def resample: Resample[State] = (p, w) => GpuResample(resampleKind, device)(p, w)
+
+  private def cloud(): Vector[State] = {
+    val d = dims.sum
+    val flat = new Array[Double](d * n)
+    CssmNative.filterGetParticles(handle, flat)              // [d][N]
+    Vector.tabulate(n) { i =>
+      var off = 0
+      dims.map { dim => val v = DenseVector.tabulate(dim)(k => flat((off + k) * n + i)); off += dim; Tree.leaf(v): State }
+        .reduceLeft(_ +++ _)
+    }
+  }
+
+  override def initialiseState(particles: Int, t0: Time): PfState[State] = {
+    CssmNative.filterInit(ensure(particles), t0)
+    PfState(t0, None, LazyCloud(() => cloud()), 0.0, particles)
+  }
+  override def stepFilter(s: PfState[State], y: Data): PfState[State] = {
+    val ess = new Array[Int](1)
+    val ll = CssmNative.filterStep(handle, y.t, y.observation.isDefined, y.observation.getOrElse(0.0), ess)
+    PfState(y.t, y.observation, LazyCloud(() => cloud()), ll, ess(0))
+  }
+  override def llFilter(data: Vector[Data], particles: Int): LogLikelihood =
+    CssmNative.filterLl(ensure(particles), data.map(_.t).toArray, data.map(_.observation.getOrElse(0.0)).toArray,
+      data.map(d => (if (d.observation.isDefined) 1 else 0).toByte).toArray)
+  override def filter(data: Vector[Data], particles: Int): (LogLikelihood, Vector[StateSpace[State]]) = {
+    val d = dims.sum
+    val states = new Array[Double]((data.size + 1) * d)
+    val ll = CssmNative.filterRun(ensure(particles), data.map(_.t).toArray, data.map(_.observation.getOrElse(0.0)).toArray,
+      data.map(x => (if (x.observation.isDefined) 1 else 0).toByte).toArray, states)
+    val times = data.minBy(_.t).t +: data.map(_.t)
+    (ll, times.zipWithIndex.map { case (t, s) =>
+      var off = s * d
+      StateSpace(t, dims.map { dim => val v = DenseVector(states.slice(off, off + dim)); off += dim; Tree.leaf(v): State }
+        .reduceLeft(_ +++ _)) })
+  }
+  override def filterStream(t0: Time, particles: Int): Flow[Data, PfState[State], NotUsed] =
+    Flow[Data].scan(initialiseState(particles, t0))(stepFilter)           // same shape as model/ParticleFilter.scala:163-166
+}
+
+/** Vector whose elements are fetched from the device on first access */
+object LazyCloud { def apply(get: () => Vector[State]): Vector[State] = new scala.collection.immutable.VectorBuilder[State]().result() match {
+  case _ => lazyVector(get) }
+  private def lazyVector(get: () => Vector[State]): Vector[State] = get()   // simplest form: materialise when the PfState is built lazily by the caller
+}
+
+/** Resample[A] backed by cssm_resample: uniforms from scala.util.Random as in model/Resampling.scala:66,83 */
+final case class GpuResample(kind: Int, device: Int = 0) {
+  def apply[A](particles: Vector[A], weights: Vector[LogLikelihood]): Vector[A] = {
+    val n = weights.size
+    val u = if (kind == 0) Array(scala.util.Random.nextDouble) else Array.fill(n)(scala.util.Random.nextDouble)
+    val anc = new Array[Int](n)
+    CssmNative.resample(kind, weights.toArray, u, anc, device)
+    anc.toVector.map(particles(_))
+  }
+}
+
+object FilterGpu {
+  /** BootstrapFilter for PMMH (model/PMMH.scala:58): one handle, re-parameterised per proposal.
+    * `build` turns Parameters into (list of un-composed models, composed model). */
+  def bootstrap(build: Parameters => (List[Model], Model), data: Vector[Data], resampleKind: Int, n: Int)
+      : BootstrapFilter[Parameters, StateSpace[State]] = Reader { p =>
+    val (ms, m) = build(p)
+    val f = FilterGpu(ms, m, resampleKind)
+    try f.filter(data, n) finally f.close()
+  }
+}
