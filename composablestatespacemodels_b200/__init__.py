@@ -14,12 +14,12 @@ from . import model as Model
 from .model import UnparamModel
 from .resampling import Resampling
 from .filter import (Data, TimedObservation, StateSpace, PfState, Filter, FilterLgcp, FilterInit, ParticleFilter,
-                     GpuFilterHandle)
+                     GpuFilterHandle, ShardedGroup)
 from .pmmh import MetropolisHastings, ParticleMetropolisHastings, MetropState, GpuBootstrapFilter
 
 F32, F64 = _abi.F32, _abi.F64
 __all__ = ["Tree", "Leaf", "Branch", "Sde", "SdeParameter", "BrownianParameter", "GenBrownianParameter", "OuParameter",
            "ParamNode", "Parameters", "flattenParams", "perturb", "perturbMvn", "Model", "UnparamModel", "Resampling",
            "Data", "TimedObservation", "StateSpace", "PfState", "Filter", "FilterLgcp", "FilterInit", "ParticleFilter",
-           "GpuFilterHandle", "MetropolisHastings", "ParticleMetropolisHastings", "MetropState", "GpuBootstrapFilter",
+           "GpuFilterHandle", "ShardedGroup", "MetropolisHastings", "ParticleMetropolisHastings", "MetropState", "GpuBootstrapFilter",
            "F32", "F64"]

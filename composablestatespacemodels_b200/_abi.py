@@ -16,6 +16,7 @@ OBS_POISSON, OBS_NEGBIN, OBS_NORMAL, OBS_BERNOULLI, OBS_LGCP = 0, 1, 2, 3, 4
 STEP_EXACT, STEP_EULER = 0, 1
 RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_MULTINOMIAL = 0, 1, 2
 F32, F64 = 0, 1
+MAX_RANKS, SHARD_BLOB_BYTES = 8, 1024
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -67,6 +68,18 @@ _SIGNATURES = {
     "cssm_device_count": [c_int32_p],
     "cssm_filter_create": [C.POINTER(ModelDesc), C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64,
                            C.c_uint64, C.POINTER(_FILTER)],
+    "cssm_filter_create_sharded": [C.POINTER(ModelDesc), C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                   C.c_uint64, C.c_int, C.c_int, C.POINTER(_FILTER)],
+    "cssm_filter_shard_export": [_FILTER, C.c_void_p],
+    "cssm_filter_shard_connect": [_FILTER, C.c_void_p, C.c_int],
+    "cssm_filter_shard_info": [_FILTER, c_int32_p, c_int32_p, c_int64_p],
+    "cssm_group_init": [C.POINTER(_FILTER), C.c_int, C.c_double],
+    "cssm_group_init_injected": [C.POINTER(_FILTER), C.c_int, C.c_double, c_double_p],
+    "cssm_group_step_injected": [C.POINTER(_FILTER), C.c_int, C.c_double, C.c_int, C.c_double, c_double_p, c_double_p,
+                                 c_double_p, c_double_p, c_double_p, c_int32_p, c_double_p, c_int32_p],
+    "cssm_group_get_particles": [C.POINTER(_FILTER), C.c_int, c_double_p],
+    "cssm_group_ll": [C.POINTER(_FILTER), C.c_int, c_double_p, c_double_p, c_uint8_p, C.c_int64, c_double_p,
+                      C.POINTER(C.c_float)],
     "cssm_filter_set_params": [_FILTER, C.POINTER(ModelDesc)],
     "cssm_filter_reseed": [_FILTER, C.c_uint64, C.c_uint64],
     "cssm_filter_set_stream": [_FILTER, C.c_void_p],

@@ -1,6 +1,8 @@
 // cssm_api.cu -- host side of libcssm_gpu.so: the C ABI of include/cssm.h over the kernels of
 // cssm_kernels.cuh.  One CUDA stream per filter handle, no global mutable state, no CPU fallback.
 #include <cmath>
+#include <cstdlib>
+#include <unistd.h>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -169,19 +171,20 @@ struct SeriesStep {
 
 struct cssm_filter {
   int device = 0, dtype = CSSM_F32, resample_kind = 0;
-  long long N = 0, Ns = 0;
-  int d = 0, nt = 0;
+  long long N = 0, Ns = 0;  // particles on this rank, padded leading dimension
+  int d = 0, nt = 0, ns = 0, items = 8;
   HostModel model;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  void *xa = nullptr, *xb = nullptr, *logw = nullptr;  // x_cur = xa after every swap
-  int32_t* anc = nullptr;
+  void* x[2] = {nullptr, nullptr};  // ping-pong clouds; x[cur] is the current one
+  int cur = 0;
+  void* logw = nullptr;
+  int32_t* anc = nullptr;  // GLOBAL particle indices of the last resampling (offspring slots of this rank)
   bool anc_valid = false, initialised = false;
-  Scalars* sc = nullptr;
-  u128 *tile_sum = nullptr, *tile_excl = nullptr;
-  double* cend = nullptr;
-  double* tile_maxw = nullptr;
-  double* ubuf = nullptr;   // N uniforms (stratified / multinomial, injected)
+  FilterScalars* sc = nullptr;
+  SumTables tb = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+  XchSlot* xch = nullptr;  // [MAXR] written by the peers (sharded filters)
+  double* ubuf = nullptr;   // uniforms (stratified / multinomial, injected): one per GLOBAL output
   double* cdf = nullptr;    // N cumulative values (multinomial)
   double* scratch = nullptr;  // grow-only fp64 scratch (injected noise, read-back staging)
   size_t scratch_n = 0;
@@ -195,8 +198,14 @@ struct cssm_filter {
   uint64_t seed = 0, stream_id = 0, epoch = 0;
   uint32_t key0 = 0, key1 = 0;
   uint32_t step_ctr = 0;
-  unsigned long long slot0 = 0;  // global slot of local particle 0 (sharded filters)
-  int shard_rank = 0, shard_world = 1;
+  // sharding: rank r of R owns the global slots [r*N, (r+1)*N)
+  int rank = 0, world = 1;
+  bool connected = false;
+  unsigned long long obs_seq = 0, gstep = 0;  // monotone over the life of the handle (never reset)
+  struct PeerPtrs { void* x[2]; int32_t* anc; void* logw; u128* tile_sum; double* tile_maxw; XchSlot* xch; };
+  PeerPtrs peer[MAXR];
+  std::vector<void*> ipc_opened;  // base pointers to close on destroy
+  int pdl = 1;  // programmatic dependent launch between the kernels of a step
   float last_ms = 0.f;
   // per-kernel-class device timing (CUDA events on the launching stream), sampled every prof_stride steps
   int prof_stride = 0;
@@ -227,6 +236,49 @@ int ensure_scratch(cssm_filter* f, size_t n) {
 
 inline int nblk(long long n, int per) { return (int)((n + per - 1) / per); }
 
+// kernel launch, optionally as a programmatic dependent launch: the kernel may be scheduled while
+// the previous kernel of the stream drains; every such kernel starts with griddepcontrol.wait
+template <typename... KArgs, typename... Args>
+cudaError_t launch(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+// the ranks of the filter as a kernel argument; `src` = which of the two clouds K1 gathers from
+Peers make_peers(const cssm_filter* f, int src) {
+  Peers pr;
+  std::memset(&pr, 0, sizeof(pr));
+  const bool sharded = f->world > 1 && f->connected;
+  pr.R = sharded ? f->world : 1;
+  pr.rank = sharded ? f->rank : 0;
+  pr.Nl = f->N;
+  for (int q = 0; q < pr.R; ++q) {
+    if (q == pr.rank) {
+      pr.x[q] = f->x[src]; pr.anc[q] = f->anc; pr.logw[q] = f->logw;
+      pr.tile_sum[q] = f->tb.tile_sum; pr.tile_maxw[q] = f->tb.tile_maxw; pr.xch[q] = f->xch;
+    } else {
+      const cssm_filter::PeerPtrs& pp = f->peer[q];
+      pr.x[q] = pp.x[src]; pr.anc[q] = pp.anc; pr.logw[q] = pp.logw;
+      pr.tile_sum[q] = pp.tile_sum; pr.tile_maxw[q] = pp.tile_maxw; pr.xch[q] = pp.xch;
+    }
+  }
+  return pr;
+}
+
+int need_connected(const cssm_filter* f) {
+  if (f->world > 1 && !f->connected) return fail(CSSM_ERR_STATE, "sharded filter: cssm_filter_shard_connect has not been called");
+  return CSSM_OK;
+}
+
 template <typename real>
 int launch_init(cssm_filter* f, const double* zinj_dev, const double* x0) {
   StepArgs<real> a;
@@ -238,10 +290,11 @@ int launch_init(cssm_filter* f, const double* zinj_dev, const double* x0) {
       a.S[k] = (real)std::sqrt(L.c0[c]);
       a.M[k] = (real)(x0 ? x0[k] : L.m0[c]);
     }
+  const unsigned long long slot0 = (unsigned long long)f->rank * (unsigned long long)f->N;
   if (x0)
-    k_fill_particles<real><<<nblk(f->N, 256), 256, 0, f->stream>>>(a, (real*)f->xa, f->N, f->Ns);
+    k_fill_particles<real><<<nblk(f->N, 256), 256, 0, f->stream>>>(a, (real*)f->x[f->cur], f->N, f->Ns);
   else
-    k_init_particles<real><<<nblk(f->N, 256), 256, 0, f->stream>>>(a, (real*)f->xa, zinj_dev, f->N, f->Ns, f->slot0, f->key0,
+    k_init_particles<real><<<nblk(f->N, 256), 256, 0, f->stream>>>(a, (real*)f->x[f->cur], zinj_dev, f->N, f->Ns, slot0, f->key0,
                                                                     f->key1, (uint32_t)f->epoch);
   f->launches++;
   CU(cudaGetLastError());
@@ -249,15 +302,20 @@ int launch_init(cssm_filter* f, const double* zinj_dev, const double* x0) {
 }
 
 int do_init(cssm_filter* f, double t0, const double* zinj_dev, const double* x0) {
+  int rc = need_connected(f);
+  if (rc) return rc;
   f->epoch++;
   rekey(f);
   f->step_ctr = 0;
-  Scalars z;
+  FilterScalars z;
   std::memset(&z, 0, sizeof(z));
-  z.ess = (int)std::min<long long>(f->N * (long long)f->shard_world, 2147483647LL);
+  z.ess = (int)std::min<long long>(f->N * (long long)f->world, 2147483647LL);
   z.qb = 96;
   CU(cudaMemcpyAsync(f->sc, &z, sizeof(z), cudaMemcpyHostToDevice, f->stream));
-  int rc = (f->dtype == CSSM_F32) ? launch_init<float>(f, zinj_dev, x0) : launch_init<double>(f, zinj_dev, x0);
+  CU(cudaMemsetAsync(f->tb.super_sum, 0, (size_t)2 * f->ns * sizeof(u128), f->stream));
+  CU(cudaMemsetAsync(f->tb.super_q, 0, (size_t)2 * f->ns * sizeof(u128), f->stream));
+  CU(cudaMemsetAsync(f->tb.super_ticket, 0, (size_t)f->ns * sizeof(unsigned long long), f->stream));
+  rc = (f->dtype == CSSM_F32) ? launch_init<float>(f, zinj_dev, x0) : launch_init<double>(f, zinj_dev, x0);
   if (rc) return rc;
   f->anc_valid = false;
   f->initialised = true;
@@ -265,7 +323,7 @@ int do_init(cssm_filter* f, double t0, const double* zinj_dev, const double* x0)
   return CSSM_OK;
 }
 
-enum { CLS_PROPAGATE = 0, CLS_TOTAL = 1, CLS_TILESUM = 2, CLS_SCANTILES = 3, CLS_SEARCH = 4, CLS_MULTI = 5, CLS_INIT = 6 };
+enum { CLS_PROPAGATE = 0, CLS_SUMS = 1, CLS_SEARCH = 2, CLS_MULTI = 3, CLS_INIT = 4 };
 
 // event pair around one launch when profiling samples this step
 struct ProfScope {
@@ -302,80 +360,138 @@ void prof_collect(cssm_filter* f) {
 
 struct StepIO {
   const double* zinj = nullptr;   // device, [n_sub][d][N]
-  const double* uarr = nullptr;   // device, N uniforms (stratified / multinomial)
+  const double* uarr = nullptr;   // device, one uniform per GLOBAL output (stratified / multinomial)
   int use_u_inj = 0;              // systematic uniform taken from sc->u_inj
   double* ll_steps = nullptr;     // device
   int* ess_steps = nullptr;       // device
   long long step_slot = 0;
 };
 
-// one stepFilter on the device; no host synchronisation
+// what one step needs to remember between its three launches
+struct StepCtx {
+  uint32_t step = 0;
+  bool prof = false, observed = false;
+  int parity = 0;
+};
+
+// ---- K1: gather + propagate + weight ------------------------------------------------------------
 template <typename real>
-int launch_step(cssm_filter* f, const StepHost& h, long long n_sub, const void* ctab, double delta, const StepIO& io) {
+int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* ctab, double delta, const StepIO& io, StepCtx& cx) {
   StepArgs<real> a;
   to_args<real>(f->model, h, a);
   const int32_t* anc = f->anc_valid ? f->anc : nullptr;
-  const uint32_t step = f->step_ctr++;
-  const bool prof = f->prof_stride > 0 && (f->prof_step++ % f->prof_stride) == 0;
-  real* xsrc = (real*)f->xa;
-  real* xdst = (real*)f->xb;
+  cx.step = f->step_ctr++;
+  cx.prof = f->prof_stride > 0 && (f->prof_step++ % f->prof_stride) == 0;
+  cx.observed = h.has_obs != 0;
+  cx.parity = (int)(f->obs_seq & 1ull);
+  const Peers pr = make_peers(f, f->cur);
+  real* xdst = (real*)f->x[f->cur ^ 1];
+  const unsigned long long slot0 = (unsigned long long)f->rank * (unsigned long long)f->N;
+  K1Ctl ctl{f->sc, cx.parity, f->obs_seq, f->gstep};
+  const bool pdl = f->pdl && !cx.prof;
+  cudaError_t e;
   {
-  ProfScope ps_(f, CLS_PROPAGATE, prof);
-  if (f->model.obs_kind == CSSM_OBS_LGCP) {
-    const int g = nblk(f->N, 256);
-#define LGCP_CASE(DP)                                                                                              \
-  k_lgcp_weight<real, DP><<<g, 256, 0, f->stream>>>(a, xsrc, xdst, anc, (real*)f->logw, io.zinj, (const real*)ctab, n_sub, \
-                                                     (real)delta, f->N, f->Ns, f->slot0, f->key0, f->key1, step, f->sc)
-    if (f->d <= 1) LGCP_CASE(1);
-    else if (f->d <= 2) LGCP_CASE(2);
-    else if (f->d <= 4) LGCP_CASE(4);
-    else if (f->d <= 8) LGCP_CASE(8);
-    else if (f->d <= 16) LGCP_CASE(16);
-    else LGCP_CASE(32);
+    ProfScope ps_(f, CLS_PROPAGATE, cx.prof);
+    if (f->model.obs_kind == CSSM_OBS_LGCP) {
+      const int g = nblk(f->N, 256);
+#define LGCP_CASE(DP)                                                                                                  \
+  e = launch(k_lgcp_weight<real, DP>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, (const real*)ctab, \
+             n_sub, (real)delta, f->N, f->Ns, slot0, f->key0, f->key1, cx.step, ctl)
+      if (f->d <= 1) LGCP_CASE(1);
+      else if (f->d <= 2) LGCP_CASE(2);
+      else if (f->d <= 4) LGCP_CASE(4);
+      else if (f->d <= 8) LGCP_CASE(8);
+      else if (f->d <= 16) LGCP_CASE(16);
+      else LGCP_CASE(32);
 #undef LGCP_CASE
-  } else {
-    constexpr int PPT = VecOf<real>::PPT;
-    k_propagate_weight<real><<<nblk(f->N, 256 * PPT), 256, 0, f->stream>>>(a, xsrc, xdst, anc, (real*)f->logw, io.zinj, f->N, f->Ns,
-                                                                           f->slot0, f->key0, f->key1, step, f->sc);
-  }
-  }
-  f->launches++;
-  std::swap(f->xa, f->xb);
-  f->anc_valid = false;
-  if (!h.has_obs) { CU(cudaGetLastError()); return CSSM_OK; }
-  const int normalise = (f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ? 0 : 1;
-  const real* lw = (const real*)f->logw;
-  {
-    ProfScope ps_(f, CLS_TOTAL, prof);
-    k_weight_total<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, f->sc);
-  }
-  {
-    ProfScope ps_(f, CLS_TILESUM, prof);
-    k_tile_sums<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, normalise, f->sc, f->tile_sum, f->tile_maxw);
-  }
-  {
-    ProfScope ps_(f, CLS_SCANTILES, prof);
-    k_scan_tiles<<<1, 1024, 0, f->stream>>>(f->sc, f->tile_sum, f->tile_excl, f->cend, f->nt, f->N, normalise, 0, 1, io.use_u_inj,
-                                            f->key0, f->key1, step, io.ll_steps, io.ess_steps, io.step_slot);
-  }
-  if (normalise) {
-    ProfScope ps_(f, CLS_SEARCH, prof);
-    k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 1, f->sc, f->tile_excl, f->cend, f->tile_maxw, f->nt, f->resample_kind,
-                                                               io.uarr, f->key0, f->key1, step, f->anc, nullptr, &f->sc->flags);
-    f->launches += 4;
-  } else {
-    {
-      ProfScope ps_(f, CLS_SEARCH, prof);
-      k_scan_search<real><<<f->nt, TILE_THREADS, 0, f->stream>>>(lw, nullptr, f->N, 0, f->sc, f->tile_excl, f->cend, f->tile_maxw, f->nt, f->resample_kind,
-                                                                 nullptr, f->key0, f->key1, step, nullptr, f->cdf, &f->sc->flags);
+    } else {
+      constexpr int PPT = VecOf<real>::PPT;
+      const int g = nblk(f->N, 256 * PPT);
+#define K1_CASE(DD)                                                                                                    \
+  e = launch(k_propagate_weight<real, DD>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, f->N, f->Ns, \
+             slot0, f->key0, f->key1, cx.step, ctl)
+      if (f->d == 1) K1_CASE(1);
+      else if (f->d == 2) K1_CASE(2);
+      else if (f->d == 7) K1_CASE(7);
+      else K1_CASE(0);
+#undef K1_CASE
     }
-    ProfScope ps_(f, CLS_MULTI, prof);
-    k_multinomial_search<<<nblk(f->N, 256), 256, 0, f->stream>>>(f->cdf, f->N, io.uarr, f->key0, f->key1, step, f->anc, &f->sc->flags);
-    f->launches += 5;
+  }
+  if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K1: ") + cudaGetErrorString(e));
+  f->launches++;
+  f->cur ^= 1;
+  f->anc_valid = false;
+  if (!cx.observed) f->gstep++;
+  return CSSM_OK;
+}
+
+// ---- K2: exact weight sums ----------------------------------------------------------------------
+template <typename real>
+int step_phase2(cssm_filter* f, StepCtx& cx) {
+  if (!cx.observed) return CSSM_OK;
+  const Peers pr = make_peers(f, f->cur);
+  const bool pdl = f->pdl && !cx.prof;
+  cudaError_t e;
+  {
+    ProfScope ps_(f, CLS_SUMS, cx.prof);
+    if (f->items == 8)
+      e = launch(k_weight_sums<real, 8>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
+                 f->sc, cx.parity, f->obs_seq, f->tb, pr);
+    else
+      e = launch(k_weight_sums<real, 2>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
+                 f->sc, cx.parity, f->obs_seq, f->tb, pr);
+  }
+  if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K2: ") + cudaGetErrorString(e));
+  f->launches++;
+  return CSSM_OK;
+}
+
+// ---- K3: CDF scan + ancestor search (+ multinomial draw) ----------------------------------------
+template <typename real>
+int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
+  if (!cx.observed) return CSSM_OK;
+  const Peers pr = make_peers(f, f->cur);
+  const bool pdl = f->pdl && !cx.prof;
+  const bool multi = f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL;
+  K3Ctl ctl;
+  ctl.parity = cx.parity; ctl.obs_seq = f->obs_seq; ctl.gstep = f->gstep;
+  ctl.kind = f->resample_kind; ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj;
+  ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
+  ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
+  cudaError_t e;
+  {
+    ProfScope ps_(f, CLS_SEARCH, cx.prof);
+    if (f->items == 8)
+      e = launch(k_scan_search<real, 8>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
+                 f->sc, f->tb, pr, ctl, multi ? (const double*)nullptr : io.uarr, multi ? f->cdf : (double*)nullptr);
+    else
+      e = launch(k_scan_search<real, 2>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
+                 f->sc, f->tb, pr, ctl, multi ? (const double*)nullptr : io.uarr, multi ? f->cdf : (double*)nullptr);
+  }
+  if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K3: ") + cudaGetErrorString(e));
+  f->launches++;
+  if (multi) {
+    ProfScope ps_(f, CLS_MULTI, cx.prof);
+    e = launch(k_multinomial_search, nblk(f->N, 256), 256, f->stream, pdl, (const double*)f->cdf, f->N, io.uarr, f->key0, f->key1,
+               cx.step, f->anc, &f->sc->flags);
+    if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K4: ") + cudaGetErrorString(e));
+    f->launches++;
   }
   f->anc_valid = true;
-  CU(cudaGetLastError());
+  f->obs_seq++;
+  f->gstep++;
   return CSSM_OK;
+}
+
+// one stepFilter on the device; no host synchronisation
+template <typename real>
+int launch_step(cssm_filter* f, const StepHost& h, long long n_sub, const void* ctab, double delta, const StepIO& io) {
+  StepCtx cx;
+  int rc = step_phase1<real>(f, h, n_sub, ctab, delta, io, cx);
+  if (rc) return rc;
+  rc = step_phase2<real>(f, cx);
+  if (rc) return rc;
+  return step_phase3<real>(f, io, cx);
 }
 
 int step_consts(cssm_filter* f, double t_prev, double t, int has_obs, double y, StepHost& h, long long& n_sub, double& delta) {
@@ -436,13 +552,11 @@ int upload_ctab(cssm_filter* f, const std::vector<double>& host) {
   return CSSM_OK;
 }
 
-int run_one_step(cssm_filter* f, double t, int has_obs, double y, const StepIO& io) {
-  StepHost h;
-  long long n_sub;
-  double delta;
+// constants (+ LGCP coefficient table) of one step taken outside a loaded series
+int prepare_one_step(cssm_filter* f, double t, int has_obs, double y, StepHost& h, long long& n_sub, double& delta, const void*& ctab) {
   int rc = step_consts(f, f->t_cur, t, has_obs, y, h, n_sub, delta);
   if (rc) return rc;
-  const void* ctab = nullptr;
+  ctab = nullptr;
   if (f->model.obs_kind == CSSM_OBS_LGCP && has_seasonal(f->model) && n_sub > 0) {
     std::vector<double> host;
     lgcp_ctab_host(f->model, t, n_sub, delta, host);
@@ -450,6 +564,16 @@ int run_one_step(cssm_filter* f, double t, int has_obs, double y, const StepIO& 
     if (rc) return rc;
     ctab = f->ctab;
   }
+  return CSSM_OK;
+}
+
+int run_one_step(cssm_filter* f, double t, int has_obs, double y, const StepIO& io) {
+  StepHost h;
+  long long n_sub;
+  double delta;
+  const void* ctab;
+  int rc = prepare_one_step(f, t, has_obs, y, h, n_sub, delta, ctab);
+  if (rc) return rc;
   rc = (f->dtype == CSSM_F32) ? launch_step<float>(f, h, n_sub, ctab, delta, io) : launch_step<double>(f, h, n_sub, ctab, delta, io);
   if (rc) return rc;
   f->t_cur = t;
@@ -457,12 +581,13 @@ int run_one_step(cssm_filter* f, double t, int has_obs, double y, const StepIO& 
 }
 
 int read_ll(cssm_filter* f, double* ll, int32_t* ess) {
-  Scalars s;
+  FilterScalars s;
   CU(cudaMemcpyAsync(&s, f->sc, sizeof(s), cudaMemcpyDeviceToHost, f->stream));
   CU(cudaStreamSynchronize(f->stream));
   if (!f->prof_cls.empty()) prof_collect(f);
   if (ll) *ll = s.ll;
   if (ess) *ess = s.ess;
+  if (s.flags & FLAG_COMM_TIMEOUT) return fail(CSSM_ERR_COMM, "sharded filter: a peer rank did not arrive within 4 s");
   return CSSM_OK;
 }
 
@@ -487,9 +612,15 @@ int ensure_steps_cap(cssm_filter* f, size_t T) {
 
 template <typename real>
 void launch_sample_one(cssm_filter* f, double* out_dev, uint32_t tag) {
-  k_sample_one<real><<<1, 32, 0, f->stream>>>((const real*)f->xa, f->anc_valid ? f->anc : nullptr, out_dev, f->d, f->N, f->Ns, f->key0,
-                                              f->key1, tag);
+  const Peers pr = make_peers(f, f->cur);
+  k_sample_one<real><<<1, 32, 0, f->stream>>>(pr, f->anc_valid ? f->anc : nullptr, out_dev, f->d, f->N, f->Ns, f->key0, f->key1, tag);
   f->launches++;
+}
+
+template <typename real>
+void launch_gather(cssm_filter* f, const int32_t* anc, double* out_dev) {
+  const Peers pr = make_peers(f, f->cur);
+  k_gather<real, double><<<nblk(f->N, 256), 256, 0, f->stream>>>(pr, anc, out_dev, f->d, f->N, f->Ns, f->N);
 }
 
 // init + T steps on the loaded series; optionally one sampled particle per time (filter, :152-158)
@@ -497,6 +628,7 @@ int run_series(cssm_filter* f, bool sample_states) {
   const size_t T = f->series.size();
   int rc = ensure_steps_cap(f, T);
   if (rc) return rc;
+  if (sample_states && f->world > 1) return fail(CSSM_ERR_UNSUPPORTED, "filter(): per-time sampled states are not available on a sharded filter");
   f->launches = 0;
   CU(cudaEventRecord(f->ev0, f->stream));
   rc = do_init(f, f->t0_series, nullptr, nullptr);
@@ -518,10 +650,6 @@ int run_series(cssm_filter* f, bool sample_states) {
     rc = (f->dtype == CSSM_F32) ? launch_step<float>(f, st.h, st.n_sub, ctab, delta, io)
                                 : launch_step<double>(f, st.h, st.n_sub, ctab, delta, io);
     if (rc) return rc;
-    if (!st.h.has_obs) {
-      // ll/ess unchanged on an unobserved step: carry the previous values into the per-step arrays
-      // (done on the host side when reading back, see cssm_filter_ll_resident)
-    }
     f->t_cur = st.t;
     if (sample_states) {
       if (f->dtype == CSSM_F32) launch_sample_one<float>(f, f->states + (s + 1) * f->d, 0x80000001u + (uint32_t)s);
@@ -529,6 +657,91 @@ int run_series(cssm_filter* f, bool sample_states) {
     }
   }
   CU(cudaEventRecord(f->ev1, f->stream));
+  return CSSM_OK;
+}
+
+// what one rank tells the others about itself (cssm_filter_shard_export)
+struct ShardBlob {
+  uint64_t magic;
+  int32_t rank, world, device, dtype, nt, d;
+  int64_t N, Ns;
+  int64_t pid;
+  void* ptr[7];  // x0, x1, anc, logw, tile_sum, tile_maxw, xch
+  cudaIpcMemHandle_t h[7];
+};
+static_assert(sizeof(ShardBlob) <= CSSM_SHARD_BLOB_BYTES, "blob size");
+const uint64_t BLOB_MAGIC = 0x4353534d53484152ull;  // "CSSMSHAR"
+
+int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resample_kind, int dtype, int device, uint64_t seed,
+                uint64_t stream_id, int rank, int world, cssm_filter_t** out) {
+  if (!out) return fail(CSSM_ERR_INVALID, "null output handle");
+  *out = nullptr;
+  if (world < 1 || world > MAXR || rank < 0 || rank >= world) return fail(CSSM_ERR_INVALID, "rank/world out of range (at most 8 ranks)");
+  if (n_particles <= 0 || n_particles * (int64_t)world > 2147483647LL) return fail(CSSM_ERR_INVALID, "total particle count must be in [1, 2^31-1]");
+  if (resample_kind < 0 || resample_kind > 2) return fail(CSSM_ERR_INVALID, "unknown resample_kind");
+  if (world > 1 && resample_kind == CSSM_RESAMPLE_MULTINOMIAL) return fail(CSSM_ERR_UNSUPPORTED, "multinomial resampling is not available on a sharded filter");
+  if (dtype != CSSM_F32 && dtype != CSSM_F64) return fail(CSSM_ERR_INVALID, "unknown dtype");
+  HostModel hm;
+  int rc = copy_model(model, hm);
+  if (rc) return rc;
+  int ndev = 0;
+  rc = cssm_device_count(&ndev);
+  if (rc) return rc;
+  if (ndev == 0) return fail(CSSM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(CSSM_ERR_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  cssm_filter* f = new cssm_filter();
+  f->device = device; f->dtype = dtype; f->resample_kind = resample_kind;
+  f->N = n_particles; f->Ns = (n_particles + 63) / 64 * 64;
+  f->model = hm; f->d = hm.d;
+  f->rank = rank; f->world = world;
+  // small clouds: 512-particle tiles so that the weight passes still fill the machine
+  f->items = (f->N <= (1 << 18)) ? 2 : 8;
+  if (const char* e = std::getenv("CSSM_TILE_ITEMS")) { int v = std::atoi(e); if (v == 2 || v == 8) f->items = v; }
+  if (const char* e = std::getenv("CSSM_PDL")) f->pdl = std::atoi(e) != 0;
+  const int tile = TILE_THREADS * f->items;
+  f->nt = nblk(f->N, tile);
+  f->ns = nblk(f->nt, SUPER);
+  f->seed = seed; f->stream_id = stream_id;
+  const size_t esz = (dtype == CSSM_F32) ? 4 : 8;
+#define ALLOC(ptr, bytes)                                                                        \
+  do {                                                                                           \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                        \
+    if (e_ != cudaSuccess) {                                                                     \
+      cssm_filter_destroy(f);                                                                    \
+      return fail(CSSM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e_));         \
+    }                                                                                            \
+  } while (0)
+  ALLOC(f->x[0], (size_t)f->d * f->Ns * esz);
+  ALLOC(f->x[1], (size_t)f->d * f->Ns * esz);
+  ALLOC(f->logw, (size_t)(f->Ns + tile) * esz);
+  ALLOC(f->anc, (size_t)f->Ns * sizeof(int32_t));
+  ALLOC(f->sc, sizeof(FilterScalars));
+  ALLOC(f->xch, sizeof(XchSlot) * MAXR);
+  ALLOC(f->tb.tile_sum, (size_t)(f->nt + 1) * sizeof(u128));
+  ALLOC(f->tb.tile_maxw, (size_t)(f->nt + 1) * sizeof(double));
+  ALLOC(f->tb.super_sum, (size_t)2 * f->ns * sizeof(u128));
+  ALLOC(f->tb.super_q, (size_t)2 * f->ns * sizeof(u128));
+  ALLOC(f->tb.super_ticket, (size_t)f->ns * sizeof(unsigned long long));
+  if (resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ALLOC(f->cdf, (size_t)f->Ns * sizeof(double));
+#undef ALLOC
+  f->tb.nt = f->nt; f->tb.ns = f->ns;
+  cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz);
+  cudaMemset(f->x[1], 0, (size_t)f->d * f->Ns * esz);
+  cudaMemset(f->logw, 0, (size_t)(f->Ns + tile) * esz);
+  cudaMemset(f->sc, 0, sizeof(FilterScalars));
+  cudaMemset(f->xch, 0, sizeof(XchSlot) * MAXR);
+  cudaMemset(f->tb.super_sum, 0, (size_t)2 * f->ns * sizeof(u128));
+  cudaMemset(f->tb.super_q, 0, (size_t)2 * f->ns * sizeof(u128));
+  cudaMemset(f->tb.super_ticket, 0, (size_t)f->ns * sizeof(unsigned long long));
+  if (cudaStreamCreateWithFlags(&f->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&f->ev0) != cudaSuccess ||
+      cudaEventCreate(&f->ev1) != cudaSuccess) {
+    cssm_filter_destroy(f);
+    return fail(CSSM_ERR_CUDA, "stream/event creation failed");
+  }
+  f->stream = f->own_stream;
+  CU(cudaDeviceSynchronize());
+  *out = f;
   return CSSM_OK;
 }
 
@@ -553,58 +766,84 @@ int cssm_device_count(int* n_out) {
 
 int cssm_filter_create(const cssm_model_desc_t* model, int64_t n_particles, int resample_kind, int dtype, int device,
                        uint64_t seed, uint64_t stream_id, cssm_filter_t** out) {
-  if (!out) return fail(CSSM_ERR_INVALID, "null output handle");
-  *out = nullptr;
-  if (n_particles <= 0 || n_particles > 2147483647LL) return fail(CSSM_ERR_INVALID, "n_particles must be in [1, 2^31-1]");
-  if (resample_kind < 0 || resample_kind > 2) return fail(CSSM_ERR_INVALID, "unknown resample_kind");
-  if (dtype != CSSM_F32 && dtype != CSSM_F64) return fail(CSSM_ERR_INVALID, "unknown dtype");
-  HostModel hm;
-  int rc = copy_model(model, hm);
+  return create_impl(model, n_particles, resample_kind, dtype, device, seed, stream_id, 0, 1, out);
+}
+
+int cssm_filter_create_sharded(const cssm_model_desc_t* model, int64_t n_local, int resample_kind, int dtype, int device,
+                               uint64_t seed, uint64_t stream_id, int rank, int world, cssm_filter_t** out) {
+  return create_impl(model, n_local, resample_kind, dtype, device, seed, stream_id, rank, world, out);
+}
+
+int cssm_filter_shard_export(cssm_filter_t* f, void* blob_out) {
+  int rc = enter(f);
   if (rc) return rc;
-  int ndev = 0;
-  rc = cssm_device_count(&ndev);
-  if (rc) return rc;
-  if (ndev == 0) return fail(CSSM_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
-  if (device < 0 || device >= ndev) return fail(CSSM_ERR_INVALID, "device index out of range");
-  CU(cudaSetDevice(device));
-  cssm_filter* f = new cssm_filter();
-  f->device = device; f->dtype = dtype; f->resample_kind = resample_kind;
-  f->N = n_particles; f->Ns = (n_particles + 63) / 64 * 64;
-  f->model = hm; f->d = hm.d;
-  f->nt = nblk(f->N, TILE);
-  f->seed = seed; f->stream_id = stream_id;
-  const size_t esz = (dtype == CSSM_F32) ? 4 : 8;
-#define ALLOC(ptr, bytes)                                                                        \
-  do {                                                                                           \
-    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                        \
-    if (e_ != cudaSuccess) {                                                                     \
-      cssm_filter_destroy(f);                                                                    \
-      return fail(CSSM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e_));         \
-    }                                                                                            \
-  } while (0)
-  ALLOC(f->xa, (size_t)f->d * f->Ns * esz);
-  ALLOC(f->xb, (size_t)f->d * f->Ns * esz);
-  ALLOC(f->logw, (size_t)(f->Ns + TILE) * esz);
-  ALLOC(f->anc, (size_t)f->Ns * sizeof(int32_t));
-  ALLOC(f->sc, sizeof(Scalars));
-  ALLOC(f->tile_sum, (size_t)(f->nt + 1) * sizeof(u128));
-  ALLOC(f->tile_excl, (size_t)(f->nt + 1) * sizeof(u128));
-  ALLOC(f->cend, (size_t)(f->nt + 1) * sizeof(double));
-  ALLOC(f->tile_maxw, (size_t)(f->nt + 1) * sizeof(double));
-  if (resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ALLOC(f->cdf, (size_t)f->Ns * sizeof(double));
-#undef ALLOC
-  cudaMemset(f->xa, 0, (size_t)f->d * f->Ns * esz);
-  cudaMemset(f->xb, 0, (size_t)f->d * f->Ns * esz);
-  cudaMemset(f->logw, 0, (size_t)(f->Ns + TILE) * esz);
-  cudaMemset(f->sc, 0, sizeof(Scalars));
-  if (cudaStreamCreateWithFlags(&f->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&f->ev0) != cudaSuccess ||
-      cudaEventCreate(&f->ev1) != cudaSuccess) {
-    cssm_filter_destroy(f);
-    return fail(CSSM_ERR_CUDA, "stream/event creation failed");
+  if (!blob_out) return fail(CSSM_ERR_INVALID, "null blob");
+  ShardBlob b;
+  std::memset(&b, 0, sizeof(b));
+  b.magic = BLOB_MAGIC;
+  b.rank = f->rank; b.world = f->world; b.device = f->device; b.dtype = f->dtype; b.nt = f->nt; b.d = f->d;
+  b.N = f->N; b.Ns = f->Ns; b.pid = (int64_t)getpid();
+  void* ptrs[7] = {f->x[0], f->x[1], f->anc, f->logw, f->tb.tile_sum, f->tb.tile_maxw, f->xch};
+  for (int i = 0; i < 7; ++i) {
+    b.ptr[i] = ptrs[i];
+    if (f->world > 1) {
+      cudaError_t e = cudaIpcGetMemHandle(&b.h[i], ptrs[i]);
+      if (e != cudaSuccess) {
+        // in-process groups never open the handles; a multi-process job will fail at connect
+        cudaGetLastError();
+        std::memset(&b.h[i], 0, sizeof(b.h[i]));
+      }
+    }
   }
-  f->stream = f->own_stream;
-  CU(cudaDeviceSynchronize());
-  *out = f;
+  std::memset(blob_out, 0, CSSM_SHARD_BLOB_BYTES);
+  std::memcpy(blob_out, &b, sizeof(b));
+  return CSSM_OK;
+}
+
+int cssm_filter_shard_connect(cssm_filter_t* f, const void* blobs, int world) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!blobs || world != f->world) return fail(CSSM_ERR_INVALID, "shard_connect: world size differs from the one the filter was created with");
+  if (f->connected) return fail(CSSM_ERR_STATE, "shard_connect: already connected");
+  const int64_t mypid = (int64_t)getpid();
+  for (int q = 0; q < world; ++q) {
+    ShardBlob b;
+    std::memcpy(&b, (const char*)blobs + (size_t)q * CSSM_SHARD_BLOB_BYTES, sizeof(b));
+    if (b.magic != BLOB_MAGIC || b.rank != q || b.world != world) return fail(CSSM_ERR_INVALID, "shard_connect: malformed blob (expected one blob per rank, in rank order)");
+    if (b.N != f->N || b.Ns != f->Ns || b.dtype != f->dtype || b.nt != f->nt || b.d != f->d)
+      return fail(CSSM_ERR_INVALID, "shard_connect: ranks disagree on particle count, dtype or model shape");
+    if (q == f->rank) continue;
+    void* p[7];
+    if (b.pid == mypid) {  // same process (one host thread driving several shards): plain pointers
+      if (b.device != f->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, f->device, b.device));
+        if (!can) return fail(CSSM_ERR_COMM, "shard_connect: no peer access between the devices of two ranks");
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(CSSM_ERR_COMM, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      for (int i = 0; i < 7; ++i) p[i] = b.ptr[i];
+    } else {  // another process on this node: CUDA IPC mapping of the peer's allocations (NVLink P2P)
+      for (int i = 0; i < 7; ++i) {
+        cudaError_t e = cudaIpcOpenMemHandle(&p[i], b.h[i], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(CSSM_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        f->ipc_opened.push_back(p[i]);
+      }
+    }
+    cssm_filter::PeerPtrs& pp = f->peer[q];
+    pp.x[0] = p[0]; pp.x[1] = p[1]; pp.anc = (int32_t*)p[2]; pp.logw = p[3];
+    pp.tile_sum = (u128*)p[4]; pp.tile_maxw = (double*)p[5]; pp.xch = (XchSlot*)p[6];
+  }
+  f->connected = true;
+  return CSSM_OK;
+}
+
+int cssm_filter_shard_info(const cssm_filter_t* f, int32_t* rank_out, int32_t* world_out, int64_t* slot0_out) {
+  if (!f) return fail(CSSM_ERR_INVALID, "null filter handle");
+  if (rank_out) *rank_out = f->rank;
+  if (world_out) *world_out = f->world;
+  if (slot0_out) *slot0_out = (int64_t)f->rank * f->N;
   return CSSM_OK;
 }
 
@@ -649,8 +888,9 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   if (!f) return CSSM_OK;
   cudaSetDevice(f->device);
   if (f->own_stream) cudaStreamSynchronize(f->own_stream);
-  void* ptrs[] = {f->xa, f->xb, f->logw, f->anc, f->sc, f->tile_sum, f->tile_excl, f->cend, f->tile_maxw, f->ubuf, f->cdf,
-                  f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states};
+  for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
+  void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
+                  f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (f->ev0) cudaEventDestroy(f->ev0);
@@ -725,62 +965,293 @@ int cssm_filter_n_substeps(const cssm_filter_t* f, double dt, int64_t* n_out) {
   return CSSM_OK;
 }
 
-int cssm_filter_step_injected(cssm_filter_t* f, double t, int has_obs, double y, const double* z, const double* u,
-                              double* x_prop_out, double* logw_out, double* w1_out, int32_t* anc_out, double* ll_out,
-                              int32_t* ess_out) {
-  int rc = enter(f);
+}  // extern "C"
+
+namespace {
+
+// uploads of one injected step: noise rows [n_sub*d] x N taken from a host matrix whose rows have
+// `ld` columns starting at column `col0` (a shard's slice of the global noise), and the uniforms
+int upload_injected(cssm_filter* f, int64_t n_sub, const double* z, long long ld, long long col0, const double* u, long long n_u,
+                    bool weighted, StepIO& io, size_t& nz) {
+  nz = (size_t)std::max<int64_t>(n_sub, 1) * f->d * f->N;
+  int rc = ensure_scratch(f, nz + (size_t)f->d * f->N);
   if (rc) return rc;
-  if (!f->initialised) return fail(CSSM_ERR_STATE, "stepFilter before initialiseState");
-  int64_t n_sub = 1;
-  cssm_filter_n_substeps(f, t - f->t_cur, &n_sub);
-  const bool lgcp = f->model.obs_kind == CSSM_OBS_LGCP;
-  const bool weighted = lgcp || has_obs;
-  if (n_sub > 0 && !z) return fail(CSSM_ERR_INVALID, "null noise");
-  if (weighted && !u) return fail(CSSM_ERR_INVALID, "null uniforms");
-  const size_t nz = (size_t)std::max<int64_t>(n_sub, 1) * f->d * f->N;
-  rc = ensure_scratch(f, nz + (size_t)f->d * f->N);
-  if (rc) return rc;
-  if (n_sub > 0) CU(cudaMemcpyAsync(f->scratch, z, (size_t)n_sub * f->d * f->N * sizeof(double), cudaMemcpyHostToDevice, f->stream));
-  StepIO io;
+  if (n_sub > 0)
+    CU(cudaMemcpy2DAsync(f->scratch, (size_t)f->N * sizeof(double), z + col0, (size_t)ld * sizeof(double), (size_t)f->N * sizeof(double),
+                         (size_t)n_sub * f->d, cudaMemcpyHostToDevice, f->stream));
   io.zinj = f->scratch;
   if (weighted) {
     if (f->resample_kind == CSSM_RESAMPLE_SYSTEMATIC) {
       CU(cudaMemcpyAsync(&f->sc->u_inj, u, sizeof(double), cudaMemcpyHostToDevice, f->stream));
       io.use_u_inj = 1;
     } else {
-      if (!f->ubuf) CU(cudaMalloc(&f->ubuf, (size_t)f->N * sizeof(double)));
-      CU(cudaMemcpyAsync(f->ubuf, u, (size_t)f->N * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+      if (!f->ubuf) CU(cudaMalloc(&f->ubuf, (size_t)n_u * sizeof(double)));
+      CU(cudaMemcpyAsync(f->ubuf, u, (size_t)n_u * sizeof(double), cudaMemcpyHostToDevice, f->stream));
       io.uarr = f->ubuf;
     }
   }
-  f->launches = 0;
-  rc = run_one_step(f, t, has_obs, y, io);
-  if (rc) return rc;
+  return CSSM_OK;
+}
+
+// read-backs of one injected step into host rows of `ld` columns at column col0
+int read_injected(cssm_filter* f, size_t nz, bool weighted, long long ld, long long col0, double* x_prop_out, double* logw_out,
+                  double* w1_out, int32_t* anc_out) {
   double* stage = f->scratch + nz;  // d*N doubles
   const int g = nblk(f->N, 256);
   if (x_prop_out) {
-    if (f->dtype == CSSM_F32) k_gather<float, double><<<g, 256, 0, f->stream>>>((const float*)f->xa, nullptr, stage, f->d, f->N, f->Ns, f->N);
-    else k_gather<double, double><<<g, 256, 0, f->stream>>>((const double*)f->xa, nullptr, stage, f->d, f->N, f->Ns, f->N);
-    CU(cudaMemcpyAsync(x_prop_out, stage, (size_t)f->d * f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    if (f->dtype == CSSM_F32) launch_gather<float>(f, nullptr, stage);
+    else launch_gather<double>(f, nullptr, stage);
+    CU(cudaMemcpy2DAsync(x_prop_out + col0, (size_t)ld * sizeof(double), stage, (size_t)f->N * sizeof(double), (size_t)f->N * sizeof(double),
+                         (size_t)f->d, cudaMemcpyDeviceToHost, f->stream));
     CU(cudaStreamSynchronize(f->stream));
   }
   if (weighted) {
     if (logw_out) {
       if (f->dtype == CSSM_F32) k_to_double<float><<<g, 256, 0, f->stream>>>((const float*)f->logw, stage, f->N);
       else k_to_double<double><<<g, 256, 0, f->stream>>>((const double*)f->logw, stage, f->N);
-      CU(cudaMemcpyAsync(logw_out, stage, (size_t)f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+      CU(cudaMemcpyAsync(logw_out + col0, stage, (size_t)f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
       CU(cudaStreamSynchronize(f->stream));
     }
     if (w1_out) {
       if (f->dtype == CSSM_F32) k_w1_out<float><<<g, 256, 0, f->stream>>>((const float*)f->logw, f->sc, stage, f->N);
       else k_w1_out<double><<<g, 256, 0, f->stream>>>((const double*)f->logw, f->sc, stage, f->N);
-      CU(cudaMemcpyAsync(w1_out, stage, (size_t)f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+      CU(cudaMemcpyAsync(w1_out + col0, stage, (size_t)f->N * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
       CU(cudaStreamSynchronize(f->stream));
     }
-    if (anc_out) CU(cudaMemcpyAsync(anc_out, f->anc, (size_t)f->N * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+    if (anc_out) {
+      CU(cudaMemcpyAsync(anc_out + col0, f->anc, (size_t)f->N * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+      CU(cudaStreamSynchronize(f->stream));
+    }
   }
+  return CSSM_OK;
+}
+
+int check_group(cssm_filter_t* const* sh, int R) {
+  if (!sh || R < 1 || R > MAXR) return fail(CSSM_ERR_INVALID, "group: bad shard array");
+  for (int r = 0; r < R; ++r) {
+    if (!sh[r]) return fail(CSSM_ERR_INVALID, "group: null shard");
+    if (sh[r]->world != R || sh[r]->rank != r) return fail(CSSM_ERR_INVALID, "group: shards must be passed in rank order, one per rank");
+    if (R > 1 && !sh[r]->connected) return fail(CSSM_ERR_STATE, "group: shards are not connected");
+  }
+  // shards that share a device must share a stream: the lock-step launch order below is what
+  // guarantees that every wait inside a kernel is already satisfied when the kernel runs
+  for (int r = 1; r < R; ++r)
+    for (int q = 0; q < r; ++q)
+      if (sh[r]->device == sh[q]->device) { sh[r]->stream = sh[q]->stream; break; }
+  return CSSM_OK;
+}
+
+#define EACH_SHARD(body)                      \
+  for (int r = 0; r < R; ++r) {               \
+    cssm_filter* f = sh[r];                   \
+    int rc_ = enter(f);                       \
+    if (rc_) return rc_;                      \
+    body                                      \
+  }
+
+// one stepFilter of the whole group in lock-step: K1 on every shard, then K2, then K3
+int group_step(cssm_filter_t* const* sh, int R, const StepHost* hs, const long long* n_subs, const void* const* ctabs, double delta,
+               const StepIO* ios) {
+  StepCtx cx[MAXR];
+  EACH_SHARD({
+    int rc = (f->dtype == CSSM_F32) ? step_phase1<float>(f, hs[r], n_subs[r], ctabs[r], delta, ios[r], cx[r])
+                                    : step_phase1<double>(f, hs[r], n_subs[r], ctabs[r], delta, ios[r], cx[r]);
+    if (rc) return rc;
+  })
+  EACH_SHARD({
+    int rc = (f->dtype == CSSM_F32) ? step_phase2<float>(f, cx[r]) : step_phase2<double>(f, cx[r]);
+    if (rc) return rc;
+  })
+  EACH_SHARD({
+    int rc = (f->dtype == CSSM_F32) ? step_phase3<float>(f, ios[r], cx[r]) : step_phase3<double>(f, ios[r], cx[r]);
+    if (rc) return rc;
+  })
+  return CSSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cssm_filter_step_injected(cssm_filter_t* f, double t, int has_obs, double y, const double* z, const double* u,
+                              double* x_prop_out, double* logw_out, double* w1_out, int32_t* anc_out, double* ll_out,
+                              int32_t* ess_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "stepFilter before initialiseState");
+  if (f->world > 1) return fail(CSSM_ERR_UNSUPPORTED, "step_injected on one shard: use cssm_group_step_injected");
+  int64_t n_sub = 1;
+  cssm_filter_n_substeps(f, t - f->t_cur, &n_sub);
+  const bool lgcp = f->model.obs_kind == CSSM_OBS_LGCP;
+  const bool weighted = lgcp || has_obs;
+  if (n_sub > 0 && !z) return fail(CSSM_ERR_INVALID, "null noise");
+  if (weighted && !u) return fail(CSSM_ERR_INVALID, "null uniforms");
+  StepIO io;
+  size_t nz;
+  rc = upload_injected(f, n_sub, z, f->N, 0, u, f->N, weighted, io, nz);
+  if (rc) return rc;
+  f->launches = 0;
+  rc = run_one_step(f, t, has_obs, y, io);
+  if (rc) return rc;
+  rc = read_injected(f, nz, weighted, f->N, 0, x_prop_out, logw_out, w1_out, anc_out);
+  if (rc) return rc;
   f->last_launches = f->launches;
   return read_ll(f, ll_out, ess_out);
+}
+
+/* ---- in-process groups: R shards of one filter driven in lock-step by one host thread ---------- */
+
+int cssm_group_init_injected(cssm_filter_t* const* sh, int R, double t0, const double* z0) {
+  int rc = check_group(sh, R);
+  if (rc) return rc;
+  if (!z0) return fail(CSSM_ERR_INVALID, "null noise");
+  const long long Ng = (long long)R * sh[0]->N;
+  EACH_SHARD({
+    size_t n = (size_t)f->d * f->N;
+    int rc2 = ensure_scratch(f, n);
+    if (rc2) return rc2;
+    CU(cudaMemcpy2DAsync(f->scratch, (size_t)f->N * sizeof(double), z0 + (long long)r * f->N, (size_t)Ng * sizeof(double),
+                         (size_t)f->N * sizeof(double), (size_t)f->d, cudaMemcpyHostToDevice, f->stream));
+    f->launches = 0;
+    rc2 = do_init(f, t0, f->scratch, nullptr);
+    if (rc2) return rc2;
+  })
+  EACH_SHARD({ CU(cudaStreamSynchronize(f->stream)); })
+  return CSSM_OK;
+}
+
+int cssm_group_init(cssm_filter_t* const* sh, int R, double t0) {
+  int rc = check_group(sh, R);
+  if (rc) return rc;
+  EACH_SHARD({
+    f->launches = 0;
+    int rc2 = do_init(f, t0, nullptr, nullptr);
+    if (rc2) return rc2;
+  })
+  return CSSM_OK;
+}
+
+int cssm_group_step_injected(cssm_filter_t* const* sh, int R, double t, int has_obs, double y, const double* z, const double* u,
+                             double* x_prop_out, double* logw_out, double* w1_out, int32_t* anc_out, double* ll_out,
+                             int32_t* ess_out) {
+  int rc = check_group(sh, R);
+  if (rc) return rc;
+  const long long Ng = (long long)R * sh[0]->N;
+  StepHost hs[MAXR];
+  long long n_subs[MAXR];
+  const void* ctabs[MAXR];
+  StepIO ios[MAXR];
+  size_t nzs[MAXR];
+  double delta = 0.0;
+  const bool lgcp = sh[0]->model.obs_kind == CSSM_OBS_LGCP;
+  const bool weighted = lgcp || has_obs;
+  if (weighted && !u) return fail(CSSM_ERR_INVALID, "null uniforms");
+  EACH_SHARD({
+    if (!f->initialised) return fail(CSSM_ERR_STATE, "stepFilter before initialiseState");
+    int rc2 = prepare_one_step(f, t, has_obs, y, hs[r], n_subs[r], delta, ctabs[r]);
+    if (rc2) return rc2;
+    if (n_subs[r] > 0 && !z) return fail(CSSM_ERR_INVALID, "null noise");
+    rc2 = upload_injected(f, n_subs[r], z, Ng, (long long)r * f->N, u, Ng, weighted, ios[r], nzs[r]);
+    if (rc2) return rc2;
+    f->launches = 0;
+  })
+  rc = group_step(sh, R, hs, n_subs, ctabs, delta, ios);
+  if (rc) return rc;
+  EACH_SHARD({
+    f->t_cur = t;
+    int rc2 = read_injected(f, nzs[r], weighted, Ng, (long long)r * f->N, x_prop_out, logw_out, w1_out, anc_out);
+    if (rc2) return rc2;
+    f->last_launches = f->launches;
+  })
+  double ll = 0.0;
+  int32_t ess = 0;
+  EACH_SHARD({
+    double l;
+    int32_t e;
+    int rc2 = read_ll(f, &l, &e);
+    if (rc2) return rc2;
+    if (r == 0) { ll = l; ess = e; }
+    else if (std::memcmp(&l, &ll, sizeof(double)) != 0 || e != ess) return fail(CSSM_ERR_COMM, "group: ranks disagree on the log-likelihood");
+  })
+  if (ll_out) *ll_out = ll;
+  if (ess_out) *ess_out = ess;
+  return CSSM_OK;
+}
+
+int cssm_group_get_particles(cssm_filter_t* const* sh, int R, double* x_out) {
+  int rc = check_group(sh, R);
+  if (rc) return rc;
+  if (!x_out) return fail(CSSM_ERR_INVALID, "null output");
+  const long long Ng = (long long)R * sh[0]->N;
+  EACH_SHARD({
+    if (!f->initialised) return fail(CSSM_ERR_STATE, "no particles yet");
+    size_t n = (size_t)f->d * f->N;
+    int rc2 = ensure_scratch(f, n);
+    if (rc2) return rc2;
+    const int32_t* anc = f->anc_valid ? f->anc : nullptr;
+    if (f->dtype == CSSM_F32) launch_gather<float>(f, anc, f->scratch);
+    else launch_gather<double>(f, anc, f->scratch);
+    CU(cudaMemcpy2DAsync(x_out + (long long)r * f->N, (size_t)Ng * sizeof(double), f->scratch, (size_t)f->N * sizeof(double),
+                         (size_t)f->N * sizeof(double), (size_t)f->d, cudaMemcpyDeviceToHost, f->stream));
+  })
+  EACH_SHARD({ CU(cudaStreamSynchronize(f->stream)); })
+  return CSSM_OK;
+}
+
+int cssm_group_ll(cssm_filter_t* const* sh, int R, const double* t, const double* y, const uint8_t* has_obs, int64_t T,
+                  double* ll_out, float* ms_out) {
+  int rc = check_group(sh, R);
+  if (rc) return rc;
+  EACH_SHARD({
+    int rc2 = cssm_filter_load_series(f, t, y, has_obs, T);
+    if (rc2) return rc2;
+    rc2 = ensure_steps_cap(f, (size_t)T);
+    if (rc2) return rc2;
+    f->launches = 0;
+    CU(cudaEventRecord(f->ev0, f->stream));
+    rc2 = do_init(f, f->t0_series, nullptr, nullptr);
+    if (rc2) return rc2;
+  })
+  StepHost hs[MAXR];
+  long long n_subs[MAXR];
+  const void* ctabs[MAXR];
+  StepIO ios[MAXR];
+  for (int64_t s = 0; s < T; ++s) {
+    double delta = 0.0;
+    for (int r = 0; r < R; ++r) {
+      cssm_filter* f = sh[r];
+      const SeriesStep& st = f->series[(size_t)s];
+      hs[r] = st.h;
+      n_subs[r] = st.n_sub;
+      ctabs[r] = nullptr;
+      if (f->ctab && st.n_sub > 0 && !f->ctab_host.empty())
+        ctabs[r] = (const char*)f->ctab + st.ctab_off * ((f->dtype == CSSM_F32) ? 4 : 8);
+      delta = (f->model.obs_kind == CSSM_OBS_LGCP) ? std::pow(10, -f->model.lgcp_precision) : 0.0;
+      ios[r] = StepIO();
+      ios[r].ll_steps = f->ll_steps;
+      ios[r].ess_steps = f->ess_steps;
+      ios[r].step_slot = (long long)s;
+    }
+    rc = group_step(sh, R, hs, n_subs, ctabs, delta, ios);
+    if (rc) return rc;
+    for (int r = 0; r < R; ++r) sh[r]->t_cur = sh[r]->series[(size_t)s].t;
+  }
+  EACH_SHARD({ CU(cudaEventRecord(f->ev1, f->stream)); })
+  double ll = 0.0;
+  float ms = 0.f;
+  EACH_SHARD({
+    double l;
+    int rc2 = read_ll(f, &l, nullptr);
+    if (rc2) return rc2;
+    CU(cudaEventElapsedTime(&f->last_ms, f->ev0, f->ev1));
+    f->last_launches = f->launches;
+    ms = std::max(ms, f->last_ms);
+    if (r == 0) ll = l;
+    else if (std::memcmp(&l, &ll, sizeof(double)) != 0) return fail(CSSM_ERR_COMM, "group: ranks disagree on the log-likelihood");
+  })
+  if (ll_out) *ll_out = ll;
+  if (ms_out) *ms_out = ms;
+  return CSSM_OK;
 }
 
 int cssm_filter_load_series(cssm_filter_t* f, const double* t, const double* y, const uint8_t* has_obs, int64_t T) {
@@ -833,7 +1304,7 @@ int cssm_filter_ll_resident(cssm_filter_t* f, double* ll_out, double* ll_steps_o
     CU(cudaMemcpy(lls.data(), f->ll_steps, T * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(esss.data(), f->ess_steps, T * sizeof(int), cudaMemcpyDeviceToHost));
     double pl = 0.0;
-    int pe = (int)std::min<long long>(f->N, 2147483647LL);
+    int pe = (int)std::min<long long>(f->N * (long long)f->world, 2147483647LL);
     for (size_t s = 0; s < T; ++s) {
       if (f->series[s].h.has_obs) { pl = lls[s]; pe = esss[s]; }  // unobserved step: ll, ess unchanged (:121)
       if (ll_steps_out) ll_steps_out[s] = pl;
@@ -897,10 +1368,9 @@ int cssm_filter_get_particles(cssm_filter_t* f, double* x_out) {
   size_t n = (size_t)f->d * f->N;
   rc = ensure_scratch(f, n);
   if (rc) return rc;
-  const int g = nblk(f->N, 256);
   const int32_t* anc = f->anc_valid ? f->anc : nullptr;
-  if (f->dtype == CSSM_F32) k_gather<float, double><<<g, 256, 0, f->stream>>>((const float*)f->xa, anc, f->scratch, f->d, f->N, f->Ns, f->N);
-  else k_gather<double, double><<<g, 256, 0, f->stream>>>((const double*)f->xa, anc, f->scratch, f->d, f->N, f->Ns, f->N);
+  if (f->dtype == CSSM_F32) launch_gather<float>(f, anc, f->scratch);
+  else launch_gather<double>(f, anc, f->scratch);
   CU(cudaMemcpyAsync(x_out, f->scratch, n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   CU(cudaStreamSynchronize(f->stream));
   return CSSM_OK;
@@ -937,8 +1407,9 @@ int cssm_filter_mean_state(cssm_filter_t* f, double* mean_out) {
   CU(cudaMemsetAsync(f->scratch, 0, (size_t)f->d * sizeof(double), f->stream));
   dim3 grid((unsigned)std::min<long long>(nblk(f->N, 256), 1184), (unsigned)f->d);
   const int32_t* anc = f->anc_valid ? f->anc : nullptr;
-  if (f->dtype == CSSM_F32) k_mean_state<float><<<grid, 256, 0, f->stream>>>((const float*)f->xa, anc, f->scratch, f->d, f->N, f->Ns);
-  else k_mean_state<double><<<grid, 256, 0, f->stream>>>((const double*)f->xa, anc, f->scratch, f->d, f->N, f->Ns);
+  const Peers pr = make_peers(f, f->cur);
+  if (f->dtype == CSSM_F32) k_mean_state<float><<<grid, 256, 0, f->stream>>>(pr, anc, f->scratch, f->d, f->N, f->Ns);
+  else k_mean_state<double><<<grid, 256, 0, f->stream>>>(pr, anc, f->scratch, f->d, f->N, f->Ns);
   CU(cudaMemcpyAsync(mean_out, f->scratch, (size_t)f->d * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
   CU(cudaStreamSynchronize(f->stream));
   return CSSM_OK;
@@ -955,11 +1426,14 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
   if (device < 0 || device >= ndev) return fail(CSSM_ERR_INVALID, "device index out of range");
   CU(cudaSetDevice(device));
   const long long N = n;
-  const int nt = nblk(N, TILE);
-  double *dw = nullptr, *du = nullptr, *dcend = nullptr, *dcdf = nullptr, *dmaxw = nullptr;
+  const int items = (N <= (1 << 18)) ? 2 : 8;
+  const int tile = TILE_THREADS * items;
+  const int nt = nblk(N, tile), ns = nblk(nt, SUPER);
+  double *dw = nullptr, *du = nullptr, *dcdf = nullptr;
   int32_t* danc = nullptr;
-  Scalars* sc = nullptr;
-  u128 *ts = nullptr, *te = nullptr;
+  FilterScalars* sc = nullptr;
+  XchSlot* xch = nullptr;
+  SumTables tb = {nullptr, nullptr, nullptr, nullptr, nullptr, nt, ns};
   cudaStream_t st = nullptr;
   int status = CSSM_OK;
 #define RCU(call)                                                                                  \
@@ -969,42 +1443,52 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
       status = fail(CSSM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
   } while (0)
   RCU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  RCU(cudaMalloc(&dw, (size_t)(N + TILE) * sizeof(double)));
+  RCU(cudaMalloc(&dw, (size_t)(N + tile) * sizeof(double)));
   RCU(cudaMalloc(&du, (size_t)std::max<int64_t>(n_u, 1) * sizeof(double)));
   RCU(cudaMalloc(&danc, (size_t)N * sizeof(int32_t)));
-  RCU(cudaMalloc(&sc, sizeof(Scalars)));
-  RCU(cudaMalloc(&ts, (size_t)(nt + 1) * sizeof(u128)));
-  RCU(cudaMalloc(&te, (size_t)(nt + 1) * sizeof(u128)));
-  RCU(cudaMalloc(&dcend, (size_t)(nt + 1) * sizeof(double)));
-  RCU(cudaMalloc(&dmaxw, (size_t)(nt + 1) * sizeof(double)));
+  RCU(cudaMalloc(&sc, sizeof(FilterScalars)));
+  RCU(cudaMalloc(&xch, sizeof(XchSlot)));
+  RCU(cudaMalloc(&tb.tile_sum, (size_t)(nt + 1) * sizeof(u128)));
+  RCU(cudaMalloc(&tb.tile_maxw, (size_t)(nt + 1) * sizeof(double)));
+  RCU(cudaMalloc(&tb.super_sum, (size_t)2 * ns * sizeof(u128)));
+  RCU(cudaMalloc(&tb.super_q, (size_t)2 * ns * sizeof(u128)));
+  RCU(cudaMalloc(&tb.super_ticket, (size_t)ns * sizeof(unsigned long long)));
   if (kind == CSSM_RESAMPLE_MULTINOMIAL) RCU(cudaMalloc(&dcdf, (size_t)N * sizeof(double)));
   if (status == CSSM_OK) {
-    Scalars z;
+    FilterScalars z;
     std::memset(&z, 0, sizeof(z));
     z.qb = 96;
     if (kind == CSSM_RESAMPLE_SYSTEMATIC) z.u_inj = u[0];
-    RCU(cudaMemsetAsync(dw, 0, (size_t)(N + TILE) * sizeof(double), st));
+    RCU(cudaMemsetAsync(dw, 0, (size_t)(N + tile) * sizeof(double), st));
     RCU(cudaMemcpyAsync(dw, w, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st));
     RCU(cudaMemcpyAsync(du, u, (size_t)((kind == CSSM_RESAMPLE_SYSTEMATIC) ? 1 : N) * sizeof(double), cudaMemcpyHostToDevice, st));
     RCU(cudaMemcpyAsync(sc, &z, sizeof(z), cudaMemcpyHostToDevice, st));
-    const int normalise = (kind == CSSM_RESAMPLE_MULTINOMIAL) ? 0 : 1;
+    RCU(cudaMemsetAsync(tb.super_sum, 0, (size_t)2 * ns * sizeof(u128), st));
+    RCU(cudaMemsetAsync(tb.super_q, 0, (size_t)2 * ns * sizeof(u128), st));
+    RCU(cudaMemsetAsync(tb.super_ticket, 0, (size_t)ns * sizeof(unsigned long long), st));
+    Peers pr;
+    std::memset(&pr, 0, sizeof(pr));
+    pr.R = 1; pr.rank = 0; pr.Nl = N; pr.anc[0] = danc; pr.xch[0] = xch; pr.tile_sum[0] = tb.tile_sum; pr.tile_maxw[0] = tb.tile_maxw;
+    K3Ctl ctl;
+    std::memset(&ctl, 0, sizeof(ctl));
+    ctl.kind = kind; ctl.direct = 1; ctl.add_ll = 0; ctl.use_u_inj = 1;
+    const bool multi = kind == CSSM_RESAMPLE_MULTINOMIAL;
+    const double* ua = (kind == CSSM_RESAMPLE_STRATIFIED) ? du : nullptr;
     k_max_direct<<<std::min(nblk(N, 256), 1184), 256, 0, st>>>(dw, N, sc);
-    k_weight_total<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc);
-    k_tile_sums<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, normalise, sc, ts, dmaxw);
-    k_scan_tiles<<<1, 1024, 0, st>>>(sc, ts, te, dcend, nt, N, normalise, 1, 0, 1, 0u, 0u, 0u, nullptr, nullptr, 0);
-    if (normalise) {
-      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 1, sc, te, dcend, dmaxw, nt, kind,
-                                                         (kind == CSSM_RESAMPLE_STRATIFIED) ? du : nullptr, 0u, 0u, 0u, danc, nullptr, &sc->flags);
+    if (items == 8) {
+      k_weight_sums<double, 8><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, 0, 0ull, tb, pr);
+      k_scan_search<double, 8><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, tb, pr, ctl, ua, multi ? dcdf : nullptr);
     } else {
-      k_scan_search<double><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, 0, sc, te, dcend, dmaxw, nt, kind, nullptr, 0u, 0u, 0u, nullptr, dcdf, &sc->flags);
-      k_multinomial_search<<<nblk(N, 256), 256, 0, st>>>(dcdf, N, du, 0u, 0u, 0u, danc, &sc->flags);
+      k_weight_sums<double, 2><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, 0, 0ull, tb, pr);
+      k_scan_search<double, 2><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, tb, pr, ctl, ua, multi ? dcdf : nullptr);
     }
+    if (multi) k_multinomial_search<<<nblk(N, 256), 256, 0, st>>>(dcdf, N, du, 0u, 0u, 0u, danc, &sc->flags);
     RCU(cudaGetLastError());
     RCU(cudaMemcpyAsync(ancestors_out, danc, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     RCU(cudaStreamSynchronize(st));
   }
 #undef RCU
-  void* ptrs[] = {dw, du, danc, sc, ts, te, dcend, dcdf, dmaxw};
+  void* ptrs[] = {dw, du, danc, sc, xch, tb.tile_sum, tb.tile_maxw, tb.super_sum, tb.super_q, tb.super_ticket, dcdf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (st) cudaStreamDestroy(st);

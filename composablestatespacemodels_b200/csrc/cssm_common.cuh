@@ -22,8 +22,12 @@ __host__ __device__ __forceinline__ u128 make_u128(unsigned long long lo, unsign
 }
 __host__ __device__ __forceinline__ u128 add128(u128 a, u128 b) {
   u128 r;
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u64 %0, %2, %4;\n\taddc.u64 %1, %3, %5;" : "=l"(r.lo), "=l"(r.hi) : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi));
+#else
   r.lo = a.lo + b.lo;
   r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+#endif
   return r;
 }
 __host__ __device__ __forceinline__ bool is_zero128(u128 a) { return (a.lo | a.hi) == 0ull; }
@@ -97,6 +101,24 @@ __host__ __device__ __forceinline__ double unfixq(u128 e, int q) {
 }
 
 #ifdef __CUDACC__
+// floor(w * 2^q) for 0 <= w with w * 2^q < 2^128, q >= 64: the same integer as fixq, by two exact
+// truncating conversions (scaling by a power of two and taking the fractional part are exact).
+// NaN and negative inputs give 0 (cvt.rzi.u64.f64 saturates).
+__device__ __forceinline__ u128 fix_fast(double w, int q) {
+  const double a = __dmul_rn(w, __longlong_as_double((long long)(q - 64 + 1023) << 52));
+  const unsigned long long hi = __double2ull_rz(a);
+  const double r = __dsub_rn(a, __ull2double_rn(hi));  // exact: hi <= a < 2^53 * ulp
+  const unsigned long long lo = __double2ull_rz(__dmul_rn(r, 18446744073709551616.0));
+  return make_u128(lo, hi);
+}
+// the device's conversion of an exact sum to fp64: (double)hi * 2^64 + (double)lo, scaled by 2^-q.
+// Two correctly rounded conversions and one add: bit-identical to oracle/cssm_oracle.cpp dbl128,
+// monotone in e, within 1.5 ulp of e * 2^-q.
+__device__ __forceinline__ double dbl128(u128 e, int q) {
+  const double c = __dadd_rn(__dmul_rn(__ull2double_rn(e.hi), 18446744073709551616.0), __ull2double_rn(e.lo));
+  return __dmul_rn(c, __longlong_as_double((long long)(1023 - q) << 52));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Deterministic exp: the same fma/mul/add sequence as oracle/cssm_oracle.cpp orc_exp_det, so the
 // weights w1 = exp(logw - max) have identical bits on the device and in the checker.
@@ -158,15 +180,14 @@ __device__ __forceinline__ double u64_to_unit_double(uint32_t a, uint32_t b) {
   return (double)(v >> 11) * (1.0 / 9007199254740992.0);  // [0, 1)
 }
 
-// two uint32 -> two N(0,1) floats (Box-Muller on the SFU)
+// two uint32 -> two N(0,1) floats (Box-Muller entirely on the SFU: lg2, sqrt, sin, cos approx)
 __device__ __forceinline__ void box_muller_f(uint32_t a, uint32_t b, float& z0, float& z1) {
   float u1 = fmaf(__uint2float_rz(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1)
-  float u2 = __uint2float_rz(b) * 2.3283064365386963e-10f;                                 // [0,1)
-  float r = sqrtf(-1.3862943611198906f * __log2f(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
+  float ang = __uint2float_rz(b) * 1.4629180792671596e-09f;                                 // 2 pi * [0,1)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));
+  z0 = r * __cosf(ang);
+  z1 = r * __sinf(ang);
 }
 // four uint32 -> two N(0,1) doubles
 __device__ __forceinline__ void box_muller_d(uint4 v, double& z0, double& z1) {
@@ -227,6 +248,41 @@ __device__ __forceinline__ void atomic_add128(u128* dst, u128 v) {
   unsigned long long carry = (old + v.lo < old) ? 1ull : 0ull;
   if (v.hi | carry) atomicAdd(&dst->hi, v.hi + carry);
 }
+
+// ---------------------------------------------------------------------------------------------
+// flags and small payloads exchanged between the ranks of a sharded filter.  The slots live in
+// the DESTINATION rank's memory and are written by peers over NVLink (P2P mapped pointers).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// L2-coherent read of a value other blocks of this grid updated with atomics
+__device__ __forceinline__ unsigned long long ld_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// programmatic dependent launch: wait for the preceding kernel of the stream / let the next start
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif  // __CUDACC__
 
 }  // namespace cssm

@@ -1,22 +1,32 @@
 // cssm_kernels.cuh -- the sm_100a kernels of the particle-filter hot path.
 //
-//   k_init_particles      K0  Sde.initialState                model/Sde.scala:75-80,104-108,152-156
-//   k_propagate_weight    K1  stepFunction + f + dataLikelihood + running max, with the gather of
-//                             the previous resampling fused into the load
-//                                                              model/ParticleFilter.scala:118,123-124
-//   k_lgcp_weight         K1' FilterLgcp.calcWeight            model/ParticleFilter.scala:184-217
-//   k_weight_total        K2a sum of w1 = exp(logw - max)      model/ParticleFilter.scala:125, :522-524
-//   k_tile_sums           K2b normalise + per-tile sums + ESS  model/Resampling.scala:21-24, PF :431-434
-//   k_scan_tiles          K2c tile prefix, ll increment, ESS   model/ParticleFilter.scala:127-128
-//   k_scan_search         K3+K4 inclusive CDF + ancestor search (systematic / stratified)
-//                                                              model/Resampling.scala:36-86
-//   k_multinomial_search  K4' per-draw inverse CDF             model/Resampling.scala:92-96
-//   k_gather              K5  particles(ancestor)              model/Resampling.scala:42,95
+// One observed stepFilter (model/ParticleFilter.scala:116-132) is THREE launches:
 //
-// Layout: structure of arrays, x[k*Ns + i] (Ns = N rounded up to 64) -- every access below is
-// unit-stride across a warp except the ancestor gather, whose indices are non-decreasing for
-// systematic/stratified resampling.  All weight sums are exact 2^-96 fixed point (cssm_common.cuh),
-// so no result depends on the launch geometry.
+//   k_propagate_weight  K1  gather of the previous resampling (fused into the load, over NVLink
+//                           when the ancestor lives on another rank) + stepFunction + f +
+//                           dataLikelihood + block max            model/ParticleFilter.scala:118,123-124
+//     (k_lgcp_weight    K1' FilterLgcp.calcWeight                 model/ParticleFilter.scala:184-217)
+//   k_weight_sums       K2  w1 = exp(logw - max), exact per-tile / per-super-tile / total sums of
+//                           w1 and w1^2                           :125, :522-524, :431-434
+//   k_scan_search       K3  tile prefix (from the super-tile sums, no separate scan launch),
+//                           inclusive CDF of the tile in shared memory, ancestor search with the
+//                           TreeMap duplicate-key rule, ll += max + log(mean w1), ESS
+//                                                                 model/Resampling.scala:36-86, PF :127-128
+//   k_multinomial_search K4' per-draw inverse CDF                 model/Resampling.scala:92-96
+//   k_init_particles, k_gather, k_sample_one, k_mean_state        PF :105-108, Resampling :42,:95,:151-154
+//
+// Layout: structure of arrays, x[k*Ns + i] (Ns = N rounded up to 64) -- every access is unit-stride
+// across a warp except the ancestor gather, whose indices are non-decreasing for systematic /
+// stratified resampling.  All weight sums are exact 2^-96 fixed point (cssm_common.cuh), so no
+// result depends on the tile size, the grid or the number of GPUs a cloud is sharded over.
+//
+// Sharded filters (R ranks, one GPU each, N_l particles per rank): the same three kernels.  The
+// three per-step exchanges -- max log-weight, (sum w, sum w^2), "resampling done" -- are 8..32 byte
+// stores into the peers' memory with a release flag, written by the last block of the producing
+// kernel and awaited by the first instruction of the consuming kernel (an all-gather without a
+// collective launch).  K3 scatters ancestor indices to the rank that owns the offspring slot and
+// the next K1 gathers the parent state from the rank that owns the parent: both are plain
+// st.global / ld.global on peer-mapped pointers.
 #pragma once
 #include "cssm_common.cuh"
 #include "../../include/cssm.h"
@@ -24,9 +34,9 @@
 namespace cssm {
 
 constexpr int MAXD = 32;          // by-value kernel argument budget (5*32*8 B = 1.25 KB)
-constexpr int TILE = 2048;        // elements per scan tile
-constexpr int TILE_THREADS = 256; // 8 elements per thread
-constexpr int TILE_ITEMS = TILE / TILE_THREADS;
+constexpr int MAXR = CSSM_MAX_RANKS;
+constexpr int TILE_THREADS = 256;
+constexpr int SUPER = 256;        // tiles per super tile (second level of the prefix)
 
 // per-observation constants, built on the host in fp64 and rounded to the filter dtype.
 // transition of coordinate k:  x' = A*(x - M) + M + D + S*z     (exact or Euler-Maruyama)
@@ -43,17 +53,45 @@ struct StepArgs {
   int d, obs_kind, has_obs;
 };
 
-// device-resident scalars of one filter
-struct Scalars {
+// accumulators of one observed step; double-buffered by the parity of the observed-step counter,
+// the buffer of the NEXT observed step is zeroed by K3
+struct StepAcc {
   unsigned long long gmax_key;  // ordered key of max(logw), atomicMax target (0 = below everything)
-  u128 tot;                     // sum fix(w1, qb)
-  u128 ess_acc;                 // sum fix(wn^2, 96)
-  double gmax, total, u, ll, ll_incr;
-  int ess, flags, qb, pad;
-  double u_inj;                 // injected systematic uniform
-  unsigned long long n_launch_dummy;
+  u128 tot;                     // sum fix(w1, qb)          (this rank)
+  u128 q;                       // sum fix(w1^2, 96)        (this rank)
+  unsigned long long pad;
 };
-enum : int { FLAG_NAN_WEIGHT = 1, FLAG_ZERO_TOTAL = 2, FLAG_CLAMPED = 4 };
+// device-resident scalars of one filter
+struct FilterScalars {
+  StepAcc acc[2];
+  unsigned long long ticket1, ticket2, ticket3;  // monotone "last block" tickets of K1 / K2 / K3
+  double ll, ll_incr, u_inj;
+  double gmax, total;  // of the last observed step (read-back of w1, tests)
+  int ess, flags, qb, pad;
+};
+enum : int { FLAG_NAN_WEIGHT = 1, FLAG_ZERO_TOTAL = 2, FLAG_CLAMPED = 4, FLAG_COMM_TIMEOUT = 8 };
+
+// what rank q writes into the memory of every rank (slot [q] of the destination's array)
+struct XchSlot {
+  unsigned long long max_key[2], max_seq[2];                  // after K1
+  unsigned long long tot_lo[2], tot_hi[2], q_lo[2], q_hi[2];  // after K2
+  unsigned long long sum_seq[2];
+  unsigned long long progress;  // number of completed steps (after K3, or after K1 of an unobserved step)
+  unsigned long long pad;
+};
+static_assert(sizeof(XchSlot) == 128, "XchSlot is one 128-byte line");
+
+// the ranks of a sharded filter as one kernel argument (R == 1: the plain single-GPU filter)
+struct Peers {
+  int R, rank;
+  long long Nl;                  // particles per rank (the same on every rank)
+  const void* x[MAXR];           // cloud each rank wrote in the previous step (K1 gathers from it)
+  int32_t* anc[MAXR];            // ancestor buffers (K3 scatters into them)
+  const void* logw[MAXR];        // log-weights, tile sums, tile maxima: only read when a run of
+  const u128* tile_sum[MAXR];    // duplicate keys crosses a rank boundary
+  const double* tile_maxw[MAXR];
+  XchSlot* xch[MAXR];            // xch[q] = slot array in rank q's memory; this rank writes xch[q][rank]
+};
 
 // ---------------------------------------------------------------------------------------------
 template <typename real> struct VecOf;
@@ -124,6 +162,35 @@ template <> struct Normals<double> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// exchange helpers (sharded filters only; every call site is behind `pr.R > 1`)
+// ---------------------------------------------------------------------------------------------
+// spin until *p >= want.  Bounded: after 4 s the filter is flagged and every later wait returns
+// at once, so a dead peer costs seconds, not a hung GPU.
+__device__ __forceinline__ void wait_ge(const unsigned long long* p, unsigned long long want, FilterScalars* sc) {
+  if (ld_acquire_sys(p) >= want) return;
+  if (*(volatile int*)&sc->flags & FLAG_COMM_TIMEOUT) return;
+  const unsigned long long t0 = global_timer_ns();
+  while (ld_acquire_sys(p) < want) {
+    __nanosleep(64);
+    if (global_timer_ns() - t0 > 4000000000ull) {
+      atomicOr(&sc->flags, FLAG_COMM_TIMEOUT);
+      return;
+    }
+  }
+}
+// one thread: wait for every peer's progress counter (steps completed) to reach `gstep`
+__device__ __forceinline__ void wait_progress(const Peers& pr, unsigned long long gstep, FilterScalars* sc) {
+  const XchSlot* mine = pr.xch[pr.rank];
+  for (int q = 0; q < pr.R; ++q)
+    if (q != pr.rank) wait_ge(&mine[q].progress, gstep, sc);
+}
+__device__ __forceinline__ void push_progress(const Peers& pr, unsigned long long gstep_done) {
+  __threadfence_system();
+  for (int q = 0; q < pr.R; ++q)
+    if (q != pr.rank) st_release_sys(&pr.xch[q][pr.rank].progress, gstep_done);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K0  x0[k][i] = sqrt(c0_k) * z + m0_k        (a.S = sqrt(c0), a.M = m0)
 // ---------------------------------------------------------------------------------------------
 template <typename real>
@@ -158,50 +225,123 @@ __global__ void __launch_bounds__(256) k_fill_particles(StepArgs<real> a, real* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// tail of K1 / K1': block max -> one atomicMax per block; sharded: the last block of the grid
+// publishes the rank's max (observed step) or its progress (unobserved step) to the peers
+// ---------------------------------------------------------------------------------------------
+struct K1Ctl {
+  FilterScalars* sc;
+  int parity;                   // observed-step parity
+  unsigned long long obs_seq;   // observed steps completed before this one
+  unsigned long long gstep;     // steps completed before this one
+};
+__device__ __forceinline__ void k1_tail(double mx, bool bad, int has_obs, const Peers& pr, const K1Ctl& ctl) {
+  __shared__ double s_mx[8];
+  __shared__ int s_bad;
+  FilterScalars* sc = ctl.sc;
+  if (has_obs) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m2 = s_mx[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m2 = fmax(m2, s_mx[w]);
+      atomicMax(&sc->acc[ctl.parity].gmax_key, ord_key(m2));
+      if (s_bad) atomicOr(&sc->flags, FLAG_NAN_WEIGHT);
+    }
+  }
+  if (pr.R > 1 && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long tk = atomicAdd(&sc->ticket1, 1ull);
+    if (tk % gridDim.x == gridDim.x - 1) {  // every block of this launch has contributed
+      __threadfence();
+      if (has_obs) {
+        const unsigned long long key = ld_gpu(&sc->acc[ctl.parity].gmax_key);
+        __threadfence_system();
+        for (int q = 0; q < pr.R; ++q) {
+          XchSlot* s = &pr.xch[q][pr.rank];
+          st_relaxed_sys(&s->max_key[ctl.parity], key);
+          st_release_sys(&s->max_seq[ctl.parity], ctl.obs_seq + 1);
+        }
+      } else {
+        push_progress(pr, ctl.gstep + 1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1  fused gather + propagate + f + log-weight + max
 //     one thread = PPT consecutive particles (16-byte stores); the loads go through the ancestor
 //     index (non-decreasing for systematic/stratified, so a warp still touches few sectors).
+//     D > 0: latent dimension known at compile time (everything unrolls, constants become
+//     immediate constant-bank operands); D == 0: any d <= MAXD.
 // ---------------------------------------------------------------------------------------------
-template <typename real>
+template <typename real, int D>
 __global__ void __launch_bounds__(256)
-k_propagate_weight(const __grid_constant__ StepArgs<real> a, const real* __restrict__ xsrc, real* __restrict__ xdst,
+k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
                    const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
                    long long N, long long Ns, unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
-                   Scalars* __restrict__ sc) {
+                   K1Ctl ctl) {
   constexpr int PPT = VecOf<real>::PPT;
   typedef typename VecOf<real>::type vec_t;
   constexpr int PC = Normals<real>::PER_CALL;
+  const int d = (D > 0) ? D : a.d;
+  griddep_wait();
+  griddep_launch();
+  if (pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
+    if (threadIdx.x == 0) wait_progress(pr, ctl.gstep, ctl.sc);
+    __syncthreads();
+  }
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PPT;
   const bool full = (i0 + PPT <= N);
-  long long src[PPT];
+  const real* src[PPT];
   bool valid[PPT];
+  {
+    const real* xloc = reinterpret_cast<const real*>(pr.x[pr.rank]);
+    long long s[PPT];
 #pragma unroll
-  for (int p = 0; p < PPT; ++p) {
-    valid[p] = (i0 + p < N);
-    src[p] = i0 + p;
-  }
-  if (anc != nullptr) {
-    if (full && PPT == 4) {
-      int4 v = *reinterpret_cast<const int4*>(anc + i0);
-      src[0] = v.x; src[1] = v.y; src[PPT > 2 ? 2 : 0] = v.z; src[PPT > 3 ? 3 : 0] = v.w;
-    } else {
+    for (int p = 0; p < PPT; ++p) {
+      valid[p] = (i0 + p < N);
+      s[p] = i0 + p;
+    }
+    if (anc != nullptr) {
+      if (full && PPT == 4) {
+        int4 v = *reinterpret_cast<const int4*>(anc + i0);
+        s[0] = v.x; s[1] = v.y; s[PPT > 2 ? 2 : 0] = v.z; s[PPT > 3 ? 3 : 0] = v.w;
+      } else {
 #pragma unroll
-      for (int p = 0; p < PPT; ++p)
-        if (valid[p]) src[p] = anc[i0 + p];
+        for (int p = 0; p < PPT; ++p)
+          if (valid[p]) s[p] = anc[i0 + p];
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+      if (pr.R > 1 && anc != nullptr) {  // ancestors are GLOBAL particle indices: owner rank + local index
+        const unsigned g = (unsigned)s[p];
+        const unsigned q = g / (unsigned)pr.Nl;
+        src[p] = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+      } else {
+        src[p] = xloc + s[p];
+      }
     }
   }
   real g[PPT];
 #pragma unroll
   for (int p = 0; p < PPT; ++p) g[p] = (real)0;
 
-  for (int kk = 0; kk < a.d; kk += 4) {
+#pragma unroll
+  for (int kk = 0; kk < d; kk += 4) {
     // issue the loads of this chunk of (up to) 4 coordinates first
     real xv[4][PPT];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = kk + j;
 #pragma unroll
-      for (int p = 0; p < PPT; ++p) xv[j][p] = (k < a.d && valid[p]) ? __ldg(xsrc + (long long)k * Ns + src[p]) : (real)0;
+      for (int p = 0; p < PPT; ++p) xv[j][p] = (k < d && valid[p]) ? __ldg(src[p] + (long long)k * Ns) : (real)0;
     }
     // noise: counter = (global slot, step, chunk)
     real z[4][PPT];
@@ -214,7 +354,7 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const real* __restr
           Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)(kk >> 2), key0, key1, zz);
         } else {
           Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)(kk >> 1), key0, key1, zz);
-          if (kk + 2 < a.d)
+          if (kk + 2 < d)
             Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)((kk >> 1) + 1), key0, key1, zz + 2);
           else
             zz[2] = zz[3] = (real)0;
@@ -227,17 +367,17 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const real* __restr
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int p = 0; p < PPT; ++p)
-          z[j][p] = (kk + j < a.d && valid[p]) ? (real)zinj[(long long)(kk + j) * N + i0 + p] : (real)0;
+          z[j][p] = (kk + j < d && valid[p]) ? (real)zinj[(long long)(kk + j) * N + i0 + p] : (real)0;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = kk + j;
-      if (k < a.d) {
-        real A = a.A[k], M = a.M[k], D = a.D[k], S = a.S[k], Cc = a.C[k];
+      if (k < d) {
+        real A = a.A[k], M = a.M[k], Dk = a.D[k], S = a.S[k], Cc = a.C[k];
         real xn[PPT];
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
-          real mean = r_fma<real>(A, xv[j][p] - M, M) + D;
+          real mean = r_fma<real>(A, xv[j][p] - M, M) + Dk;
           xn[p] = r_fma<real>(S, z[j][p], mean);
           g[p] = r_fma<real>(Cc, xn[p], g[p]);
         }
@@ -256,46 +396,33 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const real* __restr
       }
     }
   }
-  if (!a.has_obs) return;
-
-  real lw[PPT];
   double mx = -__longlong_as_double(0x7FF0000000000000ll);  // -inf
   bool bad = false;
+  if (a.has_obs) {
+    real lw[PPT];
 #pragma unroll
-  for (int p = 0; p < PPT; ++p) {
-    lw[p] = obs_loglik<real>(a, g[p]);
-    if (valid[p]) {
-      if (lw[p] != lw[p]) bad = true;
-      else mx = fmax(mx, (double)lw[p]);
+    for (int p = 0; p < PPT; ++p) {
+      lw[p] = obs_loglik<real>(a, g[p]);
+      if (valid[p]) {
+        if (lw[p] != lw[p]) bad = true;
+        else mx = fmax(mx, (double)lw[p]);
+      }
     }
-  }
-  if (full) {
-    vec_t v;
-    real* vp = reinterpret_cast<real*>(&v);
+    if (full) {
+      vec_t v;
+      real* vp = reinterpret_cast<real*>(&v);
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) vp[p] = lw[p];
-    *reinterpret_cast<vec_t*>(logw + i0) = v;
-  } else {
+      for (int p = 0; p < PPT; ++p) vp[p] = lw[p];
+      *reinterpret_cast<vec_t*>(logw + i0) = v;
+    } else {
 #pragma unroll
-    for (int p = 0; p < PPT; ++p)
-      if (valid[p]) logw[i0 + p] = lw[p];
+      for (int p = 0; p < PPT; ++p)
+        if (valid[p]) logw[i0 + p] = lw[p];
+    }
+  } else if (pr.R == 1) {
+    return;
   }
-  // block max -> one atomic per block
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-  __shared__ double s_mx[8];
-  __shared__ int s_bad;
-  if (threadIdx.x == 0) s_bad = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
-  if (bad) s_bad = 1;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m2 = s_mx[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m2 = fmax(m2, s_mx[w]);
-    atomicMax(&sc->gmax_key, ord_key(m2));
-    if (s_bad) atomicOr(&sc->flags, FLAG_NAN_WEIGHT);
-  }
+  k1_tail(mx, bad, a.has_obs, pr, ctl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -307,20 +434,35 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const real* __restr
 // ---------------------------------------------------------------------------------------------
 template <typename real, int DP>
 __global__ void __launch_bounds__(256)
-k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const real* __restrict__ xsrc, real* __restrict__ xdst,
+k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
               const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
               const real* __restrict__ ctab, long long n_sub, real delta, long long N, long long Ns,
-              unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step, Scalars* __restrict__ sc) {
+              unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step, K1Ctl ctl) {
   constexpr int PC = Normals<real>::PER_CALL;
+  griddep_wait();
+  griddep_launch();
+  if (pr.R > 1) {
+    if (threadIdx.x == 0) wait_progress(pr, ctl.gstep, ctl.sc);
+    __syncthreads();
+  }
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < N;
   double mx = -__longlong_as_double(0x7FF0000000000000ll);
   bool bad = false;
   if (valid) {
-    long long src = anc ? (long long)anc[i] : i;
+    const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
+    if (anc) {
+      if (pr.R > 1) {
+        const unsigned g = (unsigned)anc[i];
+        const unsigned q = g / (unsigned)pr.Nl;
+        src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+      } else {
+        src = reinterpret_cast<const real*>(pr.x[0]) + anc[i];
+      }
+    }
     real x[DP];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) x[k] = (k < a.d) ? xsrc[(long long)k * Ns + src] : (real)0;
+    for (int k = 0; k < DP; ++k) x[k] = (k < a.d) ? src[(long long)k * Ns] : (real)0;
     unsigned long long slot = slot0 + (unsigned long long)i;
     real hz = (real)0;
     const uint32_t calls = (uint32_t)((a.d + PC - 1) / PC);
@@ -364,21 +506,7 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const real* __restrict__
     if (lw != lw) bad = true;
     else mx = (double)lw;
   }
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-  __shared__ double s_mx[8];
-  __shared__ int s_bad;
-  if (threadIdx.x == 0) s_bad = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
-  if (bad) s_bad = 1;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m2 = s_mx[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m2 = fmax(m2, s_mx[w]);
-    atomicMax(&sc->gmax_key, ord_key(m2));
-    if (s_bad) atomicOr(&sc->flags, FLAG_NAN_WEIGHT);
-  }
+  k1_tail(mx, bad, 1, pr, ctl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -395,23 +523,22 @@ struct WeightSrc {
   }
 };
 
-// max of a caller-given weight array -> sc->gmax_key (cssm_resample only)
-__global__ void __launch_bounds__(256) k_max_direct(const double* __restrict__ w, long long N, Scalars* sc) {
+// max of a caller-given weight array -> acc[0].gmax_key (cssm_resample only)
+__global__ void __launch_bounds__(256) k_max_direct(const double* __restrict__ w, long long N, FilterScalars* sc) {
   double mx = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) mx = fmax(mx, w[i]);
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-  if ((threadIdx.x & 31) == 0) atomicMax(&sc->gmax_key, ord_key(mx));
+  if ((threadIdx.x & 31) == 0) atomicMax(&sc->acc[0].gmax_key, ord_key(mx));
 }
-// Before k_scan_tiles runs, the max lives in sc->gmax_key.  In-filter: gmax = that max, weights
-// are <= 1, quantum 2^-96.  Direct weights: power-of-two pre-scale so that every weight is <= 1,
-// qb = 96 - e with max = f * 2^e, f in [0.5, 1).
+// In-filter: gmax = the max log-weight, weights are <= 1, quantum 2^-96.  Direct weights:
+// power-of-two pre-scale so that every weight is <= 1, qb = 96 - e with max = f * 2^e, f in [0.5, 1).
 struct PreScan {
   double gmax;
   int qb;
 };
-__device__ __forceinline__ PreScan pre_scan(const Scalars* sc, bool direct) {
-  double mx = ord_unkey(sc->gmax_key);
+__device__ __forceinline__ PreScan pre_scan(unsigned long long gmax_key, bool direct) {
+  double mx = ord_unkey(gmax_key);
   PreScan p;
   p.gmax = direct ? 0.0 : mx;
   p.qb = 96;
@@ -422,157 +549,132 @@ __device__ __forceinline__ PreScan pre_scan(const Scalars* sc, bool direct) {
   return p;
 }
 
-// K2a  total of the weights (exact).  Strided access: order is irrelevant for an exact sum.
-template <typename real>
-__global__ void __launch_bounds__(TILE_THREADS)
-k_weight_total(const real* __restrict__ logw, const double* __restrict__ direct, long long N, Scalars* __restrict__ sc) {
-  const PreScan ps = pre_scan(sc, direct != nullptr);
-  WeightSrc<real> ws{logw, direct, ps.gmax};
-  const int qb = ps.qb;
-  const long long base = (long long)blockIdx.x * TILE;
-  u128 acc = make_u128(0, 0);
-#pragma unroll
-  for (int j = 0; j < TILE_ITEMS; ++j) {
-    long long idx = base + j * TILE_THREADS + threadIdx.x;
-    if (idx < N) acc = add128(acc, fixq(ws(idx), qb));
-  }
-  acc = warp_sum128(acc);
-  __shared__ u128 s_acc[TILE_THREADS / 32];
-  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+// per-filter tables of the weight pass
+struct SumTables {
+  u128* tile_sum;             // [nt]   exact sum of fix(w) over the tile
+  double* tile_maxw;          // [nt]   max weight of the tile
+  u128* super_sum;            // [2][ns] by observed-step parity, zeroed for the next step by K3
+  u128* super_q;              // [2][ns]
+  unsigned long long* super_ticket;  // [ns] monotone
+  int nt, ns;
+};
+
+__device__ __forceinline__ u128 block_sum128(u128 v, u128* s_warp) {  // result valid in thread 0
+  v = warp_sum128(v);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    u128 t = s_acc[0];
-    for (int w = 1; w < TILE_THREADS / 32; ++w) t = add128(t, s_acc[w]);
-    atomic_add128(&sc->tot, t);
-  }
+  u128 t = make_u128(0, 0);
+  if (threadIdx.x == 0)
+    for (int w = 0; w < TILE_THREADS / 32; ++w) t = add128(t, s_warp[w]);
+  return t;
+}
+__device__ __forceinline__ u128 ld_gpu128(const u128* p) {
+  return make_u128(ld_gpu(&p->lo), ld_gpu(&p->hi));
 }
 
-// K2b  per-tile sums of the (normalised) weights and the ESS accumulator
-//      normalise = 1: CDF over wn = w/total (systematic, stratified; model/Resampling.scala:52-58)
-//      normalise = 0: CDF over w itself       (multinomial; Breeze Multinomial uses raw params)
-template <typename real>
+// K2  w1 = exp(logw - max); exact sums of w1 and w1^2 per tile, per super tile and per rank.
+//     Strided access inside the tile: the order is irrelevant for an exact sum.
+template <typename real, int ITEMS>
 __global__ void __launch_bounds__(TILE_THREADS)
-k_tile_sums(const real* __restrict__ logw, const double* __restrict__ direct, long long N, int normalise,
-            Scalars* __restrict__ sc, u128* __restrict__ tile_sum, double* __restrict__ tile_maxw) {
-  const PreScan ps = pre_scan(sc, direct != nullptr);
+k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
+              int parity, unsigned long long obs_seq, SumTables tb, const __grid_constant__ Peers pr) {
+  constexpr int TILE = TILE_THREADS * ITEMS;
+  __shared__ u128 s_w[TILE_THREADS / 32];
+  __shared__ double s_mxw[TILE_THREADS / 32];
+  __shared__ unsigned long long s_key;
+  griddep_wait();
+  griddep_launch();
+  StepAcc* A = &sc->acc[parity];
+  if (threadIdx.x == 0) {
+    unsigned long long key;
+    if (pr.R > 1) {  // all-gather of the per-rank maxima: every rank pushed its own into our slots
+      const XchSlot* mine = pr.xch[pr.rank];
+      key = 0;
+      for (int q = 0; q < pr.R; ++q) {
+        wait_ge(&mine[q].max_seq[parity], obs_seq + 1, sc);
+        const unsigned long long kq = ld_relaxed_sys(&mine[q].max_key[parity]);
+        key = kq > key ? kq : key;
+      }
+    } else {
+      key = A->gmax_key;
+    }
+    s_key = key;
+  }
+  __syncthreads();
+  const PreScan ps = pre_scan(s_key, direct != nullptr);
   WeightSrc<real> ws{logw, direct, ps.gmax};
   const int qb = ps.qb;
-  const double total = unfixq(sc->tot, qb);
+  const double q2scale = __longlong_as_double((long long)(1023 - (96 - qb)) << 52);  // direct weights: w * 2^-(96-qb) <= 1
   const long long base = (long long)blockIdx.x * TILE;
   u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
   double mxw = 0.0;
 #pragma unroll
-  for (int j = 0; j < TILE_ITEMS; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     long long idx = base + j * TILE_THREADS + threadIdx.x;
     if (idx < N) {
-      double w = ws(idx);
-      double wn = __ddiv_rn(w, total);
-      acc = add128(acc, normalise ? fixq(wn, 96) : fixq(w, qb));
-      acc2 = add128(acc2, fixq(__dmul_rn(wn, wn), 96));
-      mxw = fmax(mxw, wn);
+      const double w = ws(idx);
+      acc = add128(acc, fix_fast(w, qb));
+      const double wsq = __dmul_rn(w, q2scale);
+      acc2 = add128(acc2, fix_fast(__dmul_rn(wsq, wsq), 96));
+      mxw = fmax(mxw, w);
     }
   }
-  acc = warp_sum128(acc);
   acc2 = warp_sum128(acc2);
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
-  __shared__ u128 s_acc[TILE_THREADS / 32], s_acc2[TILE_THREADS / 32];
-  __shared__ double s_mxw[TILE_THREADS / 32];
+  __shared__ u128 s_w2[TILE_THREADS / 32];
   if ((threadIdx.x & 31) == 0) {
-    s_acc[threadIdx.x >> 5] = acc;
-    s_acc2[threadIdx.x >> 5] = acc2;
+    s_w2[threadIdx.x >> 5] = acc2;
     s_mxw[threadIdx.x >> 5] = mxw;
   }
-  __syncthreads();
+  const u128 t = block_sum128(acc, s_w);  // contains the __syncthreads that publishes s_w2 / s_mxw
   if (threadIdx.x == 0) {
-    u128 t = s_acc[0], t2 = s_acc2[0];
+    u128 t2 = s_w2[0];
     double m2 = s_mxw[0];
     for (int w = 1; w < TILE_THREADS / 32; ++w) {
-      t = add128(t, s_acc[w]);
-      t2 = add128(t2, s_acc2[w]);
+      t2 = add128(t2, s_w2[w]);
       m2 = fmax(m2, s_mxw[w]);
     }
-    tile_sum[blockIdx.x] = t;
-    tile_maxw[blockIdx.x] = m2;
-    atomic_add128(&sc->ess_acc, t2);
-  }
-}
-
-// K2c  one block: exclusive prefix over the tile sums, rounded tile-end CDF values, the ll
-//      increment max + log(mean(w1)) and ESS = floor(1/sum wn^2)  (model/ParticleFilter.scala:127-128),
-//      the resampling uniform, and the reset of the accumulators for the next step.
-__global__ void __launch_bounds__(1024)
-k_scan_tiles(Scalars* __restrict__ sc, const u128* __restrict__ tile_sum, u128* __restrict__ tile_excl,
-             double* __restrict__ cend, int nt, long long N, int normalise, int direct, int add_ll, int use_u_inj,
-             uint32_t key0, uint32_t key1, uint32_t step, double* __restrict__ ll_steps, int* __restrict__ ess_steps,
-             long long step_slot) {
-  __shared__ u128 s_part[1024];
-  const int per = (nt + 1023) / 1024;
-  const int b = threadIdx.x * per, e = min(nt, b + per);
-  u128 acc = make_u128(0, 0);
-  for (int t = b; t < e; ++t) acc = add128(acc, tile_sum[t]);
-  s_part[threadIdx.x] = acc;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 partials (exact integers: order irrelevant)
-  for (int off = 1; off < 1024; off <<= 1) {
-    u128 v = make_u128(0, 0);
-    if ((int)threadIdx.x >= off) v = s_part[threadIdx.x - off];
-    __syncthreads();
-    s_part[threadIdx.x] = add128(s_part[threadIdx.x], v);
-    __syncthreads();
-  }
-  u128 run = (threadIdx.x == 0) ? make_u128(0, 0) : s_part[threadIdx.x - 1];
-  const PreScan ps = pre_scan(sc, direct != 0);
-  const int q = normalise ? 96 : ps.qb;
-  for (int t = b; t < e; ++t) {
-    tile_excl[t] = run;
-    run = add128(run, tile_sum[t]);
-    cend[t] = unfixq(run, q);
-  }
-  __syncthreads();  // every thread has read sc->gmax_key before thread 0 resets it
-  if (threadIdx.x == 0) {
-    const int qb = ps.qb;
-    double total = unfixq(sc->tot, qb);
-    double gmax = ps.gmax;
-    double s2 = unfixq(sc->ess_acc, 96);
-    sc->gmax = gmax;
-    sc->qb = qb;
-    double incr = gmax + log(total / (double)N);
-    int flags = 0;
-    if (!(total > 0.0) || gmax != gmax || gmax - gmax != 0.0) {  // all weights zero / NaN / infinite max
-      incr = __longlong_as_double(0x7FF8000000000000ll);
-      flags |= FLAG_ZERO_TOTAL;
+    tb.tile_sum[blockIdx.x] = t;
+    tb.tile_maxw[blockIdx.x] = m2;
+    const int sidx = blockIdx.x / SUPER;
+    u128* ssum = tb.super_sum + (size_t)parity * tb.ns + sidx;
+    u128* ssq = tb.super_q + (size_t)parity * tb.ns + sidx;
+    atomic_add128(ssum, t);
+    atomic_add128(ssq, t2);
+    __threadfence();
+    const unsigned long long in_super = (unsigned long long)min(SUPER, tb.nt - sidx * SUPER);
+    const unsigned long long tk = atomicAdd(&tb.super_ticket[sidx], 1ull);
+    if (tk % in_super == in_super - 1) {  // last tile of this super tile: fold it into the rank totals
+      __threadfence();
+      atomic_add128(&A->tot, ld_gpu128(ssum));
+      atomic_add128(&A->q, ld_gpu128(ssq));
+      __threadfence();
+      const unsigned long long tk2 = atomicAdd(&sc->ticket2, 1ull);
+      if (pr.R > 1 && tk2 % (unsigned long long)tb.ns == (unsigned long long)tb.ns - 1) {
+        // last block of the grid: all-gather of (sum w, sum w^2) by direct stores into the peers
+        __threadfence();
+        const u128 tot = ld_gpu128(&A->tot), qq = ld_gpu128(&A->q);
+        __threadfence_system();
+        for (int q = 0; q < pr.R; ++q) {
+          XchSlot* s = &pr.xch[q][pr.rank];
+          st_relaxed_sys(&s->tot_lo[parity], tot.lo);
+          st_relaxed_sys(&s->tot_hi[parity], tot.hi);
+          st_relaxed_sys(&s->q_lo[parity], qq.lo);
+          st_relaxed_sys(&s->q_hi[parity], qq.hi);
+          st_release_sys(&s->sum_seq[parity], obs_seq + 1);
+        }
+      }
     }
-    sc->total = total;
-    sc->ll_incr = incr;
-    double inv = floor(1.0 / s2);
-    int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
-    if (add_ll) {
-      sc->ll = sc->ll + incr;
-      sc->ess = ess;
-      if (ll_steps) ll_steps[step_slot] = sc->ll;
-      if (ess_steps) ess_steps[step_slot] = ess;
-    }
-    if (flags) atomicOr(&sc->flags, flags);
-    if (use_u_inj) {
-      sc->u = sc->u_inj;
-    } else {
-      uint4 v = philox4x32_10(make_uint4(0u, 0u, step, RNG_RESAMPLE), key0, key1);
-      sc->u = u64_to_unit_double(v.x, v.y);
-    }
-    // accumulators for the next step (gmax/total stay for K3)
-    sc->gmax_key = 0ull;
-    sc->tot = make_u128(0, 0);
-    sc->ess_acc = make_u128(0, 0);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3+K4  systematic / stratified: inclusive CDF of a tile in shared memory + ancestor search
+// K3  systematic / stratified: inclusive CDF of a tile in shared memory + ancestor search
 // ---------------------------------------------------------------------------------------------
-struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stratified)
+struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stratified), times the total
   int kind;
-  double u, n;
+  double u, n, total;
   const double* uarr;  // stratified, injected
   uint32_t key0, key1, step;
   __device__ __forceinline__ double ui(long long i) const {
@@ -580,14 +682,16 @@ struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stra
     uint4 v = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), step, RNG_RESAMPLE | 1u), key0, key1);
     return u64_to_unit_double(v.x, v.y);
   }
-  __device__ __forceinline__ double operator()(long long i) const {
+  __device__ __forceinline__ double k(long long i) const {
     if (kind == CSSM_RESAMPLE_SYSTEMATIC) return __ddiv_rn(__dadd_rn(u, (double)i), n);
     return __ddiv_rn(__dadd_rn((double)i, ui(i)), n);
   }
-  // number of outputs i in [0, N) with k_i <= c   (k_i is non-decreasing in i)
+  // the key of output i in the un-normalised domain: C_j >= k_i  <=>  P_j >= k_i * total
+  __device__ __forceinline__ double operator()(long long i) const { return __dmul_rn(k(i), total); }
+  // number of outputs i in [0, N) with key_i <= c   (key_i is non-decreasing in i)
   __device__ long long count_le(double c, long long N) const {
     if (!(c >= 0.0)) return 0;
-    double est = c * n - (kind == CSSM_RESAMPLE_SYSTEMATIC ? u : 0.0);
+    double est = c / total * n - (kind == CSSM_RESAMPLE_SYSTEMATIC ? u : 0.0);
     long long i = (est >= (double)N) ? N - 1 : (long long)floor(est);
     if (i < 0) i = 0;
     if (i > N - 1) i = N - 1;
@@ -597,26 +701,21 @@ struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stra
   }
 };
 
-// inclusive CDF values (rounded fp64) of tile t into Cs[0..TILE); returns nothing, all threads call
-template <typename real>
-__device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int normalise, double total, int qb,
-                                         const u128* __restrict__ tile_excl, int t, long long N, double* Cs,
-                                         double* Ws, u128* s_warp) {
-  const long long base = (long long)t * TILE + (long long)threadIdx.x * TILE_ITEMS;
-  u128 e[TILE_ITEMS];
+// inclusive CDF values P_j = dbl128(exact prefix) of one tile into Ps[0..TILE) and the weights
+// into Ws; `excl` = exact sum of everything before the tile.  All threads call.
+template <typename real, int ITEMS>
+__device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128 excl, long long tile0, long long N,
+                                         double* Ps, double* Ws, u128* s_warp) {
+  const long long base = tile0 + (long long)threadIdx.x * ITEMS;
+  u128 e[ITEMS];
   u128 run = make_u128(0, 0);
 #pragma unroll
-  for (int j = 0; j < TILE_ITEMS; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     long long idx = base + j;
-    u128 q = make_u128(0, 0);
-    double wv = 0.0;
-    if (idx < N) {
-      double w = ws(idx);
-      wv = normalise ? __ddiv_rn(w, total) : w;
-      q = normalise ? fixq(wv, 96) : fixq(w, qb);
-    }
-    if (Ws) Ws[threadIdx.x * TILE_ITEMS + j] = wv;
-    run = add128(run, q);
+    double w = 0.0;
+    if (idx < N) w = ws(idx);
+    if (Ws) Ws[threadIdx.x * ITEMS + j] = w;
+    run = add128(run, fix_fast(w, qb));
     e[j] = run;
   }
   // exclusive scan of the thread totals across the block
@@ -627,133 +726,295 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int normalis
     u128 o = shfl_up128(incl, d);
     if (lane >= d) incl = add128(incl, o);
   }
+  __syncthreads();  // s_warp may still be read by the caller's previous use
   if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
-  u128 off = tile_excl[t];
+  u128 off = excl;
   for (int w = 0; w < wid; ++w) off = add128(off, s_warp[w]);
-  // exclusive within warp = inclusive - own total; recompute by adding the lower lanes instead
-  u128 excl = shfl_up128(incl, 1);
-  if (lane == 0) excl = make_u128(0, 0);
-  off = add128(off, excl);
-  const int q = normalise ? 96 : qb;
+  u128 ex = shfl_up128(incl, 1);
+  if (lane == 0) ex = make_u128(0, 0);
+  off = add128(off, ex);
 #pragma unroll
-  for (int j = 0; j < TILE_ITEMS; ++j) Cs[threadIdx.x * TILE_ITEMS + j] = unfixq(add128(off, e[j]), q);
+  for (int j = 0; j < ITEMS; ++j) Ps[threadIdx.x * ITEMS + j] = dbl128(add128(off, e[j]), qb);
   __syncthreads();
 }
 
-// does adding w leave c unchanged?  This is what makes a TreeMap key repeat in the reference
-// (model/Resampling.scala:55-57): the next cumulative sum equals the previous one.
-__device__ __forceinline__ bool vanishes(double c, double w) { return __dadd_rn(c, w) == c; }
+// does adding the next weight leave the cumulative value unchanged?  This is what makes a TreeMap
+// key repeat in the reference (model/Resampling.scala:55-57), tested in the reference's normalised
+// domain: C = fl(P/total), wn = fl(w/total).  A weight above 2^-52 * P cannot vanish (cheap filter).
+__device__ __forceinline__ bool vanishes(double P, double w, double total) {
+  if (w > P * 2.220446049250313e-16) return false;
+  const double c = __ddiv_rn(P, total);
+  return __dadd_rn(c, __ddiv_rn(w, total)) == c;
+}
 
-// mode 0: search (systematic / stratified), writes anc;  mode 1: write the CDF to cdf_out (multinomial)
-template <typename real>
+struct K3Ctl {
+  int parity;
+  unsigned long long obs_seq, gstep;
+  int kind;             // systematic / stratified
+  int direct;           // cssm_resample: caller weights, no ll update
+  int add_ll, use_u_inj;
+  uint32_t key0, key1, step;
+  double* ll_steps;
+  int* ess_steps;
+  long long step_slot;
+};
+
+// cdf_out == NULL: search (systematic / stratified), writes ancestors;
+// cdf_out != NULL: write the un-normalised CDF (multinomial), no search
+template <typename real, int ITEMS>
 __global__ void __launch_bounds__(TILE_THREADS)
-k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, int normalise,
-              const Scalars* __restrict__ sc, const u128* __restrict__ tile_excl, const double* __restrict__ cend,
-              const double* __restrict__ tile_maxw, int nt, int kind, const double* __restrict__ uarr, uint32_t key0,
-              uint32_t key1, uint32_t step, int32_t* __restrict__ anc, double* __restrict__ cdf_out,
-              int* __restrict__ flags_out) {
-  __shared__ double Cs[TILE];
+k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
+              SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
+              double* __restrict__ cdf_out) {
+  constexpr int TILE = TILE_THREADS * ITEMS;
+  __shared__ double Ps[TILE];
   __shared__ double Ws[TILE];
   __shared__ u128 s_warp[TILE_THREADS / 32];
+  __shared__ u128 s_excl, s_tot, s_q;
+  __shared__ unsigned long long s_key;
   __shared__ long long s_lo, s_hi, s_pend, s_jfinal;
-  __shared__ double s_wnext, s_c;
+  __shared__ double s_wnext, s_u;
+  __shared__ u128 s_run;
   __shared__ int s_tp, s_brk;
 
-  const int t = blockIdx.x;
-  WeightSrc<real> ws{logw, direct, sc->gmax};
-  const int qb = sc->qb;
-  const double total = sc->total;
-  tile_cdf<real>(ws, normalise, total, qb, tile_excl, t, N, Cs, cdf_out ? nullptr : Ws, s_warp);
+  griddep_wait();
+  griddep_launch();
+  const int t = blockIdx.x, nt = tb.nt, p = ctl.parity;
+  StepAcc* A = &sc->acc[p];
+  const long long Ng = (long long)pr.R * N;  // outputs of the whole (possibly sharded) filter
+
+  // ---- totals: this rank's from the accumulators, the other ranks' from the exchange slots ------
+  if (threadIdx.x == 0) {
+    u128 tot, qq, before = make_u128(0, 0);
+    unsigned long long key;
+    if (pr.R > 1) {
+      const XchSlot* mine = pr.xch[pr.rank];
+      tot = make_u128(0, 0);
+      qq = make_u128(0, 0);
+      key = 0;
+      for (int q = 0; q < pr.R; ++q) {
+        wait_ge(&mine[q].sum_seq[p], ctl.obs_seq + 1, sc);
+        const u128 tq = make_u128(ld_relaxed_sys(&mine[q].tot_lo[p]), ld_relaxed_sys(&mine[q].tot_hi[p]));
+        if (q < pr.rank) before = add128(before, tq);
+        tot = add128(tot, tq);
+        qq = add128(qq, make_u128(ld_relaxed_sys(&mine[q].q_lo[p]), ld_relaxed_sys(&mine[q].q_hi[p])));
+        const unsigned long long kq = ld_relaxed_sys(&mine[q].max_key[p]);
+        key = kq > key ? kq : key;
+      }
+    } else {
+      tot = A->tot;
+      qq = A->q;
+      key = A->gmax_key;
+    }
+    s_tot = tot;
+    s_q = qq;
+    s_key = key;
+    s_excl = before;
+  }
+  // ---- exact sum of everything before this tile: whole super tiles + the tiles of this super ----
+  {
+    const int sidx = t / SUPER;
+    const u128* ssum = tb.super_sum + (size_t)p * tb.ns;
+    u128 acc = make_u128(0, 0);
+    for (int s = threadIdx.x; s < sidx; s += TILE_THREADS) acc = add128(acc, ssum[s]);
+    for (int tt = sidx * SUPER + threadIdx.x; tt < t; tt += TILE_THREADS) acc = add128(acc, tb.tile_sum[tt]);
+    const u128 local = block_sum128(acc, s_warp);
+    if (threadIdx.x == 0) s_excl = add128(s_excl, local);
+  }
+  __syncthreads();
+  const PreScan ps = pre_scan(s_key, direct != nullptr);
+  const int qb = ps.qb;
+  const double total = dbl128(s_tot, qb);
+  const u128 excl = s_excl;
+
+  // ---- block 0: ll increment max + log(mean w1), ESS = floor(1/sum wn^2), the resampling uniform
+  //      is derived by every block; zero the accumulators of the next observed step ----------------
+  if (threadIdx.x == 0) {
+    double u;
+    if (ctl.use_u_inj) {
+      u = sc->u_inj;
+    } else {
+      uint4 v = philox4x32_10(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
+      u = u64_to_unit_double(v.x, v.y);
+    }
+    s_u = u;
+    if (t == 0) {
+      const double gmax = ps.gmax;
+      double incr = gmax + log(total / (double)Ng);
+      int flags = 0;
+      if (!(total > 0.0) || gmax != gmax || gmax - gmax != 0.0) {  // all weights zero / NaN / infinite max
+        incr = __longlong_as_double(0x7FF8000000000000ll);
+        flags |= FLAG_ZERO_TOTAL;
+      }
+      const double s2 = __ddiv_rn(dbl128(s_q, 96), __dmul_rn(total, total));
+      const double inv = floor(1.0 / s2);
+      const int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
+      sc->gmax = gmax;
+      sc->total = total;
+      sc->qb = qb;
+      sc->ll_incr = incr;
+      if (ctl.add_ll) {
+        const double ll = sc->ll + incr;
+        sc->ll = ll;
+        sc->ess = ess;
+        if (ctl.ll_steps) ctl.ll_steps[ctl.step_slot] = ll;
+        if (ctl.ess_steps) ctl.ess_steps[ctl.step_slot] = ess;
+      }
+      if (flags) atomicOr(&sc->flags, flags);
+      StepAcc* nx = &sc->acc[p ^ 1];
+      nx->gmax_key = 0ull;
+      nx->tot = make_u128(0, 0);
+      nx->q = make_u128(0, 0);
+    }
+  }
+  if (t < tb.ns && threadIdx.x == 1) {
+    tb.super_sum[(size_t)(p ^ 1) * tb.ns + t] = make_u128(0, 0);
+    tb.super_q[(size_t)(p ^ 1) * tb.ns + t] = make_u128(0, 0);
+  }
+
+  WeightSrc<real> ws{logw, direct, ps.gmax};
   const long long tile0 = (long long)t * TILE;
   const int tile_n = (int)min((long long)TILE, N - tile0);
+  tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp);
 
   if (cdf_out != nullptr) {
-    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) cdf_out[tile0 + j] = Cs[j];
+    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) cdf_out[tile0 + j] = Ps[j];
     return;
   }
 
-  KFun kf{kind, sc->u, (double)N, uarr, key0, key1, step};
-  const double c_end = Cs[tile_n - 1];
+  bool wrote_remote = false;
+  // all weights zero / NaN (the reference divides by a zero total here and fails later): keep every
+  // particle as its own ancestor; FLAG_ZERO_TOTAL is already raised
+  const bool usable = (total > 0.0) && (total - total == 0.0);
+  if (!usable) {
+    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) pr.anc[pr.rank][tile0 + j] = (int32_t)((long long)pr.rank * N + tile0 + j);
+  } else {
+  KFun kf{ctl.kind, s_u, (double)Ng, total, uarr, ctl.key0, ctl.key1, ctl.step};
+  const double c_end = Ps[tile_n - 1];
+  const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
+  const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
   if (threadIdx.x == 0) {
-    s_lo = (t == 0) ? 0 : kf.count_le(cend[t - 1], N);
-    s_hi = (t == nt - 1) ? N : kf.count_le(c_end, N);
-    s_wnext = (t < nt - 1) ? __ddiv_rn(ws(tile0 + TILE), total) : 0.0;  // first weight of the next tile
+    s_lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_le(dbl128(excl, qb), Ng);
+    s_hi = last_tile ? Ng : kf.count_le(c_end, Ng);
+    // first weight after this tile (next tile, possibly the next rank's first particle)
+    double wn = 0.0;
+    if (t < nt - 1) wn = ws(tile0 + TILE);
+    else if (pr.rank < pr.R - 1) wn = WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[pr.rank + 1]), nullptr, ps.gmax}(0);
+    s_wnext = wn;
     s_pend = 0x7FFFFFFFFFFFFFFFll;
   }
   __syncthreads();
   const long long lo = s_lo, hi = s_hi;
   // does the run of repeated keys at the end of this tile continue into the next tile?
-  const bool cont = (t < nt - 1) && vanishes(c_end, s_wnext);
-  if (t == nt - 1 && threadIdx.x == 0 && kf(N - 1) > c_end) atomicOr(flags_out, FLAG_CLAMPED);  // reference would throw (m.head)
+  const bool cont = !last_tile && vanishes(c_end, s_wnext, total);
+  if (last_tile && threadIdx.x == 0 && kf(Ng - 1) > c_end) atomicOr(&sc->flags, FLAG_CLAMPED);  // reference would throw (m.head)
 
   for (long long i = lo + threadIdx.x; i < hi; i += TILE_THREADS) {
-    double k = kf(i);
-    // first j with Cs[j] >= k (exists unless this is the clamped tail of the last tile)
+    const double key = kf(i);
+    // first j with Ps[j] >= key (exists unless this is the clamped tail of the last tile)
     int a = 0, b = tile_n - 1;
     while (a < b) {
       int m = (a + b) >> 1;
-      if (Cs[m] >= k) b = m; else a = m + 1;
+      if (Ps[m] >= key) b = m; else a = m + 1;
     }
     // TreeMap: a duplicated key keeps the last particle inserted
     int j = a;
-    while (j + 1 < tile_n && vanishes(Cs[j], Ws[j + 1])) ++j;
+    while (j + 1 < tile_n && vanishes(Ps[j], Ws[j + 1], total)) ++j;
     if (cont && j == tile_n - 1) atomicMin(&s_pend, i);
-    anc[i] = (int32_t)(tile0 + j);
+    const int32_t val = (int32_t)(gbase + j);
+    if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+      const long long q = i / N;
+      pr.anc[q][i - q * N] = val;
+      wrote_remote |= (q != pr.rank);
+    } else {
+      pr.anc[0][i] = val;
+    }
   }
   __syncthreads();
   const long long pend = s_pend;
-  if (pend >= hi) return;
-  // The selected run of repeated keys continues past this tile; its last element is the ancestor.
-  // Walk forward: whole tiles are skipped from the tables when every weight in them is strictly
-  // below half an ulp of the running value (same binade), otherwise the tile is recomputed.
-  if (threadIdx.x == 0) { s_tp = t + 1; s_c = c_end; s_jfinal = -1; }
-  __syncthreads();
-  for (;;) {
-    if (threadIdx.x == 0) {
-      int tp = s_tp;
-      double c = s_c;
-      while (tp < nt) {
-        double ce = cend[tp];
-        // half ulp of c (c > 0 here; a zero running value never skips)
-        long long cb = __double_as_longlong(c), eb = __double_as_longlong(ce);
-        bool same_binade = (cb >> 52) == (eb >> 52) && ((cb >> 52) & 0x7ff) > 54;
-        double half_ulp = same_binade ? __longlong_as_double((((cb >> 52) & 0x7ff) - 53) << 52) : 0.0;
-        if (same_binade && tile_maxw[tp] < half_ulp) { c = ce; ++tp; } else break;
+  if (pend < hi) {
+    // The selected run of repeated keys continues past this tile; its last element is the ancestor.
+    // Walk forward over the GLOBAL tile sequence (rank-major): whole tiles are skipped from the
+    // tables when every weight in them is strictly below half an ulp of the running (normalised)
+    // value and the value stays in its binade, otherwise the tile is recomputed.
+    const long long gnt = (long long)pr.R * nt;
+    if (threadIdx.x == 0) { s_tp = pr.rank * nt + t + 1; s_run = add128(excl, tb.tile_sum[t]); s_jfinal = -1; }
+    __syncthreads();
+    for (;;) {
+      if (threadIdx.x == 0) {
+        long long tp = s_tp;
+        u128 run = s_run;
+        while (tp < gnt) {
+          const int q = (int)(tp / nt), tl = (int)(tp % nt);
+          const u128 tsum = (q == pr.rank) ? tb.tile_sum[tl] : ld_gpu128(&pr.tile_sum[q][tl]);
+          const double mxw = (q == pr.rank) ? tb.tile_maxw[tl] : __longlong_as_double((long long)ld_gpu((const unsigned long long*)&pr.tile_maxw[q][tl]));
+          const u128 nrun = add128(run, tsum);
+          const double c = __ddiv_rn(dbl128(run, qb), total), ce = __ddiv_rn(dbl128(nrun, qb), total);
+          const long long cb = __double_as_longlong(c), eb = __double_as_longlong(ce);
+          const bool same_binade = (cb >> 52) == (eb >> 52) && ((cb >> 52) & 0x7ff) > 54;
+          const double half_ulp = same_binade ? __longlong_as_double((((cb >> 52) & 0x7ff) - 53) << 52) : 0.0;
+          if (same_binade && __ddiv_rn(mxw, total) < half_ulp) { run = nrun; ++tp; } else break;
+        }
+        s_tp = (int)tp;
+        s_run = run;
+        s_brk = TILE;
+        if (tp >= gnt) s_jfinal = Ng - 1;
       }
-      s_tp = tp;
-      s_c = c;
-      s_brk = TILE;
-      if (tp >= nt) s_jfinal = N - 1;
+      __syncthreads();
+      if (s_jfinal >= 0) break;
+      const int tp = s_tp;
+      const int q = tp / nt, tl = tp % nt;
+      const double c = dbl128(s_run, qb);
+      WeightSrc<real> wq{(q == pr.rank) ? logw : reinterpret_cast<const real*>(pr.logw[q]), direct, ps.gmax};
+      tile_cdf<real, ITEMS>(wq, qb, s_run, (long long)tl * TILE, N, Ps, Ws, s_warp);
+      const int tn = (int)min((long long)TILE, N - (long long)tl * TILE);
+      // first element of tile tp that does NOT vanish against its predecessor's value
+      for (int j = threadIdx.x; j < tn; j += TILE_THREADS) {
+        double prev = (j == 0) ? c : Ps[j - 1];
+        if (!vanishes(prev, Ws[j], total)) atomicMin(&s_brk, j);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (s_brk < tn) s_jfinal = (long long)q * N + (long long)tl * TILE + s_brk - 1;
+        else if (tp == gnt - 1) s_jfinal = Ng - 1;
+        else {
+          const u128 tsum = (q == pr.rank) ? tb.tile_sum[tl] : ld_gpu128(&pr.tile_sum[q][tl]);
+          s_run = add128(s_run, tsum);
+          s_tp = tp + 1;
+        }
+      }
+      __syncthreads();
+      if (s_jfinal >= 0) break;
     }
-    __syncthreads();
-    if (s_jfinal >= 0) break;
-    const int tp = s_tp;
-    const double c = s_c;
-    tile_cdf<real>(ws, normalise, total, qb, tile_excl, tp, N, Cs, Ws, s_warp);
-    const int tn = (int)min((long long)TILE, N - (long long)tp * TILE);
-    // first element of tile tp that does NOT vanish against its predecessor's value
-    for (int j = threadIdx.x; j < tn; j += TILE_THREADS) {
-      double prev = (j == 0) ? c : Cs[j - 1];
-      if (!vanishes(prev, Ws[j])) atomicMin(&s_brk, j);
+    const long long jfinal = s_jfinal;
+    for (long long i = pend + threadIdx.x; i < hi; i += TILE_THREADS) {
+      if (pr.R > 1) {
+        const long long q = i / N;
+        pr.anc[q][i - q * N] = (int32_t)jfinal;
+        wrote_remote |= (q != pr.rank);
+      } else {
+        pr.anc[0][i] = (int32_t)jfinal;
+      }
     }
+  }
+  }  // usable
+  if (pr.R > 1) {  // "resampling done": the last block tells the peers this step is complete
+    if (wrote_remote) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-      if (s_brk < tn) s_jfinal = (long long)tp * TILE + s_brk - 1;
-      else if (tp == nt - 1) s_jfinal = N - 1;
-      else { s_c = Cs[tn - 1]; s_tp = tp + 1; }
+      __threadfence();
+      const unsigned long long tk = atomicAdd(&sc->ticket3, 1ull);
+      if (tk % gridDim.x == gridDim.x - 1) push_progress(pr, ctl.gstep + 1);
     }
-    __syncthreads();
-    if (s_jfinal >= 0) break;
   }
-  const long long jfinal = s_jfinal;
-  for (long long i = pend + threadIdx.x; i < hi; i += TILE_THREADS) anc[i] = (int32_t)jfinal;
 }
 
 // K4'  multinomial: Breeze Multinomial.draw first-draw walk = first j with cumulative >= u*sum
 __global__ void __launch_bounds__(256)
 k_multinomial_search(const double* __restrict__ cdf, long long N, const double* __restrict__ uarr, uint32_t key0,
                      uint32_t key1, uint32_t step, int32_t* __restrict__ anc, int* __restrict__ flags_out) {
+  griddep_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double u;
@@ -773,16 +1034,22 @@ k_multinomial_search(const double* __restrict__ cdf, long long N, const double* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5  gather (only when the resampled cloud has to be materialised: get_particles, shard export)
+// K5  gather (only when the resampled cloud has to be materialised: get_particles, tests)
+//     anc holds global indices; pr tells where each parent lives
 // ---------------------------------------------------------------------------------------------
 template <typename real, typename out_t>
 __global__ void __launch_bounds__(256)
-k_gather(const real* __restrict__ x, const int32_t* __restrict__ anc, out_t* __restrict__ out, int d, long long N,
+k_gather(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, out_t* __restrict__ out, int d, long long N,
          long long Ns, long long out_stride) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  long long s = anc ? (long long)anc[i] : i;
-  for (int k = 0; k < d; ++k) out[(long long)k * out_stride + i] = (out_t)x[(long long)k * Ns + s];
+  const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
+  if (anc) {
+    const unsigned g = (unsigned)anc[i];
+    const unsigned q = (pr.R > 1) ? g / (unsigned)pr.Nl : 0u;
+    src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+  }
+  for (int k = 0; k < d; ++k) out[(long long)k * out_stride + i] = (out_t)src[(long long)k * Ns];
 }
 
 // copy with dtype conversion (logw / propagated state read-back)
@@ -793,34 +1060,44 @@ __global__ void __launch_bounds__(256) k_to_double(const real* __restrict__ in, 
 }
 template <typename real>
 __global__ void __launch_bounds__(256)
-k_w1_out(const real* __restrict__ logw, const Scalars* __restrict__ sc, double* __restrict__ out, long long n) {
+k_w1_out(const real* __restrict__ logw, const FilterScalars* __restrict__ sc, double* __restrict__ out, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = exp_det((double)logw[i] - sc->gmax);
 }
 
-// Resampling.sampleOne (model/Resampling.scala:151-154): one uniformly chosen particle of the
-// current (resampled) cloud -> out[d] (double)
+// Resampling.sampleOne (model/Resampling.scala:151-154): one uniformly chosen particle of this
+// rank's part of the current (resampled) cloud -> out[d] (double)
 template <typename real>
-__global__ void k_sample_one(const real* __restrict__ x, const int32_t* __restrict__ anc, double* __restrict__ out, int d,
-                             long long N, long long Ns, uint32_t key0, uint32_t key1, uint32_t step) {
+__global__ void k_sample_one(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, double* __restrict__ out,
+                             int d, long long N, long long Ns, uint32_t key0, uint32_t key1, uint32_t step) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   uint4 v = philox4x32_10(make_uint4(0u, 0u, step, RNG_SAMPLE_ONE), key0, key1);
   unsigned long long r = ((unsigned long long)v.x << 32) | v.y;
   long long i = (long long)(r % (unsigned long long)N);
-  long long s = anc ? (long long)anc[i] : i;
-  for (int k = 0; k < d; ++k) out[k] = (double)x[(long long)k * Ns + s];
+  const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
+  if (anc) {
+    const unsigned g = (unsigned)anc[i];
+    const unsigned q = (pr.R > 1) ? g / (unsigned)pr.Nl : 0u;
+    src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+  }
+  for (int k = 0; k < d; ++k) out[k] = (double)src[(long long)k * Ns];
 }
 
 // per-coordinate mean of the resampled cloud (ParticleFilter.meanState); fp64 accumulation
 template <typename real>
 __global__ void __launch_bounds__(256)
-k_mean_state(const real* __restrict__ x, const int32_t* __restrict__ anc, double* __restrict__ out, int d, long long N,
+k_mean_state(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, double* __restrict__ out, int d, long long N,
              long long Ns) {
   const int k = blockIdx.y;
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-    long long s = anc ? (long long)anc[i] : i;
-    acc += (double)x[(long long)k * Ns + s];
+    const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
+    if (anc) {
+      const unsigned g = (unsigned)anc[i];
+      const unsigned q = (pr.R > 1) ? g / (unsigned)pr.Nl : 0u;
+      src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+    }
+    acc += (double)src[(long long)k * Ns];
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);

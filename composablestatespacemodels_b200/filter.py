@@ -47,14 +47,34 @@ class PfState:
 class GpuFilterHandle:
     """Owner of one cssm_filter_t (AutoCloseable on the JVM side)."""
 
-    def __init__(self, mod, resample_kind, n, dtype=_abi.F32, device=0, seed=0, stream_id=0):
+    def __init__(self, mod, resample_kind, n, dtype=_abi.F32, device=0, seed=0, stream_id=0, rank=0, world=1):
+        """`world` > 1: this handle is rank `rank` of a filter sharded over `world` GPUs and `n` is
+        the number of particles of THIS rank (see include/cssm.h, cssm_filter_create_sharded)."""
         self._lib = _abi.lib()
         self._h = C.c_void_p()
         self.mod, self.n, self.d = mod, int(n), mod.dimension
+        self.rank, self.world = int(rank), int(world)
         desc, keep = mod.desc()
-        _abi.check(self._lib.cssm_filter_create(C.byref(desc), self.n, resample_kind, dtype, device, seed, stream_id,
-                                                C.byref(self._h)))
+        if world > 1:
+            _abi.check(self._lib.cssm_filter_create_sharded(C.byref(desc), self.n, resample_kind, dtype, device, seed,
+                                                            stream_id, rank, world, C.byref(self._h)))
+        else:
+            _abi.check(self._lib.cssm_filter_create(C.byref(desc), self.n, resample_kind, dtype, device, seed, stream_id,
+                                                    C.byref(self._h)))
         self.resample_kind, self.dtype = resample_kind, dtype
+
+    # ---- sharding ---------------------------------------------------------------------------
+    def shard_export(self):
+        """This rank's connection blob (bytes) for the other ranks."""
+        buf = C.create_string_buffer(_abi.SHARD_BLOB_BYTES)
+        _abi.check(self._lib.cssm_filter_shard_export(self._h, buf))
+        return buf.raw
+
+    def shard_connect(self, blobs):
+        """`blobs`: the blobs of all ranks, in rank order."""
+        joined = b"".join(blobs)
+        assert len(joined) == _abi.SHARD_BLOB_BYTES * self.world
+        _abi.check(self._lib.cssm_filter_shard_connect(self._h, joined, self.world))
 
     def close(self):
         if self._h:
@@ -179,7 +199,7 @@ class GpuFilterHandle:
         _abi.check(self._lib.cssm_filter_last_launches(self._h, C.byref(n)))
         return n.value
 
-    KERNEL_CLASSES = ("propagate_weight", "weight_total", "tile_sums", "scan_tiles", "scan_search", "multinomial_search")
+    KERNEL_CLASSES = ("propagate_weight", "weight_sums", "scan_search", "multinomial_search")
 
     def profile(self, stride):
         _abi.check(self._lib.cssm_filter_profile(self._h, int(stride)))
@@ -210,6 +230,66 @@ class GpuFilterHandle:
         m = np.empty(self.d)
         _abi.check(self._lib.cssm_filter_mean_state(self._h, _abi.dptr(m)))
         return m
+
+
+class ShardedGroup:
+    """R shards of ONE filter inside one process, driven in lock-step by the cssm_group_* entry
+    points: virtual ranks on one GPU (devices all equal) or one process over several GPUs.  This
+    is how the sharded path is tested without a multi-process launch; the multi-process form is
+    one GpuFilterHandle(rank=r, world=R) per process plus shard_export / shard_connect."""
+
+    def __init__(self, mod, resample_kind, n_local, world, dtype=_abi.F32, devices=None, seed=0, stream_id=0):
+        devices = [0] * world if devices is None else list(devices)
+        self.world, self.n_local, self.n, self.d = world, int(n_local), int(n_local) * world, mod.dimension
+        self.shards = [GpuFilterHandle(mod, resample_kind, n_local, dtype, devices[r], seed, stream_id, rank=r, world=world)
+                       for r in range(world)]
+        if world > 1:
+            blobs = [s.shard_export() for s in self.shards]
+            for s in self.shards:
+                s.shard_connect(blobs)
+        self._lib = _abi.lib()
+        self._arr = (C.c_void_p * world)(*[s._h for s in self.shards])
+
+    def close(self):
+        for s in self.shards:
+            s.close()
+
+    def init(self, t0):
+        _abi.check(self._lib.cssm_group_init(self._arr, self.world, float(t0)))
+
+    def init_injected(self, t0, z0):
+        z0 = np.ascontiguousarray(z0, dtype=np.float64)
+        assert z0.shape == (self.d, self.n)
+        _abi.check(self._lib.cssm_group_init_injected(self._arr, self.world, float(t0), _abi.dptr(z0)))
+
+    def step_injected(self, t, observation, z, u):
+        has = 0 if observation is None else 1
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        u = None if u is None else np.ascontiguousarray(np.atleast_1d(u), dtype=np.float64)
+        xp, lw, w1 = np.empty((self.d, self.n)), np.empty(self.n), np.empty(self.n)
+        anc = np.empty(self.n, dtype=np.int32)
+        ll, ess = C.c_double(), C.c_int32()
+        _abi.check(self._lib.cssm_group_step_injected(
+            self._arr, self.world, float(t), has, 0.0 if observation is None else float(observation), _abi.dptr(z),
+            _abi.dptr(u), _abi.dptr(xp), _abi.dptr(lw), _abi.dptr(w1), anc.ctypes.data_as(_abi.c_int32_p), C.byref(ll),
+            C.byref(ess)))
+        return dict(x_prop=xp, logw=lw, w1=w1, anc=anc, ll=ll.value, ess=ess.value)
+
+    def get_particles(self):
+        x = np.empty((self.d, self.n))
+        _abi.check(self._lib.cssm_group_get_particles(self._arr, self.world, _abi.dptr(x)))
+        return x
+
+    def ll_arrays(self, t, y, has_obs=None):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        h = None if has_obs is None else np.ascontiguousarray(has_obs, dtype=np.uint8)
+        ll, ms = C.c_double(), C.c_float()
+        _abi.check(self._lib.cssm_group_ll(self._arr, self.world, _abi.dptr(t), _abi.dptr(y),
+                                           None if h is None else h.ctypes.data_as(_abi.c_uint8_p), t.size, C.byref(ll),
+                                           C.byref(ms)))
+        self.last_ms = ms.value
+        return ll.value
 
 
 class _ParticleFilterBase:

@@ -31,6 +31,8 @@ extern "C" {
 
 #define CSSM_VERSION 100 /* 0.1.0 */
 #define CSSM_MAX_DIM 32  /* total latent dimension (sum of leaf dimensions) */
+#define CSSM_MAX_RANKS 8 /* GPUs one particle cloud can be sharded over (one NVSwitch domain) */
+#define CSSM_SHARD_BLOB_BYTES 1024
 
 typedef enum {
   CSSM_OK = 0,
@@ -118,6 +120,51 @@ int cssm_filter_create(const cssm_model_desc_t* model, int64_t n_particles, int 
                        int dtype, int device, uint64_t seed, uint64_t stream_id,
                        cssm_filter_t** out);
 
+/* ------------------------------------------------------------------------------------------
+ * one filter sharded over several GPUs  (no reference analogue: a reference filter is one JVM
+ * thread).  Rank r of `world` owns the global particle slots
+ * [r*n_local, (r+1)*n_local).  Every rank runs the same three kernels per step as a single-GPU
+ * filter; the per-step exchanges (max log-weight, sum w / sum w^2, "resampling done") are small
+ * stores with a release flag into the peers' memory over NVLink, ancestor indices are scattered to
+ * the rank that owns the offspring slot and parent states are gathered from the rank that owns
+ * the parent, all through peer-mapped pointers.  Because every weight sum is exact fixed point,
+ * log-likelihood, ESS, ancestors and states are bit-identical to the unsharded filter of
+ * world*n_local particles with the same seed, for every `world`.
+ *
+ *   1. every rank:  cssm_filter_create_sharded(...)           (its own device)
+ *   2. every rank:  cssm_filter_shard_export(f, blob)         CSSM_SHARD_BLOB_BYTES bytes
+ *   3. the host all-gathers the blobs in rank order (torch.distributed, MPI, a JVM socket ...)
+ *   4. every rank:  cssm_filter_shard_connect(f, blobs, world)
+ *   5. every rank makes the SAME sequence of init / step / ll calls (SPMD).  Log-likelihood and
+ *      ESS are the global ones on every rank; get_particles / sample_one / mean_state return the
+ *      rank's own slots.  A rank whose peers do not arrive within 4 s fails with CSSM_ERR_COMM.
+ * Ranks may be separate processes (CUDA IPC) or, for tests, several handles of one process (on
+ * one device or several; use the cssm_group_* drivers below, which launch in lock-step).
+ * Multinomial resampling and the per-time sampled states of cssm_filter_run are not available.
+ * ---------------------------------------------------------------------------------------- */
+int cssm_filter_create_sharded(const cssm_model_desc_t* model, int64_t n_local, int resample_kind,
+                               int dtype, int device, uint64_t seed, uint64_t stream_id, int rank,
+                               int world, cssm_filter_t** out);
+int cssm_filter_shard_export(cssm_filter_t* f, void* blob_out);
+int cssm_filter_shard_connect(cssm_filter_t* f, const void* blobs, int world);
+int cssm_filter_shard_info(const cssm_filter_t* f, int32_t* rank_out, int32_t* world_out,
+                           int64_t* slot0_out);
+
+/* In-process group drivers: `shards[r]` = rank r, all connected.  One host thread launches every
+ * phase of a step on every shard in lock-step (virtual ranks on one GPU, or one process driving
+ * several GPUs).  z0 / z / outputs are GLOBAL arrays ([d][world*n_local] etc.), u holds one
+ * uniform per global output for stratified resampling.  cssm_group_ll is llFilter for the group;
+ * ms_out = slowest shard's device time. */
+int cssm_group_init(cssm_filter_t* const* shards, int world, double t0);
+int cssm_group_init_injected(cssm_filter_t* const* shards, int world, double t0, const double* z0);
+int cssm_group_step_injected(cssm_filter_t* const* shards, int world, double t, int has_obs,
+                             double y, const double* z, const double* u, double* x_prop_out,
+                             double* logw_out, double* w1_out, int32_t* anc_out, double* ll_out,
+                             int32_t* ess_out);
+int cssm_group_get_particles(cssm_filter_t* const* shards, int world, double* x_out);
+int cssm_group_ll(cssm_filter_t* const* shards, int world, const double* t, const double* y,
+                  const uint8_t* has_obs, int64_t T, double* ll_out, float* ms_out);
+
 /* New parameter values, same shapes: what PMMH does through model.run(p) per iteration
  * (examples/DetermineParameters.scala:70-72, model/PMMH.scala:71).  No reallocation. */
 int cssm_filter_set_params(cssm_filter_t* f, const cssm_model_desc_t* model);
@@ -184,8 +231,8 @@ int cssm_filter_last_launches(const cssm_filter_t* f, int64_t* n_out);
 
 /* Per-kernel device timing for the roofline report: with stride > 0 every stride-th stepFilter
  * brackets each of its kernels with CUDA events on the launching stream (0 switches it off and
- * clears the sums).  Classes: 0 propagate+weight, 1 weight total, 2 tile sums, 3 tile scan,
- * 4 CDF scan + ancestor search, 5 multinomial search.  ms_sum_out[8], count_out[8]. */
+ * clears the sums).  Classes: 0 gather+propagate+weight, 1 exact weight sums, 2 CDF scan +
+ * ancestor search, 3 multinomial search.  ms_sum_out[8], count_out[8]. */
 int cssm_filter_profile(cssm_filter_t* f, int stride);
 int cssm_filter_profile_read(cssm_filter_t* f, double* ms_sum_out, int64_t* count_out);
 

@@ -35,6 +35,7 @@ def lib():
             "orc_exp_det": ([C.c_double], C.c_double),
             "orc_fix96": ([C.c_double, _abi.c_uint64_p, _abi.c_uint64_p], None),
             "orc_unfix96": ([C.c_uint64, C.c_uint64], C.c_double),
+            "orc_dbl128": ([C.c_uint64, C.c_uint64, C.c_int], C.c_double),
             "orc_dim": ([MD], C.c_int),
             "orc_init_state": ([MD, C.c_int64, dp, dp], None),
             "orc_propagate": ([MD, C.c_int64, C.c_double, dp, dp, dp], None),

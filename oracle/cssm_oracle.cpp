@@ -17,12 +17,21 @@
 //
 // Two summation orders are provided for everything that feeds the ancestor search:
 //   ORC_ORDER_REFERENCE  the reference's sequential fp64 foldLeft/scanLeft, literally;
-//   ORC_ORDER_DEVICE     the order-invariant definition the GPU uses: weights are summed
-//                        EXACTLY as 2^-96 fixed-point integers (any association gives the same
-//                        integer) and each cumulative value is that exact sum rounded once to
-//                        fp64.  Here it is a plain sequential loop over unsigned __int128.
-//                        The TreeMap "duplicate key" rule is applied through the test that
-//                        creates duplicate keys in the reference, fl(C_j + w_{j+1}) == C_j.
+//   ORC_ORDER_DEVICE     the order-invariant definition the GPU uses.  The weights
+//                        w1 = exp(logw - max) are summed EXACTLY as 2^-96 fixed-point integers
+//                        (any association -- any tile size, grid size or GPU count -- gives the
+//                        same integer); a cumulative value is that exact integer S_j converted by
+//                        dbl128 (below; within 1.5 ulp, monotone), P_j = dbl128(S_j), and
+//                        total = P_{N-1}.  The reference normalises first and compares
+//                        C_j = cumsum(w/total)_j >= k_i; the device compares the same inequality
+//                        multiplied through by the total, P_j >= fl(k_i * total), which saves a
+//                        division per particle and differs from the reference only when a key is
+//                        within a few ulps of a cumulative value.  ESS = floor(1/(sum w^2 /
+//                        total^2)) with sum w^2 exact as well.  Here all of it is a plain
+//                        sequential loop over unsigned __int128.  The TreeMap "duplicate key"
+//                        rule is applied through the test that creates duplicate keys in the
+//                        reference, fl(C_j + wn_{j+1}) == C_j, evaluated in the reference's
+//                        normalised domain: C_j = fl(P_j/total), wn = fl(w/total).
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -111,6 +120,18 @@ static inline double unfixq(u128 e, int q) {
   }
   return std::ldexp((double)mant, s - q);
 }
+
+// the device's conversion of an exact 128-bit sum to fp64: (double)hi * 2^64 + (double)lo, then
+// the exact power-of-two scale.  Three correctly rounded IEEE operations (two conversions, one
+// add), so CPU and GPU agree bit for bit; monotone in e; within 1.5 ulp of e * 2^-q.
+static inline double dbl128(u128 e, int q) {
+  uint64_t hi = (uint64_t)(e >> 64), lo = (uint64_t)e;
+  volatile double a = (double)hi * 18446744073709551616.0;
+  volatile double b = (double)lo;
+  volatile double c = a + b;
+  return std::ldexp(c, -q);
+}
+double orc_dbl128(uint64_t lo, uint64_t hi, int q) { return dbl128(((u128)hi << 64) | lo, q); }
 
 void orc_fix96(double x, uint64_t* lo, uint64_t* hi) {
   u128 e = fixq(x, 96);
@@ -282,7 +303,7 @@ double orc_total(int64_t N, const double* w, int order) {
   int sh = weight_shift(N, w);
   u128 e = 0;
   for (int64_t i = 0; i < N; ++i) e += fixq(w[i], 96 - sh);
-  return unfixq(e, 96 - sh);
+  return dbl128(e, 96 - sh);
 }
 
 // ll increment and ESS of stepFilter (model/ParticleFilter.scala:127-128, :431-434, :522-524)
@@ -297,14 +318,22 @@ void orc_ll_ess(int64_t N, const double* w1, double mx, int order, double* ll_in
       s2 = s2 + wn * wn;
     }
   } else {
+    // sum of squares exact (weights pre-scaled to <= 1 by a power of two), then one division by
+    // total^2: sum (w/total)^2 = (sum w^2) / total^2
+    int sh = weight_shift(N, w1);
+    double sc = std::ldexp(1.0, -sh);
     u128 e = 0;
     for (int64_t i = 0; i < N; ++i) {
-      double wn = w1[i] / total;
-      e += fixq(wn * wn, 96);
+      volatile double ws = w1[i] * sc;
+      volatile double sq = ws * ws;
+      e += fixq(sq, 96);
     }
-    s2 = unfixq(e, 96);
+    volatile double ts = total * sc;
+    volatile double tt = ts * ts;
+    s2 = dbl128(e, 96) / tt;
   }
-  *ess = (int32_t)std::floor(1 / s2);
+  double inv = std::floor(1 / s2);
+  *ess = (inv != inv) ? 0 : (inv >= 2147483647.0 ? 2147483647 : (int32_t)inv);  // Scala .toInt saturates
 }
 
 // a9  Resampling (model/Resampling.scala:36-96).
@@ -337,7 +366,7 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
       int sh = weight_shift(N, w);
       std::vector<double> C(N);
       u128 e = 0;
-      for (int64_t i = 0; i < N; ++i) { e += fixq(w[i], 96 - sh); C[i] = unfixq(e, 96 - sh); }
+      for (int64_t i = 0; i < N; ++i) { e += fixq(w[i], 96 - sh); C[i] = dbl128(e, 96 - sh); }
       double sum = C[N - 1];
       for (int64_t o = 0; o < N; ++o) {
         double target = u[o] * sum;
@@ -349,16 +378,43 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
     if (n_clamped) *n_clamped = clamped;
     return 0;
   }
-  // cumulative sums of the normalised weights
+  if (order == ORC_ORDER_DEVICE) {
+    // P_j = dbl128(exact cumulative sum), keys compared in the un-normalised domain
+    int sh = weight_shift(N, w);
+    std::vector<double> P(N);
+    u128 e = 0;
+    for (int64_t i = 0; i < N; ++i) { e += fixq(w[i], 96 - sh); P[i] = dbl128(e, 96 - sh); }
+    const double total = P[N - 1], n = (double)N;
+    int64_t j = 0;
+    for (int64_t i = 0; i < N; ++i) {
+      volatile double k = (kind == CSSM_RESAMPLE_SYSTEMATIC) ? (u[0] + (double)i) / n : ((double)i + u[i]) / n;
+      volatile double target = k * total;
+      while (j < N && P[j] < target) ++j;  // first key >= k
+      if (j >= N) { anc[i] = (int32_t)(N - 1); ++clamped; continue; }
+      // duplicate key: last insert wins.  In the reference a key repeats exactly when adding the
+      // next normalised weight does not change the running sum, fl(C_j + wn_{j+1}) == C_j; the
+      // device applies that same test to its own C_j = fl(P_j / total), so a run of vanishing
+      // weights is skipped as a whole in both orders.
+      int64_t jj = j;
+      while (jj + 1 < N) {
+        volatile double c = P[jj] / total;
+        volatile double wn = w[jj + 1] / total;
+        volatile double nx = c + wn;
+        if (nx != c) break;
+        ++jj;
+      }
+      anc[i] = (int32_t)jj;
+    }
+    if (n_clamped) *n_clamped = clamped;
+    return 0;
+  }
+  // reference order: cumulative sums of the normalised weights
   std::vector<double> C(N), wn(N);
   double total = orc_total(N, w, order);
   for (int64_t i = 0; i < N; ++i) wn[i] = w[i] / total;
-  if (order == ORC_ORDER_REFERENCE) {
+  {
     double c = 0.0;
     for (int64_t i = 0; i < N; ++i) { c = c + wn[i]; C[i] = c; }
-  } else {
-    u128 e = 0;
-    for (int64_t i = 0; i < N; ++i) { e += fixq(wn[i], 96); C[i] = unfixq(e, 96); }
   }
   // TreeMap semantics by a merge over the two sorted sequences
   int64_t j = 0;
@@ -367,20 +423,9 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
     double k = (kind == CSSM_RESAMPLE_SYSTEMATIC) ? (u[0] + (double)i) / n : ((double)i + u[i]) / n;
     while (j < N && C[j] < k) ++j;  // first key >= k
     if (j >= N) { anc[i] = (int32_t)(N - 1); ++clamped; continue; }
-    // duplicate key: last insert wins.  In the reference a key repeats exactly when adding the
-    // next weight does not change the running sum, fl(C_j + wn_{j+1}) == C_j; the device order
-    // applies that same test to its own (exactly accumulated, once-rounded) C_j, so a run of
-    // vanishing weights is skipped as a whole in both orders.
+    // duplicate key: last insert wins (model/Resampling.scala:55-57)
     int64_t jj = j;
-    if (order == ORC_ORDER_REFERENCE) {
-      while (jj + 1 < N && C[jj + 1] == C[jj]) ++jj;
-    } else {
-      while (jj + 1 < N) {
-        volatile double nx = C[jj] + wn[jj + 1];
-        if (nx != C[jj]) break;
-        ++jj;
-      }
-    }
+    while (jj + 1 < N && C[jj + 1] == C[jj]) ++jj;
     anc[i] = (int32_t)jj;
   }
   if (n_clamped) *n_clamped = clamped;

@@ -90,6 +90,15 @@ def test_step_parity_ragged_and_missing():
     run_steps(c1(), 2049, 3, STRAT, _abi.F32, seed=5)
 
 
+def test_step_parity_large_tiles(monkeypatch):
+    # clouds above 2^18 particles use 2048-particle tiles; force them on a small cloud
+    monkeypatch.setenv("CSSM_TILE_ITEMS", "8")
+    run_steps(c2(), 5000, 3, SYS, _abi.F32, seed=8)
+    run_steps(c2(), 4100, 3, STRAT, _abi.F64, seed=9)
+    monkeypatch.setenv("CSSM_PDL", "0")  # and without programmatic dependent launch
+    run_steps(c2(), 3000, 3, SYS, _abi.F32, seed=10)
+
+
 def test_step_parity_euler():
     run_steps(c2().withStepMode(_abi.STEP_EULER), 1500, 4, SYS, _abi.F64, seed=6)
     run_steps(ALL["c4"]().withStepMode(_abi.STEP_EULER), 1500, 4, SYS, _abi.F32, seed=7)
