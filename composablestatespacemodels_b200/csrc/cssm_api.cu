@@ -147,7 +147,8 @@ template <typename real>
 void to_args(const HostModel& m, const StepHost& h, StepArgs<real>& a) {
   std::memset(&a, 0, sizeof(a));
   for (int k = 0; k < m.d; ++k) {
-    a.A[k] = (real)h.A[k]; a.M[k] = (real)h.M[k]; a.D[k] = (real)h.D[k]; a.S[k] = (real)h.S[k]; a.C[k] = (real)h.C[k];
+    // x' = A*(x - M) + M + D + S*z  ==  A*x + B + S*z  with  B = M - A*M + D  (formed in fp64)
+    a.A[k] = (real)h.A[k]; a.M[k] = (real)h.M[k]; a.D[k] = (real)(h.M[k] - h.A[k] * h.M[k] + h.D[k]); a.S[k] = (real)h.S[k]; a.C[k] = (real)h.C[k];
   }
   a.y = (real)h.y; a.k0 = (real)h.k0; a.k1 = (real)h.k1; a.k2 = (real)h.k2; a.k3 = (real)h.k3;
   a.d = m.d; a.obs_kind = m.obs_kind; a.has_obs = h.has_obs;
@@ -446,10 +447,23 @@ int step_phase2(cssm_filter* f, StepCtx& cx) {
   return CSSM_OK;
 }
 
+// K3 keeps two padded tiles of doubles in shared memory (37 KB per block with 2048-particle tiles):
+// prefer the large shared-memory carveout so that four blocks fit an SM
+template <typename real>
+void k3_carveout_once() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(k_scan_search<real, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_scan_search<real, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  cudaGetLastError();
+  done = true;
+}
+
 // ---- K3: CDF scan + ancestor search (+ multinomial draw) ----------------------------------------
 template <typename real>
 int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   if (!cx.observed) return CSSM_OK;
+  k3_carveout_once<real>();
   const Peers pr = make_peers(f, f->cur);
   const bool pdl = f->pdl && !cx.prof;
   const bool multi = f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL;

@@ -120,37 +120,80 @@ __device__ __forceinline__ double dbl128(u128 e, int q) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Deterministic exp: the same fma/mul/add sequence as oracle/cssm_oracle.cpp orc_exp_det, so the
-// weights w1 = exp(logw - max) have identical bits on the device and in the checker.
+// Deterministic exp: the same fma/mul/add sequence as oracle/cssm_oracle.cpp orc_exp_det /
+// orc_expf_det, so the weights w1 = exp(logw - max) have identical bits on the device and in the
+// checker.  Coefficients live in constant memory so that every DFMA/FFMA takes its constant as a
+// direct operand (the compiler otherwise re-materialises each 64-bit literal per use).
 // ---------------------------------------------------------------------------------------------
+__constant__ double c_expd[17] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0,       1.0 / 720.0,       1.0 / 120.0,       1.0 / 24.0,      1.0 / 6.0,      0.5,
+    1.4426950408889634074 /* log2 e */, -6.93147180369123816490e-01 /* -ln2 hi */, -1.90821492927058770002e-10 /* -ln2 lo */,
+    6755399441055744.0 /* 1.5 * 2^52 */, 18446744073709551616.0 /* 2^64 */};
+__constant__ float c_expf[11] = {1.0f / 5040.0f, 1.0f / 720.0f, 1.0f / 120.0f, 1.0f / 24.0f, 1.0f / 6.0f, 0.5f,
+                                 1.442695040888963f /* log2 e */, -0.693145751953125f /* -ln2 hi (0x3f317200) */,
+                                 -1.428606765330187e-06f /* -ln2 lo */, 12582912.0f /* 1.5 * 2^23 */, 0.0f};
+
+// fp64 weights (F64 filters, cssm_resample).  |error| < 1 ulp.
 __device__ __forceinline__ double exp_det(double x) {
-  if (x != x) return x;
-  if (x < -745.5) return 0.0;
-  const double LOG2E = 1.4426950408889634074;
-  const double LN2_HI = 6.93147180369123816490e-01;
-  const double LN2_LO = 1.90821492927058770002e-10;
-  double kf = rint(__dmul_rn(x, LOG2E));
-  double r = __fma_rn(kf, -LN2_HI, x);
-  r = __fma_rn(kf, -LN2_LO, r);
-  double p = 1.0 / 6227020800.0;
-  p = __fma_rn(p, r, 1.0 / 479001600.0);
-  p = __fma_rn(p, r, 1.0 / 39916800.0);
-  p = __fma_rn(p, r, 1.0 / 3628800.0);
-  p = __fma_rn(p, r, 1.0 / 362880.0);
-  p = __fma_rn(p, r, 1.0 / 40320.0);
-  p = __fma_rn(p, r, 1.0 / 5040.0);
-  p = __fma_rn(p, r, 1.0 / 720.0);
-  p = __fma_rn(p, r, 1.0 / 120.0);
-  p = __fma_rn(p, r, 1.0 / 24.0);
-  p = __fma_rn(p, r, 1.0 / 6.0);
-  p = __fma_rn(p, r, 0.5);
+  if (!(x >= -745.5)) return (x != x) ? x : 0.0;
+  // k = rint(x * log2 e) by the magic-number add (round to nearest even, like nearbyint)
+  const double t = __dadd_rn(__dmul_rn(x, c_expd[12]), c_expd[15]);
+  const double kf = __dsub_rn(t, c_expd[15]);
+  const int k = __double2loint(t);  // low word of 1.5*2^52 + k is k in two's complement
+  double r = __fma_rn(kf, c_expd[13], x);
+  r = __fma_rn(kf, c_expd[14], r);
+  double p = c_expd[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) p = __fma_rn(p, r, c_expd[i]);
   p = __fma_rn(p, r, 1.0);
   p = __fma_rn(p, r, 1.0);
-  int k = (int)kf;
-  int k1 = k / 2, k2 = k - k1;
-  double s1 = __longlong_as_double((long long)(k1 + 1023) << 52);
-  double s2 = __longlong_as_double((long long)(k2 + 1023) << 52);
+  if (k > -1000)  // p in (0.7, 1.42): scaling by 2^k is an exponent add while the result is normal
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  // near the subnormal range: scale in two exact steps so that the result rounds once
+  const int k1 = k / 2, k2 = k - k1;
+  const double s1 = __longlong_as_double((long long)(k1 + 1023) << 52);
+  const double s2 = __longlong_as_double((long long)(k2 + 1023) << 52);
   return __dmul_rn(__dmul_rn(p, s1), s2);
+}
+
+// fp32 weights (F32 filters): everything on the full-rate fp32 / integer pipes.  Arguments below
+// -86 give exactly 0 (the result would be subnormal in fp32); |error| < 1 ulp(fp32) above.
+__device__ __forceinline__ float expf_det(float x) {
+  if (!(x >= -86.0f)) return (x != x) ? x : 0.0f;
+  const float t = __fadd_rn(__fmul_rn(x, c_expf[6]), c_expf[9]);
+  const float kf = __fsub_rn(t, c_expf[9]);
+  const int k = (int)(__float_as_uint(t) << 10) >> 10;  // low 22 bits of 1.5*2^23 + k, sign-extended
+  float r = __fmaf_rn(kf, c_expf[7], x);
+  r = __fmaf_rn(kf, c_expf[8], r);
+  float p = c_expf[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) p = __fmaf_rn(p, r, c_expf[i]);
+  p = __fmaf_rn(p, r, 1.0f);
+  p = __fmaf_rn(p, r, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + ((unsigned)k << 23));  // k >= -124: the result is normal
+}
+
+// floor(w * 2^96) and floor(w*w * 2^96) of an fp32 weight 0 <= w <= 1 (0 or normal), integer only
+__device__ __forceinline__ u128 shl_u64_to_128(unsigned long long m, int s) {  // m * 2^s, s in (-128, 128), floor
+  if (s >= 64) return make_u128(0, s >= 128 ? 0ull : m << (s - 64));
+  if (s > 0) return make_u128(m << s, m >> (64 - s));
+  if (s > -64) return make_u128(m >> (-s), 0);
+  return make_u128(0, 0);
+}
+__device__ __forceinline__ u128 fix_f32(float w) {
+  const unsigned b = __float_as_uint(w);
+  const int e = (int)(b >> 23);  // sign is 0
+  if (e == 0) return make_u128(0, 0);
+  const unsigned long long m = (unsigned long long)((b & 0x7FFFFFu) | 0x800000u);
+  return shl_u64_to_128(m, e - 150 + 96);  // w = m * 2^(e-150)
+}
+__device__ __forceinline__ u128 fix_sq_f32(float w) {
+  const unsigned b = __float_as_uint(w);
+  const int e = (int)(b >> 23);
+  if (e == 0) return make_u128(0, 0);
+  const unsigned m = (b & 0x7FFFFFu) | 0x800000u;
+  return shl_u64_to_128((unsigned long long)m * m, 2 * (e - 150) + 96);  // w^2 = m^2 * 2^(2(e-150)), exact
 }
 
 // ---------------------------------------------------------------------------------------------

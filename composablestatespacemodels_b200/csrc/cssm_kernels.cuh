@@ -39,7 +39,9 @@ constexpr int TILE_THREADS = 256;
 constexpr int SUPER = 256;        // tiles per super tile (second level of the prefix)
 
 // per-observation constants, built on the host in fp64 and rounded to the filter dtype.
-// transition of coordinate k:  x' = A*(x - M) + M + D + S*z     (exact or Euler-Maruyama)
+// transition of coordinate k:  x' = A*(x - M) + M + D + S*z     (exact or Euler-Maruyama),
+// evaluated as fma(S, z, fma(A, x, B)) with B = M - A*M + D formed on the host in fp64 (StepArgs.D
+// carries B; StepArgs.M is only used by the initial-state kernels)
 //   Brownian      exact: A=1 M=0 D=0      S=sqrt(sigma*dt)        EM: D=dt        S=sigma*sqrt(dt)
 //   GenBrownian   exact: A=1 M=0 D=mu*dt  S=sqrt(sigma*dt)        EM: D=mu*dt     S=sigma*sqrt(dt)
 //   OU            exact: A=exp(-phi dt) M=mu D=0 S=sqrt(sigma^2/(2phi)(1-exp(-2phi dt)))
@@ -373,12 +375,11 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
     for (int j = 0; j < 4; ++j) {
       int k = kk + j;
       if (k < d) {
-        real A = a.A[k], M = a.M[k], Dk = a.D[k], S = a.S[k], Cc = a.C[k];
+        real A = a.A[k], Bk = a.D[k], S = a.S[k], Cc = a.C[k];
         real xn[PPT];
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
-          real mean = r_fma<real>(A, xv[j][p] - M, M) + Dk;
-          xn[p] = r_fma<real>(S, z[j][p], mean);
+          xn[p] = r_fma<real>(S, z[j][p], r_fma<real>(A, xv[j][p], Bk));
           g[p] = r_fma<real>(Cc, xn[p], g[p]);
         }
         real* dst = xdst + (long long)k * Ns + i0;
@@ -400,14 +401,16 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
   bool bad = false;
   if (a.has_obs) {
     real lw[PPT];
+    real mxr = (real)mx;
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
       lw[p] = obs_loglik<real>(a, g[p]);
       if (valid[p]) {
         if (lw[p] != lw[p]) bad = true;
-        else mx = fmax(mx, (double)lw[p]);
+        else mxr = lw[p] > mxr ? lw[p] : mxr;
       }
     }
+    mx = (double)mxr;
     if (full) {
       vec_t v;
       real* vp = reinterpret_cast<real*>(&v);
@@ -484,8 +487,7 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
           for (int j = 0; j < PC; ++j) {
             int k = kk + j;
             if (k < DP && k < a.d) {
-              real mean = r_fma<real>(a.A[k], x[k] - a.M[k], a.M[k]) + a.D[k];
-              x[k] = r_fma<real>(a.S[k], z[j], mean);
+              x[k] = r_fma<real>(a.S[k], z[j], r_fma<real>(a.A[k], x[k], a.D[k]));
               real cc = ctab ? ctab[s * a.d + k] : a.C[k];
               gs = r_fma<real>(cc, x[k], gs);
             }
@@ -510,16 +512,34 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// weights: either w1 = exp_det(logw - gmax) (in-filter) or a caller-given fp64 array (cssm_resample)
+// weights: w1 = exp(logw - gmax) in the filter's own precision (F32 filters: expf_det on the fp32
+// pipe and integer-only fixed point; F64 filters: exp_det), or a caller-given fp64 array
+// (cssm_resample, real = double).  `wt` is the type a weight is held in; (double)w is exact.
 // ---------------------------------------------------------------------------------------------
-template <typename real>
-struct WeightSrc {
-  const real* logw;    // in-filter source (NULL when `direct` is used)
+template <typename real> struct WeightSrc;
+template <> struct WeightSrc<float> {
+  typedef float wt;
+  const float* logw;
+  const double* direct;  // never set for fp32 filters
+  double gmax;           // the max of fp32 log-weights: exactly an fp32 value
+  __device__ __forceinline__ float operator()(long long idx) const { return expf_det(__fsub_rn(logw[idx], (float)gmax)); }
+  __device__ __forceinline__ static u128 fix(float w, int) { return fix_f32(w); }
+  __device__ __forceinline__ static u128 fix_sq(float w, double) { return fix_sq_f32(w); }
+};
+template <> struct WeightSrc<double> {
+  typedef double wt;
+  const double* logw;    // in-filter source (NULL when `direct` is used)
   const double* direct;
   double gmax;
   __device__ __forceinline__ double operator()(long long idx) const {
     if (direct) return direct[idx];
-    return exp_det((double)logw[idx] - gmax);
+    return exp_det(__dsub_rn(logw[idx], gmax));
+  }
+  __device__ __forceinline__ static u128 fix(double w, int qb) { return fix_fast(w, qb); }
+  // direct weights are pre-scaled to <= 1 by q2scale = 2^-(96-qb) before squaring
+  __device__ __forceinline__ static u128 fix_sq(double w, double q2scale) {
+    const double ws = __dmul_rn(w, q2scale);
+    return fix_fast(__dmul_rn(ws, ws), 96);
   }
 };
 
@@ -603,22 +623,25 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
   __syncthreads();
   const PreScan ps = pre_scan(s_key, direct != nullptr);
   WeightSrc<real> ws{logw, direct, ps.gmax};
+  typedef typename WeightSrc<real>::wt wt;
   const int qb = ps.qb;
   const double q2scale = __longlong_as_double((long long)(1023 - (96 - qb)) << 52);  // direct weights: w * 2^-(96-qb) <= 1
   const long long base = (long long)blockIdx.x * TILE;
   u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
-  double mxw = 0.0;
+  wt wv[ITEMS];
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    long long idx = base + j * TILE_THREADS + threadIdx.x;
-    if (idx < N) {
-      const double w = ws(idx);
-      acc = add128(acc, fix_fast(w, qb));
-      const double wsq = __dmul_rn(w, q2scale);
-      acc2 = add128(acc2, fix_fast(__dmul_rn(wsq, wsq), 96));
-      mxw = fmax(mxw, w);
-    }
+    const long long idx = base + j * TILE_THREADS + threadIdx.x;
+    wv[j] = (idx < N) ? ws(idx) : (wt)0;
   }
+  wt mxv = (wt)0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
+    acc2 = add128(acc2, WeightSrc<real>::fix_sq(wv[j], q2scale));
+    mxv = wv[j] > mxv ? wv[j] : mxv;
+  }
+  double mxw = (double)mxv;
   acc2 = warp_sum128(acc2);
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
@@ -701,21 +724,28 @@ struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stra
   }
 };
 
-// inclusive CDF values P_j = dbl128(exact prefix) of one tile into Ps[0..TILE) and the weights
-// into Ws; `excl` = exact sum of everything before the tile.  All threads call.
+// shared-memory index of element i of a tile.  A thread owns ITEMS consecutive elements; with 8
+// doubles per thread the warp's stores would all fall into two bank groups, one pad double per 8
+// elements spreads them over all banks.
+template <int ITEMS> __device__ __forceinline__ int phys(int i) { return ITEMS == 8 ? i + (i >> 3) : i; }
+template <int ITEMS> struct TileSmem { static constexpr int SIZE = TILE_THREADS * ITEMS + (ITEMS == 8 ? TILE_THREADS : 0); };
+
+// inclusive CDF values P_j = dbl128(exact prefix) of one tile into Ps[phys(0..TILE)) and the
+// weights (as double) into Ws; `excl` = exact sum of everything before the tile.  All threads call.
 template <typename real, int ITEMS>
 __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128 excl, long long tile0, long long N,
                                          double* Ps, double* Ws, u128* s_warp) {
+  typedef typename WeightSrc<real>::wt wt;
   const long long base = tile0 + (long long)threadIdx.x * ITEMS;
+  wt wv[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) wv[j] = (base + j < N) ? ws(base + j) : (wt)0;
   u128 e[ITEMS];
   u128 run = make_u128(0, 0);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    long long idx = base + j;
-    double w = 0.0;
-    if (idx < N) w = ws(idx);
-    if (Ws) Ws[threadIdx.x * ITEMS + j] = w;
-    run = add128(run, fix_fast(w, qb));
+    if (Ws) Ws[phys<ITEMS>(threadIdx.x * ITEMS + j)] = (double)wv[j];
+    run = add128(run, WeightSrc<real>::fix(wv[j], qb));
     e[j] = run;
   }
   // exclusive scan of the thread totals across the block
@@ -735,7 +765,7 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128
   if (lane == 0) ex = make_u128(0, 0);
   off = add128(off, ex);
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) Ps[threadIdx.x * ITEMS + j] = dbl128(add128(off, e[j]), qb);
+  for (int j = 0; j < ITEMS; ++j) Ps[phys<ITEMS>(threadIdx.x * ITEMS + j)] = dbl128(add128(off, e[j]), qb);
   __syncthreads();
 }
 
@@ -763,13 +793,13 @@ struct K3Ctl {
 // cdf_out == NULL: search (systematic / stratified), writes ancestors;
 // cdf_out != NULL: write the un-normalised CDF (multinomial), no search
 template <typename real, int ITEMS>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
               double* __restrict__ cdf_out) {
   constexpr int TILE = TILE_THREADS * ITEMS;
-  __shared__ double Ps[TILE];
-  __shared__ double Ws[TILE];
+  __shared__ double Ps[TileSmem<ITEMS>::SIZE];
+  __shared__ double Ws[TileSmem<ITEMS>::SIZE];
   __shared__ u128 s_warp[TILE_THREADS / 32];
   __shared__ u128 s_excl, s_tot, s_q;
   __shared__ unsigned long long s_key;
@@ -879,7 +909,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp);
 
   if (cdf_out != nullptr) {
-    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) cdf_out[tile0 + j] = Ps[j];
+    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) cdf_out[tile0 + j] = Ps[phys<ITEMS>(j)];
     return;
   }
 
@@ -891,7 +921,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) pr.anc[pr.rank][tile0 + j] = (int32_t)((long long)pr.rank * N + tile0 + j);
   } else {
   KFun kf{ctl.kind, s_u, (double)Ng, total, uarr, ctl.key0, ctl.key1, ctl.step};
-  const double c_end = Ps[tile_n - 1];
+  const double c_end = Ps[phys<ITEMS>(tile_n - 1)];
   const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
   const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
   if (threadIdx.x == 0) {
@@ -910,25 +940,56 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const bool cont = !last_tile && vanishes(c_end, s_wnext, total);
   if (last_tile && threadIdx.x == 0 && kf(Ng - 1) > c_end) atomicOr(&sc->flags, FLAG_CLAMPED);  // reference would throw (m.head)
 
-  for (long long i = lo + threadIdx.x; i < hi; i += TILE_THREADS) {
-    const double key = kf(i);
-    // first j with Ps[j] >= key (exists unless this is the clamped tail of the last tile)
-    int a = 0, b = tile_n - 1;
-    while (a < b) {
-      int m = (a + b) >> 1;
-      if (Ps[m] >= key) b = m; else a = m + 1;
+  // Each thread takes 8 CONSECUTIVE outputs: one binary search for the first, then a merge walk
+  // (keys and CDF are both non-decreasing; a long jump falls back to a binary search), and the 8
+  // ancestors leave as two 16-byte stores.
+  for (long long c0 = (lo & ~7ll) + (long long)threadIdx.x * 8; c0 < hi; c0 += (long long)TILE_THREADS * 8) {
+    int res[8];
+    int j = 0;
+    bool first = true;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const long long i = c0 + m;
+      res[m] = 0;
+      if (i >= lo && i < hi) {
+        const double key = kf(i);
+        // first j with Ps[j] >= key (exists unless this is the clamped tail of the last tile)
+        int steps = 0;
+        if (!first)
+          while (j < tile_n - 1 && Ps[phys<ITEMS>(j)] < key && steps < 6) { ++j; ++steps; }
+        if (first || steps == 6) {
+          int a = j, b = tile_n - 1;
+          while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (Ps[phys<ITEMS>(mid)] >= key) b = mid; else a = mid + 1;
+          }
+          j = a;
+          first = false;
+        }
+        // TreeMap: a duplicated key keeps the last particle inserted
+        int jt = j;
+        while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+        if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
+        res[m] = (int)(gbase + jt);
+      }
     }
-    // TreeMap: a duplicated key keeps the last particle inserted
-    int j = a;
-    while (j + 1 < tile_n && vanishes(Ps[j], Ws[j + 1], total)) ++j;
-    if (cont && j == tile_n - 1) atomicMin(&s_pend, i);
-    const int32_t val = (int32_t)(gbase + j);
-    if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
-      const long long q = i / N;
-      pr.anc[q][i - q * N] = val;
+    const long long q = (pr.R > 1) ? c0 / N : 0;
+    const long long li = c0 - q * N;  // index into the owner's ancestor buffer
+    if (c0 >= lo && c0 + 8 <= hi && li + 8 <= N && (li & 3) == 0) {
+      int4* dst = reinterpret_cast<int4*>(pr.anc[q] + li);
+      dst[0] = make_int4(res[0], res[1], res[2], res[3]);
+      dst[1] = make_int4(res[4], res[5], res[6], res[7]);
       wrote_remote |= (q != pr.rank);
     } else {
-      pr.anc[0][i] = val;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const long long i = c0 + m;
+        if (i >= lo && i < hi) {
+          const long long qi = (pr.R > 1) ? i / N : 0;
+          pr.anc[qi][i - qi * N] = res[m];
+          wrote_remote |= (qi != pr.rank);
+        }
+      }
     }
   }
   __syncthreads();
@@ -971,8 +1032,8 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
       const int tn = (int)min((long long)TILE, N - (long long)tl * TILE);
       // first element of tile tp that does NOT vanish against its predecessor's value
       for (int j = threadIdx.x; j < tn; j += TILE_THREADS) {
-        double prev = (j == 0) ? c : Ps[j - 1];
-        if (!vanishes(prev, Ws[j], total)) atomicMin(&s_brk, j);
+        double prev = (j == 0) ? c : Ps[phys<ITEMS>(j - 1)];
+        if (!vanishes(prev, Ws[phys<ITEMS>(j)], total)) atomicMin(&s_brk, j);
       }
       __syncthreads();
       if (threadIdx.x == 0) {

@@ -14,7 +14,12 @@ from composablestatespacemodels_b200 import _abi  # descriptor struct definition
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libcssm_oracle.so")
-ORDER_REFERENCE, ORDER_DEVICE = 0, 1
+ORDER_REFERENCE, ORDER_DEVICE, ORDER_DEVICE_F32 = 0, 1, 2
+
+
+def device_order(dtype):
+    """The device definition that matches a filter dtype (F32 filters evaluate w1 in fp32)."""
+    return ORDER_DEVICE_F32 if dtype == _abi.F32 else ORDER_DEVICE
 _lib = None
 
 dp, ip, i64p, u8p = _abi.c_double_p, _abi.c_int32_p, _abi.c_int64_p, _abi.c_uint8_p
@@ -33,6 +38,7 @@ def lib():
         l = C.CDLL(_SO)
         sig = {
             "orc_exp_det": ([C.c_double], C.c_double),
+            "orc_expf_det": ([C.c_float], C.c_float),
             "orc_fix96": ([C.c_double, _abi.c_uint64_p, _abi.c_uint64_p], None),
             "orc_unfix96": ([C.c_uint64, C.c_uint64], C.c_double),
             "orc_dbl128": ([C.c_uint64, C.c_uint64, C.c_int], C.c_double),
@@ -165,6 +171,10 @@ def lgcp_nsub(dt, precision):
 
 def exp_det(x):
     return lib().orc_exp_det(float(x))
+
+
+def expf_det(x):
+    return lib().orc_expf_det(float(x))
 
 
 def w1(logw, mx, order=ORDER_DEVICE):

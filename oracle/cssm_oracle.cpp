@@ -46,7 +46,8 @@
 typedef unsigned __int128 u128;
 
 #define ORC_ORDER_REFERENCE 0
-#define ORC_ORDER_DEVICE 1
+#define ORC_ORDER_DEVICE 1      // device definition, fp64 weights (F64 filters, cssm_resample)
+#define ORC_ORDER_DEVICE_F32 2  // device definition, weights w1 evaluated in fp32 (F32 filters)
 
 extern "C" {
 
@@ -87,6 +88,34 @@ double orc_exp_det(double x) {
   std::memcpy(&s1, &b1, 8);
   std::memcpy(&s2, &b2, 8);
   return (p * s1) * s2;
+}
+
+// The F32 filter evaluates w1 = exp(logw - max) in fp32 (its log-weights are fp32 anyway): same
+// construction with fmaf only; arguments below -86 give exactly 0.  Everything after w1 (exact
+// sums, CDF, keys) is the fp64 / integer arithmetic of ORC_ORDER_DEVICE applied to (double)w1.
+float orc_expf_det(float x) {
+  if (!(x >= -86.0f)) return (x != x) ? x : 0.0f;
+  const float LOG2E = 1.442695040888963f, NLN2_HI = -0.693145751953125f, NLN2_LO = -1.428606765330187e-06f;
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23: adding it rounds to the nearest integer (ties to even)
+  volatile float prod = x * LOG2E;
+  volatile float t = prod + MAGIC;
+  float kf = t - MAGIC;
+  float r = std::fmaf(kf, NLN2_HI, x);
+  r = std::fmaf(kf, NLN2_LO, r);
+  float p = 1.0f / 5040.0f;
+  p = std::fmaf(p, r, 1.0f / 720.0f);
+  p = std::fmaf(p, r, 1.0f / 120.0f);
+  p = std::fmaf(p, r, 1.0f / 24.0f);
+  p = std::fmaf(p, r, 1.0f / 6.0f);
+  p = std::fmaf(p, r, 0.5f);
+  p = std::fmaf(p, r, 1.0f);
+  p = std::fmaf(p, r, 1.0f);
+  int k = (int)kf;  // in [-124, 0]: the scaled result is a normal fp32 number
+  uint32_t b;
+  std::memcpy(&b, &p, 4);
+  b += (uint32_t)k << 23;
+  std::memcpy(&p, &b, 4);
+  return p;
 }
 
 // floor(x * 2^q) for 0 <= x, result must fit 128 bits (callers guarantee x*2^q < 2^100)
@@ -278,8 +307,13 @@ double orc_max(int64_t N, const double* w) {
   return mx;
 }
 void orc_w1(int64_t N, const double* logw, double mx, int order, double* w1) {
-  for (int64_t i = 0; i < N; ++i)
-    w1[i] = (order == ORC_ORDER_DEVICE) ? orc_exp_det(logw[i] - mx) : std::exp(logw[i] - mx);
+  for (int64_t i = 0; i < N; ++i) {
+    if (order == ORC_ORDER_DEVICE) w1[i] = orc_exp_det(logw[i] - mx);
+    else if (order == ORC_ORDER_DEVICE_F32) {
+      volatile float x = (float)logw[i] - (float)mx;  // log-weights of an F32 filter are fp32 values
+      w1[i] = (double)orc_expf_det(x);
+    } else w1[i] = std::exp(logw[i] - mx);
+  }
 }
 
 // power-of-two pre-scale so that every weight is <= 1 before it is made fixed point
@@ -378,7 +412,7 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
     if (n_clamped) *n_clamped = clamped;
     return 0;
   }
-  if (order == ORC_ORDER_DEVICE) {
+  if (order != ORC_ORDER_REFERENCE) {
     // P_j = dbl128(exact cumulative sum), keys compared in the un-normalised domain
     int sh = weight_shift(N, w);
     std::vector<double> P(N);

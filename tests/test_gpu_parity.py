@@ -30,6 +30,7 @@ def run_steps(mod, N, T, kind, dtype, seed=0, missing=()):
     t, y, _ = orc.simulate(T, 0.1, seed + 11)
     h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, seed=3)
     tol = TOL[dtype]
+    DEV = oracle.device_order(dtype)   # F32 filters evaluate w1 = exp(logw - max) in fp32
     z0 = rng.standard_normal((d, N))
     h.init_injected(t[0], z0)
     x = h.get_particles()
@@ -43,7 +44,7 @@ def run_steps(mod, N, T, kind, dtype, seed=0, missing=()):
         # stage 1: propagate + weight, from the device's own previous cloud
         o = oracle.Oracle(mod)
         o.reset(N)
-        r = o.step(x, tp, t[s], obs, z, u, kind, oracle.ORDER_DEVICE)
+        r = o.step(x, tp, t[s], obs, z, u, kind, DEV)
         rel_close(g["x_prop"], r["x_prop"], tol, f"step {s} propagated state")
         if obs is None:
             x = h.get_particles()
@@ -53,13 +54,13 @@ def run_steps(mod, N, T, kind, dtype, seed=0, missing=()):
         rel_close(g["logw"], r["logw"], tol, f"step {s} log-weights")
         # stage 2: from the device's log-weights -> w1, ll increment, ESS, ancestors
         mx = float(np.max(g["logw"]))
-        w1 = oracle.w1(g["logw"], mx, oracle.ORDER_DEVICE)
+        w1 = oracle.w1(g["logw"], mx, DEV)
         np.testing.assert_array_equal(g["w1"], w1)  # deterministic exp: identical bits
-        incr, ess = oracle.ll_ess(w1, mx, oracle.ORDER_DEVICE)
+        incr, ess = oracle.ll_ess(w1, mx, DEV)
         ll_ref += incr
         assert g["ess"] == ess
         rel_close(g["ll"], ll_ref, 1e-12, f"step {s} log-likelihood")
-        anc = oracle.resample(kind, w1, u, oracle.ORDER_DEVICE)
+        anc = oracle.resample(kind, w1, u, DEV)
         np.testing.assert_array_equal(g["anc"], anc)
         # the reference-order (sequential fp64) restatement agrees except for last-ulp ties
         anc_ref = oracle.resample(kind, oracle.w1(g["logw"], mx, oracle.ORDER_REFERENCE), u, oracle.ORDER_REFERENCE)
@@ -158,11 +159,11 @@ def test_lgcp_step_parity():
             u = rng.random(N)
             g = h.step_injected(t, 1.0, z if n > 0 else None, u)
             o = oracle.Oracle(mod); o.reset(N)
-            r = o.step(x, tp, t, 1.0, z, u, STRAT, oracle.ORDER_DEVICE)
+            r = o.step(x, tp, t, 1.0, z, u, STRAT, oracle.device_order(dtype))
             rel_close(g["x_prop"], r["x_prop"], TOL[dtype], "lgcp state")
             np.testing.assert_allclose(g["logw"], r["logw"], rtol=TOL[dtype] * 10, atol=TOL[dtype] * 10)
             mx = float(np.max(g["logw"]))
-            w1 = oracle.w1(g["logw"], mx)
+            w1 = oracle.w1(g["logw"], mx, oracle.device_order(dtype))
             np.testing.assert_array_equal(g["anc"], oracle.resample(STRAT, w1, u))
             x = h.get_particles()
             tp = t

@@ -47,7 +47,7 @@ def run_pair(mod, n_local, R, T, kind, dtype, seed, ys=None, missing=()):
             assert b["ess"] == a["ess"] and b["ll"] == a["ll"]
             # and both are what the oracle says for these weights
             mx = float(np.max(a["logw"]))
-            np.testing.assert_array_equal(a["anc"], oracle.resample(kind, oracle.w1(a["logw"], mx), u))
+            np.testing.assert_array_equal(a["anc"], oracle.resample(kind, oracle.w1(a["logw"], mx, oracle.device_order(dtype)), u))
         np.testing.assert_array_equal(grp.get_particles(), one.get_particles())
     one.close()
     grp.close()

@@ -28,6 +28,21 @@ def test_exp_det_is_accurate_and_monotone():
     assert np.all(np.diff(es) >= 0)
 
 
+def test_expf_det_is_accurate_and_monotone():
+    """The fp32 weight evaluation of F32 filters (ORDER_DEVICE_F32)."""
+    xs = np.sort(-np.abs(np.random.default_rng(3).normal(0, 25, 20000)).astype(np.float32))
+    e = np.array([oracle.expf_det(x) for x in xs], dtype=np.float64)
+    r = np.exp(xs.astype(np.float64))
+    ok = xs >= -86.0
+    assert np.max(np.abs(e[ok] - r[ok]) / r[ok]) < 1.2e-7            # < 1 ulp(fp32) = 2^-23
+    assert np.all(e[~ok] == 0.0)                                     # would be subnormal: flushed to exactly 0
+    assert np.all(np.diff(e) >= 0) and oracle.expf_det(0.0) == 1.0
+    lw = np.random.default_rng(4).normal(-5, 3, 1000).astype(np.float32).astype(np.float64)
+    w = oracle.w1(lw, lw.max(), oracle.ORDER_DEVICE_F32)
+    assert np.all(w == w.astype(np.float32)) and w.max() == 1.0      # fp32 values, the max weight is exactly 1
+    np.testing.assert_allclose(w, np.exp(lw - lw.max()), rtol=4e-6)   # + the rounding of the fp32 subtraction
+
+
 def test_fixed_point_round_trip():
     L = oracle.lib()
     import ctypes as C
