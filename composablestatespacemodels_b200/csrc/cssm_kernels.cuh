@@ -1123,7 +1123,7 @@ template <typename real>
 __global__ void __launch_bounds__(256)
 k_w1_out(const real* __restrict__ logw, const FilterScalars* __restrict__ sc, double* __restrict__ out, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = exp_det((double)logw[i] - sc->gmax);
+  if (i < n) out[i] = (double)WeightSrc<real>{logw, nullptr, sc->gmax}(i);
 }
 
 // Resampling.sampleOne (model/Resampling.scala:151-154): one uniformly chosen particle of this
