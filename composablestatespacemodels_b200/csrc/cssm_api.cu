@@ -453,8 +453,10 @@ template <typename real>
 void k3_carveout_once() {
   static bool done = false;
   if (done) return;
-  cudaFuncSetAttribute(k_scan_search<real, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_scan_search<real, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
   cudaGetLastError();
   done = true;
 }
@@ -469,18 +471,23 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   const bool multi = f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL;
   K3Ctl ctl;
   ctl.parity = cx.parity; ctl.obs_seq = f->obs_seq; ctl.gstep = f->gstep;
-  ctl.kind = f->resample_kind; ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj;
+  const long long Ng = f->N * (long long)pr.R;
+  ctl.inv_n = ((Ng & (Ng - 1)) == 0) ? 1.0 / (double)Ng : 0.0;
+  ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj;
   ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
   ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
+  const bool strat = f->resample_kind == CSSM_RESAMPLE_STRATIFIED;
+  const double* ua = multi ? (const double*)nullptr : io.uarr;
+  double* cdf = multi ? f->cdf : (double*)nullptr;
   cudaError_t e;
   {
     ProfScope ps_(f, CLS_SEARCH, cx.prof);
-    if (f->items == 8)
-      e = launch(k_scan_search<real, 8>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
-                 f->sc, f->tb, pr, ctl, multi ? (const double*)nullptr : io.uarr, multi ? f->cdf : (double*)nullptr);
-    else
-      e = launch(k_scan_search<real, 2>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
-                 f->sc, f->tb, pr, ctl, multi ? (const double*)nullptr : io.uarr, multi ? f->cdf : (double*)nullptr);
+#define K3_CASE(IT, KD)                                                                                                 \
+  e = launch(k_scan_search<real, IT, KD>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, \
+             f->N, f->sc, f->tb, pr, ctl, ua, cdf)
+    if (f->items == 8) { if (strat) K3_CASE(8, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(8, CSSM_RESAMPLE_SYSTEMATIC); }
+    else { if (strat) K3_CASE(2, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(2, CSSM_RESAMPLE_SYSTEMATIC); }
+#undef K3_CASE
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K3: ") + cudaGetErrorString(e));
   f->launches++;
@@ -1485,17 +1492,21 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
     pr.R = 1; pr.rank = 0; pr.Nl = N; pr.anc[0] = danc; pr.xch[0] = xch; pr.tile_sum[0] = tb.tile_sum; pr.tile_maxw[0] = tb.tile_maxw;
     K3Ctl ctl;
     std::memset(&ctl, 0, sizeof(ctl));
-    ctl.kind = kind; ctl.direct = 1; ctl.add_ll = 0; ctl.use_u_inj = 1;
+    ctl.inv_n = ((N & (N - 1)) == 0) ? 1.0 / (double)N : 0.0;
+    ctl.direct = 1; ctl.add_ll = 0; ctl.use_u_inj = 1;
     const bool multi = kind == CSSM_RESAMPLE_MULTINOMIAL;
-    const double* ua = (kind == CSSM_RESAMPLE_STRATIFIED) ? du : nullptr;
+    const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
+    const double* ua = strat ? du : nullptr;
+    double* cdf = multi ? dcdf : nullptr;
     k_max_direct<<<std::min(nblk(N, 256), 1184), 256, 0, st>>>(dw, N, sc);
-    if (items == 8) {
-      k_weight_sums<double, 8><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, 0, 0ull, tb, pr);
-      k_scan_search<double, 8><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, tb, pr, ctl, ua, multi ? dcdf : nullptr);
-    } else {
-      k_weight_sums<double, 2><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, 0, 0ull, tb, pr);
-      k_scan_search<double, 2><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, tb, pr, ctl, ua, multi ? dcdf : nullptr);
-    }
+#define RS_CASE(IT, KD)                                                                   \
+  do {                                                                                    \
+    k_weight_sums<double, IT><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, 0, 0ull, tb, pr); \
+    k_scan_search<double, IT, KD><<<nt, TILE_THREADS, 0, st>>>(nullptr, dw, N, sc, tb, pr, ctl, ua, cdf); \
+  } while (0)
+    if (items == 8) { if (strat) RS_CASE(8, CSSM_RESAMPLE_STRATIFIED); else RS_CASE(8, CSSM_RESAMPLE_SYSTEMATIC); }
+    else { if (strat) RS_CASE(2, CSSM_RESAMPLE_STRATIFIED); else RS_CASE(2, CSSM_RESAMPLE_SYSTEMATIC); }
+#undef RS_CASE
     if (multi) k_multinomial_search<<<nblk(N, 256), 256, 0, st>>>(dcdf, N, du, 0u, 0u, 0u, danc, &sc->flags);
     RCU(cudaGetLastError());
     RCU(cudaMemcpyAsync(ancestors_out, danc, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -174,26 +174,36 @@ __device__ __forceinline__ float expf_det(float x) {
   return __uint_as_float(__float_as_uint(p) + ((unsigned)k << 23));  // k >= -124: the result is normal
 }
 
-// floor(w * 2^96) and floor(w*w * 2^96) of an fp32 weight 0 <= w <= 1 (0 or normal), integer only
-__device__ __forceinline__ u128 shl_u64_to_128(unsigned long long m, int s) {  // m * 2^s, s in (-128, 128), floor
-  if (s >= 64) return make_u128(0, s >= 128 ? 0ull : m << (s - 64));
-  if (s > 0) return make_u128(m << s, m >> (64 - s));
-  if (s > -64) return make_u128(m >> (-s), 0);
-  return make_u128(0, 0);
-}
+// floor(w * 2^96) of an fp32 weight 0 <= w <= 1: two exact truncating conversions, as fix_fast.
+// hi = floor(w * 2^32); when w * 2^32 >= 2^24 it is an integer and the remainder is 0, otherwise
+// the remainder w * 2^32 - hi is exact in fp32.  NaN -> 0.
 __device__ __forceinline__ u128 fix_f32(float w) {
-  const unsigned b = __float_as_uint(w);
-  const int e = (int)(b >> 23);  // sign is 0
-  if (e == 0) return make_u128(0, 0);
-  const unsigned long long m = (unsigned long long)((b & 0x7FFFFFu) | 0x800000u);
-  return shl_u64_to_128(m, e - 150 + 96);  // w = m * 2^(e-150)
+  const float a = __fmul_rn(w, 4294967296.0f);
+  const unsigned long long hi = __float2ull_rz(a);
+  const float r = __fsub_rn(a, __ull2float_rn(hi));
+  const unsigned long long lo = __float2ull_rz(__fmul_rn(r, 18446744073709551616.0f));
+  return make_u128(lo, hi);
 }
+// PTX shifts clamp the amount at the register width (an amount >= 64, or a negative one read as
+// unsigned, gives 0), which is exactly what a 128-bit shift assembled from 64-bit pieces needs
+__device__ __forceinline__ unsigned long long shl64c(unsigned long long x, int n) {
+  unsigned long long r;
+  asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n));
+  return r;
+}
+__device__ __forceinline__ unsigned long long shr64c(unsigned long long x, int n) {
+  unsigned long long r;
+  asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n));
+  return r;
+}
+// floor(w*w * 2^96) of an fp32 weight: w^2 = m^2 * 2^(2(e-150)) exactly, m^2 < 2^48; branch-free
 __device__ __forceinline__ u128 fix_sq_f32(float w) {
   const unsigned b = __float_as_uint(w);
-  const int e = (int)(b >> 23);
-  if (e == 0) return make_u128(0, 0);
-  const unsigned m = (b & 0x7FFFFFu) | 0x800000u;
-  return shl_u64_to_128((unsigned long long)m * m, 2 * (e - 150) + 96);  // w^2 = m^2 * 2^(2(e-150)), exact
+  const int e = (int)(b >> 23) & 0xff;
+  const unsigned m = (e == 0 || e == 255) ? 0u : ((b & 0x7FFFFFu) | 0x800000u);
+  const unsigned long long m2 = (unsigned long long)m * m;
+  const int s = 2 * (e - 150) + 96;  // in [-202, 50]
+  return make_u128(shl64c(m2, s) | shr64c(m2, -s), shl64c(m2, s - 64) | shr64c(m2, 64 - s));
 }
 
 // ---------------------------------------------------------------------------------------------

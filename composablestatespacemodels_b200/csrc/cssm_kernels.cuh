@@ -695,10 +695,13 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
 // ---------------------------------------------------------------------------------------------
 // K3  systematic / stratified: inclusive CDF of a tile in shared memory + ancestor search
 // ---------------------------------------------------------------------------------------------
-struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stratified), times the total
-  int kind;
-  double u, n, total;
-  const double* uarr;  // stratified, injected
+// k_i of model/Resampling.scala:69 (systematic) and :82-83 (stratified), times the total.  KIND is a
+// template parameter so that the systematic kernel carries no Philox code at all.  When n is a
+// power of two the division by n is the (exact) multiplication by inv_n -- same bits, no DDIV call.
+template <int KIND>
+struct KFun {
+  double u, n, inv_n, total;  // inv_n == 0: n is not a power of two
+  const double* uarr;         // stratified, injected
   uint32_t key0, key1, step;
   __device__ __forceinline__ double ui(long long i) const {
     if (uarr) return uarr[i];
@@ -706,15 +709,15 @@ struct KFun {  // k_i of model/Resampling.scala:69 (systematic) and :82-83 (stra
     return u64_to_unit_double(v.x, v.y);
   }
   __device__ __forceinline__ double k(long long i) const {
-    if (kind == CSSM_RESAMPLE_SYSTEMATIC) return __ddiv_rn(__dadd_rn(u, (double)i), n);
-    return __ddiv_rn(__dadd_rn((double)i, ui(i)), n);
+    const double num = (KIND == CSSM_RESAMPLE_SYSTEMATIC) ? __dadd_rn(u, (double)i) : __dadd_rn((double)i, ui(i));
+    return (inv_n != 0.0) ? __dmul_rn(num, inv_n) : __ddiv_rn(num, n);
   }
   // the key of output i in the un-normalised domain: C_j >= k_i  <=>  P_j >= k_i * total
   __device__ __forceinline__ double operator()(long long i) const { return __dmul_rn(k(i), total); }
   // number of outputs i in [0, N) with key_i <= c   (key_i is non-decreasing in i)
   __device__ long long count_le(double c, long long N) const {
     if (!(c >= 0.0)) return 0;
-    double est = c / total * n - (kind == CSSM_RESAMPLE_SYSTEMATIC ? u : 0.0);
+    double est = c / total * n - (KIND == CSSM_RESAMPLE_SYSTEMATIC ? u : 0.0);
     long long i = (est >= (double)N) ? N - 1 : (long long)floor(est);
     if (i < 0) i = 0;
     if (i > N - 1) i = N - 1;
@@ -781,7 +784,7 @@ __device__ __forceinline__ bool vanishes(double P, double w, double total) {
 struct K3Ctl {
   int parity;
   unsigned long long obs_seq, gstep;
-  int kind;             // systematic / stratified
+  double inv_n;         // 1 / (number of outputs) when that is a power of two, else 0
   int direct;           // cssm_resample: caller weights, no ll update
   int add_ll, use_u_inj;
   uint32_t key0, key1, step;
@@ -792,7 +795,7 @@ struct K3Ctl {
 
 // cdf_out == NULL: search (systematic / stratified), writes ancestors;
 // cdf_out != NULL: write the un-normalised CDF (multinomial), no search
-template <typename real, int ITEMS>
+template <typename real, int ITEMS, int KIND>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
@@ -800,6 +803,8 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   constexpr int TILE = TILE_THREADS * ITEMS;
   __shared__ double Ps[TileSmem<ITEMS>::SIZE];
   __shared__ double Ws[TileSmem<ITEMS>::SIZE];
+  constexpr int WIN = TILE + TILE_THREADS;  // outputs staged per pass (a tile has ~TILE offspring)
+  __shared__ int32_t s_res[WIN];
   __shared__ u128 s_warp[TILE_THREADS / 32];
   __shared__ u128 s_excl, s_tot, s_q;
   __shared__ unsigned long long s_key;
@@ -920,19 +925,22 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   if (!usable) {
     for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) pr.anc[pr.rank][tile0 + j] = (int32_t)((long long)pr.rank * N + tile0 + j);
   } else {
-  KFun kf{ctl.kind, s_u, (double)Ng, total, uarr, ctl.key0, ctl.key1, ctl.step};
+  KFun<KIND> kf{s_u, (double)Ng, ctl.inv_n, total, uarr, ctl.key0, ctl.key1, ctl.step};
   const double c_end = Ps[phys<ITEMS>(tile_n - 1)];
   const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
   const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
+  // the tile's range of outputs: two threads of different warps count the two ends concurrently
   if (threadIdx.x == 0) {
     s_lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_le(dbl128(excl, qb), Ng);
+    s_pend = 0x7FFFFFFFFFFFFFFFll;
+  }
+  if (threadIdx.x == 32) {
     s_hi = last_tile ? Ng : kf.count_le(c_end, Ng);
     // first weight after this tile (next tile, possibly the next rank's first particle)
     double wn = 0.0;
-    if (t < nt - 1) wn = ws(tile0 + TILE);
-    else if (pr.rank < pr.R - 1) wn = WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[pr.rank + 1]), nullptr, ps.gmax}(0);
+    if (t < nt - 1) wn = (double)ws(tile0 + TILE);
+    else if (pr.rank < pr.R - 1) wn = (double)WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[pr.rank + 1]), nullptr, ps.gmax}(0);
     s_wnext = wn;
-    s_pend = 0x7FFFFFFFFFFFFFFFll;
   }
   __syncthreads();
   const long long lo = s_lo, hi = s_hi;
@@ -940,57 +948,48 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const bool cont = !last_tile && vanishes(c_end, s_wnext, total);
   if (last_tile && threadIdx.x == 0 && kf(Ng - 1) > c_end) atomicOr(&sc->flags, FLAG_CLAMPED);  // reference would throw (m.head)
 
-  // Each thread takes 8 CONSECUTIVE outputs: one binary search for the first, then a merge walk
-  // (keys and CDF are both non-decreasing; a long jump falls back to a binary search), and the 8
-  // ancestors leave as two 16-byte stores.
-  for (long long c0 = (lo & ~7ll) + (long long)threadIdx.x * 8; c0 < hi; c0 += (long long)TILE_THREADS * 8) {
-    int res[8];
+  // Outputs [lo, hi) in passes of WIN.  Each thread takes a run of CONSECUTIVE outputs (the pass
+  // split evenly over the block): one binary search for the first, then a merge walk -- keys and
+  // CDF are both non-decreasing; a long jump falls back to a binary search.  Results are staged in
+  // shared memory and leave as fully coalesced stores.
+  for (long long win0 = lo; win0 < hi; win0 += WIN) {
+    const int n_out = (int)min((long long)WIN, hi - win0);
+    const int per = (n_out + TILE_THREADS - 1) / TILE_THREADS;
+    const int o0 = threadIdx.x * per, o1 = min(n_out, o0 + per);
     int j = 0;
-    bool first = true;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const long long i = c0 + m;
-      res[m] = 0;
-      if (i >= lo && i < hi) {
-        const double key = kf(i);
-        // first j with Ps[j] >= key (exists unless this is the clamped tail of the last tile)
-        int steps = 0;
-        if (!first)
-          while (j < tile_n - 1 && Ps[phys<ITEMS>(j)] < key && steps < 6) { ++j; ++steps; }
-        if (first || steps == 6) {
-          int a = j, b = tile_n - 1;
-          while (a < b) {
-            const int mid = (a + b) >> 1;
-            if (Ps[phys<ITEMS>(mid)] >= key) b = mid; else a = mid + 1;
-          }
-          j = a;
-          first = false;
+    for (int o = o0; o < o1; ++o) {
+      const long long i = win0 + o;
+      const double key = kf(i);
+      // first j with Ps[j] >= key (exists unless this is the clamped tail of the last tile)
+      int steps = 0;
+      if (o != o0)
+        while (j < tile_n - 1 && Ps[phys<ITEMS>(j)] < key && steps < 6) { ++j; ++steps; }
+      if (o == o0 || steps == 6) {
+        int a = j, b = tile_n - 1;
+        while (a < b) {
+          const int mid = (a + b) >> 1;
+          if (Ps[phys<ITEMS>(mid)] >= key) b = mid; else a = mid + 1;
         }
-        // TreeMap: a duplicated key keeps the last particle inserted
-        int jt = j;
-        while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
-        if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
-        res[m] = (int)(gbase + jt);
+        j = a;
+      }
+      // TreeMap: a duplicated key keeps the last particle inserted
+      int jt = j;
+      while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+      if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
+      s_res[o] = (int32_t)(gbase + jt);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < n_out; o += TILE_THREADS) {
+      const long long i = win0 + o;
+      if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+        const long long q = i / N;
+        pr.anc[q][i - q * N] = s_res[o];
+        wrote_remote |= (q != pr.rank);
+      } else {
+        pr.anc[0][i] = s_res[o];
       }
     }
-    const long long q = (pr.R > 1) ? c0 / N : 0;
-    const long long li = c0 - q * N;  // index into the owner's ancestor buffer
-    if (c0 >= lo && c0 + 8 <= hi && li + 8 <= N && (li & 3) == 0) {
-      int4* dst = reinterpret_cast<int4*>(pr.anc[q] + li);
-      dst[0] = make_int4(res[0], res[1], res[2], res[3]);
-      dst[1] = make_int4(res[4], res[5], res[6], res[7]);
-      wrote_remote |= (q != pr.rank);
-    } else {
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const long long i = c0 + m;
-        if (i >= lo && i < hi) {
-          const long long qi = (pr.R > 1) ? i / N : 0;
-          pr.anc[qi][i - qi * N] = res[m];
-          wrote_remote |= (qi != pr.rank);
-        }
-      }
-    }
+    __syncthreads();
   }
   __syncthreads();
   const long long pend = s_pend;
