@@ -160,7 +160,6 @@ __device__ __forceinline__ double exp_det(double x) {
 // fp32 weights (F32 filters): everything on the full-rate fp32 / integer pipes.  Arguments below
 // -86 give exactly 0 (the result would be subnormal in fp32); |error| < 1 ulp(fp32) above.
 __device__ __forceinline__ float expf_det(float x) {
-  if (!(x >= -86.0f)) return (x != x) ? x : 0.0f;
   const float t = __fadd_rn(__fmul_rn(x, c_expf[6]), c_expf[9]);
   const float kf = __fsub_rn(t, c_expf[9]);
   const int k = (int)(__float_as_uint(t) << 10) >> 10;  // low 22 bits of 1.5*2^23 + k, sign-extended
@@ -171,7 +170,8 @@ __device__ __forceinline__ float expf_det(float x) {
   for (int i = 1; i < 6; ++i) p = __fmaf_rn(p, r, c_expf[i]);
   p = __fmaf_rn(p, r, 1.0f);
   p = __fmaf_rn(p, r, 1.0f);
-  return __uint_as_float(__float_as_uint(p) + ((unsigned)k << 23));  // k >= -124: the result is normal
+  const float v = __uint_as_float(__float_as_uint(p) + ((unsigned)k << 23));  // k >= -124: the result is normal
+  return (x >= -86.0f) ? v : ((x != x) ? x : 0.0f);  // selects, no branch: the loads of a tile stay batched
 }
 
 // floor(w * 2^96) of an fp32 weight 0 <= w <= 1: two exact truncating conversions, as fix_fast.
@@ -196,14 +196,15 @@ __device__ __forceinline__ unsigned long long shr64c(unsigned long long x, int n
   asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n));
   return r;
 }
-// floor(w*w * 2^96) of an fp32 weight: w^2 = m^2 * 2^(2(e-150)) exactly, m^2 < 2^48; branch-free
-__device__ __forceinline__ u128 fix_sq_f32(float w) {
+// floor(w*w * 2^48) of an fp32 weight (the ESS accumulator of F32 filters; fits 64 bits):
+// w^2 = m^2 * 2^(2(e-150)) exactly, m^2 < 2^48; branch-free
+__device__ __forceinline__ unsigned long long fix_sq48_f32(float w) {
   const unsigned b = __float_as_uint(w);
   const int e = (int)(b >> 23) & 0xff;
   const unsigned m = (e == 0 || e == 255) ? 0u : ((b & 0x7FFFFFu) | 0x800000u);
   const unsigned long long m2 = (unsigned long long)m * m;
-  const int s = 2 * (e - 150) + 96;  // in [-202, 50]
-  return make_u128(shl64c(m2, s) | shr64c(m2, -s), shl64c(m2, s - 64) | shr64c(m2, 64 - s));
+  const int s = 2 * e - 252;  // in [-250, 2]
+  return shl64c(m2, s) | shr64c(m2, -s);
 }
 
 // ---------------------------------------------------------------------------------------------

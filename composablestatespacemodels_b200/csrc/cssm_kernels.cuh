@@ -519,27 +519,66 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
 template <typename real> struct WeightSrc;
 template <> struct WeightSrc<float> {
   typedef float wt;
+  static constexpr int Q2 = 48;  // quantum of the sum of squares: 2^-48 (64-bit partial sums)
   const float* logw;
   const double* direct;  // never set for fp32 filters
   double gmax;           // the max of fp32 log-weights: exactly an fp32 value
-  __device__ __forceinline__ float operator()(long long idx) const { return expf_det(__fsub_rn(logw[idx], (float)gmax)); }
+  __device__ __forceinline__ float weight(float lw) const { return expf_det(__fsub_rn(lw, (float)gmax)); }
+  __device__ __forceinline__ float operator()(long long idx) const { return weight(logw[idx]); }
   __device__ __forceinline__ static u128 fix(float w, int) { return fix_f32(w); }
-  __device__ __forceinline__ static u128 fix_sq(float w, double) { return fix_sq_f32(w); }
+  __device__ __forceinline__ static u128 fix_sq(float w, double) { return make_u128(fix_sq48_f32(w), 0); }
+  // weights of ITEMS elements base, base+stride, ...: loads first, then the arithmetic
+  template <int ITEMS>
+  __device__ __forceinline__ void load(long long base, int stride, long long N, float* wv) const {
+    float lw[ITEMS];
+    if (base + (long long)(ITEMS - 1) * stride < N) {
+      if (stride == 1 && ITEMS == 8 && (base & 3) == 0) {
+        const float4 a = *reinterpret_cast<const float4*>(logw + base), b = *reinterpret_cast<const float4*>(logw + base + 4);
+        lw[0] = a.x; lw[1] = a.y; lw[2 % ITEMS] = a.z; lw[3 % ITEMS] = a.w;
+        lw[4 % ITEMS] = b.x; lw[5 % ITEMS] = b.y; lw[6 % ITEMS] = b.z; lw[7 % ITEMS] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) lw[j] = logw[base + (long long)j * stride];
+      }
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) wv[j] = weight(lw[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        const long long idx = base + (long long)j * stride;
+        wv[j] = (idx < N) ? weight(logw[idx]) : 0.0f;
+      }
+    }
+  }
 };
 template <> struct WeightSrc<double> {
   typedef double wt;
+  static constexpr int Q2 = 96;
   const double* logw;    // in-filter source (NULL when `direct` is used)
   const double* direct;
   double gmax;
-  __device__ __forceinline__ double operator()(long long idx) const {
-    if (direct) return direct[idx];
-    return exp_det(__dsub_rn(logw[idx], gmax));
-  }
+  __device__ __forceinline__ double weight(double raw) const { return direct ? raw : exp_det(__dsub_rn(raw, gmax)); }
+  __device__ __forceinline__ double operator()(long long idx) const { return direct ? direct[idx] : weight(logw[idx]); }
   __device__ __forceinline__ static u128 fix(double w, int qb) { return fix_fast(w, qb); }
   // direct weights are pre-scaled to <= 1 by q2scale = 2^-(96-qb) before squaring
   __device__ __forceinline__ static u128 fix_sq(double w, double q2scale) {
     const double ws = __dmul_rn(w, q2scale);
     return fix_fast(__dmul_rn(ws, ws), 96);
+  }
+  template <int ITEMS>
+  __device__ __forceinline__ void load(long long base, int stride, long long N, double* wv) const {
+    const double* src = direct ? direct : logw;
+    double raw[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const long long idx = base + (long long)j * stride;
+      raw[j] = (idx < N) ? src[idx] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const long long idx = base + (long long)j * stride;
+      wv[j] = (idx < N) ? weight(raw[j]) : 0.0;
+    }
   }
 };
 
@@ -629,11 +668,7 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
   const long long base = (long long)blockIdx.x * TILE;
   u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
   wt wv[ITEMS];
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const long long idx = base + j * TILE_THREADS + threadIdx.x;
-    wv[j] = (idx < N) ? ws(idx) : (wt)0;
-  }
+  ws.template load<ITEMS>(base + threadIdx.x, TILE_THREADS, N, wv);
   wt mxv = (wt)0;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
@@ -714,8 +749,27 @@ struct KFun {
   }
   // the key of output i in the un-normalised domain: C_j >= k_i  <=>  P_j >= k_i * total
   __device__ __forceinline__ double operator()(long long i) const { return __dmul_rn(k(i), total); }
-  // number of outputs i in [0, N) with key_i <= c   (key_i is non-decreasing in i)
-  __device__ long long count_le(double c, long long N) const {
+  // count_le(P) by arithmetic.  The keys are (nearly) an arithmetic progression, so the count is
+  // floor(P*n/total - u) + 1 (systematic) or floor(P*n/total) plus one exactly evaluated key
+  // (stratified) -- unless the real number being floored is within 1e-5 of an integer: the rounding
+  // of the keys and of this estimate moves the boundary by less than 1.5e-6 for n <= 2^31, so
+  // outside that band the result is provably the exact count, inside it the exact loop decides.
+  // scale = fl(n / total).
+  __device__ __forceinline__ long long count_fast(double P, double scale, long long N) const {
+    const double x = (KIND == CSSM_RESAMPLE_SYSTEMATIC) ? __dsub_rn(__dmul_rn(P, scale), u) : __dmul_rn(P, scale);
+    const double fl = floor(x);
+    const double fr = __dsub_rn(x, fl);
+    if (!(fr >= 1e-5 && fr <= 1.0 - 1e-5) || !(x < 4.0e9) || !(x > -4.0e9)) return count_le(P, N);
+    long long i0 = (long long)fl;
+    if (KIND == CSSM_RESAMPLE_SYSTEMATIC) {
+      i0 += 1;
+    } else {
+      if (i0 >= 0 && i0 < N) i0 += ((*this)(i0) <= P) ? 1 : 0;
+    }
+    return i0 < 0 ? 0 : (i0 > N ? N : i0);
+  }
+  // number of outputs i in [0, N) with key_i <= c   (key_i is non-decreasing in i); exact, by evaluation
+  __device__ __noinline__ long long count_le(double c, long long N) const {
     if (!(c >= 0.0)) return 0;
     double est = c / total * n - (KIND == CSSM_RESAMPLE_SYSTEMATIC ? u : 0.0);
     long long i = (est >= (double)N) ? N - 1 : (long long)floor(est);
@@ -737,12 +791,11 @@ template <int ITEMS> struct TileSmem { static constexpr int SIZE = TILE_THREADS 
 // weights (as double) into Ws; `excl` = exact sum of everything before the tile.  All threads call.
 template <typename real, int ITEMS>
 __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128 excl, long long tile0, long long N,
-                                         double* Ps, double* Ws, u128* s_warp) {
+                                         double* Ps, double* Ws, u128* s_warp, double* Pv = nullptr) {
   typedef typename WeightSrc<real>::wt wt;
   const long long base = tile0 + (long long)threadIdx.x * ITEMS;
   wt wv[ITEMS];
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) wv[j] = (base + j < N) ? ws(base + j) : (wt)0;
+  ws.template load<ITEMS>(base, 1, N, wv);
   u128 e[ITEMS];
   u128 run = make_u128(0, 0);
 #pragma unroll
@@ -768,7 +821,11 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128
   if (lane == 0) ex = make_u128(0, 0);
   off = add128(off, ex);
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) Ps[phys<ITEMS>(threadIdx.x * ITEMS + j)] = dbl128(add128(off, e[j]), qb);
+  for (int j = 0; j < ITEMS; ++j) {
+    const double P = dbl128(add128(off, e[j]), qb);
+    Ps[phys<ITEMS>(threadIdx.x * ITEMS + j)] = P;
+    if (Pv) Pv[j] = P;
+  }
   __syncthreads();
 }
 
@@ -808,8 +865,10 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   __shared__ u128 s_warp[TILE_THREADS / 32];
   __shared__ u128 s_excl, s_tot, s_q;
   __shared__ unsigned long long s_key;
-  __shared__ long long s_lo, s_hi, s_pend, s_jfinal;
-  __shared__ double s_wnext, s_u;
+  constexpr int FILLCAP = 64;  // particles with more than 32 offspring: their ranges are filled by the whole block
+  __shared__ int s_cnt[TILE_THREADS], s_fill_a[FILLCAP], s_fill_b[FILLCAP], s_fill_v[FILLCAP], s_nfill;
+  __shared__ long long s_pend, s_jfinal;
+  __shared__ double s_wnext, s_u, s_scale;
   __shared__ u128 s_run;
   __shared__ int s_tp, s_brk;
 
@@ -874,6 +933,9 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
       u = u64_to_unit_double(v.x, v.y);
     }
     s_u = u;
+    s_scale = __ddiv_rn((double)Ng, total);
+    s_nfill = 0;
+    s_pend = 0x7FFFFFFFFFFFFFFFll;
     if (t == 0) {
       const double gmax = ps.gmax;
       double incr = gmax + log(total / (double)Ng);
@@ -882,7 +944,9 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
         incr = __longlong_as_double(0x7FF8000000000000ll);
         flags |= FLAG_ZERO_TOTAL;
       }
-      const double s2 = __ddiv_rn(dbl128(s_q, 96), __dmul_rn(total, total));
+      // sum (w/total)^2 = (exact sum w^2) / total^2; direct weights were pre-scaled by 2^-(96-qb)
+      const double tsc = __dmul_rn(total, __longlong_as_double((long long)(1023 - (96 - qb)) << 52));
+      const double s2 = __ddiv_rn(dbl128(s_q, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
       const double inv = floor(1.0 / s2);
       const int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
       sc->gmax = gmax;
@@ -911,7 +975,8 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   WeightSrc<real> ws{logw, direct, ps.gmax};
   const long long tile0 = (long long)t * TILE;
   const int tile_n = (int)min((long long)TILE, N - tile0);
-  tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp);
+  double Pv[ITEMS];
+  tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp, Pv);
 
   if (cdf_out != nullptr) {
     for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) cdf_out[tile0 + j] = Ps[phys<ITEMS>(j)];
@@ -929,13 +994,28 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const double c_end = Ps[phys<ITEMS>(tile_n - 1)];
   const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
   const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
-  // the tile's range of outputs: two threads of different warps count the two ends concurrently
-  if (threadIdx.x == 0) {
-    s_lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_le(dbl128(excl, qb), Ng);
-    s_pend = 0x7FFFFFFFFFFFFFFFll;
+  auto store_out = [&](long long i, int32_t val) {
+    if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+      const long long q = i / N;
+      pr.anc[q][i - q * N] = val;
+      wrote_remote |= (q != pr.rank);
+    } else {
+      pr.anc[0][i] = val;
+    }
+  };
+  // ---- offspring counts: c_j = #{outputs with key <= P_j}; particle j owns the outputs [c_{j-1}, c_j) ----
+  const double scale = s_scale;
+  const long long lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_fast(dbl128(excl, qb), scale, Ng);
+  int cr[ITEMS];  // counts relative to lo
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int idx = threadIdx.x * ITEMS + j;
+    long long c = (last_tile && idx >= tile_n - 1) ? Ng : kf.count_fast(Pv[j], scale, Ng);
+    c = c < lo ? 0 : c - lo;
+    cr[j] = (int)(c > 0x7FFFFFFFll ? 0x7FFFFFFFll : c);
   }
+  s_cnt[threadIdx.x] = cr[ITEMS - 1];
   if (threadIdx.x == 32) {
-    s_hi = last_tile ? Ng : kf.count_le(c_end, Ng);
     // first weight after this tile (next tile, possibly the next rank's first particle)
     double wn = 0.0;
     if (t < nt - 1) wn = (double)ws(tile0 + TILE);
@@ -943,53 +1023,50 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     s_wnext = wn;
   }
   __syncthreads();
-  const long long lo = s_lo, hi = s_hi;
+  const int n_out = s_cnt[TILE_THREADS - 1];
+  const long long hi = lo + n_out;
   // does the run of repeated keys at the end of this tile continue into the next tile?
   const bool cont = !last_tile && vanishes(c_end, s_wnext, total);
   if (last_tile && threadIdx.x == 0 && kf(Ng - 1) > c_end) atomicOr(&sc->flags, FLAG_CLAMPED);  // reference would throw (m.head)
 
-  // Outputs [lo, hi) in passes of WIN.  Each thread takes a run of CONSECUTIVE outputs (the pass
-  // split evenly over the block): one binary search for the first, then a merge walk -- keys and
-  // CDF are both non-decreasing; a long jump falls back to a binary search.  Results are staged in
-  // shared memory and leave as fully coalesced stores.
-  for (long long win0 = lo; win0 < hi; win0 += WIN) {
-    const int n_out = (int)min((long long)WIN, hi - win0);
-    const int per = (n_out + TILE_THREADS - 1) / TILE_THREADS;
-    const int o0 = threadIdx.x * per, o1 = min(n_out, o0 + per);
-    int j = 0;
-    for (int o = o0; o < o1; ++o) {
-      const long long i = win0 + o;
-      const double key = kf(i);
-      // first j with Ps[j] >= key (exists unless this is the clamped tail of the last tile)
-      int steps = 0;
-      if (o != o0)
-        while (j < tile_n - 1 && Ps[phys<ITEMS>(j)] < key && steps < 6) { ++j; ++steps; }
-      if (o == o0 || steps == 6) {
-        int a = j, b = tile_n - 1;
-        while (a < b) {
-          const int mid = (a + b) >> 1;
-          if (Ps[phys<ITEMS>(mid)] >= key) b = mid; else a = mid + 1;
+  // ---- expansion: small ranges are staged in shared memory and leave as coalesced stores, a range of
+  //      more than 32 outputs (a heavy particle) is filled by the whole block ------------------------------
+  {
+    int prev = threadIdx.x ? s_cnt[threadIdx.x - 1] : 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int c = cr[j];
+      if (c > prev) {
+        // TreeMap: a duplicated key keeps the last particle inserted
+        int jt = threadIdx.x * ITEMS + j;
+        while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+        if (cont && jt == tile_n - 1) atomicMin(&s_pend, lo + prev);
+        const int32_t val = (int32_t)(gbase + jt);
+        bool serial = (c - prev <= 32);
+        if (!serial) {
+          const int slot = atomicAdd(&s_nfill, 1);
+          if (slot < FILLCAP) { s_fill_a[slot] = prev; s_fill_b[slot] = c; s_fill_v[slot] = val; }
+          else serial = true;
         }
-        j = a;
-      }
-      // TreeMap: a duplicated key keeps the last particle inserted
-      int jt = j;
-      while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
-      if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
-      s_res[o] = (int32_t)(gbase + jt);
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < n_out; o += TILE_THREADS) {
-      const long long i = win0 + o;
-      if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
-        const long long q = i / N;
-        pr.anc[q][i - q * N] = s_res[o];
-        wrote_remote |= (q != pr.rank);
-      } else {
-        pr.anc[0][i] = s_res[o];
+        if (serial)
+          for (int o = prev; o < c; ++o) {
+            if (o < WIN) s_res[o] = val;
+            else store_out(lo + o, val);
+          }
+        prev = c;
       }
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < min(n_out, WIN); o += TILE_THREADS) store_out(lo + o, s_res[o]);
+  __syncthreads();  // the fills below overwrite whatever the copy-out wrote into their ranges
+  {
+    const int nfill = min(s_nfill, FILLCAP);
+    for (int f = 0; f < nfill; ++f) {
+      const int a = s_fill_a[f], b = s_fill_b[f];
+      const int32_t val = s_fill_v[f];
+      for (int o = a + threadIdx.x; o < b; o += TILE_THREADS) store_out(lo + o, val);
+    }
   }
   __syncthreads();
   const long long pend = s_pend;

@@ -356,15 +356,16 @@ void orc_ll_ess(int64_t N, const double* w1, double mx, int order, double* ll_in
     // total^2: sum (w/total)^2 = (sum w^2) / total^2
     int sh = weight_shift(N, w1);
     double sc = std::ldexp(1.0, -sh);
+    const int q2 = (order == ORC_ORDER_DEVICE_F32) ? 48 : 96;  // F32 filters: 64-bit partial sums of w^2
     u128 e = 0;
     for (int64_t i = 0; i < N; ++i) {
       volatile double ws = w1[i] * sc;
-      volatile double sq = ws * ws;
-      e += fixq(sq, 96);
+      volatile double sq = ws * ws;  // exact for fp32-valued weights
+      e += fixq(sq, q2);
     }
     volatile double ts = total * sc;
     volatile double tt = ts * ts;
-    s2 = dbl128(e, 96) / tt;
+    s2 = dbl128(e, q2) / tt;
   }
   double inv = std::floor(1 / s2);
   *ess = (inv != inv) ? 0 : (inv >= 2147483647.0 ? 2147483647 : (int32_t)inv);  // Scala .toInt saturates
