@@ -768,6 +768,26 @@ struct KFun {
     }
     return i0 < 0 ? 0 : (i0 > N ? N : i0);
   }
+  // the same count minus `lo` (as a double, lo <= count), clamped to [0, n_rel]: 32-bit arithmetic
+  __device__ __forceinline__ int count_rel(double P, double scale, long long N, long long lo, double lo_d, int n_rel) const {
+    const double x = (KIND == CSSM_RESAMPLE_SYSTEMATIC) ? __dsub_rn(__dmul_rn(P, scale), u) : __dmul_rn(P, scale);
+    const double fl = floor(x);
+    const double fr = __dsub_rn(x, fl);
+    int c;
+    if (!(fr >= 1e-5 && fr <= 1.0 - 1e-5) || !(x < 4.0e9) || !(x > -4.0e9)) {
+      const long long d = count_le(P, N) - lo;
+      c = (int)(d > 0x7FFFFFFFll ? 0x7FFFFFFFll : d);
+    } else {
+      c = __double2int_rn(__dsub_rn(fl, lo_d));  // exact integers; the conversion saturates
+      if (KIND == CSSM_RESAMPLE_SYSTEMATIC) {
+        c = (c == 0x7FFFFFFF) ? c : c + 1;
+      } else {
+        const long long i0 = (long long)fl;
+        if (i0 >= 0 && i0 < N && (*this)(i0) <= P) c = (c == 0x7FFFFFFF) ? c : c + 1;
+      }
+    }
+    return min(max(c, 0), n_rel);
+  }
   // number of outputs i in [0, N) with key_i <= c   (key_i is non-decreasing in i); exact, by evaluation
   __device__ __noinline__ long long count_le(double c, long long N) const {
     if (!(c >= 0.0)) return 0;
@@ -852,8 +872,11 @@ struct K3Ctl {
 
 // cdf_out == NULL: search (systematic / stratified), writes ancestors;
 // cdf_out != NULL: write the un-normalised CDF (multinomial), no search
+#ifndef CSSM_K3_MINBLOCKS
+#define CSSM_K3_MINBLOCKS 4
+#endif
 template <typename real, int ITEMS, int KIND>
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+__global__ void __launch_bounds__(TILE_THREADS, CSSM_K3_MINBLOCKS)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
               double* __restrict__ cdf_out) {
@@ -865,8 +888,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   __shared__ u128 s_warp[TILE_THREADS / 32];
   __shared__ u128 s_excl, s_tot, s_q;
   __shared__ unsigned long long s_key;
-  constexpr int FILLCAP = 64;  // particles with more than 32 offspring: their ranges are filled by the whole block
-  __shared__ int s_cnt[TILE_THREADS], s_fill_a[FILLCAP], s_fill_b[FILLCAP], s_fill_v[FILLCAP], s_nfill;
+  __shared__ int s_cnt[TILE_THREADS], s_cnt2[TILE_THREADS / 32];
   __shared__ long long s_pend, s_jfinal;
   __shared__ double s_wnext, s_u, s_scale;
   __shared__ u128 s_run;
@@ -934,7 +956,6 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     }
     s_u = u;
     s_scale = __ddiv_rn((double)Ng, total);
-    s_nfill = 0;
     s_pend = 0x7FFFFFFFFFFFFFFFll;
     if (t == 0) {
       const double gmax = ps.gmax;
@@ -994,25 +1015,16 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const double c_end = Ps[phys<ITEMS>(tile_n - 1)];
   const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
   const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
-  auto store_out = [&](long long i, int32_t val) {
-    if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
-      const long long q = i / N;
-      pr.anc[q][i - q * N] = val;
-      wrote_remote |= (q != pr.rank);
-    } else {
-      pr.anc[0][i] = val;
-    }
-  };
   // ---- offspring counts: c_j = #{outputs with key <= P_j}; particle j owns the outputs [c_{j-1}, c_j) ----
   const double scale = s_scale;
   const long long lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_fast(dbl128(excl, qb), scale, Ng);
+  const double lo_d = (double)lo;
+  const int n_rel = (int)(Ng - lo);
   int cr[ITEMS];  // counts relative to lo
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const int idx = threadIdx.x * ITEMS + j;
-    long long c = (last_tile && idx >= tile_n - 1) ? Ng : kf.count_fast(Pv[j], scale, Ng);
-    c = c < lo ? 0 : c - lo;
-    cr[j] = (int)(c > 0x7FFFFFFFll ? 0x7FFFFFFFll : c);
+    cr[j] = (last_tile && idx >= tile_n - 1) ? n_rel : kf.count_rel(Pv[j], scale, Ng, lo, lo_d, n_rel);
   }
   s_cnt[threadIdx.x] = cr[ITEMS - 1];
   if (threadIdx.x == 32) {
@@ -1029,43 +1041,63 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const bool cont = !last_tile && vanishes(c_end, s_wnext, total);
   if (last_tile && threadIdx.x == 0 && kf(Ng - 1) > c_end) atomicOr(&sc->flags, FLAG_CLAMPED);  // reference would throw (m.head)
 
-  // ---- expansion: small ranges are staged in shared memory and leave as coalesced stores, a range of
-  //      more than 32 outputs (a heavy particle) is filled by the whole block ------------------------------
+  // ---- expansion, WIN outputs per pass: every particle with offspring drops its local index at the
+  //      head of its range, an inclusive max-scan (indices grow with the position) fills the ranges,
+  //      and the pass leaves as coalesced stores.  A heavy particle simply spans many passes. ----------
   {
-    int prev = threadIdx.x ? s_cnt[threadIdx.x - 1] : 0;
+    constexpr int PER = WIN / TILE_THREADS;  // outputs per thread and pass
+    const int prev0 = threadIdx.x ? s_cnt[threadIdx.x - 1] : 0;
+    int carry = 0;  // local index of the particle that owns the last output of the previous pass
+    for (int w0 = 0; w0 < n_out; w0 += WIN) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const int c = cr[j];
-      if (c > prev) {
-        // TreeMap: a duplicated key keeps the last particle inserted
-        int jt = threadIdx.x * ITEMS + j;
-        while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
-        if (cont && jt == tile_n - 1) atomicMin(&s_pend, lo + prev);
-        const int32_t val = (int32_t)(gbase + jt);
-        bool serial = (c - prev <= 32);
-        if (!serial) {
-          const int slot = atomicAdd(&s_nfill, 1);
-          if (slot < FILLCAP) { s_fill_a[slot] = prev; s_fill_b[slot] = c; s_fill_v[slot] = val; }
-          else serial = true;
+      for (int k = 0; k < PER; ++k) s_res[threadIdx.x * PER + k] = -1;
+      __syncthreads();
+      {
+        int prev = prev0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          if (cr[j] > prev && prev >= w0 && prev < w0 + WIN) s_res[prev - w0] = threadIdx.x * ITEMS + j;
+          prev = cr[j];
         }
-        if (serial)
-          for (int o = prev; o < c; ++o) {
-            if (o < WIN) s_res[o] = val;
-            else store_out(lo + o, val);
-          }
-        prev = c;
       }
-    }
-  }
-  __syncthreads();
-  for (int o = threadIdx.x; o < min(n_out, WIN); o += TILE_THREADS) store_out(lo + o, s_res[o]);
-  __syncthreads();  // the fills below overwrite whatever the copy-out wrote into their ranges
-  {
-    const int nfill = min(s_nfill, FILLCAP);
-    for (int f = 0; f < nfill; ++f) {
-      const int a = s_fill_a[f], b = s_fill_b[f];
-      const int32_t val = s_fill_v[f];
-      for (int o = a + threadIdx.x; o < b; o += TILE_THREADS) store_out(lo + o, val);
+      __syncthreads();
+      // inclusive max-scan of s_res: thread-local, then across the block
+      int v[PER];
+      int run = -1;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) { run = max(run, s_res[threadIdx.x * PER + k]); v[k] = run; }
+      int incl = run;
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = max(incl, o); }
+      if (lane == 31) s_cnt2[wid] = incl;
+      __syncthreads();
+      int before = carry;
+      for (int ww = 0; ww < wid; ++ww) before = max(before, s_cnt2[ww]);
+      { const int o = __shfl_up_sync(0xffffffffu, incl, 1); if (lane > 0) before = max(before, o); }
+      carry = max(carry, s_cnt2[TILE_THREADS / 32 - 1]);
+      for (int ww = 0; ww < TILE_THREADS / 32 - 1; ++ww) carry = max(carry, s_cnt2[ww]);
+#pragma unroll
+      for (int k = 0; k < PER; ++k) s_res[threadIdx.x * PER + k] = max(v[k], before);
+      __syncthreads();
+      // copy-out: the duplicate-key rule per output, then a coalesced store
+      const int n_w = min(WIN, n_out - w0);
+      for (int o = threadIdx.x; o < n_w; o += TILE_THREADS) {
+        int jt = s_res[o];
+        // TreeMap: a duplicated key keeps the last particle inserted
+        while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+        const long long i = lo + w0 + o;
+        if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
+        const int32_t val = (int32_t)(gbase + jt);
+        if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+          const long long q = i / N;
+          pr.anc[q][i - q * N] = val;
+          wrote_remote |= (q != pr.rank);
+        } else {
+          pr.anc[0][i] = val;
+        }
+      }
+      __syncthreads();
     }
   }
   __syncthreads();
