@@ -1,16 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- particle-steps/sec of the bootstrap particle filter hot path on B200.
+"""bench.py -- the bootstrap particle filter hot path on B200 (BASELINE.json metric).
 
-One "step" = one llFilter (model/ParticleFilter.scala:137-140) over T observations with N
-particles on each GPU: init + T x (propagate, weight, log-sum-exp, resample).  Metric =
-particle-steps/sec = N * T / time, summed over the GPUs of the job (each rank filters its own
-independent cloud: the reference's only parallelism is across independent filters / PMMH chains,
-so scaling is weak and there is no data-path collective).
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload target|c2|c1|c3|c4|c5] [--impl reference]
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload target|c2|c1|c4|c5|c3] [--impl reference]
+Workloads:
+  target  Poisson + seasonal(24,3) + OU, 2^24 particles x 1000 observations, systematic   (default)
+  c2      the same model, 2^20 particles                                  (BASELINE.json configs[1])
+  c1      Poisson + OU, 1000 particles x 500 observations                 (configs[0], the CPU-sized case)
+  c3      LGCP + Brownian motion, 2^22 particles x 200 events, stratified, 10^-3 sub-steps (configs[2])
+  c4      PMMH, negative binomial + linear trend, 2^16 particles x 500 observations per likelihood
+          evaluation, one chain per GPU; metric = PMMH iterations/sec     (configs[3])
+  c5      ONE filter of 2^27 particles, Normal + seasonal + OU, 100 observations, sharded over the
+          GPUs of the job (in-kernel NVLink exchange); strong scaling      (configs[4])
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
-(oracle/, all host cores, independent filters in parallel) on a bounded sample of the same workload.
+One "step" = one llFilter (model/ParticleFilter.scala:137-140) over the T observations -- for c4 one
+PMMH iteration (model/PMMH.scala:68-81).  For target/c1/c2/c3/c4 every rank runs its own independent
+filter / chain (the reference's only parallelism: Streaming.pilotRun, PMMH chains), so scaling is
+weak and there is no data-path collective; c5 shards one cloud and the ranks exchange inside the
+kernels.  Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
+reference (oracle/, all host cores) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -26,43 +34,51 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (description, model builder name, particles, observations, resampler, dt)
+    # name: (description, model builder name, particles, observations, resampler)
     "target": ("composed Poisson + seasonal(24,3) + OU, 2^24 particles x 1000 observations, systematic, fp32 "
                "(BASELINE.json target)", "c2", 1 << 24, 1000, "systematic"),
     "c2": ("composed Poisson + seasonal(24,3) + OU, 2^20 particles x 1000 observations, systematic, fp32 "
            "(BASELINE.json configs[1])", "c2", 1 << 20, 1000, "systematic"),
     "c1": ("Poisson + OU, 1000 particles x 500 observations, systematic (BASELINE.json configs[0])", "c1", 1000, 500,
            "systematic"),
-    "c4": ("negative binomial + linear trend, 2^16 particles x 500 observations, systematic (configs[3] likelihood)", "c4",
-           1 << 16, 500, "systematic"),
-    "c5": ("Normal + seasonal(24,3) + OU, 2^24 particles per GPU x 100 observations, systematic (configs[4] per-rank shard)",
-           "c5", 1 << 24, 100, "systematic"),
-    "c3": ("LGCP + Brownian motion, 2^22 particles x 200 events, stratified, precision 3 (configs[2])", "c3", 1 << 22, 200,
-           "stratified"),
+    "c4": ("PMMH, negative binomial + linear trend, 2^16 particles x 500 observations per likelihood evaluation, "
+           "one chain per GPU (BASELINE.json configs[3])", "c4", 1 << 16, 500, "systematic"),
+    "c5": ("ONE filter, Normal + seasonal(24,3) + OU, 2^27 particles x 100 observations, systematic, sharded over the "
+           "GPUs of the job (BASELINE.json configs[4])", "c5", 1 << 27, 100, "systematic"),
+    "c3": ("LGCP + Brownian motion, 2^22 particles x 200 events, stratified, sub-step 10^-3 (BASELINE.json configs[2])",
+           "c3", 1 << 22, 200, "stratified"),
 }
 
 
-def build_model(name):
+def build_unparam(name):
+    """(unparameterised model, parameters) with the reference's example values."""
     from composablestatespacemodels_b200 import Model, Sde, SdeParameter, Parameters
-    import composablestatespacemodels_b200 as cs
     ou1 = SdeParameter.ouParameter([1.0], [0.5], [0.2], [1.5], [0.05])   # examples/Simulation.scala:16
     ou6 = SdeParameter.ouParameter([0.1], [1.0], [0.4], [0.1], [0.5])    # examples/Simulation.scala:64-67
     if name == "c1":
-        return Model.poisson(Sde.ouProcess(1))(Parameters(None, ou1))
+        return Model.poisson(Sde.ouProcess(1)), Parameters(None, ou1)
     if name == "c2":
-        return (Model.poisson(Sde.ouProcess(1)) | Model.seasonal(24, 3, Sde.ouProcess(6)))(
-            Parameters(None, ou1) | Parameters(None, ou6))
+        return (Model.poisson(Sde.ouProcess(1)) | Model.seasonal(24, 3, Sde.ouProcess(6)),
+                Parameters(None, ou1) | Parameters(None, ou6))
     if name == "c4":
-        return (Model.negativeBinomial(Sde.brownianMotion(1)) | Model.linear(Sde.genBrownianMotion(1)))(
-            Parameters(2.0, SdeParameter.brownianParameter([0.0], [1.0], [0.01])) |
-            Parameters(None, SdeParameter.genBrownianParameter([0.0], [1.0], [0.01], [0.01])))
+        return (Model.negativeBinomial(Sde.brownianMotion(1)) | Model.linear(Sde.genBrownianMotion(1)),
+                Parameters(2.0, SdeParameter.brownianParameter([0.0], [1.0], [0.01])) |
+                Parameters(None, SdeParameter.genBrownianParameter([0.0], [1.0], [0.01], [0.01])))
     if name == "c5":
-        return (Model.linear(Sde.ouProcess(1)) | Model.seasonal(24, 3, Sde.ouProcess(6)))(
-            Parameters(0.0, ou1) | Parameters(None, ou6))
+        return (Model.linear(Sde.ouProcess(1)) | Model.seasonal(24, 3, Sde.ouProcess(6)),
+                Parameters(0.0, ou1) | Parameters(None, ou6))
     if name == "c3":
-        m = Model.lgcp(Sde.brownianMotion(1))(Parameters(None, SdeParameter.brownianParameter([0.0], [1.0], [0.01])))
-        return cs.model.Model(m.leaves, m.step_mode, 3)
+        return Model.lgcp(Sde.brownianMotion(1)), Parameters(None, SdeParameter.brownianParameter([0.0], [1.0], [0.01]))
     raise SystemExit(f"unknown model {name}")
+
+
+def build_model(name):
+    import composablestatespacemodels_b200 as cs
+    um, p = build_unparam(name)
+    m = um(p)
+    if name == "c3":
+        return cs.model.Model(m.leaves, m.step_mode, 3)  # FilterLgcp precision 3: sub-step 10^-3
+    return m
 
 
 def synth_series(mod, wl_model, T):
@@ -128,8 +144,10 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_baseline(wl_model, resampler, T_full, budget_s, threads):
-    """The CPU restatement of the reference (oracle/, kind "port") on a bounded sample."""
+def cpu_baseline(wl_model, resampler, T_full, budget_s, threads, pmmh=False):
+    """The CPU restatement of the reference (oracle/, kind "port") on a bounded sample.
+    Particle-steps/s of llFilter; for PMMH the iteration rate that follows from it (an iteration IS
+    one llFilter of N x T particle-steps plus O(#parameters) host work, model/PMMH.scala:68-81)."""
     import oracle
     from composablestatespacemodels_b200.resampling import Resampling
     mod = build_model(wl_model)
@@ -138,28 +156,35 @@ def cpu_baseline(wl_model, resampler, T_full, budget_s, threads):
     T = min(T_full, 100 if wl_model != "c3" else 10)
     t, y = synth_series(mod, wl_model, T)
     # calibrate on a small cloud, then size the sample for ~budget_s seconds of CPU work
-    n0 = 2048
+    n0 = 2048 if wl_model != "c3" else 256
     t0 = time.perf_counter()
     orc.filter_ll(n0, kind, t, y, seed=1, variant=1)
     rate0 = n0 * T / (time.perf_counter() - t0)
-    n = int(min(1 << 18, max(4096, rate0 * budget_s / T)))
+    n = int(min(1 << 18, max(1024, rate0 * budget_s / T)))
     t0 = time.perf_counter()
     orc.filter_ll_many(n, kind, t, y, seed=2, variant=1, R=threads, threads=threads)
     el = time.perf_counter() - t0
     flat = threads * n * T / el
     # the reference-faithful cost model (per-particle objects, TreeMap ECDF) on a smaller sample
-    nf = max(1024, n // 8)
+    nf = max(512, n // 8)
     t0 = time.perf_counter()
     orc.filter_ll_many(nf, kind, t, y, seed=3, variant=0, R=threads, threads=threads)
     faithful = threads * nf * T / (time.perf_counter() - t0)
-    return {"value": flat, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{threads} independent filter(s), {n} particles x {T} observations each, flat-array C++ restatement "
-                      f"(oracle/, fp64); reference-faithful variant (per-particle objects + std::map ECDF, {nf} particles): "
-                      f"{faithful:.3e} particle-steps/s",
-            "faithful_value": faithful}
+    out = {"value": flat, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+           "sample": f"{threads} independent filter(s), {n} particles x {T} observations each, flat-array C++ restatement "
+                     f"(oracle/, fp64); reference-faithful variant (per-particle objects + std::map ECDF, {nf} particles): "
+                     f"{faithful:.3e} particle-steps/s",
+           "faithful_value": faithful}
+    if pmmh:
+        N, Tf = WORKLOADS["c4"][2], WORKLOADS["c4"][3]
+        out["particle_steps_per_s"] = flat
+        out["value"] = flat / (N * Tf)
+        out["unit"] = "pmmh-iterations/s"
+        out["sample"] += f"; iterations/s = particle-steps/s / ({N} x {Tf}), {threads} chain(s), one per core"
+    return out
 
 
-def run_reference(args, wl):
+def run_reference(args, wl, wl_name):
     """--impl reference: the reference's CPU algorithm (oracle port; the Scala original cannot run:
     no JVM in this image) on all host cores, bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -167,20 +192,23 @@ def run_reference(args, wl):
         return
     desc, wl_model, N, T, resampler = wl
     cores = os.cpu_count() or 1
+    pmmh = wl_name == "c4"
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(wl_model, resampler, T, budget_s=max(2.0, 20.0 / max(1, args.steps)), threads=cores)
+        last = cpu_baseline(wl_model, resampler, T, budget_s=max(2.0, 20.0 / max(1, args.steps)), threads=cores, pmmh=pmmh)
         if i >= args.warmup:
             vals.append(last["value"])
     v = float(np.mean(vals))
     last["value"] = v
-    out = {"metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    metric, unit = ("pmmh-iterations/sec", "pmmh-iterations/s") if pmmh else ("particle-steps/sec", "particle-steps/s")
+    out = {"metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+           "scaling": "strong" if wl_name == "c5" else "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "impl": "reference",
            "config": {"workload": desc, "note": "CPU restatement of the reference (not the JVM), bounded sample"},
            "cpu_baseline": last,
-           "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
 
@@ -188,11 +216,11 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default 5; 100 PMMH iterations for c4)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
-    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--particles", type=int, default=0, help="override particles (per GPU; for c5 the global count)")
     ap.add_argument("--obs", type=int, default=0, help="override number of observations")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -202,13 +230,15 @@ def main():
         wl[2] = args.particles
     if args.obs:
         wl[3] = args.obs
+    if not args.steps:
+        args.steps = 100 if args.workload == "c4" else 5
     if args.impl == "reference":
-        return run_reference(args, wl)
+        return run_reference(args, wl, args.workload)
 
     import torch
     import torch.distributed as dist
     import composablestatespacemodels_b200 as cs
-    from composablestatespacemodels_b200 import _abi
+    from composablestatespacemodels_b200 import _abi, sharding
     from composablestatespacemodels_b200.resampling import Resampling
 
     rank = int(os.environ.get("RANK", "0"))
@@ -221,100 +251,196 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     desc, wl_model, N, T, resampler = wl
+    sharded = args.workload == "c5"
+    pmmh = args.workload == "c4"
     mod = build_model(wl_model)
     t, y = synth_series(mod, wl_model, T)
     dtype = _abi.F32 if args.dtype == "f32" else _abi.F64
     b = 4 if dtype == _abi.F32 else 8
     d = mod.dimension
-    h = cs.GpuFilterHandle(mod, Resampling.kind_of(resampler), N, dtype=dtype, device=local, seed=2, stream_id=rank)
+    kind = Resampling.kind_of(resampler)
     stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)
-    h.load_series(t, y)  # inputs resident in HBM before the timed region
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        h.ll_resident()
-    # ---- timed region: K steps, device events on the launching stream, max over ranks ----------
+    def max_over_ranks(v):
+        if world > 1:
+            tv = torch.tensor([v], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            return float(tv.item())
+        return v
+
+    if sharded:
+        # ONE cloud of N particles over `world` GPUs; rank r owns the slots [r*N/world, (r+1)*N/world)
+        if world > 1:
+            h = sharding.create_sharded(mod, kind, N, dtype=dtype, device=local, seed=2)
+        else:
+            h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, device=local, seed=2)
+        n_local, n_total = N // world, N
+    else:
+        h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, device=local, seed=2, stream_id=rank)
+        n_local, n_total = N, N * world
+    h.set_stream(stream.cuda_stream)
+    h.load_series(t, y)  # inputs resident in HBM before the timed region
+
     sampler = ClockSampler(local)
-    h.profile(10)  # per-kernel CUDA events on every 10th observation (roofline of the dominant kernel)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
     launches = 0
     lls = []
-    for _ in range(args.steps):
-        lls.append(h.ll_resident())
-        launches += h.last_launches()
-    e1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    prof = h.profile_read()
-    h.profile(0)
-    if world > 1:
-        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    value = world * N * T * args.steps / (ms * 1e-3)
-
-    # ---- end to end through the public API: host observations in, log-likelihood out ----------
-    from composablestatespacemodels_b200 import Filter, Data
-    data = [Data(tt, yy) for tt, yy in zip(t, y)]
-    flt = Filter(mod, Resampling.systematicResampling if resampler == "systematic" else Resampling.stratifiedResampling,
-                 dtype=dtype, device=local, seed=3, stream_id=rank) if wl_model != "c3" else None
-    h.close()
-    if flt is not None:
-        flt.llFilter(data[: max(2, T // 50)], N)  # allocate the cloud once (not timed), as a long-lived filter would
+    extra = {}
+    if pmmh:
+        # ---- PMMH: K iterations of the chain; every iteration = new parameters + one llFilter ----------
+        from composablestatespacemodels_b200 import MetropolisHastings, GpuBootstrapFilter, Data, perturb
+        h.close()
+        um, p0 = build_unparam(wl_model)
+        data = [Data(tt, yy) for tt, yy in zip(t, y)]
+        rng = np.random.default_rng(100 + rank)
+        pf = GpuBootstrapFilter(um, p0, data, Resampling.systematicResampling, N, dtype=dtype, device=local, seed=5,
+                                stream_id=rank)
+        pf.handle.set_stream(stream.cuda_stream)
+        # examples/DetermineParameters.scala:59,73: Parameters.perturb(0.05), flat prior, symmetric proposal
+        mh = MetropolisHastings(p0, perturb(0.05, rng), lambda a, c: 0.0, lambda p: 0.0, pf, rng)
+        it = mh.iters()
+        for _ in range(args.warmup):
+            next(it)
+        pf.handle.profile(50)
         barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
-        k_e2e = max(1, min(args.steps, 3))
-        for _ in range(k_e2e):
-            flt.llFilter(data, N)
+        e0.record(stream)
+        acc0 = None
+        for _ in range(args.steps):
+            s = next(it)
+            lls.append(s.ll)
+            launches += pf.handle.last_launches() + 1
+        e1.record(stream)
         torch.cuda.synchronize()
-        el = time.perf_counter() - w0
-        if world > 1:
-            tel = torch.tensor([el], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tel, op=dist.ReduceOp.MAX)
-            el = float(tel.item())
-        e2e_v = world * N * T * k_e2e / el
-        flt.close()
+        wall = time.perf_counter() - w0
+        barrier()
+        clocks = sampler.stop()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        wall = max_over_ranks(wall)
+        prof = pf.handle.profile_read()
+        value = world * args.steps / (ms * 1e-3)
+        e2e_v = world * args.steps / wall
+        extra = {"accepted": int(s.accepted), "particle_steps_per_s": value * N * T,
+                 "device_ms_per_likelihood": pf.handle.last_elapsed_ms()}
+        e2e = {"value": e2e_v, "unit": "pmmh-iterations/s", "h2d_bytes_per_step": int(T * 17), "d2h_bytes_per_step": 8 + 8 * d,
+               "note": "MetropolisHastings(...).iters() with a GpuBootstrapFilter: per iteration the proposed parameters go "
+                       "in (per-observation constants rebuilt on the host), one log-likelihood and one sampled state come "
+                       "out; wall clock"}
+        pf.close()
     else:
-        e2e_v = None
-    e2e = {"value": e2e_v, "unit": "particle-steps/s", "h2d_bytes_per_step": int(T * 17), "d2h_bytes_per_step": 8,
-           "note": "Filter.llFilter(data, n): host observations (t, y, has_obs) in, per-observation constants built on the "
-                   "host and passed as kernel arguments, one fp64 log-likelihood out; wall clock"}
+        for _ in range(args.warmup):
+            h.ll_resident()
+        # ---- timed region: K steps, device events on the launching stream, max over ranks ----------
+        h.profile(10)  # per-kernel CUDA events on every 10th observation (roofline of the dominant kernel)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            lls.append(h.ll_resident())
+            launches += h.last_launches()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        prof = h.profile_read()
+        h.profile(0)
+        value = n_total * T * args.steps / (ms * 1e-3)
+
+        # ---- end to end through the public API: host observations in, log-likelihood out ----------
+        from composablestatespacemodels_b200 import Filter, FilterLgcp, Data
+        data = [Data(tt, yy) for tt, yy in zip(t, y)]
+        k_e2e = max(1, min(args.steps, 3))
+        if sharded:
+            # the sharded handle IS the public object (there is no reference class for it): host series in, ll out
+            h.ll_arrays(t, y)
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(k_e2e):
+                h.ll_arrays(t, y)
+            torch.cuda.synchronize()
+            el = max_over_ranks(time.perf_counter() - w0)
+            h.close()
+        else:
+            h.close()
+            rs = Resampling.systematicResampling if resampler == "systematic" else Resampling.stratifiedResampling
+            if wl_model == "c3":
+                flt = FilterLgcp(mod, rs, 3, dtype=dtype, device=local, seed=3, stream_id=rank)
+            else:
+                flt = Filter(mod, rs, dtype=dtype, device=local, seed=3, stream_id=rank)
+            flt.llFilter(data[: max(2, T // 50)], N)  # allocate the cloud once (not timed), as a long-lived filter would
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(k_e2e):
+                flt.llFilter(data, N)
+            torch.cuda.synchronize()
+            el = max_over_ranks(time.perf_counter() - w0)
+            flt.close()
+        e2e_v = n_total * T * k_e2e / el
+        e2e = {"value": e2e_v, "unit": "particle-steps/s", "h2d_bytes_per_step": int(T * 17), "d2h_bytes_per_step": 8,
+               "note": "Filter.llFilter(data, n): host observations (t, y, has_obs) in, per-observation constants built on the "
+                       "host and passed as kernel arguments, one fp64 log-likelihood out; wall clock"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
         k1_ms, k1_n = prof["propagate_weight"]
-        k1_bytes = (2 * d * b + b + 4) * N  # anc + gathered state in, state + log-weight out
+        k1_bpp = 2 * d * b + b + 4  # anc + gathered state in, state + log-weight out
         roof = None
-        if k1_n:
-            ach = k1_bytes / (k1_ms / k1_n * 1e-3) / 1e9
-            step_bytes = (4 * d * b + 5 * b + 8) * N * T * args.steps  # SURVEY.md 8(d) B_step accounting
+        if k1_n and wl_model != "c3":
+            ach = k1_bpp * n_local / (k1_ms / k1_n * 1e-3) / 1e9
+            per_launch = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}
+            tot = sum(per_launch.values())
+            # what one observed step moves with the gather fused into the next propagate and no CDF written:
+            # K1 2db+b+4, K2 b, K3 b+4
+            real_bpp = k1_bpp + b + b + 4
             roof = {"bound": "hbm", "kernel": "k_propagate_weight (gather + propagate + weight, fused)",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_particle": 2 * d * b + b + 4,
+                    "peak_source": peak_src, "algorithmic_bytes_per_particle": k1_bpp,
                     "avg_launch_ms": k1_ms / k1_n, "sampled_launches": k1_n,
-                    "step_frac_survey_accounting": step_bytes / (ms * 1e-3) / 1e9 / peak,
-                    "kernel_share_of_step": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}}
+                    "kernel_ms_per_launch": per_launch,
+                    "whole_step": {"bytes_per_particle_fused": real_bpp,
+                                   "achieved_gbs_fused": real_bpp * n_local / (tot * 1e-3) / 1e9 if tot else None,
+                                   "frac_fused": real_bpp * n_local / (tot * 1e-3) / 1e9 / peak if tot else None,
+                                   "bytes_per_particle_survey_8d": 4 * d * b + 5 * b + 8,
+                                   "frac_survey_8d": (4 * d * b + 5 * b + 8) * n_local / (tot * 1e-3) / 1e9 / peak if tot else None}}
+        elif k1_n:
+            # LGCP: the state lives in registers for ~100 sub-steps per event: SFU/ALU bound, not HBM bound
+            nsub = float(np.sum(np.ceil(np.diff(np.concatenate([[t[0]], t])) / 1e-3)))
+            roof = {"bound": "hbm", "kernel": "k_lgcp_weight (sub-stepped propagate + hazard, fused)",
+                    "achieved": k1_bpp * n_local / (k1_ms / k1_n * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": k1_bpp * n_local / (k1_ms / k1_n * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "note": "instruction bound: Philox + Box-Muller + exp per sub-step, state in registers",
+                    "particle_substeps_per_s": n_total * nsub * args.steps / (ms * 1e-3),
+                    "avg_launch_ms": k1_ms / k1_n, "sampled_launches": k1_n}
         cpu = None
         if not args.no_cpu:
-            cpu = cpu_baseline(wl_model, resampler, T, budget_s=12.0, threads=1)
-        out = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            cpu = cpu_baseline(wl_model, resampler, T, budget_s=12.0, threads=1, pmmh=pmmh)
+        metric, unit = ("pmmh-iterations/sec", "pmmh-iterations/s") if pmmh else ("particle-steps/sec", "particle-steps/s")
+        if sharded:
+            par = (f"one filter of {n_total} particles sharded over {world} GPU(s), {n_local} per GPU; per step three in-kernel "
+                   "exchanges (max, sums, done) + ancestor scatter / parent gather over NVLink peer pointers" if world > 1
+                   else "one filter on one GPU (the unsharded case of the strong-scaling series)")
+        else:
+            par = f"{world} independent {'chain' if pmmh else 'filter'}(s), one per GPU, no collective"
+        ws_bytes = k1_bpp * n_local
+        out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "strong" if sharded else "weak",
                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-               "config": {"workload": desc, "particles_per_gpu": N, "observations": T, "latent_dim": d, "resampler": resampler,
+               "config": {"workload": desc, "particles_per_gpu": n_local, "particles_total": n_total, "observations": T,
+                          "latent_dim": d, "resampler": resampler,
                           "l2": "working set %.0f MB per GPU %s the 126 MB L2, no flush" % (
-                              (2 * d * b + b + 4) * N / 1e6, "exceeds" if (2 * d * b + b + 4) * N > 126e6 else "is below"),
-                          "parallelism": f"{world} independent filter(s), one per GPU, no collective"},
+                              ws_bytes / 1e6, "exceeds" if ws_bytes > 126e6 else "is below"),
+                          "parallelism": par},
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                "log_likelihood_mean": float(np.mean(lls))}
+        out.update(extra)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
