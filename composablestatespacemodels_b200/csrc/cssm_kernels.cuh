@@ -67,6 +67,7 @@ struct StepAcc {
 struct FilterScalars {
   StepAcc acc[2];
   unsigned long long ticket1, ticket2, ticket3;  // monotone "last block" tickets of K1 / K2 / K3
+  unsigned long long gate1, gate2, gate3;        // sharded: highest exchange value already seen complete by a block
   double ll, ll_incr, u_inj;
   double gmax, total;  // of the last observed step (read-back of w1, tests)
   int ess, flags, qb, pad;
@@ -169,22 +170,36 @@ template <> struct Normals<double> {
 // spin until *p >= want.  Bounded: after 4 s the filter is flagged and every later wait returns
 // at once, so a dead peer costs seconds, not a hung GPU.
 __device__ __forceinline__ void wait_ge(const unsigned long long* p, unsigned long long want, FilterScalars* sc) {
-  if (ld_acquire_sys(p) >= want) return;
+  if (ld_relaxed_sys(p) >= want) return;
   if (*(volatile int*)&sc->flags & FLAG_COMM_TIMEOUT) return;
   const unsigned long long t0 = global_timer_ns();
-  while (ld_acquire_sys(p) < want) {
-    __nanosleep(64);
+  while (ld_relaxed_sys(p) < want) {
+    __nanosleep(32);
     if (global_timer_ns() - t0 > 4000000000ull) {
       atomicOr(&sc->flags, FLAG_COMM_TIMEOUT);
       return;
     }
   }
 }
-// one thread: wait for every peer's progress counter (steps completed) to reach `gstep`
-__device__ __forceinline__ void wait_progress(const Peers& pr, unsigned long long gstep, FilterScalars* sc) {
-  const XchSlot* mine = pr.xch[pr.rank];
-  for (int q = 0; q < pr.R; ++q)
-    if (q != pr.rank) wait_ge(&mine[q].progress, gstep, sc);
+// First warp of a block: wait until the flag every peer q keeps in our memory (flag_of(q)) has
+// reached `want`.  Lane q polls peer q, so the R waits overlap; and once one block has seen all of
+// them the per-filter gate lets every later block through with a single L2 read.  No load of the
+// exchanged data (or of peer clouds) is issued by any block before it has passed here, and L1 is
+// clean at kernel entry, so the relaxed polling cannot be followed by a stale read.
+template <typename FlagOf>
+__device__ __forceinline__ void gate_wait(unsigned long long* gate, unsigned long long want, const Peers& pr, FilterScalars* sc,
+                                          FlagOf flag_of) {
+  if (threadIdx.x < 32) {
+    if (ld_gpu(gate) < want) {
+      if ((int)threadIdx.x < pr.R) wait_ge(flag_of((int)threadIdx.x), want, sc);
+      __syncwarp();
+      if (threadIdx.x == 0) {
+        (void)ld_acquire_sys(flag_of(pr.rank));  // orders this block's later reads after the flags
+        atomicMax(gate, want);
+      }
+    }
+  }
+  __syncthreads();
 }
 __device__ __forceinline__ void push_progress(const Peers& pr, unsigned long long gstep_done) {
   __threadfence_system();
@@ -295,8 +310,8 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
   griddep_wait();
   griddep_launch();
   if (pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
-    if (threadIdx.x == 0) wait_progress(pr, ctl.gstep, ctl.sc);
-    __syncthreads();
+    const XchSlot* mine = pr.xch[pr.rank];
+    gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
   }
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PPT;
   const bool full = (i0 + PPT <= N);
@@ -445,8 +460,8 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
   griddep_wait();
   griddep_launch();
   if (pr.R > 1) {
-    if (threadIdx.x == 0) wait_progress(pr, ctl.gstep, ctl.sc);
-    __syncthreads();
+    const XchSlot* mine = pr.xch[pr.rank];
+    gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
   }
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < N;
@@ -468,30 +483,33 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
     for (int k = 0; k < DP; ++k) x[k] = (k < a.d) ? src[(long long)k * Ns] : (real)0;
     unsigned long long slot = slot0 + (unsigned long long)i;
     real hz = (real)0;
-    const uint32_t calls = (uint32_t)((a.d + PC - 1) / PC);
+    // the normals of this particle and step form one stream n = s*d + k; Philox call n / PC yields
+    // elements n % PC, so every generated normal is used (a d = 1 model takes one call per 4 sub-steps)
+    real zb[PC];
+    int zpos = PC;
+    uint32_t ncall = 0;
     for (long long s = 0; s < n_sub; ++s) {
       real gs = (real)0;
 #pragma unroll
-      for (int kk = 0; kk < DP; kk += PC) {
-        real z[PC];
-        if (kk < a.d) {
+      for (int k = 0; k < DP; ++k) {
+        if (k < a.d) {
+          real z;
           if (zinj == nullptr) {
-            Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step,
-                                RNG_STEP | (uint32_t)(s * calls + (kk / PC)), key0, key1, z);
-          } else {
-#pragma unroll
-            for (int j = 0; j < PC; ++j)
-              z[j] = (kk + j < a.d) ? (real)zinj[((long long)s * a.d + kk + j) * N + i] : (real)0;
-          }
-#pragma unroll
-          for (int j = 0; j < PC; ++j) {
-            int k = kk + j;
-            if (k < DP && k < a.d) {
-              x[k] = r_fma<real>(a.S[k], z[j], r_fma<real>(a.A[k], x[k], a.D[k]));
-              real cc = ctab ? ctab[s * a.d + k] : a.C[k];
-              gs = r_fma<real>(cc, x[k], gs);
+            if (zpos == PC) {
+              Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | ncall, key0, key1, zb);
+              ++ncall;
+              zpos = 0;
             }
+            z = zb[0];
+#pragma unroll
+            for (int q = 1; q < PC; ++q) z = (zpos == q) ? zb[q] : z;
+            ++zpos;
+          } else {
+            z = (real)zinj[((long long)s * a.d + k) * N + i];
           }
+          x[k] = r_fma<real>(a.S[k], z, r_fma<real>(a.A[k], x[k], a.D[k]));
+          real cc = ctab ? ctab[s * a.d + k] : a.C[k];
+          gs = r_fma<real>(cc, x[k], gs);
         }
       }
       hz += r_exp<real>(gs) * delta;
@@ -644,20 +662,20 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
   griddep_wait();
   griddep_launch();
   StepAcc* A = &sc->acc[parity];
-  if (threadIdx.x == 0) {
-    unsigned long long key;
-    if (pr.R > 1) {  // all-gather of the per-rank maxima: every rank pushed its own into our slots
-      const XchSlot* mine = pr.xch[pr.rank];
-      key = 0;
-      for (int q = 0; q < pr.R; ++q) {
-        wait_ge(&mine[q].max_seq[parity], obs_seq + 1, sc);
-        const unsigned long long kq = ld_relaxed_sys(&mine[q].max_key[parity]);
-        key = kq > key ? kq : key;
+  if (pr.R > 1) {  // all-gather of the per-rank maxima: every rank pushed its own into our slots
+    const XchSlot* mine = pr.xch[pr.rank];
+    gate_wait(&sc->gate2, obs_seq + 1, pr, sc, [&](int q) { return &mine[q].max_seq[parity]; });
+    if (threadIdx.x < 32) {
+      unsigned long long key = ((int)threadIdx.x < pr.R) ? ld_relaxed_sys(&mine[threadIdx.x].max_key[parity]) : 0ull;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
+        key = o > key ? o : key;
       }
-    } else {
-      key = A->gmax_key;
+      if (threadIdx.x == 0) s_key = key;
     }
-    s_key = key;
+  } else if (threadIdx.x == 0) {
+    s_key = A->gmax_key;
   }
   __syncthreads();
   const PreScan ps = pre_scan(s_key, direct != nullptr);
@@ -901,32 +919,31 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const long long Ng = (long long)pr.R * N;  // outputs of the whole (possibly sharded) filter
 
   // ---- totals: this rank's from the accumulators, the other ranks' from the exchange slots ------
-  if (threadIdx.x == 0) {
-    u128 tot, qq, before = make_u128(0, 0);
-    unsigned long long key;
-    if (pr.R > 1) {
-      const XchSlot* mine = pr.xch[pr.rank];
-      tot = make_u128(0, 0);
-      qq = make_u128(0, 0);
-      key = 0;
-      for (int q = 0; q < pr.R; ++q) {
-        wait_ge(&mine[q].sum_seq[p], ctl.obs_seq + 1, sc);
-        const u128 tq = make_u128(ld_relaxed_sys(&mine[q].tot_lo[p]), ld_relaxed_sys(&mine[q].tot_hi[p]));
-        if (q < pr.rank) before = add128(before, tq);
-        tot = add128(tot, tq);
-        qq = add128(qq, make_u128(ld_relaxed_sys(&mine[q].q_lo[p]), ld_relaxed_sys(&mine[q].q_hi[p])));
-        const unsigned long long kq = ld_relaxed_sys(&mine[q].max_key[p]);
-        key = kq > key ? kq : key;
+  if (pr.R > 1) {
+    const XchSlot* mine = pr.xch[pr.rank];
+    gate_wait(&sc->gate3, ctl.obs_seq + 1, pr, sc, [&](int q) { return &mine[q].sum_seq[p]; });
+    if (threadIdx.x < 32) {  // lane q reads rank q's slot; sums by shuffles
+      const int q = threadIdx.x;
+      const bool on = q < pr.R;
+      u128 tq = on ? make_u128(ld_relaxed_sys(&mine[q].tot_lo[p]), ld_relaxed_sys(&mine[q].tot_hi[p])) : make_u128(0, 0);
+      u128 qq = on ? make_u128(ld_relaxed_sys(&mine[q].q_lo[p]), ld_relaxed_sys(&mine[q].q_hi[p])) : make_u128(0, 0);
+      unsigned long long key = on ? ld_relaxed_sys(&mine[q].max_key[p]) : 0ull;
+      u128 before = (on && q < pr.rank) ? tq : make_u128(0, 0);
+      tq = warp_sum128(tq);
+      qq = warp_sum128(qq);
+      before = warp_sum128(before);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
+        key = o > key ? o : key;
       }
-    } else {
-      tot = A->tot;
-      qq = A->q;
-      key = A->gmax_key;
+      if (threadIdx.x == 0) { s_tot = tq; s_q = qq; s_key = key; s_excl = before; }
     }
-    s_tot = tot;
-    s_q = qq;
-    s_key = key;
-    s_excl = before;
+  } else if (threadIdx.x == 0) {
+    s_tot = A->tot;
+    s_q = A->q;
+    s_key = A->gmax_key;
+    s_excl = make_u128(0, 0);
   }
   // ---- exact sum of everything before this tile: whole super tiles + the tiles of this super ----
   {
