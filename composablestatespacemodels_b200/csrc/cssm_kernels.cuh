@@ -190,7 +190,8 @@ template <typename FlagOf>
 __device__ __forceinline__ void gate_wait(unsigned long long* gate, unsigned long long want, const Peers& pr, FilterScalars* sc,
                                           FlagOf flag_of) {
   if (threadIdx.x < 32) {
-    if (ld_gpu(gate) < want) {
+    const unsigned long long seen = __shfl_sync(0xffffffffu, ld_gpu(gate), 0);  // warp-uniform decision
+    if (seen < want) {
       if ((int)threadIdx.x < pr.R) wait_ge(flag_of((int)threadIdx.x), want, sc);
       __syncwarp();
       if (threadIdx.x == 0) {
@@ -203,8 +204,8 @@ __device__ __forceinline__ void gate_wait(unsigned long long* gate, unsigned lon
 }
 __device__ __forceinline__ void push_progress(const Peers& pr, unsigned long long gstep_done) {
   __threadfence_system();
-  for (int q = 0; q < pr.R; ++q)
-    if (q != pr.rank) st_release_sys(&pr.xch[q][pr.rank].progress, gstep_done);
+  // every rank's slot array gets the flag, our own included: gate_wait polls all R slots alike
+  for (int q = 0; q < pr.R; ++q) st_release_sys(&pr.xch[q][pr.rank].progress, gstep_done);
 }
 
 // ---------------------------------------------------------------------------------------------
