@@ -305,7 +305,7 @@ def main():
         it = mh.iters()
         for _ in range(args.warmup):
             next(it)
-        pf.handle.profile(50)
+        pf.handle.profile(1)
         barrier()
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -391,6 +391,7 @@ def main():
         peak, peak_src = measured_peak()
         k1_ms, k1_n = prof["propagate_weight"]
         k1_bpp = 2 * d * b + b + 4  # anc + gathered state in, state + log-weight out
+        ws_bytes_small = k1_bpp * n_local
         roof = None
         if k1_n and wl_model != "c3":
             ach = k1_bpp * n_local / (k1_ms / k1_n * 1e-3) / 1e9
@@ -409,6 +410,20 @@ def main():
                                    "frac_fused": real_bpp * n_local / (tot * 1e-3) / 1e9 / peak if tot else None,
                                    "bytes_per_particle_survey_8d": 4 * d * b + 5 * b + 8,
                                    "frac_survey_8d": (4 * d * b + 5 * b + 8) * n_local / (tot * 1e-3) / 1e9 / peak if tot else None}}
+        elif prof.get("series", (0, 0))[1]:
+            # small cloud: the whole llFilter is ONE cooperative launch (cssm_series.cuh); per launch it moves
+            # T x N x (K1 2db+b+4, K2 b, K3 b+4) bytes, all of it L2 resident: latency bound, not HBM bound
+            s_ms, s_n = prof["series"]
+            real_bpp = k1_bpp + b + b + 4
+            ach = real_bpp * n_local * T / (s_ms / s_n * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_series_small (whole llFilter in one cooperative launch: propagate + weight, "
+                                              "exact sums, scan + search per observation, grid barriers in between)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_particle": real_bpp,
+                    "avg_launch_ms": s_ms / s_n, "sampled_launches": s_n,
+                    "us_per_observation": s_ms / s_n * 1e3 / T,
+                    "note": "latency bound: the 2^16-particle cloud (%.1f MB) lives in L2; three grid barriers per observation"
+                            % (ws_bytes_small / 1e6)}
         elif k1_n:
             # LGCP: the state lives in registers for ~100 sub-steps per event: SFU/ALU bound, not HBM bound
             nsub = float(np.sum(np.ceil(np.diff(np.concatenate([[t[0]], t])) / 1e-3)))

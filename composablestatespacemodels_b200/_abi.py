@@ -16,6 +16,7 @@ OBS_POISSON, OBS_NEGBIN, OBS_NORMAL, OBS_BERNOULLI, OBS_LGCP = 0, 1, 2, 3, 4
 STEP_EXACT, STEP_EULER = 0, 1
 RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_MULTINOMIAL = 0, 1, 2
 F32, F64 = 0, 1
+SERIES_AUTO, SERIES_THREE_LAUNCH, SERIES_SINGLE_LAUNCH = 0, 1, 2
 MAX_RANKS, SHARD_BLOB_BYTES = 8, 1024
 
 c_double_p = C.POINTER(C.c_double)
@@ -95,6 +96,7 @@ _SIGNATURES = {
     "cssm_filter_run": [_FILTER, c_double_p, c_double_p, c_uint8_p, C.c_int64, c_double_p, c_double_p],
     "cssm_filter_last_elapsed_ms": [_FILTER, C.POINTER(C.c_float)],
     "cssm_filter_last_launches": [_FILTER, c_int64_p],
+    "cssm_filter_series_mode": [_FILTER, C.c_int],
     "cssm_filter_profile": [_FILTER, C.c_int],
     "cssm_filter_profile_read": [_FILTER, c_double_p, c_int64_p],
     "cssm_filter_get_particles": [_FILTER, c_double_p],

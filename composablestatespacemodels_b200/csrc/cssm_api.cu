@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "cssm_kernels.cuh"
+#include "cssm_series.cuh"
 
 using namespace cssm;
 
@@ -206,6 +207,15 @@ struct cssm_filter {
   struct PeerPtrs { void* x[2]; int32_t* anc; void* logw; u128* tile_sum; double* tile_maxw; XchSlot* xch; };
   PeerPtrs peer[MAXR];
   std::vector<void*> ipc_opened;  // base pointers to close on destroy
+  // single-launch series kernel (small clouds, cssm_series.cuh)
+  u128* tile_q = nullptr;          // [nt] exact tile sums of w1^2
+  SeriesCtl* series_ctl = nullptr;
+  void* recs = nullptr;            // per-observation records of the loaded series (filter dtype)
+  size_t recs_cap = 0;             // bytes
+  bool recs_valid = false;
+  int series_mode = CSSM_SERIES_AUTO;
+  int series_max_blocks = -1;      // co-resident blocks of k_series_small on this device (-1: not queried)
+  bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
   float last_ms = 0.f;
   // per-kernel-class device timing (CUDA events on the launching stream), sampled every prof_stride steps
@@ -324,7 +334,7 @@ int do_init(cssm_filter* f, double t0, const double* zinj_dev, const double* x0)
   return CSSM_OK;
 }
 
-enum { CLS_PROPAGATE = 0, CLS_SUMS = 1, CLS_SEARCH = 2, CLS_MULTI = 3, CLS_INIT = 4 };
+enum { CLS_PROPAGATE = 0, CLS_SUMS = 1, CLS_SEARCH = 2, CLS_MULTI = 3, CLS_INIT = 4, CLS_SERIES = 5 };
 
 // event pair around one launch when profiling samples this step
 struct ProfScope {
@@ -644,6 +654,112 @@ void launch_gather(cssm_filter* f, const int32_t* anc, double* out_dev) {
   k_gather<real, double><<<nblk(f->N, 256), 256, 0, f->stream>>>(pr, anc, out_dev, f->d, f->N, f->Ns, f->N);
 }
 
+// ---- single-launch series kernel ------------------------------------------------------------------
+template <typename real>
+void* series_kernel_ptr(int d, int kind) {
+  const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
+  if (d == 2) return strat ? (void*)k_series_small<real, 2, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 2, CSSM_RESAMPLE_SYSTEMATIC>;
+  return strat ? (void*)k_series_small<real, 0, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 0, CSSM_RESAMPLE_SYSTEMATIC>;
+}
+void* series_kernel(const cssm_filter* f) {
+  return (f->dtype == CSSM_F32) ? series_kernel_ptr<float>(f->d, f->resample_kind) : series_kernel_ptr<double>(f->d, f->resample_kind);
+}
+
+// may this filter's loaded series run as one launch?  One 512-particle tile per block, every block resident.
+bool series_eligible(cssm_filter* f, bool sample_states) {
+  if (f->series_mode == CSSM_SERIES_THREE_LAUNCH || sample_states || f->world > 1 || f->items != 2) return false;
+  if (f->model.obs_kind == CSSM_OBS_LGCP || f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) return false;
+  if (f->series.empty() || f->series.size() > 0x7fffffffull) return false;
+  if (f->series_max_blocks < 0) {
+    int per_sm = 0, sms = 0, coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, series_kernel(f), TILE_THREADS, 0) != cudaSuccess) per_sm = 0;
+    cudaGetLastError();
+    f->series_max_blocks = coop ? per_sm * sms : 0;
+  }
+  return f->nt <= f->series_max_blocks;
+}
+
+// the per-observation records of the loaded series: [A D S C | y k0 k1 k2 k3 has_obs 0 0] in the filter dtype
+template <typename real>
+int upload_recs(cssm_filter* f) {
+  const size_t T = f->series.size(), len = (size_t)4 * f->d + SERIES_REC_EXTRA;
+  std::vector<real> host(T * len);
+  for (size_t s = 0; s < T; ++s) {
+    StepArgs<real> a;
+    to_args<real>(f->model, f->series[s].h, a);
+    real* r = host.data() + s * len;
+    for (int k = 0; k < f->d; ++k) {
+      r[k] = a.A[k]; r[f->d + k] = a.D[k]; r[2 * f->d + k] = a.S[k]; r[3 * f->d + k] = a.C[k];
+    }
+    real* e = r + 4 * f->d;
+    e[0] = a.y; e[1] = a.k0; e[2] = a.k1; e[3] = a.k2; e[4] = a.k3; e[5] = a.has_obs ? (real)1 : (real)0; e[6] = e[7] = (real)0;
+  }
+  const size_t bytes = host.size() * sizeof(real);
+  if (bytes > f->recs_cap) {
+    if (f->recs) cudaFree(f->recs);
+    f->recs = nullptr; f->recs_cap = 0;
+    CU(cudaMalloc(&f->recs, bytes));
+    f->recs_cap = bytes;
+  }
+  CU(cudaMemcpyAsync(f->recs, host.data(), bytes, cudaMemcpyHostToDevice, f->stream));
+  CU(cudaStreamSynchronize(f->stream));  // `host` is pageable and goes out of scope
+  f->recs_valid = true;
+  return CSSM_OK;
+}
+
+int run_series_single_launch(cssm_filter* f) {
+  const size_t T = f->series.size();
+  int rc = CSSM_OK;
+  if (!f->recs_valid) rc = (f->dtype == CSSM_F32) ? upload_recs<float>(f) : upload_recs<double>(f);
+  if (rc) return rc;
+  CU(cudaEventRecord(f->ev0, f->stream));
+  rc = do_init(f, f->t0_series, nullptr, nullptr);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(f->series_ctl, 0, sizeof(SeriesCtl), f->stream));
+  SeriesArgs sa;
+  std::memset(&sa, 0, sizeof(sa));
+  sa.x[0] = f->x[f->cur]; sa.x[1] = f->x[f->cur ^ 1];
+  sa.logw = f->logw; sa.anc = f->anc; sa.sc = f->sc;
+  sa.tile_sum = f->tb.tile_sum; sa.tile_q = f->tile_q; sa.tile_maxw = f->tb.tile_maxw;
+  sa.ctl = f->series_ctl; sa.recs = f->recs; sa.ll_steps = f->ll_steps; sa.ess_steps = f->ess_steps;
+  sa.N = f->N; sa.Ns = f->Ns; sa.T = (int)T; sa.d = f->d; sa.nt = f->nt; sa.obs_kind = f->model.obs_kind;
+  sa.key0 = f->key0; sa.key1 = f->key1; sa.step0 = f->step_ctr;
+  sa.inv_n = ((f->N & (f->N - 1)) == 0) ? 1.0 / (double)f->N : 0.0;
+  static const bool debug_stamps = std::getenv("CSSM_SERIES_DEBUG") != nullptr;
+  if (debug_stamps) {
+    int rc2 = ensure_scratch(f, 8);
+    if (rc2) return rc2;
+    CU(cudaMemsetAsync(f->scratch, 0, 64, f->stream));
+    sa.dbg = (unsigned long long*)f->scratch;
+  }
+  void* args[] = {&sa};
+  const bool prof = f->prof_stride > 0;
+  cudaError_t e;
+  {
+    ProfScope ps_(f, CLS_SERIES, prof);
+    e = cudaLaunchCooperativeKernel(series_kernel(f), dim3((unsigned)f->nt), dim3(TILE_THREADS), args, 0, f->stream);
+  }
+  if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch series kernel: ") + cudaGetErrorString(e));
+  f->launches++;
+  // host mirror of what the kernel did: T steps, the cloud flipped T times, ancestors valid iff the last step was observed
+  f->step_ctr += (uint32_t)T;
+  f->cur ^= (int)(T & 1);
+  f->anc_valid = f->series.back().h.has_obs != 0;
+  f->t_cur = f->series.back().t;
+  CU(cudaEventRecord(f->ev1, f->stream));
+  if (debug_stamps) {
+    unsigned long long c[8];
+    CU(cudaMemcpyAsync(c, f->scratch, 64, cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    std::fprintf(stderr, "series kernel, block 0, cycles per step: head %.0f P1 %.0f B1 %.0f P2 %.0f B2 %.0f P3 %.0f B3 %.0f (T=%zu, blocks %d)\n",
+                 c[6] / (double)T, c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T,
+                 c[5] / (double)T, T, f->nt);
+  }
+  return CSSM_OK;
+}
+
 // init + T steps on the loaded series; optionally one sampled particle per time (filter, :152-158)
 int run_series(cssm_filter* f, bool sample_states) {
   const size_t T = f->series.size();
@@ -651,6 +767,11 @@ int run_series(cssm_filter* f, bool sample_states) {
   if (rc) return rc;
   if (sample_states && f->world > 1) return fail(CSSM_ERR_UNSUPPORTED, "filter(): per-time sampled states are not available on a sharded filter");
   f->launches = 0;
+  f->last_single_launch = series_eligible(f, sample_states);
+  if (f->last_single_launch) return run_series_single_launch(f);
+  if (f->series_mode == CSSM_SERIES_SINGLE_LAUNCH)
+    return fail(CSSM_ERR_UNSUPPORTED, "the single-launch series kernel does not cover this filter (cloud too large for one resident "
+                                      "grid, LGCP, multinomial, sharded, or per-time sampled states)");
   CU(cudaEventRecord(f->ev0, f->stream));
   rc = do_init(f, f->t0_series, nullptr, nullptr);
   if (rc) return rc;
@@ -720,6 +841,7 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   f->items = (f->N <= (1 << 18)) ? 2 : 8;
   if (const char* e = std::getenv("CSSM_TILE_ITEMS")) { int v = std::atoi(e); if (v == 2 || v == 8) f->items = v; }
   if (const char* e = std::getenv("CSSM_PDL")) f->pdl = std::atoi(e) != 0;
+  if (const char* e = std::getenv("CSSM_SERIES_KERNEL")) f->series_mode = std::atoi(e) ? CSSM_SERIES_AUTO : CSSM_SERIES_THREE_LAUNCH;
   const int tile = TILE_THREADS * f->items;
   f->nt = nblk(f->N, tile);
   f->ns = nblk(f->nt, SUPER);
@@ -745,6 +867,8 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   ALLOC(f->tb.super_q, (size_t)2 * f->ns * sizeof(u128));
   ALLOC(f->tb.super_ticket, (size_t)f->ns * sizeof(unsigned long long));
   if (resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ALLOC(f->cdf, (size_t)f->Ns * sizeof(double));
+  ALLOC(f->tile_q, (size_t)(f->nt + 1) * sizeof(u128));
+  ALLOC(f->series_ctl, sizeof(SeriesCtl));
 #undef ALLOC
   f->tb.nt = f->nt; f->tb.ns = f->ns;
   cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz);
@@ -911,7 +1035,8 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   if (f->own_stream) cudaStreamSynchronize(f->own_stream);
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
-                  f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states};
+                  f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl,
+                  f->recs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (f->ev0) cudaEventDestroy(f->ev0);
@@ -1302,6 +1427,7 @@ int cssm_filter_load_series(cssm_filter_t* f, const double* t, const double* y, 
   f->series.swap(series);
   f->ctab_host.swap(ctab_host);
   f->t0_series = t0;
+  f->recs_valid = false;
   return CSSM_OK;
 }
 
@@ -1365,6 +1491,14 @@ int cssm_filter_last_elapsed_ms(const cssm_filter_t* f, float* ms_out) {
 int cssm_filter_last_launches(const cssm_filter_t* f, int64_t* n_out) {
   if (!f || !n_out) return fail(CSSM_ERR_INVALID, "null argument");
   *n_out = f->last_launches;
+  return CSSM_OK;
+}
+
+int cssm_filter_series_mode(cssm_filter_t* f, int mode) {
+  if (!f) return fail(CSSM_ERR_INVALID, "null filter handle");
+  if (mode != CSSM_SERIES_AUTO && mode != CSSM_SERIES_THREE_LAUNCH && mode != CSSM_SERIES_SINGLE_LAUNCH)
+    return fail(CSSM_ERR_INVALID, "unknown series mode");
+  f->series_mode = mode;
   return CSSM_OK;
 }
 

@@ -110,6 +110,15 @@ template <> __device__ __forceinline__ double r_log<double>(double x) { return l
 template <typename real> __device__ __forceinline__ real r_fma(real a, real b, real c);
 template <> __device__ __forceinline__ float r_fma<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double r_fma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <typename real> __device__ __forceinline__ real r_add(real a, real b);
+template <> __device__ __forceinline__ float r_add<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double r_add<double>(double a, double b) { return __dadd_rn(a, b); }
+template <typename real> __device__ __forceinline__ real r_sub(real a, real b);
+template <> __device__ __forceinline__ float r_sub<float>(float a, float b) { return __fsub_rn(a, b); }
+template <> __device__ __forceinline__ double r_sub<double>(double a, double b) { return __dsub_rn(a, b); }
+template <typename real> __device__ __forceinline__ real r_mul(real a, real b);
+template <> __device__ __forceinline__ float r_mul<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double r_mul<double>(double a, double b) { return __dmul_rn(a, b); }
 template <typename real> __device__ __forceinline__ real r_neg_big();
 // Bernoulli "impossible" value: -1e99 in the reference (model/Model.scala:332,334); fp32 cannot
 // hold it, the largest finite negative is used instead
@@ -122,23 +131,26 @@ template <> __device__ __forceinline__ double r_neg_big<double>() { return -1e99
 //             k3 = log(size)                                           :186-195
 //   NORMAL    k0 = sd = exp(scale), k1 = log(sqrt(2 pi)) + log(sd)     :227-233,:252-258
 //   BERNOULLI k0 = (y == 1.0)                                          :318-336
+// Written with explicit round-to-nearest operations only: the compiler never contracts intrinsics
+// into FMAs, so every instantiation of every kernel (per-step, series) evaluates the same sequence
+// and returns the same bits.
 template <typename real>
 __device__ __forceinline__ real obs_loglik(const StepArgs<real>& a, real g) {
   switch (a.obs_kind) {
     case CSSM_OBS_POISSON:
-      return r_fma<real>(a.k0, g, -r_exp<real>(g)) - a.k1;  // -mean + k*log(mean) - lgamma(k+1), log(exp(g)) = g
+      return r_sub<real>(r_fma<real>(a.k0, g, -r_exp<real>(g)), a.k1);  // -mean + k*log(mean) - lgamma(k+1), log(exp(g)) = g
     case CSSM_OBS_NEGBIN: {
-      real L = r_log<real>(r_exp<real>(g) + a.k1);  // log(mu + size)
-      return a.k2 + a.k1 * (a.k3 - L) + a.k0 * (g - L);
+      const real L = r_log<real>(r_add<real>(r_exp<real>(g), a.k1));  // log(mu + size)
+      return r_fma<real>(a.k0, r_sub<real>(g, L), r_fma<real>(a.k1, r_sub<real>(a.k3, L), a.k2));
     }
     case CSSM_OBS_NORMAL: {
-      real dd = (a.y - g) / a.k0;
-      return -dd * dd / (real)2 - a.k1;
+      const real dd = r_sub<real>(a.y, g) / a.k0;
+      return r_fma<real>(r_mul<real>((real)-0.5, dd), dd, -a.k1);
     }
     case CSSM_OBS_BERNOULLI: {
-      real p = (g > (real)6) ? (real)1 : (g < (real)-6) ? (real)0 : (real)1 / ((real)1 + r_exp<real>(-g));
+      const real p = (g > (real)6) ? (real)1 : (g < (real)-6) ? (real)0 : (real)1 / r_add<real>((real)1, r_exp<real>(-g));
       if (a.k0 != (real)0) return (p == (real)0) ? r_neg_big<real>() : r_log<real>(p);
-      return (p == (real)1) ? r_neg_big<real>() : r_log<real>((real)1 - p);
+      return (p == (real)1) ? r_neg_big<real>() : r_log<real>(r_sub<real>((real)1, p));
     }
     default: return (real)0;
   }
@@ -298,23 +310,27 @@ __device__ __forceinline__ void k1_tail(double mx, bool bad, int has_obs, const 
 //     D > 0: latent dimension known at compile time (everything unrolls, constants become
 //     immediate constant-bank operands); D == 0: any d <= MAXD.
 // ---------------------------------------------------------------------------------------------
-template <typename real, int D>
-__global__ void __launch_bounds__(256)
-k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
-                   const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
-                   long long N, long long Ns, unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
-                   K1Ctl ctl) {
-  constexpr int PPT = VecOf<real>::PPT;
-  typedef typename VecOf<real>::type vec_t;
+template <typename real, int PPT> struct VecN;
+template <> struct VecN<float, 4> { typedef float4 type; typedef int4 itype; };
+template <> struct VecN<float, 2> { typedef float2 type; typedef int2 itype; };
+template <> struct VecN<double, 2> { typedef double2 type; typedef int2 itype; };
+
+// the PPT consecutive particles i0 .. i0+PPT-1 of one thread: gather, transition, f, log-weight.
+// Returns the thread's max log-weight (mx, -inf without an observation) and whether one was NaN.
+// Shared by the per-step kernel below and by the single-launch series kernel (cssm_series.cuh), so
+// both evaluate a particle with the same instruction sequence.  COH: the cloud and the ancestors
+// were written earlier in the SAME launch by other blocks, so they are read with ld.global.cg (L2)
+// instead of the non-coherent read-only path.
+template <typename real, int D, int PPT, bool COH = false>
+__device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, const Peers& pr, real* __restrict__ xdst,
+                                                    const int32_t* __restrict__ anc, real* __restrict__ logw,
+                                                    const double* __restrict__ zinj, long long N, long long Ns,
+                                                    unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
+                                                    long long i0, double& mx, bool& bad, real* lw_out = nullptr) {
+  typedef typename VecN<real, PPT>::type vec_t;
+  typedef typename VecN<real, PPT>::itype ivec_t;
   constexpr int PC = Normals<real>::PER_CALL;
   const int d = (D > 0) ? D : a.d;
-  griddep_wait();
-  griddep_launch();
-  if (pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
-    const XchSlot* mine = pr.xch[pr.rank];
-    gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
-  }
-  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PPT;
   const bool full = (i0 + PPT <= N);
   const real* src[PPT];
   bool valid[PPT];
@@ -327,13 +343,15 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
       s[p] = i0 + p;
     }
     if (anc != nullptr) {
-      if (full && PPT == 4) {
-        int4 v = *reinterpret_cast<const int4*>(anc + i0);
-        s[0] = v.x; s[1] = v.y; s[PPT > 2 ? 2 : 0] = v.z; s[PPT > 3 ? 3 : 0] = v.w;
+      if (full) {
+        const ivec_t v = COH ? __ldcg(reinterpret_cast<const ivec_t*>(anc + i0)) : *reinterpret_cast<const ivec_t*>(anc + i0);
+        const int* vp = reinterpret_cast<const int*>(&v);
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) s[p] = vp[p];
       } else {
 #pragma unroll
         for (int p = 0; p < PPT; ++p)
-          if (valid[p]) s[p] = anc[i0 + p];
+          if (valid[p]) s[p] = COH ? __ldcg(anc + i0 + p) : anc[i0 + p];
       }
     }
 #pragma unroll
@@ -359,7 +377,7 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
     for (int j = 0; j < 4; ++j) {
       int k = kk + j;
 #pragma unroll
-      for (int p = 0; p < PPT; ++p) xv[j][p] = (k < d && valid[p]) ? __ldg(src[p] + (long long)k * Ns) : (real)0;
+      for (int p = 0; p < PPT; ++p) xv[j][p] = (k < d && valid[p]) ? (COH ? __ldcg(src[p] + (long long)k * Ns) : __ldg(src[p] + (long long)k * Ns)) : (real)0;
     }
     // noise: counter = (global slot, step, chunk)
     real z[4][PPT];
@@ -413,8 +431,8 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
       }
     }
   }
-  double mx = -__longlong_as_double(0x7FF0000000000000ll);  // -inf
-  bool bad = false;
+  mx = -__longlong_as_double(0x7FF0000000000000ll);  // -inf
+  bad = false;
   if (a.has_obs) {
     real lw[PPT];
     real mxr = (real)mx;
@@ -427,6 +445,10 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
       }
     }
     mx = (double)mxr;
+    if (lw_out != nullptr) {
+#pragma unroll
+      for (int p = 0; p < PPT; ++p) lw_out[p] = lw[p];
+    }
     if (full) {
       vec_t v;
       real* vp = reinterpret_cast<real*>(&v);
@@ -438,9 +460,27 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
       for (int p = 0; p < PPT; ++p)
         if (valid[p]) logw[i0 + p] = lw[p];
     }
-  } else if (pr.R == 1) {
-    return;
   }
+}
+
+template <typename real, int D>
+__global__ void __launch_bounds__(256)
+k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
+                   const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
+                   long long N, long long Ns, unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
+                   K1Ctl ctl) {
+  constexpr int PPT = VecOf<real>::PPT;
+  griddep_wait();
+  griddep_launch();
+  if (pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
+    const XchSlot* mine = pr.xch[pr.rank];
+    gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
+  }
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PPT;
+  double mx;
+  bool bad;
+  propagate_particles<real, D, PPT>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+  if (!a.has_obs && pr.R == 1) return;
   k1_tail(mx, bad, a.has_obs, pr, ctl);
 }
 
@@ -830,11 +870,17 @@ template <int ITEMS> struct TileSmem { static constexpr int SIZE = TILE_THREADS 
 // weights (as double) into Ws; `excl` = exact sum of everything before the tile.  All threads call.
 template <typename real, int ITEMS>
 __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128 excl, long long tile0, long long N,
-                                         double* Ps, double* Ws, u128* s_warp, double* Pv = nullptr) {
+                                         double* Ps, double* Ws, u128* s_warp, double* Pv = nullptr,
+                                         const typename WeightSrc<real>::wt* wv_in = nullptr) {
   typedef typename WeightSrc<real>::wt wt;
   const long long base = tile0 + (long long)threadIdx.x * ITEMS;
   wt wv[ITEMS];
-  ws.template load<ITEMS>(base, 1, N, wv);
+  if (wv_in != nullptr) {  // the caller already holds this thread's ITEMS weights (same values, same order)
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) wv[j] = wv_in[j];
+  } else {
+    ws.template load<ITEMS>(base, 1, N, wv);
+  }
   u128 e[ITEMS];
   u128 run = make_u128(0, 0);
 #pragma unroll
@@ -891,76 +937,55 @@ struct K3Ctl {
 
 // cdf_out == NULL: search (systematic / stratified), writes ancestors;
 // cdf_out != NULL: write the un-normalised CDF (multinomial), no search
-#ifndef CSSM_K3_MINBLOCKS
-#define CSSM_K3_MINBLOCKS 4
-#endif
-template <typename real, int ITEMS, int KIND>
-__global__ void __launch_bounds__(TILE_THREADS, CSSM_K3_MINBLOCKS)
-k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
-              SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
-              double* __restrict__ cdf_out) {
+// shared memory of the scan + search of one tile
+template <int ITEMS>
+struct K3Smem {
+  static constexpr int TILE = TILE_THREADS * ITEMS;
+  static constexpr int WIN = TILE + TILE_THREADS;  // outputs staged per pass (a tile has ~TILE offspring)
+  double Ps[TileSmem<ITEMS>::SIZE];
+  double Ws[TileSmem<ITEMS>::SIZE];
+  int32_t s_res[WIN];
+  u128 s_warp[TILE_THREADS / 32];
+  u128 s_excl, s_tot, s_q, s_run;
+  unsigned long long s_key;
+  int s_cnt[TILE_THREADS], s_cnt2[TILE_THREADS / 32];
+  long long s_pend, s_jfinal;
+  double s_wnext, s_u, s_scale;
+  int s_tp, s_brk;
+};
+
+// Tile t of the scan + search once the exact sums are known: `tot` / `qsum` = sum of fix(w1) / of
+// fix(w1^2) over the whole filter, `key` = ordered key of the max log-weight, `excl` = exact sum of
+// everything before the tile.  Block 0 also updates ll and ESS.  PROTO3: called from the
+// three-launch step (zeroes the accumulators of the next observed step); the single-launch series
+// kernel keeps its own.  All threads of the block call; returns whether a peer's memory was written.
+template <typename real, int ITEMS, int KIND, bool PROTO3>
+__device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restrict__ logw, const double* __restrict__ direct,
+                                        long long N, FilterScalars* __restrict__ sc, const SumTables& tb, const Peers& pr,
+                                        const K3Ctl& ctl, const double* __restrict__ uarr, double* __restrict__ cdf_out, int t,
+                                        u128 tot, u128 qsum, unsigned long long key, u128 excl,
+                                        const typename WeightSrc<real>::wt* wv_in = nullptr) {
   constexpr int TILE = TILE_THREADS * ITEMS;
-  __shared__ double Ps[TileSmem<ITEMS>::SIZE];
-  __shared__ double Ws[TileSmem<ITEMS>::SIZE];
-  constexpr int WIN = TILE + TILE_THREADS;  // outputs staged per pass (a tile has ~TILE offspring)
-  __shared__ int32_t s_res[WIN];
-  __shared__ u128 s_warp[TILE_THREADS / 32];
-  __shared__ u128 s_excl, s_tot, s_q;
-  __shared__ unsigned long long s_key;
-  __shared__ int s_cnt[TILE_THREADS], s_cnt2[TILE_THREADS / 32];
-  __shared__ long long s_pend, s_jfinal;
-  __shared__ double s_wnext, s_u, s_scale;
-  __shared__ u128 s_run;
-  __shared__ int s_tp, s_brk;
-
-  griddep_wait();
-  griddep_launch();
-  const int t = blockIdx.x, nt = tb.nt, p = ctl.parity;
-  StepAcc* A = &sc->acc[p];
+  constexpr int WIN = K3Smem<ITEMS>::WIN;
+  double* Ps = sm.Ps;
+  double* Ws = sm.Ws;
+  int32_t* s_res = sm.s_res;
+  u128* s_warp = sm.s_warp;
+  int* s_cnt = sm.s_cnt;
+  int* s_cnt2 = sm.s_cnt2;
+  long long& s_pend = sm.s_pend;
+  long long& s_jfinal = sm.s_jfinal;
+  double& s_wnext = sm.s_wnext;
+  double& s_u = sm.s_u;
+  double& s_scale = sm.s_scale;
+  u128& s_run = sm.s_run;
+  int& s_tp = sm.s_tp;
+  int& s_brk = sm.s_brk;
+  const int nt = tb.nt;
   const long long Ng = (long long)pr.R * N;  // outputs of the whole (possibly sharded) filter
-
-  // ---- totals: this rank's from the accumulators, the other ranks' from the exchange slots ------
-  if (pr.R > 1) {
-    const XchSlot* mine = pr.xch[pr.rank];
-    gate_wait(&sc->gate3, ctl.obs_seq + 1, pr, sc, [&](int q) { return &mine[q].sum_seq[p]; });
-    if (threadIdx.x < 32) {  // lane q reads rank q's slot; sums by shuffles
-      const int q = threadIdx.x;
-      const bool on = q < pr.R;
-      u128 tq = on ? make_u128(ld_relaxed_sys(&mine[q].tot_lo[p]), ld_relaxed_sys(&mine[q].tot_hi[p])) : make_u128(0, 0);
-      u128 qq = on ? make_u128(ld_relaxed_sys(&mine[q].q_lo[p]), ld_relaxed_sys(&mine[q].q_hi[p])) : make_u128(0, 0);
-      unsigned long long key = on ? ld_relaxed_sys(&mine[q].max_key[p]) : 0ull;
-      u128 before = (on && q < pr.rank) ? tq : make_u128(0, 0);
-      tq = warp_sum128(tq);
-      qq = warp_sum128(qq);
-      before = warp_sum128(before);
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
-        key = o > key ? o : key;
-      }
-      if (threadIdx.x == 0) { s_tot = tq; s_q = qq; s_key = key; s_excl = before; }
-    }
-  } else if (threadIdx.x == 0) {
-    s_tot = A->tot;
-    s_q = A->q;
-    s_key = A->gmax_key;
-    s_excl = make_u128(0, 0);
-  }
-  // ---- exact sum of everything before this tile: whole super tiles + the tiles of this super ----
-  {
-    const int sidx = t / SUPER;
-    const u128* ssum = tb.super_sum + (size_t)p * tb.ns;
-    u128 acc = make_u128(0, 0);
-    for (int s = threadIdx.x; s < sidx; s += TILE_THREADS) acc = add128(acc, ssum[s]);
-    for (int tt = sidx * SUPER + threadIdx.x; tt < t; tt += TILE_THREADS) acc = add128(acc, tb.tile_sum[tt]);
-    const u128 local = block_sum128(acc, s_warp);
-    if (threadIdx.x == 0) s_excl = add128(s_excl, local);
-  }
-  __syncthreads();
-  const PreScan ps = pre_scan(s_key, direct != nullptr);
+  const PreScan ps = pre_scan(key, direct != nullptr);
   const int qb = ps.qb;
-  const double total = dbl128(s_tot, qb);
-  const u128 excl = s_excl;
+  const double total = dbl128(tot, qb);
 
   // ---- block 0: ll increment max + log(mean w1), ESS = floor(1/sum wn^2), the resampling uniform
   //      is derived by every block; zero the accumulators of the next observed step ----------------
@@ -975,6 +1000,8 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     s_u = u;
     s_scale = __ddiv_rn((double)Ng, total);
     s_pend = 0x7FFFFFFFFFFFFFFFll;
+  }
+  if (threadIdx.x == 64) {  // another warp than the one deriving the uniform: the two run side by side
     if (t == 0) {
       const double gmax = ps.gmax;
       double incr = gmax + log(total / (double)Ng);
@@ -985,7 +1012,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
       }
       // sum (w/total)^2 = (exact sum w^2) / total^2; direct weights were pre-scaled by 2^-(96-qb)
       const double tsc = __dmul_rn(total, __longlong_as_double((long long)(1023 - (96 - qb)) << 52));
-      const double s2 = __ddiv_rn(dbl128(s_q, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
+      const double s2 = __ddiv_rn(dbl128(qsum, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
       const double inv = floor(1.0 / s2);
       const int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
       sc->gmax = gmax;
@@ -1000,26 +1027,36 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
         if (ctl.ess_steps) ctl.ess_steps[ctl.step_slot] = ess;
       }
       if (flags) atomicOr(&sc->flags, flags);
-      StepAcc* nx = &sc->acc[p ^ 1];
-      nx->gmax_key = 0ull;
-      nx->tot = make_u128(0, 0);
-      nx->q = make_u128(0, 0);
+      if (PROTO3) {  // three-launch protocol: zero the accumulators of the next observed step
+        StepAcc* nx = &sc->acc[ctl.parity ^ 1];
+        nx->gmax_key = 0ull;
+        nx->tot = make_u128(0, 0);
+        nx->q = make_u128(0, 0);
+      }
     }
   }
-  if (t < tb.ns && threadIdx.x == 1) {
-    tb.super_sum[(size_t)(p ^ 1) * tb.ns + t] = make_u128(0, 0);
-    tb.super_q[(size_t)(p ^ 1) * tb.ns + t] = make_u128(0, 0);
+  if (PROTO3 && t < tb.ns && threadIdx.x == 1) {
+    tb.super_sum[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
+    tb.super_q[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
   }
 
   WeightSrc<real> ws{logw, direct, ps.gmax};
   const long long tile0 = (long long)t * TILE;
   const int tile_n = (int)min((long long)TILE, N - tile0);
+  if (threadIdx.x == 32 && cdf_out == nullptr) {
+    // first weight after this tile (next tile, possibly the next rank's first particle); loaded here so
+    // that its latency hides behind the tile scan
+    double wn = 0.0;
+    if (t < nt - 1) wn = (double)ws(tile0 + TILE);
+    else if (pr.rank < pr.R - 1) wn = (double)WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[pr.rank + 1]), nullptr, ps.gmax}(0);
+    s_wnext = wn;
+  }
   double Pv[ITEMS];
-  tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp, Pv);
+  tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp, Pv, wv_in);
 
   if (cdf_out != nullptr) {
     for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) cdf_out[tile0 + j] = Ps[phys<ITEMS>(j)];
-    return;
+    return false;
   }
 
   bool wrote_remote = false;
@@ -1045,13 +1082,6 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     cr[j] = (last_tile && idx >= tile_n - 1) ? n_rel : kf.count_rel(Pv[j], scale, Ng, lo, lo_d, n_rel);
   }
   s_cnt[threadIdx.x] = cr[ITEMS - 1];
-  if (threadIdx.x == 32) {
-    // first weight after this tile (next tile, possibly the next rank's first particle)
-    double wn = 0.0;
-    if (t < nt - 1) wn = (double)ws(tile0 + TILE);
-    else if (pr.rank < pr.R - 1) wn = (double)WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[pr.rank + 1]), nullptr, ps.gmax}(0);
-    s_wnext = wn;
-  }
   __syncthreads();
   const int n_out = s_cnt[TILE_THREADS - 1];
   const long long hi = lo + n_out;
@@ -1134,8 +1164,8 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
         u128 run = s_run;
         while (tp < gnt) {
           const int q = (int)(tp / nt), tl = (int)(tp % nt);
-          const u128 tsum = (q == pr.rank) ? tb.tile_sum[tl] : ld_gpu128(&pr.tile_sum[q][tl]);
-          const double mxw = (q == pr.rank) ? tb.tile_maxw[tl] : __longlong_as_double((long long)ld_gpu((const unsigned long long*)&pr.tile_maxw[q][tl]));
+          const u128 tsum = ld_gpu128((q == pr.rank) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);  // L2: another block wrote it
+          const double mxw = __longlong_as_double((long long)ld_gpu((const unsigned long long*)((q == pr.rank) ? &tb.tile_maxw[tl] : &pr.tile_maxw[q][tl])));
           const u128 nrun = add128(run, tsum);
           const double c = __ddiv_rn(dbl128(run, qb), total), ce = __ddiv_rn(dbl128(nrun, qb), total);
           const long long cb = __double_as_longlong(c), eb = __double_as_longlong(ce);
@@ -1166,7 +1196,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
         if (s_brk < tn) s_jfinal = (long long)q * N + (long long)tl * TILE + s_brk - 1;
         else if (tp == gnt - 1) s_jfinal = Ng - 1;
         else {
-          const u128 tsum = (q == pr.rank) ? tb.tile_sum[tl] : ld_gpu128(&pr.tile_sum[q][tl]);
+          const u128 tsum = ld_gpu128((q == pr.rank) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);  // L2: another block wrote it
           s_run = add128(s_run, tsum);
           s_tp = tp + 1;
         }
@@ -1186,6 +1216,70 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     }
   }
   }  // usable
+  return wrote_remote;
+}
+
+#ifndef CSSM_K3_MINBLOCKS
+#define CSSM_K3_MINBLOCKS 4
+#endif
+template <typename real, int ITEMS, int KIND>
+__global__ void __launch_bounds__(TILE_THREADS, CSSM_K3_MINBLOCKS)
+k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
+              SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
+              double* __restrict__ cdf_out) {
+  __shared__ K3Smem<ITEMS> sm;
+  u128& s_excl = sm.s_excl;
+  u128& s_tot = sm.s_tot;
+  u128& s_q = sm.s_q;
+  unsigned long long& s_key = sm.s_key;
+  u128* s_warp = sm.s_warp;
+
+  griddep_wait();
+  griddep_launch();
+  const int t = blockIdx.x, p = ctl.parity;
+  StepAcc* A = &sc->acc[p];
+
+  // ---- totals: this rank's from the accumulators, the other ranks' from the exchange slots ------
+  if (pr.R > 1) {
+    const XchSlot* mine = pr.xch[pr.rank];
+    gate_wait(&sc->gate3, ctl.obs_seq + 1, pr, sc, [&](int q) { return &mine[q].sum_seq[p]; });
+    if (threadIdx.x < 32) {  // lane q reads rank q's slot; sums by shuffles
+      const int q = threadIdx.x;
+      const bool on = q < pr.R;
+      u128 tq = on ? make_u128(ld_relaxed_sys(&mine[q].tot_lo[p]), ld_relaxed_sys(&mine[q].tot_hi[p])) : make_u128(0, 0);
+      u128 qq = on ? make_u128(ld_relaxed_sys(&mine[q].q_lo[p]), ld_relaxed_sys(&mine[q].q_hi[p])) : make_u128(0, 0);
+      unsigned long long key = on ? ld_relaxed_sys(&mine[q].max_key[p]) : 0ull;
+      u128 before = (on && q < pr.rank) ? tq : make_u128(0, 0);
+      tq = warp_sum128(tq);
+      qq = warp_sum128(qq);
+      before = warp_sum128(before);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
+        key = o > key ? o : key;
+      }
+      if (threadIdx.x == 0) { s_tot = tq; s_q = qq; s_key = key; s_excl = before; }
+    }
+  } else if (threadIdx.x == 0) {
+    s_tot = A->tot;
+    s_q = A->q;
+    s_key = A->gmax_key;
+    s_excl = make_u128(0, 0);
+  }
+  // ---- exact sum of everything before this tile: whole super tiles + the tiles of this super ----
+  {
+    const int sidx = t / SUPER;
+    const u128* ssum = tb.super_sum + (size_t)p * tb.ns;
+    u128 acc = make_u128(0, 0);
+    for (int s = threadIdx.x; s < sidx; s += TILE_THREADS) acc = add128(acc, ssum[s]);
+    for (int tt = sidx * SUPER + threadIdx.x; tt < t; tt += TILE_THREADS) acc = add128(acc, tb.tile_sum[tt]);
+    const u128 local = block_sum128(acc, s_warp);
+    if (threadIdx.x == 0) s_excl = add128(s_excl, local);
+  }
+  __syncthreads();
+  const bool wrote_remote = k3_tile<real, ITEMS, KIND, true>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
+                                                             s_key, s_excl);
+  if (cdf_out != nullptr) return;
   if (pr.R > 1) {  // "resampling done": the last block tells the peers this step is complete
     if (wrote_remote) __threadfence_system();
     __syncthreads();

@@ -1,0 +1,295 @@
+// cssm_series.cuh -- llFilter (model/ParticleFilter.scala:137-140) of a SMALL cloud as ONE launch.
+//
+// A PMMH likelihood evaluation (model/PMMH.scala:71) filters a few tens of thousands of particles
+// over hundreds of observations: every stage of a step is a few microseconds of work and the
+// three-launch step of cssm_kernels.cuh is bound by launch and dependency latency (19 us per
+// observation at 2^16 particles).  Here the whole foldLeft over the observations runs inside one
+// cooperative kernel: one block per 512-particle tile, all blocks resident, the three stages of a
+// step separated by grid-wide barriers instead of kernel boundaries
+//
+//   P1  gather + stepFunction + f + dataLikelihood, block max -> atomicMax      PF :118,:123-124
+//   --  barrier
+//   P2  w1 = exp(logw - max), exact tile sums of w1 and w1^2                    :125, :431-434
+//   --  barrier
+//   P3  every block adds the (<= a few hundred) tile sums itself: total, ESS, its own exclusive
+//       prefix; CDF of the tile, ancestor search (k3_tile), ll += max + log(mean w1)   :126-128
+//   --  barrier (ancestors complete before the next gather)
+//
+// The per-particle arithmetic is the code of the three-launch path (propagate_particles,
+// WeightSrc, k3_tile) and the sums are the same exact fixed-point integers, so both paths return
+// the same bits (tests/test_gpu_parity.py::test_series_kernel_equals_three_launch_path).
+//
+// Memory visibility inside the launch: data written by another block in an earlier stage is read
+// either with ld.global.cg (cloud, ancestors, tile tables) or with plain loads after the barrier's
+// acquire fence, which invalidates L1 exactly as cooperative_groups::grid_group::sync() does; the
+// non-coherent read-only path (ld.global.nc / __ldg) is never used for such data.
+#pragma once
+#include "cssm_kernels.cuh"
+
+namespace cssm {
+
+// per-observation record in device memory, in the filter dtype:
+//   A[d] D[d] S[d] C[d]  y k0 k1 k2 k3 has_obs pad pad          (StepArgs without the padding)
+constexpr int SERIES_REC_EXTRA = 8;
+
+struct SeriesCtl {
+  unsigned long long bar;       // grid barrier arrivals (zero at launch)
+  unsigned long long gkey[2];   // ordered key of max(logw) by step parity (zero at launch)
+  unsigned long long pad;
+};
+
+struct SeriesArgs {
+  void* x[2];               // ping-pong clouds; x[0] is the current one at entry
+  void* logw;
+  int32_t* anc;
+  FilterScalars* sc;
+  u128* tile_sum;           // [nt]
+  u128* tile_q;             // [nt]
+  double* tile_maxw;        // [nt]
+  SeriesCtl* ctl;
+  const void* recs;         // T records
+  double* ll_steps;
+  int* ess_steps;
+  long long N, Ns;
+  int T, d, nt, obs_kind;
+  uint32_t key0, key1, step0;   // Philox step counter of the first step
+  double inv_n;                 // 1/N when N is a power of two, else 0
+  unsigned long long* dbg;      // NULL, or 8 cycle counters of block 0 (CSSM_SERIES_DEBUG): P1 B1 P2 B2 P3 B3 head
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void red_release_gpu_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// All blocks of the (cooperative, fully resident) grid.  The arrival is a release at gpu scope --
+// cumulative over the bar.sync before it, so it publishes the writes of the whole block -- and the
+// poll is an acquire, after which the bar.sync hands the peers' writes to every thread of the block
+// (ld.acquire.gpu also drops the SM's L1 lines, so later plain loads come from L2).  No stand-alone
+// fence: membar.gl costs about a microsecond and a step has three barriers.
+// Bounded: a block that waits longer than 2 s raises FLAG_COMM_TIMEOUT and every later barrier
+// falls through, so a fault cannot hang the GPU.
+__device__ __forceinline__ void grid_barrier(SeriesCtl* c, FilterScalars* sc, unsigned long long& target, unsigned G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += G;
+    red_release_gpu_add(&c->bar, 1ull);
+    if (ld_acquire_gpu(&c->bar) < target && !(*(volatile int*)&sc->flags & FLAG_COMM_TIMEOUT)) {
+      unsigned long long t0 = 0;
+      unsigned spins = 0;
+      while (ld_acquire_gpu(&c->bar) < target) {
+        if ((++spins & 1023u) == 0u) {
+          const unsigned long long now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 2000000000ull) {
+            atomicOr(&sc->flags, FLAG_COMM_TIMEOUT);
+            break;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+#define CSSM_STAMP(slot)                                              \
+  if (sa.dbg != nullptr && t == 0 && threadIdx.x == 0) {              \
+    const long long now_ = clock64();                                 \
+    atomicAdd(&sa.dbg[slot], (unsigned long long)(now_ - stamp_));    \
+    stamp_ = now_;                                                    \
+  }
+
+template <typename real, int D, int KIND>
+__global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_constant__ SeriesArgs sa) {
+  constexpr int ITEMS = 2;
+  constexpr int TILE = TILE_THREADS * ITEMS;
+  typedef typename WeightSrc<real>::wt wt;
+  __shared__ K3Smem<ITEMS> sm;
+  __shared__ StepArgs<real> a;
+  __shared__ double s_mx[TILE_THREADS / 32], s_mxw[TILE_THREADS / 32];
+  __shared__ u128 s_r[3][TILE_THREADS / 32];
+  __shared__ int s_bad;
+
+  const int t = blockIdx.x;  // one tile per block, gridDim.x == nt
+  const unsigned G = gridDim.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int d = (D > 0) ? D : sa.d;
+  const long long N = sa.N, Ns = sa.Ns;
+  real* const logw = reinterpret_cast<real*>(sa.logw);
+  unsigned long long target = 0;
+  long long stamp_ = clock64();
+
+  Peers pr;
+  pr.R = 1;
+  pr.rank = 0;
+  pr.Nl = N;
+  pr.anc[0] = sa.anc;
+  pr.logw[0] = sa.logw;
+  pr.tile_sum[0] = sa.tile_sum;
+  pr.tile_maxw[0] = sa.tile_maxw;
+  SumTables tb;
+  tb.tile_sum = sa.tile_sum;
+  tb.tile_maxw = sa.tile_maxw;
+  tb.super_sum = nullptr;
+  tb.super_q = nullptr;
+  tb.super_ticket = nullptr;
+  tb.nt = sa.nt;
+  tb.ns = 0;
+
+  int cur = 0, n_obs = 0;
+  bool anc_valid = false;
+  const int rec_len = 4 * d + SERIES_REC_EXTRA;  // <= 136 <= TILE_THREADS: one element per thread
+  // the record of the NEXT step is fetched into a register before the last barrier of a step
+  real rec_v = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
+  for (int s = 0; s < sa.T; ++s) {
+    // ---- the step's constants: record -> shared StepArgs (read-only for the whole launch) ----------
+    {
+      const int i = threadIdx.x, e = i - 4 * d;
+      if (i < 4 * d) {
+        const int which = i / d, k = i - which * d;
+        real* dst = (which == 0) ? a.A : (which == 1) ? a.D : (which == 2) ? a.S : a.C;
+        dst[k] = rec_v;
+      } else if (e == 0) a.y = rec_v;
+      else if (e == 1) a.k0 = rec_v;
+      else if (e == 2) a.k1 = rec_v;
+      else if (e == 3) a.k2 = rec_v;
+      else if (e == 4) a.k3 = rec_v;
+      else if (e == 5) a.has_obs = (rec_v != (real)0) ? 1 : 0;
+      else if (e == 6) { a.d = d; a.obs_kind = sa.obs_kind; s_bad = 0; }
+      if (s + 1 < sa.T && i < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 1) * rec_len + i);
+    }
+    __syncthreads();
+    const int has_obs = a.has_obs;
+    const int par = n_obs & 1;  // parity of the OBSERVED-step count: consecutive users of a key slot alternate
+    const uint32_t step = sa.step0 + (uint32_t)s;
+
+    CSSM_STAMP(6)
+    // ---- P1 ------------------------------------------------------------------------------------
+    pr.x[0] = sa.x[cur];
+    double mx;
+    bool bad;
+    real lw[ITEMS];
+    const long long i0 = (long long)t * TILE + (long long)threadIdx.x * ITEMS;
+    propagate_particles<real, D, ITEMS, true>(a, pr, reinterpret_cast<real*>(sa.x[cur ^ 1]), anc_valid ? sa.anc : nullptr, logw,
+                                              nullptr, N, Ns, 0ull, sa.key0, sa.key1, step, i0, mx, bad, lw);
+    cur ^= 1;
+    anc_valid = false;
+    if (!has_obs) {  // propagated only (:121); the next gather may read any slot of this cloud
+      grid_barrier(sa.ctl, sa.sc, target, G);
+      continue;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    if (lane == 0) s_mx[wid] = mx;
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m2 = s_mx[0];
+      for (int w = 1; w < TILE_THREADS / 32; ++w) m2 = fmax(m2, s_mx[w]);
+      atomicMax(&sa.ctl->gkey[par], ord_key(m2));
+      if (s_bad) atomicOr(&sa.sc->flags, FLAG_NAN_WEIGHT);
+    }
+    CSSM_STAMP(0)
+    grid_barrier(sa.ctl, sa.sc, target, G);
+    CSSM_STAMP(1)
+
+    // ---- P2 ------------------------------------------------------------------------------------
+    const unsigned long long key = ld_gpu(&sa.ctl->gkey[par]);
+    const PreScan ps = pre_scan(key, false);
+    const int qb = ps.qb;
+    WeightSrc<real> ws{logw, nullptr, ps.gmax};
+    wt wv[ITEMS];  // this thread's weights, from the log-weights it still holds in registers
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) wv[j] = (i0 + j < N) ? ws.weight(lw[j]) : (wt)0;
+    {
+      if (t == 0 && threadIdx.x == 0) sa.ctl->gkey[par ^ 1] = 0ull;  // last read before the previous barrier
+      u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
+      wt mxv = (wt)0;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
+        acc2 = add128(acc2, WeightSrc<real>::fix_sq(wv[j], 1.0));
+        mxv = wv[j] > mxv ? wv[j] : mxv;
+      }
+      double mxw = (double)mxv;
+      acc = warp_sum128(acc);
+      acc2 = warp_sum128(acc2);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
+      if (lane == 0) { s_r[0][wid] = acc; s_r[1][wid] = acc2; s_mxw[wid] = mxw; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u128 t1 = s_r[0][0], t2 = s_r[1][0];
+        double m2 = s_mxw[0];
+        for (int w = 1; w < TILE_THREADS / 32; ++w) {
+          t1 = add128(t1, s_r[0][w]);
+          t2 = add128(t2, s_r[1][w]);
+          m2 = fmax(m2, s_mxw[w]);
+        }
+        sa.tile_sum[t] = t1;
+        sa.tile_q[t] = t2;
+        sa.tile_maxw[t] = m2;
+      }
+    }
+    CSSM_STAMP(2)
+    grid_barrier(sa.ctl, sa.sc, target, G);
+    CSSM_STAMP(3)
+
+    // ---- P3 ------------------------------------------------------------------------------------
+    {
+      u128 at = make_u128(0, 0), aq = make_u128(0, 0), ae = make_u128(0, 0);
+      for (int tt = threadIdx.x; tt < sa.nt; tt += TILE_THREADS) {
+        const u128 v = ld_gpu128(&sa.tile_sum[tt]);
+        at = add128(at, v);
+        if (tt < t) ae = add128(ae, v);
+        aq = add128(aq, ld_gpu128(&sa.tile_q[tt]));
+      }
+      at = warp_sum128(at);
+      aq = warp_sum128(aq);
+      ae = warp_sum128(ae);
+      if (lane == 0) { s_r[0][wid] = at; s_r[1][wid] = aq; s_r[2][wid] = ae; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u128 r0 = s_r[0][0], r1 = s_r[1][0], r2 = s_r[2][0];
+        for (int w = 1; w < TILE_THREADS / 32; ++w) {
+          r0 = add128(r0, s_r[0][w]);
+          r1 = add128(r1, s_r[1][w]);
+          r2 = add128(r2, s_r[2][w]);
+        }
+        sm.s_tot = r0;
+        sm.s_q = r1;
+        sm.s_excl = r2;
+      }
+      __syncthreads();
+      K3Ctl kc;
+      kc.parity = 0;
+      kc.obs_seq = 0;
+      kc.gstep = 0;
+      kc.inv_n = sa.inv_n;
+      kc.direct = 0;
+      kc.add_ll = 1;
+      kc.use_u_inj = 0;
+      kc.key0 = sa.key0;
+      kc.key1 = sa.key1;
+      kc.step = step;
+      kc.ll_steps = sa.ll_steps;
+      kc.ess_steps = sa.ess_steps;
+      kc.step_slot = s;
+      k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, sm.s_tot, sm.s_q, key,
+                                        sm.s_excl, wv);
+      anc_valid = true;
+      ++n_obs;
+    }
+    CSSM_STAMP(4)
+    grid_barrier(sa.ctl, sa.sc, target, G);
+    CSSM_STAMP(5)
+  }
+}
+#undef CSSM_STAMP
+
+}  // namespace cssm

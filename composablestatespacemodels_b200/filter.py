@@ -199,7 +199,12 @@ class GpuFilterHandle:
         _abi.check(self._lib.cssm_filter_last_launches(self._h, C.byref(n)))
         return n.value
 
-    KERNEL_CLASSES = ("propagate_weight", "weight_sums", "scan_search", "multinomial_search")
+    KERNEL_CLASSES = ("propagate_weight", "weight_sums", "scan_search", "multinomial_search", "init", "series")
+
+    def series_mode(self, mode):
+        """How whole-series calls run: _abi.SERIES_AUTO (small clouds in one cooperative launch),
+        SERIES_THREE_LAUNCH or SERIES_SINGLE_LAUNCH (include/cssm.h)."""
+        _abi.check(self._lib.cssm_filter_series_mode(self._h, int(mode)))
 
     def profile(self, stride):
         _abi.check(self._lib.cssm_filter_profile(self._h, int(stride)))

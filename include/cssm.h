@@ -224,6 +224,18 @@ int cssm_filter_ll_resident(cssm_filter_t* f, double* ll_out, double* ll_steps_o
 int cssm_filter_run(cssm_filter_t* f, const double* t, const double* y, const uint8_t* has_obs,
                     int64_t T, double* ll_out, double* states_out);
 
+/* How a whole-series call (cssm_filter_ll / _ll_resident / _run) is executed.  AUTO: a cloud small
+ * enough for one resident grid (a few hundred 512-particle tiles; not LGCP, multinomial or sharded)
+ * runs the whole foldLeft of llFilter (model/ParticleFilter.scala:139) inside ONE cooperative kernel
+ * with grid barriers between the stages of a step -- the PMMH likelihood evaluation
+ * (model/PMMH.scala:71) is latency bound, not bandwidth bound; larger clouds use three launches per
+ * observation.  Both return the same bits.  THREE_LAUNCH / SINGLE_LAUNCH force one of the two
+ * (SINGLE_LAUNCH fails with CSSM_ERR_UNSUPPORTED where it does not apply). */
+#define CSSM_SERIES_AUTO 0
+#define CSSM_SERIES_THREE_LAUNCH 1
+#define CSSM_SERIES_SINGLE_LAUNCH 2
+int cssm_filter_series_mode(cssm_filter_t* f, int mode);
+
 /* device time (ms, CUDA events on the filter's stream) of the last whole-series call */
 int cssm_filter_last_elapsed_ms(const cssm_filter_t* f, float* ms_out);
 /* number of kernels the last whole-series / step call launched */
@@ -232,7 +244,8 @@ int cssm_filter_last_launches(const cssm_filter_t* f, int64_t* n_out);
 /* Per-kernel device timing for the roofline report: with stride > 0 every stride-th stepFilter
  * brackets each of its kernels with CUDA events on the launching stream (0 switches it off and
  * clears the sums).  Classes: 0 gather+propagate+weight, 1 exact weight sums, 2 CDF scan +
- * ancestor search, 3 multinomial search.  ms_sum_out[8], count_out[8]. */
+ * ancestor search, 3 multinomial search, 5 the single-launch series kernel (one sample per
+ * whole-series call).  ms_sum_out[8], count_out[8]. */
 int cssm_filter_profile(cssm_filter_t* f, int stride);
 int cssm_filter_profile_read(cssm_filter_t* f, double* ms_sum_out, int64_t* count_out);
 

@@ -7,7 +7,7 @@ import pytest
 import composablestatespacemodels_b200 as cs
 from composablestatespacemodels_b200 import _abi
 import oracle
-from configs import ALL, SYS, STRAT, MULTI, c1, c2, c3
+from configs import ALL, SYS, STRAT, MULTI, c1, c2, c3, c5
 
 pytestmark = pytest.mark.gpu
 
@@ -200,3 +200,62 @@ def test_full_filter_fp64_matches_oracle_end_to_end():
     assert abs(ll_gpu - o_dev._ll) <= 1e-12 * abs(o_dev._ll)
     assert abs(ll_gpu - o_ref._ll) <= 1e-9 * abs(o_ref._ll)
     h.close()
+
+
+@pytest.mark.parametrize("name", sorted(ALL))
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+@pytest.mark.parametrize("kind", [SYS, STRAT])
+def test_series_kernel_equals_three_launch_path(name, dtype, kind):
+    """The single-launch series kernel (small clouds, PMMH) and the three-launch step are two
+    schedules of the same arithmetic: per-step log-likelihood, ESS, the final cloud and a further
+    stepFilter on it must agree bit for bit.  The three-launch path is the one pinned stage by
+    stage against the oracle above, so this extends that parity to the series kernel.  Ragged
+    cloud (not a multiple of the tile), several tiles, missing observations."""
+    mod = ALL[name]()
+    orc = oracle.Oracle(mod)
+    N, T = 5 * 512 + 77, 30
+    t, y, _ = orc.simulate(T, 0.1, 21)
+    has = np.ones(T, dtype=np.uint8)
+    has[[4, 5, 17]] = 0
+    out = []
+    for mode in (_abi.SERIES_THREE_LAUNCH, _abi.SERIES_SINGLE_LAUNCH):
+        h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, seed=7)
+        h.series_mode(mode)
+        h.load_series(t, y, has)
+        ll, lls, ess = h.ll_resident(steps=True)
+        n_launch = h.last_launches()
+        x = h.get_particles()
+        ll2, ess2 = h.step(t[-1] + 0.1, float(y[-1]))   # the handle carries on from the same state
+        x2 = h.get_particles()
+        ll_again = h.ll_resident()                        # a second evaluation draws fresh noise (new epoch)
+        out.append((ll, lls, ess, x, ll2, ess2, x2, ll_again, n_launch))
+        h.close()
+    a, b = out
+    assert b[8] == 2 and a[8] > T            # init + ONE launch against init + 3 per observed step
+    assert a[0] == b[0] and a[4] == b[4] and a[5] == b[5] and a[7] == b[7]
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[6], b[6])
+    assert np.isfinite(a[0]) and a[7] != a[0]
+
+
+def test_series_kernel_degenerate_weights_and_large_grid():
+    """Duplicate-key runs that cross tiles inside the series kernel (extreme observations make
+    almost every weight vanish), on a cloud that needs more than one block per SM."""
+    mod = c5()
+    N, T = 200 * 512, 6
+    t = 0.1 * np.arange(T)
+    y = np.array([0.3, 75.0, -60.0, 0.0, 40.0, 0.1])
+    out = []
+    for mode in (_abi.SERIES_THREE_LAUNCH, _abi.SERIES_SINGLE_LAUNCH):
+        h = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F32, seed=11)
+        h.series_mode(mode)
+        h.load_series(t, y)
+        ll, lls, ess = h.ll_resident(steps=True)
+        out.append((ll, lls, ess, h.get_particles()))
+        h.close()
+    assert out[0][0] == out[1][0]
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    np.testing.assert_array_equal(out[0][3], out[1][3])
