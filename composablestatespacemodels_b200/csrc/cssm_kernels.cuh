@@ -321,7 +321,7 @@ template <> struct VecN<double, 2> { typedef double2 type; typedef int2 itype; }
 // both evaluate a particle with the same instruction sequence.  COH: the cloud and the ancestors
 // were written earlier in the SAME launch by other blocks, so they are read with ld.global.cg (L2)
 // instead of the non-coherent read-only path.
-template <typename real, int D, int PPT, bool COH = false>
+template <typename real, int D, int PPT, bool COH = false, bool FULLBLK = false>
 __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, const Peers& pr, real* __restrict__ xdst,
                                                     const int32_t* __restrict__ anc, real* __restrict__ logw,
                                                     const double* __restrict__ zinj, long long N, long long Ns,
@@ -331,7 +331,7 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
   typedef typename VecN<real, PPT>::itype ivec_t;
   constexpr int PC = Normals<real>::PER_CALL;
   const int d = (D > 0) ? D : a.d;
-  const bool full = (i0 + PPT <= N);
+  const bool full = FULLBLK || (i0 + PPT <= N);  // FULLBLK: the caller knows that every thread of the block is full
   const real* src[PPT];
   bool valid[PPT];
   {
@@ -339,7 +339,7 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
     long long s[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
-      valid[p] = (i0 + p < N);
+      valid[p] = FULLBLK || (i0 + p < N);
       s[p] = i0 + p;
     }
     if (anc != nullptr) {
@@ -464,7 +464,7 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
 }
 
 template <typename real, int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
                    const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
                    long long N, long long Ns, unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
@@ -479,7 +479,10 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PPT;
   double mx;
   bool bad;
-  propagate_particles<real, D, PPT>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+  if ((long long)(blockIdx.x + 1) * blockDim.x * PPT <= N)  // all but the last block: no per-particle bounds predicates
+    propagate_particles<real, D, PPT, false, true>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+  else
+    propagate_particles<real, D, PPT, false, false>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
   if (!a.has_obs && pr.R == 1) return;
   k1_tail(mx, bad, a.has_obs, pr, ctl);
 }
@@ -866,12 +869,15 @@ struct KFun {
 template <int ITEMS> __device__ __forceinline__ int phys(int i) { return ITEMS == 8 ? i + (i >> 3) : i; }
 template <int ITEMS> struct TileSmem { static constexpr int SIZE = TILE_THREADS * ITEMS + (ITEMS == 8 ? TILE_THREADS : 0); };
 
+__device__ __forceinline__ float to_float_rd(float w) { return w; }
+__device__ __forceinline__ float to_float_rd(double w) { return __double2float_rd(w); }
+
 // inclusive CDF values P_j = dbl128(exact prefix) of one tile into Ps[phys(0..TILE)) and the
 // weights (as double) into Ws; `excl` = exact sum of everything before the tile.  All threads call.
 template <typename real, int ITEMS>
 __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128 excl, long long tile0, long long N,
                                          double* Ps, double* Ws, u128* s_warp, double* Pv = nullptr,
-                                         const typename WeightSrc<real>::wt* wv_in = nullptr) {
+                                         const typename WeightSrc<real>::wt* wv_in = nullptr, float* minw_out = nullptr) {
   typedef typename WeightSrc<real>::wt wt;
   const long long base = tile0 + (long long)threadIdx.x * ITEMS;
   wt wv[ITEMS];
@@ -880,6 +886,18 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128
     for (int j = 0; j < ITEMS; ++j) wv[j] = wv_in[j];
   } else {
     ws.template load<ITEMS>(base, 1, N, wv);
+  }
+  if (minw_out != nullptr) {  // a lower bound (fp32, rounded down) of this thread's smallest weight
+    float m = 3.4028234663852886e38f;
+    if (base + ITEMS <= N) {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) m = fminf(m, to_float_rd(wv[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j)
+        if (base + j < N) m = fminf(m, to_float_rd(wv[j]));
+    }
+    *minw_out = m;
   }
   u128 e[ITEMS];
   u128 run = make_u128(0, 0);
@@ -952,6 +970,8 @@ struct K3Smem {
   long long s_pend, s_jfinal;
   double s_wnext, s_u, s_scale;
   int s_tp, s_brk;
+  unsigned s_minw[TILE_THREADS / 32];  // per-warp min weight of the tile (fp32 bits; non-negative floats order as integers)
+  int s_novanish;
 };
 
 // Tile t of the scan + search once the exact sums are known: `tot` / `qsum` = sum of fix(w1) / of
@@ -1052,7 +1072,12 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     s_wnext = wn;
   }
   double Pv[ITEMS];
-  tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp, Pv, wv_in);
+  float minw_thread;
+  tile_cdf<real, ITEMS>(ws, qb, excl, tile0, N, Ps, cdf_out ? nullptr : Ws, s_warp, Pv, wv_in, &minw_thread);
+  {
+    const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(minw_thread));
+    if ((threadIdx.x & 31) == 0) sm.s_minw[threadIdx.x >> 5] = mb;  // read after the next barrier
+  }
 
   if (cdf_out != nullptr) {
     for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) cdf_out[tile0 + j] = Ps[phys<ITEMS>(j)];
@@ -1083,6 +1108,15 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   }
   s_cnt[threadIdx.x] = cr[ITEMS - 1];
   __syncthreads();
+  if (threadIdx.x == 0) {
+    // A key can only repeat where a weight is at most 2^-52 of the cumulative value before it
+    // (vanishes()).  If even the smallest weight of the tile is above 2^-52 of the tile's LAST
+    // cumulative value, no key of this tile repeats and the per-output check is skipped.
+    unsigned mm = sm.s_minw[0];
+#pragma unroll
+    for (int w = 1; w < TILE_THREADS / 32; ++w) mm = min(mm, sm.s_minw[w]);
+    sm.s_novanish = ((double)__uint_as_float(mm) > c_end * 2.220446049250313e-16) ? 1 : 0;
+  }
   const int n_out = s_cnt[TILE_THREADS - 1];
   const long long hi = lo + n_out;
   // does the run of repeated keys at the end of this tile continue into the next tile?
@@ -1129,11 +1163,13 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
       for (int k = 0; k < PER; ++k) s_res[threadIdx.x * PER + k] = max(v[k], before);
       __syncthreads();
       // copy-out: the duplicate-key rule per output, then a coalesced store
+      const bool novanish = sm.s_novanish != 0;  // written before the barriers of this pass
       const int n_w = min(WIN, n_out - w0);
       for (int o = threadIdx.x; o < n_w; o += TILE_THREADS) {
         int jt = s_res[o];
         // TreeMap: a duplicated key keeps the last particle inserted
-        while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+        if (!novanish)
+          while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
         const long long i = lo + w0 + o;
         if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
         const int32_t val = (int32_t)(gbase + jt);
