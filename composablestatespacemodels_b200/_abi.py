@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcssm_gpu.so")
 # enums (include/cssm.h)
 SDE_BROWNIAN, SDE_GEN_BROWNIAN, SDE_OU = 0, 1, 2
 F_FIRST, F_SEASONAL = 0, 1
-OBS_POISSON, OBS_NEGBIN, OBS_NORMAL, OBS_BERNOULLI, OBS_LGCP = 0, 1, 2, 3, 4
+OBS_POISSON, OBS_NEGBIN, OBS_NORMAL, OBS_BERNOULLI, OBS_LGCP, OBS_STUDENT_T, OBS_ZIP, OBS_BETA = 0, 1, 2, 3, 4, 5, 6, 7
 STEP_EXACT, STEP_EULER = 0, 1
 RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_MULTINOMIAL = 0, 1, 2
 F32, F64 = 0, 1
@@ -50,6 +50,8 @@ class ModelDesc(C.Structure):
         ("scale", C.c_double),
         ("step_mode", C.c_int32),
         ("lgcp_precision", C.c_int32),
+        ("obs_df", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -37,13 +37,17 @@ struct HostLeaf {
 };
 struct HostModel {
   std::vector<HostLeaf> leaves;
-  int obs_kind, has_scale, step_mode, lgcp_precision, d;
+  int obs_kind, has_scale, step_mode, lgcp_precision, d, obs_df;
   double scale;
 };
 
 int copy_model(const cssm_model_desc_t* m, HostModel& out) {
   if (!m || m->n_leaves <= 0 || !m->leaves) return fail(CSSM_ERR_INVALID, "model descriptor: no leaves");
-  if (m->obs_kind < CSSM_OBS_POISSON || m->obs_kind > CSSM_OBS_LGCP) return fail(CSSM_ERR_INVALID, "model descriptor: unknown obs_kind");
+  if (m->obs_kind < CSSM_OBS_POISSON || m->obs_kind > CSSM_OBS_BETA) return fail(CSSM_ERR_INVALID, "model descriptor: unknown obs_kind");
+  if (m->obs_kind == CSSM_OBS_STUDENT_T && !m->has_scale) return fail(CSSM_ERR_INVALID, "No scale parameter provided to Student T Model");
+  if (m->obs_kind == CSSM_OBS_STUDENT_T && m->obs_df <= 0) return fail(CSSM_ERR_INVALID, "model descriptor: Student T model needs obs_df > 0");
+  if (m->obs_kind == CSSM_OBS_ZIP && !m->has_scale)
+    return fail(CSSM_ERR_INVALID, "Must provide probability parameter for zero inflated Poisson Model");
   if (m->step_mode != CSSM_STEP_EXACT && m->step_mode != CSSM_STEP_EULER) return fail(CSSM_ERR_INVALID, "model descriptor: unknown step_mode");
   if ((m->obs_kind == CSSM_OBS_NEGBIN || m->obs_kind == CSSM_OBS_NORMAL) && !m->has_scale)
     return fail(CSSM_ERR_INVALID, m->obs_kind == CSSM_OBS_NEGBIN ? "No scale parameter provided to Negativebinomial Model"
@@ -72,6 +76,7 @@ int copy_model(const cssm_model_desc_t* m, HostModel& out) {
   if (out.d > MAXD) return fail(CSSM_ERR_UNSUPPORTED, "total latent dimension exceeds 32");
   out.obs_kind = m->obs_kind; out.has_scale = m->has_scale; out.scale = m->scale;
   out.step_mode = m->step_mode; out.lgcp_precision = m->lgcp_precision;
+  out.obs_df = m->obs_df;
   return CSSM_OK;
 }
 
@@ -141,6 +146,24 @@ void obs_consts(const HostModel& m, int has_obs, double y, StepHost& s) {
     }
     case CSSM_OBS_NORMAL: { double v = std::exp(m.scale); s.k0 = v; s.k1 = std::log(std::sqrt(2 * M_PI)) + std::log(v); break; }
     case CSSM_OBS_BERNOULLI: s.k0 = (y == 1.0) ? 1.0 : 0.0; break;
+    case CSSM_OBS_STUDENT_T: {  // 1/v * StudentsT(df).logPdf((y - eta)/v), model/Model.scala:154-160
+      const double df = (double)m.obs_df;
+      s.k0 = std::exp(m.scale);                                                                   // v
+      s.k1 = df;
+      s.k2 = std::lgamma((df + 1.0) / 2.0) - std::lgamma(df / 2.0) - 0.5 * std::log(M_PI * df);   // -logNormalizer
+      s.k3 = (df + 1.0) / 2.0;
+      break;
+    }
+    case CSSM_OBS_ZIP: {  // model/Model.scala:298-306
+      const int k = (int)y;
+      const double ev = std::exp(m.scale);
+      s.k0 = k; s.k1 = std::lgamma(k + 1.0); s.k2 = ev / (1.0 + ev); s.k3 = std::log(1.0 + ev);
+      break;
+    }
+    case CSSM_OBS_BETA:  // Beta(exp(-gamma), 1.0).logPdf(y) = (a-1) log y + (1-1) log(1-y) + log a, model/Model.scala:349-352
+      s.k0 = std::log(y);
+      s.k1 = 0.0 * std::log(1.0 - y);  // NaN for y == 1, as (b-1)*log(1-x) is in the reference
+      break;
     default: break;
   }
 }
@@ -998,7 +1021,7 @@ int cssm_filter_set_params(cssm_filter_t* f, const cssm_model_desc_t* model) {
   HostModel hm;
   rc = copy_model(model, hm);
   if (rc) return rc;
-  if (hm.d != f->d || hm.leaves.size() != f->model.leaves.size() || hm.obs_kind != f->model.obs_kind)
+  if (hm.d != f->d || hm.leaves.size() != f->model.leaves.size() || hm.obs_kind != f->model.obs_kind || hm.obs_df != f->model.obs_df)
     return fail(CSSM_ERR_INVALID, "set_params: model shape differs from the one the filter was created with");
   for (size_t l = 0; l < hm.leaves.size(); ++l)
     if (hm.leaves[l].dim != f->model.leaves[l].dim || hm.leaves[l].sde_kind != f->model.leaves[l].sde_kind ||

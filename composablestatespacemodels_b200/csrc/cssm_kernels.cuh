@@ -131,6 +131,7 @@ template <> __device__ __forceinline__ double r_neg_big<double>() { return -1e99
 //             k3 = log(size)                                           :186-195
 //   NORMAL    k0 = sd = exp(scale), k1 = log(sqrt(2 pi)) + log(sd)     :227-233,:252-258
 //   BERNOULLI k0 = (y == 1.0)                                          :318-336
+//   STUDENT_T, ZIP, BETA: see the cases                                :144-162, :281-309, :339-353
 // Written with explicit round-to-nearest operations only: the compiler never contracts intrinsics
 // into FMAs, so every instantiation of every kernel (per-step, series) evaluates the same sequence
 // and returns the same bits.
@@ -152,6 +153,18 @@ __device__ __forceinline__ real obs_loglik(const StepArgs<real>& a, real g) {
       if (a.k0 != (real)0) return (p == (real)0) ? r_neg_big<real>() : r_log<real>(p);
       return (p == (real)1) ? r_neg_big<real>() : r_log<real>(r_sub<real>((real)1, p));
     }
+    case CSSM_OBS_STUDENT_T: {  // k0 = v, k1 = df, k2 = -logNormalizer, k3 = (df+1)/2
+      const real xx = r_sub<real>(a.y, g) / a.k0;
+      const real L = r_log<real>(r_add<real>((real)1, r_mul<real>(xx, xx) / a.k1));
+      return r_fma<real>(-a.k3, L, a.k2) / a.k0;
+    }
+    case CSSM_OBS_ZIP: {  // k0 = k, k1 = lgamma(k+1), k2 = p, k3 = log(1 + e^v)
+      const real lam = r_exp<real>(g);
+      if (a.k0 == (real)0) return r_log<real>(r_fma<real>(r_sub<real>((real)1, a.k2), r_exp<real>(-lam), a.k2));
+      return r_sub<real>(r_sub<real>(r_fma<real>(a.k0, g, -a.k3), lam), a.k1);
+    }
+    case CSSM_OBS_BETA:  // k0 = log y, k1 = 0*log(1-y):  (e^-g - 1) log y + 0*log(1-y) + log(e^-g)
+      return r_fma<real>(r_sub<real>(r_exp<real>(-g), (real)1), a.k0, r_sub<real>(a.k1, g));
     default: return (real)0;
   }
 }
@@ -937,6 +950,9 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128
 // domain: C = fl(P/total), wn = fl(w/total).  A weight above 2^-52 * P cannot vanish (cheap filter).
 __device__ __forceinline__ bool vanishes(double P, double w, double total) {
   if (w > P * 2.220446049250313e-16) return false;
+  // w <= 2^-55 P: fl(w/total) < 2^-54.9 fl(P/total) is below half an ulp of fl(P/total), the sum rounds
+  // back to it -- decided without the two divisions (only the three binades in between need them)
+  if (w <= P * 2.7755575615628914e-17) return true;
   const double c = __ddiv_rn(P, total);
   return __dadd_rn(c, __ddiv_rn(w, total)) == c;
 }

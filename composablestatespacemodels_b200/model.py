@@ -14,9 +14,9 @@ from .tree import Leaf, Branch
 
 
 class ModelLeaf:
-    def __init__(self, obs_kind, f_kind, sde, scale, period=0, harmonics=0):
+    def __init__(self, obs_kind, f_kind, sde, scale, period=0, harmonics=0, df=0):
         self.obs_kind, self.f_kind, self.sde, self.scale = obs_kind, f_kind, sde, scale
-        self.period, self.harmonics = period, harmonics
+        self.period, self.harmonics, self.df = period, harmonics, df
 
 
 class Model:
@@ -37,6 +37,10 @@ class Model:
     @property
     def scale(self):
         return self.leaves[0].scale
+
+    @property
+    def df(self):
+        return self.leaves[0].df
 
     @property
     def dimension(self):
@@ -66,8 +70,10 @@ class Model:
 
     def link(self, x):
         k = self.obs_kind
-        if k in (_abi.OBS_POISSON, _abi.OBS_NEGBIN):
+        if k in (_abi.OBS_POISSON, _abi.OBS_NEGBIN, _abi.OBS_ZIP):
             return math.exp(x)
+        if k == _abi.OBS_BETA:
+            return math.exp(-x)  # model/Model.scala:345
         if k == _abi.OBS_BERNOULLI:
             return 1.0 if x > 6 else 0.0 if x < -6 else 1.0 / (1 + math.exp(-x))
         return x
@@ -99,6 +105,7 @@ class Model:
         d.has_scale = 0 if self.scale is None else 1
         d.scale = 0.0 if self.scale is None else self.scale
         d.step_mode, d.lgcp_precision = self.step_mode, self.lgcp_precision
+        d.obs_df = int(self.df)
         keep.append(d)
         return d, keep
 
@@ -149,6 +156,21 @@ def bernoulli(sde):
 
 def lgcp(sde):
     return _leaf_model(_abi.OBS_LGCP, _abi.F_FIRST, sde)
+
+
+def studentsT(sde, df):
+    """model/Model.scala:76-79,144-162; the scale parameter is the log of the t scale."""
+    return _leaf_model(_abi.OBS_STUDENT_T, _abi.F_FIRST, sde, df=int(df))
+
+
+def zeroInflatedPoisson(sde):
+    """model/Model.scala:88-91,281-309; the scale parameter is the logit of the extra-zero probability."""
+    return _leaf_model(_abi.OBS_ZIP, _abi.F_FIRST, sde)
+
+
+def beta(sde):
+    """model/Model.scala:49-54,339-353."""
+    return _leaf_model(_abi.OBS_BETA, _abi.F_FIRST, sde)
 
 
 def compose(mod1, mod2):

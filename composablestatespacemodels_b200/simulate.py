@@ -30,6 +30,13 @@ def _observe(mod, gamma, rng):
         return float(gamma + math.exp(mod.scale) * rng.standard_normal())
     if k == _abi.OBS_BERNOULLI:
         return 1.0 if rng.random() < mod.link(gamma) else 0.0
+    if k == _abi.OBS_STUDENT_T:  # StudentsT(df) * v + x, model/Model.scala:145-150
+        return float(rng.standard_t(mod.df) * math.exp(mod.scale) + gamma)
+    if k == _abi.OBS_ZIP:  # model/Model.scala:282-292
+        p = math.exp(mod.scale) / (1 + math.exp(mod.scale))
+        return 0.0 if rng.random() < p else float(rng.poisson(math.exp(gamma)))
+    if k == _abi.OBS_BETA:  # new Beta(link(gamma), beta), model/Model.scala:340-343 (the scale is the second shape)
+        return float(min(max(rng.beta(mod.link(gamma), mod.scale), 1e-12), 1 - 1e-12))
     return 1.0
 
 

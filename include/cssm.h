@@ -54,7 +54,10 @@ typedef enum {
   CSSM_OBS_NEGBIN = 1,    /* :168-196 */
   CSSM_OBS_NORMAL = 2,    /* LinearModel :241-259 and SeasonalModel :204-234 */
   CSSM_OBS_BERNOULLI = 3, /* :315-337 */
-  CSSM_OBS_LGCP = 4       /* :363-369 via FilterLgcp, model/ParticleFilter.scala:169-227 */
+  CSSM_OBS_LGCP = 4,      /* :363-369 via FilterLgcp, model/ParticleFilter.scala:169-227 */
+  CSSM_OBS_STUDENT_T = 5, /* StudentsTModel :144-162 (df in obs_df; the log-density is multiplied by 1/v as written there) */
+  CSSM_OBS_ZIP = 6,       /* ZeroInflatedPoisson :281-309 (scale = logit of the extra-zero probability) */
+  CSSM_OBS_BETA = 7       /* BetaModel :339-353: Beta(exp(-gamma), 1.0).logPdf(y) -- the scale is not used by the likelihood */
 } cssm_obs_kind;
 /* exact transition (the stepFunction overrides) or Euler-Maruyama (model/Sde.scala:23-43) */
 typedef enum { CSSM_STEP_EXACT = 0, CSSM_STEP_EULER = 1 } cssm_step_mode;
@@ -86,7 +89,7 @@ typedef struct {
 /*
  * A parameterised composed model: what UnparamModel.run(params) returns in the reference
  * (model/Model.scala:110-136), flattened.  `scale` is the RAW ParamNode.scale of the left-most
- * leaf (log of the NegBin size, log of the Normal standard deviation).
+ * leaf (log of the NegBin size, log of the Normal / Student-t scale, logit of the ZIP zero probability).
  */
 typedef struct {
   int32_t n_leaves;
@@ -96,6 +99,8 @@ typedef struct {
   double scale;
   int32_t step_mode;      /* cssm_step_mode */
   int32_t lgcp_precision; /* FilterLgcp.precision: sub-step = 10^-precision */
+  int32_t obs_df;         /* StudentsTModel.df (model/Model.scala:144); 0 otherwise */
+  int32_t reserved;
 } cssm_model_desc_t;
 
 typedef struct cssm_filter cssm_filter_t;

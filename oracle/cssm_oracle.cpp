@@ -292,6 +292,25 @@ double orc_loglik_1(const cssm_model_desc_t* m, double g, double y) {
       if (y == 1.0) return (p == 0.0) ? -1e99 : std::log(p);
       return (p == 1.0) ? -1e99 : std::log(1 - p);
     }
+    case CSSM_OBS_STUDENT_T: {  // :154-160: 1/v * StudentsT(df).logPdf((y - eta)/v)  (the 1/v factor is the reference's)
+      // Breeze StudentsT(df).logPdf(x) = lgamma((df+1)/2) - lgamma(df/2) - log(pi df)/2 - (df+1)/2 * log(1 + x^2/df)
+      double v = std::exp(m->scale), df = (double)m->obs_df;
+      double x = (y - g) / v;
+      double lp = std::lgamma((df + 1.0) / 2.0) - std::lgamma(df / 2.0) - 0.5 * std::log(M_PI * df) -
+                  (df + 1.0) / 2.0 * std::log(1.0 + x * x / df);
+      return 1.0 / v * lp;
+    }
+    case CSSM_OBS_ZIP: {  // :298-306
+      double p = std::exp(m->scale) / (1 + std::exp(m->scale));
+      int k = (int)y;
+      if (k == 0) return std::log(p + (1 - p) * std::exp(-std::exp(g)));
+      return -std::log(1 + std::exp(m->scale)) + k * g - std::exp(g) - std::lgamma(k + 1.0);
+    }
+    case CSSM_OBS_BETA: {  // :349-352: new Beta(exp(-gamma), 1.0).logPdf(y);
+      // Breeze Beta(a, b).logPdf(x) = (a-1) log x + (b-1) log(1-x) - (lgamma(a) + lgamma(b) - lgamma(a+b))
+      double a = std::exp(-g), b = 1.0;
+      return (a - 1) * std::log(y) + (b - 1) * std::log(1 - y) - (std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b));
+    }
     default: return 0.0 / 0.0;  // LGCP has no dataLikelihood (:368)
   }
 }
@@ -749,6 +768,23 @@ void orc_simulate(const cssm_model_desc_t* m, int64_t T, double dt, uint64_t see
       case CSSM_OBS_BERNOULLI: {
         double p = (g > 6) ? 1.0 : (g < -6) ? 0.0 : 1.0 / (1 + std::exp(-g));
         yv = rng.uniform() < p ? 1.0 : 0.0;
+        break;
+      }
+      case CSSM_OBS_STUDENT_T: {  // StudentsT(df) * v + x (:145-150): normal / sqrt(chi2_df / df)
+        double chi2 = 0.0;
+        for (int i = 0; i < m->obs_df; ++i) { double n = rng.normal(); chi2 += n * n; }
+        yv = rng.normal() / std::sqrt(chi2 / m->obs_df) * std::exp(m->scale) + g;
+        break;
+      }
+      case CSSM_OBS_ZIP: {  // :282-292
+        double p = std::exp(m->scale) / (1 + std::exp(m->scale));
+        double nz = draw_poisson(rng, std::exp(g));
+        yv = rng.uniform() < p ? 0.0 : nz;
+        break;
+      }
+      case CSSM_OBS_BETA: {  // Beta(exp(-gamma), beta) (:340-343) as a ratio of gammas, kept inside (0, 1)
+        double ga = draw_gamma(rng, std::exp(-g), 1.0), gb = draw_gamma(rng, m->has_scale ? m->scale : 1.0, 1.0);
+        yv = std::min(std::max(ga / (ga + gb), 1e-12), 1.0 - 1e-12);
         break;
       }
       default: yv = 1.0; break;

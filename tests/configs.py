@@ -61,4 +61,21 @@ def normal_genbm():
     return Model.linear(Sde.genBrownianMotion(1))(Parameters(-0.5, SdeParameter.genBrownianParameter([0.2], [0.8], [0.05], [0.2])))
 
 
-ALL = {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "bernoulli": bernoulli_bm, "normal_genbm": normal_genbm}
+def student_ou():
+    """Student-t observations (df = 5), OU latent state (model/Model.scala:144-162)."""
+    return Model.studentsT(Sde.ouProcess(1), 5)(Parameters(-0.7, SdeParameter.ouParameter([0.5], [0.4], [0.3], [0.2], [0.3])))
+
+
+def zip_seasonal():
+    """zero-inflated Poisson + seasonal (model/Model.scala:281-309)."""
+    m = Model.zeroInflatedPoisson(Sde.ouProcess(1)) | Model.seasonal(12, 1, Sde.ouProcess(2))
+    return m(Parameters(-1.2, ou1()) | Parameters(None, SdeParameter.ouParameter([0.1], [0.5], [0.4], [0.0], [0.3])))
+
+
+def beta_bm():
+    """Beta observations, Brownian-motion latent state (model/Model.scala:339-353)."""
+    return Model.beta(Sde.brownianMotion(1))(Parameters(2.0, SdeParameter.brownianParameter([0.3], [0.2], [0.05])))
+
+
+ALL = {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "bernoulli": bernoulli_bm, "normal_genbm": normal_genbm,
+       "student_t": student_ou, "zip": zip_seasonal, "beta": beta_bm}

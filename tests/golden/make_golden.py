@@ -121,6 +121,21 @@ def log_density(model, gamma, y):
         if y == 1.0:
             return -1e99 if p == 0.0 else math.log(p)
         return -1e99 if p == 1.0 else math.log(1.0 - p)
+    if kind == "student_t":  # 1/v * StudentsT(df).logPdf((y - eta)/v), model/Model.scala:154-160 (the 1/v factor is the reference's)
+        v, df = math.exp(model["scale"]), float(model["df"])
+        x = (y - gamma) / v
+        lp = (math.lgamma((df + 1.0) / 2.0) - math.lgamma(df / 2.0) - 0.5 * math.log(math.pi * df) -
+              (df + 1.0) / 2.0 * math.log(1.0 + x * x / df))
+        return 1.0 / v * lp
+    if kind == "zip":  # model/Model.scala:298-306
+        v, k = model["scale"], int(y)
+        p = math.exp(v) / (1.0 + math.exp(v))
+        if k == 0:
+            return math.log(p + (1.0 - p) * math.exp(-math.exp(gamma)))
+        return -math.log(1.0 + math.exp(v)) + k * gamma - math.exp(gamma) - math.lgamma(k + 1.0)
+    if kind == "beta":  # new Beta(exp(-gamma), 1.0).logPdf(y), model/Model.scala:349-352
+        a, b = math.exp(-gamma), 1.0
+        return (a - 1.0) * math.log(y) + (b - 1.0) * math.log(1.0 - y) - (math.lgamma(a) + math.lgamma(b) - math.lgamma(a + b))
     raise ValueError(kind)
 
 
@@ -235,6 +250,22 @@ def model_bernoulli():
                 leaves=[dict(f="first", sde=bm_leaf(2, [0.0, 0.5], [1.0], [0.3]))])
 
 
+def model_student():
+    return dict(name="student_t", obs="student_t", scale=-0.7, df=5,
+                leaves=[dict(f="first", sde=ou_leaf(1, [0.5], [0.4], [0.3], [0.2], [0.3]))])
+
+
+def model_zip():
+    return dict(name="zip", obs="zip", scale=-1.2,
+                leaves=[dict(f="first", sde=ou_leaf(1, [1.0], [0.5], [0.2], [1.5], [0.05])),
+                        dict(f="seasonal", period=12, harmonics=1, sde=ou_leaf(2, [0.1], [0.5], [0.4], [0.0], [0.3]))])
+
+
+def model_beta():
+    return dict(name="beta", obs="beta", scale=2.0,
+                leaves=[dict(f="first", sde=bm_leaf(1, [0.3], [0.2], [0.05]))])
+
+
 def dim(model):
     return sum(l["sde"]["dim"] for l in model["leaves"])
 
@@ -290,8 +321,12 @@ def filter_case(model, N, T, seed, missing=(), euler=False, big_y=None):
         g_mean = fold_sum([model_f(model, x, t) for x in xp]) / N
         if model["obs"] in ("poisson", "negbin"):
             y = float(max(0, int(round(math.exp(g_mean) + rng.choice([-1, 0, 1, 2])))))
-        elif model["obs"] == "normal":
+        elif model["obs"] == "zip":
+            y = 0.0 if s % 2 == 0 else float(max(0, int(round(math.exp(g_mean)))))
+        elif model["obs"] in ("normal", "student_t"):
             y = g_mean + 0.3 * gauss()
+        elif model["obs"] == "beta":
+            y = min(max(0.5 + 0.2 * gauss(), 0.05), 0.95)
         else:
             y = 1.0 if rng.random() < 0.5 else 0.0
         if big_y is not None and s in big_y:
@@ -387,6 +422,9 @@ def main():
         filter_case(model_c5(), 9, 3, 4, big_y={2: 40.0}),
         filter_case(model_bernoulli(), 11, 3, 5),
         filter_case(model_c4(), 7, 3, 6, euler=True),
+        filter_case(model_student(), 9, 3, 7),
+        filter_case(model_zip(), 10, 4, 8),
+        filter_case(model_beta(), 8, 3, 9),
     ]
     json.dump(cases, open(os.path.join(HERE, "filter_steps.json"), "w"), indent=None, separators=(",", ":"))
     json.dump(resample_cases(), open(os.path.join(HERE, "resampling.json"), "w"), indent=None, separators=(",", ":"))

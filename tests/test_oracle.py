@@ -77,6 +77,24 @@ def test_densities_against_scipy():
     assert o.loglik(np.array([-7.0]), 1.0)[0] == -1e99 and o.loglik(np.array([7.0]), 0.0)[0] == -1e99  # model/Model.scala:332-334
 
 
+def test_further_densities_against_scipy():
+    """Student-t (with the reference's 1/v factor on the log-density), zero-inflated Poisson, Beta
+    (model/Model.scala:154-160, :298-306, :349-352)."""
+    g = np.linspace(-2, 2, 17)
+    o = oracle.Oracle(ALL["student_t"]())
+    v = math.exp(-0.7)
+    for y in (-1.0, 0.4, 3.0):
+        np.testing.assert_allclose(o.loglik(g, y), stats.t.logpdf((y - g) / v, 5) / v, rtol=1e-12, atol=1e-12)
+    o = oracle.Oracle(ALL["zip"]())
+    p = special.expit(-1.2)
+    np.testing.assert_allclose(o.loglik(g, 0.0), np.log(p + (1 - p) * stats.poisson.pmf(0, np.exp(g))), rtol=1e-12)
+    for y in (1.0, 6.0):
+        np.testing.assert_allclose(o.loglik(g, y), np.log1p(-p) + stats.poisson.logpmf(int(y), np.exp(g)), rtol=1e-12, atol=1e-12)
+    o = oracle.Oracle(ALL["beta"]())
+    for y in (0.1, 0.5, 0.93):
+        np.testing.assert_allclose(o.loglik(g, y), stats.beta.logpdf(y, np.exp(-g), 1.0), rtol=1e-11, atol=1e-12)
+
+
 def test_transitions_have_the_reference_moments():
     # OU exact transition: mean mu + (x - mu) e^{-phi dt}, variance sigma^2/(2 phi) (1 - e^{-2 phi dt})  (model/Sde.scala:139-150)
     m = c1()
