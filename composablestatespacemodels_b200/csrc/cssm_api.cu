@@ -295,6 +295,7 @@ Peers make_peers(const cssm_filter* f, int src) {
   pr.R = sharded ? f->world : 1;
   pr.rank = sharded ? f->rank : 0;
   pr.Nl = f->N;
+  pr.inv_nl = 1.0f / (float)f->N;
   for (int q = 0; q < pr.R; ++q) {
     if (q == pr.rank) {
       pr.x[q] = f->x[src]; pr.anc[q] = f->anc; pr.logw[q] = f->logw;
@@ -1646,7 +1647,7 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
     RCU(cudaMemsetAsync(tb.super_ticket, 0, (size_t)ns * sizeof(unsigned long long), st));
     Peers pr;
     std::memset(&pr, 0, sizeof(pr));
-    pr.R = 1; pr.rank = 0; pr.Nl = N; pr.anc[0] = danc; pr.xch[0] = xch; pr.tile_sum[0] = tb.tile_sum; pr.tile_maxw[0] = tb.tile_maxw;
+    pr.R = 1; pr.rank = 0; pr.Nl = N; pr.inv_nl = 1.0f / (float)N; pr.anc[0] = danc; pr.xch[0] = xch; pr.tile_sum[0] = tb.tile_sum; pr.tile_maxw[0] = tb.tile_maxw;
     K3Ctl ctl;
     std::memset(&ctl, 0, sizeof(ctl));
     ctl.inv_n = ((N & (N - 1)) == 0) ? 1.0 / (double)N : 0.0;

@@ -88,6 +88,7 @@ static_assert(sizeof(XchSlot) == 128, "XchSlot is one 128-byte line");
 struct Peers {
   int R, rank;
   long long Nl;                  // particles per rank (the same on every rank)
+  float inv_nl;                  // ~1/Nl (owner_of)
   const void* x[MAXR];           // cloud each rank wrote in the previous step (K1 gathers from it)
   int32_t* anc[MAXR];            // ancestor buffers (K3 scatters into them)
   const void* logw[MAXR];        // log-weights, tile sums, tile maxima: only read when a run of
@@ -95,6 +96,16 @@ struct Peers {
   const double* tile_maxw[MAXR];
   XchSlot* xch[MAXR];            // xch[q] = slot array in rank q's memory; this rank writes xch[q][rank]
 };
+
+// rank that owns global particle / slot index g (< 2^31): g / Nl without an integer division.  The
+// quotient is at most MAXR - 1, so the fp32 estimate is within one of it and one correction settles it.
+__device__ __forceinline__ unsigned owner_of(const Peers& pr, unsigned g) {
+  unsigned q = __float2uint_rz(__uint2float_rz(g) * pr.inv_nl);
+  const int r = (int)(g - q * (unsigned)pr.Nl);
+  if (r < 0) --q;
+  else if (r >= (int)pr.Nl) ++q;
+  return q;
+}
 
 // ---------------------------------------------------------------------------------------------
 template <typename real> struct VecOf;
@@ -371,7 +382,7 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
     for (int p = 0; p < PPT; ++p) {
       if (pr.R > 1 && anc != nullptr) {  // ancestors are GLOBAL particle indices: owner rank + local index
         const unsigned g = (unsigned)s[p];
-        const unsigned q = g / (unsigned)pr.Nl;
+        const unsigned q = owner_of(pr, g);
         src[p] = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
       } else {
         src[p] = xloc + s[p];
@@ -529,7 +540,7 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
     if (anc) {
       if (pr.R > 1) {
         const unsigned g = (unsigned)anc[i];
-        const unsigned q = g / (unsigned)pr.Nl;
+        const unsigned q = owner_of(pr, g);
         src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
       } else {
         src = reinterpret_cast<const real*>(pr.x[0]) + anc[i];
@@ -1190,8 +1201,8 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
         if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
         const int32_t val = (int32_t)(gbase + jt);
         if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
-          const long long q = i / N;
-          pr.anc[q][i - q * N] = val;
+          const unsigned q = owner_of(pr, (unsigned)i);
+          pr.anc[q][i - (long long)q * N] = val;
           wrote_remote |= (q != pr.rank);
         } else {
           pr.anc[0][i] = val;
@@ -1259,8 +1270,8 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     const long long jfinal = s_jfinal;
     for (long long i = pend + threadIdx.x; i < hi; i += TILE_THREADS) {
       if (pr.R > 1) {
-        const long long q = i / N;
-        pr.anc[q][i - q * N] = (int32_t)jfinal;
+        const unsigned q = owner_of(pr, (unsigned)i);
+        pr.anc[q][i - (long long)q * N] = (int32_t)jfinal;
         wrote_remote |= (q != pr.rank);
       } else {
         pr.anc[0][i] = (int32_t)jfinal;
@@ -1379,7 +1390,7 @@ k_gather(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, out_
   const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
   if (anc) {
     const unsigned g = (unsigned)anc[i];
-    const unsigned q = (pr.R > 1) ? g / (unsigned)pr.Nl : 0u;
+    const unsigned q = (pr.R > 1) ? owner_of(pr, g) : 0u;
     src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
   }
   for (int k = 0; k < d; ++k) out[(long long)k * out_stride + i] = (out_t)src[(long long)k * Ns];
@@ -1410,7 +1421,7 @@ __global__ void k_sample_one(const __grid_constant__ Peers pr, const int32_t* __
   const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
   if (anc) {
     const unsigned g = (unsigned)anc[i];
-    const unsigned q = (pr.R > 1) ? g / (unsigned)pr.Nl : 0u;
+    const unsigned q = (pr.R > 1) ? owner_of(pr, g) : 0u;
     src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
   }
   for (int k = 0; k < d; ++k) out[k] = (double)src[(long long)k * Ns];
@@ -1427,7 +1438,7 @@ k_mean_state(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, 
     const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
     if (anc) {
       const unsigned g = (unsigned)anc[i];
-      const unsigned q = (pr.R > 1) ? g / (unsigned)pr.Nl : 0u;
+      const unsigned q = (pr.R > 1) ? owner_of(pr, g) : 0u;
       src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
     }
     acc += (double)src[(long long)k * Ns];

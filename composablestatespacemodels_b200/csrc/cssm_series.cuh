@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
   pr.R = 1;
   pr.rank = 0;
   pr.Nl = N;
+  pr.inv_nl = 0.0f;
   pr.anc[0] = sa.anc;
   pr.logw[0] = sa.logw;
   pr.tile_sum[0] = sa.tile_sum;
