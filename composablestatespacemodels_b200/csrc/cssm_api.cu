@@ -238,6 +238,9 @@ struct cssm_filter {
   bool recs_valid = false;
   int series_mode = CSSM_SERIES_AUTO;
   int series_max_blocks = -1;      // co-resident blocks of k_series_small on this device (-1: not queried)
+  int series_multi_blocks = 0;     // ... of k_series_multi
+  long long series_multi_max = 1ll << 19;  // largest cloud the multi-tile series kernel is used for (CSSM_SERIES_MAX_N)
+  bool series_use_multi = false;
   bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
   float last_ms = 0.f;
@@ -688,21 +691,44 @@ void* series_kernel_ptr(int d, int kind) {
 void* series_kernel(const cssm_filter* f) {
   return (f->dtype == CSSM_F32) ? series_kernel_ptr<float>(f->d, f->resample_kind) : series_kernel_ptr<double>(f->d, f->resample_kind);
 }
+// mid-size clouds: several tiles per block
+template <typename real, int ITEMS>
+void* series_multi_ptr(int d, int kind) {
+  const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
+  if (d == 7) return strat ? (void*)k_series_multi<real, 7, CSSM_RESAMPLE_STRATIFIED, ITEMS> : (void*)k_series_multi<real, 7, CSSM_RESAMPLE_SYSTEMATIC, ITEMS>;
+  return strat ? (void*)k_series_multi<real, 0, CSSM_RESAMPLE_STRATIFIED, ITEMS> : (void*)k_series_multi<real, 0, CSSM_RESAMPLE_SYSTEMATIC, ITEMS>;
+}
+void* series_multi_kernel(const cssm_filter* f) {
+  if (f->dtype == CSSM_F32)
+    return f->items == 8 ? series_multi_ptr<float, 8>(f->d, f->resample_kind) : series_multi_ptr<float, 2>(f->d, f->resample_kind);
+  return f->items == 8 ? series_multi_ptr<double, 8>(f->d, f->resample_kind) : series_multi_ptr<double, 2>(f->d, f->resample_kind);
+}
+int resident_blocks(const cssm_filter* f, void* kern) {
+  int per_sm = 0, sms = 0, coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE_THREADS, 0) != cudaSuccess) per_sm = 0;
+  cudaGetLastError();
+  return coop ? per_sm * sms : 0;
+}
 
 // may this filter's loaded series run as one launch?  One 512-particle tile per block, every block resident.
 bool series_eligible(cssm_filter* f, bool sample_states) {
-  if (f->series_mode == CSSM_SERIES_THREE_LAUNCH || sample_states || f->world > 1 || f->items != 2) return false;
+  if (f->series_mode == CSSM_SERIES_THREE_LAUNCH || sample_states || f->world > 1) return false;
   if (f->model.obs_kind == CSSM_OBS_LGCP || f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) return false;
   if (f->series.empty() || f->series.size() > 0x7fffffffull) return false;
   if (f->series_max_blocks < 0) {
-    int per_sm = 0, sms = 0, coop = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->device);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, series_kernel(f), TILE_THREADS, 0) != cudaSuccess) per_sm = 0;
-    cudaGetLastError();
-    f->series_max_blocks = coop ? per_sm * sms : 0;
+    f->series_max_blocks = resident_blocks(f, series_kernel(f));
+    f->series_multi_blocks = resident_blocks(f, series_multi_kernel(f));
   }
-  return f->nt <= f->series_max_blocks;
+  f->series_use_multi = false;
+  if (f->items == 2 && f->nt <= f->series_max_blocks) return true;   // one tile per block, weights stay in registers
+  // several tiles per block: pays while a stage is short against the launch gaps it removes
+  if (f->series_multi_blocks > 0 && (f->N <= f->series_multi_max || f->series_mode == CSSM_SERIES_SINGLE_LAUNCH)) {
+    f->series_use_multi = true;
+    return true;
+  }
+  return false;
 }
 
 // the per-observation records of the loaded series: [A D S C | y k0 k1 k2 k3 has_obs 0 0] in the filter dtype
@@ -751,6 +777,8 @@ int run_series_single_launch(cssm_filter* f) {
   sa.N = f->N; sa.Ns = f->Ns; sa.T = (int)T; sa.d = f->d; sa.nt = f->nt; sa.obs_kind = f->model.obs_kind;
   sa.key0 = f->key0; sa.key1 = f->key1; sa.step0 = f->step_ctr;
   sa.inv_n = ((f->N & (f->N - 1)) == 0) ? 1.0 / (double)f->N : 0.0;
+  sa.pr[0] = make_peers(f, f->cur);
+  sa.pr[1] = make_peers(f, f->cur ^ 1);
   static const bool debug_stamps = std::getenv("CSSM_SERIES_DEBUG") != nullptr;
   if (debug_stamps) {
     int rc2 = ensure_scratch(f, 8);
@@ -763,7 +791,11 @@ int run_series_single_launch(cssm_filter* f) {
   cudaError_t e;
   {
     ProfScope ps_(f, CLS_SERIES, prof);
-    e = cudaLaunchCooperativeKernel(series_kernel(f), dim3((unsigned)f->nt), dim3(TILE_THREADS), args, 0, f->stream);
+    if (f->series_use_multi)
+      e = cudaLaunchCooperativeKernel(series_multi_kernel(f), dim3((unsigned)std::min(f->nt, f->series_multi_blocks)), dim3(TILE_THREADS),
+                                      args, 0, f->stream);
+    else
+      e = cudaLaunchCooperativeKernel(series_kernel(f), dim3((unsigned)f->nt), dim3(TILE_THREADS), args, 0, f->stream);
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch series kernel: ") + cudaGetErrorString(e));
   f->launches++;
@@ -865,6 +897,7 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   f->items = (f->N <= (1 << 18)) ? 2 : 8;
   if (const char* e = std::getenv("CSSM_TILE_ITEMS")) { int v = std::atoi(e); if (v == 2 || v == 8) f->items = v; }
   if (const char* e = std::getenv("CSSM_PDL")) f->pdl = std::atoi(e) != 0;
+  if (const char* e = std::getenv("CSSM_SERIES_MAX_N")) f->series_multi_max = std::atoll(e);
   if (const char* e = std::getenv("CSSM_SERIES_KERNEL")) f->series_mode = std::atoi(e) ? CSSM_SERIES_AUTO : CSSM_SERIES_THREE_LAUNCH;
   const int tile = TILE_THREADS * f->items;
   f->nt = nblk(f->N, tile);

@@ -55,6 +55,8 @@ struct SeriesArgs {
   uint32_t key0, key1, step0;   // Philox step counter of the first step
   double inv_n;                 // 1/N when N is a power of two, else 0
   unsigned long long* dbg;      // NULL, or 8 cycle counters of block 0 (CSSM_SERIES_DEBUG): P1 B1 P2 B2 P3 B3 head
+  Peers pr[2];                  // the (single-rank) topology with x[0] = the cloud read in even / odd steps: kept in
+                                // the kernel's constant bank instead of a 400-byte struct in local memory
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
@@ -124,15 +126,6 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
   unsigned long long target = 0;
   long long stamp_ = clock64();
 
-  Peers pr;
-  pr.R = 1;
-  pr.rank = 0;
-  pr.Nl = N;
-  pr.inv_nl = 0.0f;
-  pr.anc[0] = sa.anc;
-  pr.logw[0] = sa.logw;
-  pr.tile_sum[0] = sa.tile_sum;
-  pr.tile_maxw[0] = sa.tile_maxw;
   SumTables tb;
   tb.tile_sum = sa.tile_sum;
   tb.tile_maxw = sa.tile_maxw;
@@ -171,7 +164,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
 
     CSSM_STAMP(6)
     // ---- P1 ------------------------------------------------------------------------------------
-    pr.x[0] = sa.x[cur];
+    const Peers& pr = sa.pr[cur];
     double mx;
     bool bad;
     real lw[ITEMS];
@@ -292,5 +285,214 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
   }
 }
 #undef CSSM_STAMP
+
+// ---------------------------------------------------------------------------------------------
+// The same single-launch schedule for MID-SIZE clouds (up to a few million particles): more tiles
+// than resident blocks, so block b owns the tiles b, b+G, b+2G, ... and loops over them in every
+// stage; log-weights go through L2 between the stages instead of staying in registers.  At 2^20
+// particles a stage is 5-15 us of work and the launch / drain gaps of the three-launch step cost a
+// third of the step; here they shrink to three grid barriers.  Same per-particle code, same exact
+// sums: bit-identical to the other two schedules.
+// ---------------------------------------------------------------------------------------------
+template <typename real, int D, int KIND, int ITEMS>
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_series_multi(const __grid_constant__ SeriesArgs sa) {
+  constexpr int TILE = TILE_THREADS * ITEMS;
+  constexpr int PPT = VecOf<real>::PPT;
+  constexpr int CHUNK = TILE_THREADS * PPT;
+  typedef typename WeightSrc<real>::wt wt;
+  // the step constants are only read in P1 and the scan + search memory only in P3: they share storage
+  __shared__ union SmemU { K3Smem<ITEMS> sm; StepArgs<real> a; } smem_u;
+  K3Smem<ITEMS>& sm = smem_u.sm;
+  StepArgs<real>& a = smem_u.a;
+  __shared__ double s_mx[TILE_THREADS / 32], s_mxw[TILE_THREADS / 32];
+  __shared__ u128 s_r[3][TILE_THREADS / 32];
+  __shared__ u128 s_excl_run;
+  __shared__ int s_bad;
+
+  const int b = blockIdx.x;
+  const unsigned G = gridDim.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int d = (D > 0) ? D : sa.d;
+  const long long N = sa.N, Ns = sa.Ns;
+  const long long n_chunks = (N + CHUNK - 1) / CHUNK;
+  real* const logw = reinterpret_cast<real*>(sa.logw);
+  unsigned long long target = 0;
+
+  SumTables tb;
+  tb.tile_sum = sa.tile_sum;
+  tb.tile_maxw = sa.tile_maxw;
+  tb.super_sum = nullptr;
+  tb.super_q = nullptr;
+  tb.super_ticket = nullptr;
+  tb.nt = sa.nt;
+  tb.ns = 0;
+
+  int cur = 0, n_obs = 0;
+  bool anc_valid = false;
+  const int rec_len = 4 * d + SERIES_REC_EXTRA;
+  real rec_v = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
+  for (int s = 0; s < sa.T; ++s) {
+    {
+      const int i = threadIdx.x, e = i - 4 * d;
+      if (i < 4 * d) {
+        const int which = i / d, k = i - which * d;
+        real* dst = (which == 0) ? a.A : (which == 1) ? a.D : (which == 2) ? a.S : a.C;
+        dst[k] = rec_v;
+      } else if (e == 0) a.y = rec_v;
+      else if (e == 1) a.k0 = rec_v;
+      else if (e == 2) a.k1 = rec_v;
+      else if (e == 3) a.k2 = rec_v;
+      else if (e == 4) a.k3 = rec_v;
+      else if (e == 5) a.has_obs = (rec_v != (real)0) ? 1 : 0;
+      else if (e == 6) { a.d = d; a.obs_kind = sa.obs_kind; s_bad = 0; }
+      if (s + 1 < sa.T && i < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 1) * rec_len + i);
+    }
+    __syncthreads();
+    const int has_obs = a.has_obs;
+    const int par = n_obs & 1;
+    const uint32_t step = sa.step0 + (uint32_t)s;
+
+    // ---- P1: chunks b, b+G, ... of 256*PPT particles --------------------------------------------------
+    const Peers& pr = sa.pr[cur];
+    double mx = -__longlong_as_double(0x7FF0000000000000ll);
+    bool bad = false;
+    for (long long c = b; c < n_chunks; c += G) {
+      const long long i0 = c * CHUNK + (long long)threadIdx.x * PPT;
+      double mxc;
+      bool badc;
+      if ((c + 1) * CHUNK <= N)
+        propagate_particles<real, D, PPT, true, true>(a, pr, reinterpret_cast<real*>(sa.x[cur ^ 1]), anc_valid ? sa.anc : nullptr,
+                                                      logw, nullptr, N, Ns, 0ull, sa.key0, sa.key1, step, i0, mxc, badc);
+      else
+        propagate_particles<real, D, PPT, true, false>(a, pr, reinterpret_cast<real*>(sa.x[cur ^ 1]), anc_valid ? sa.anc : nullptr,
+                                                       logw, nullptr, N, Ns, 0ull, sa.key0, sa.key1, step, i0, mxc, badc);
+      mx = fmax(mx, mxc);
+      bad |= badc;
+    }
+    cur ^= 1;
+    anc_valid = false;
+    if (!has_obs) {
+      grid_barrier(sa.ctl, sa.sc, target, G);
+      continue;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    if (lane == 0) s_mx[wid] = mx;
+    if (bad) s_bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m2 = s_mx[0];
+      for (int w = 1; w < TILE_THREADS / 32; ++w) m2 = fmax(m2, s_mx[w]);
+      atomicMax(&sa.ctl->gkey[par], ord_key(m2));
+      if (s_bad) atomicOr(&sa.sc->flags, FLAG_NAN_WEIGHT);
+    }
+    grid_barrier(sa.ctl, sa.sc, target, G);
+
+    // ---- P2: exact sums of the tiles b, b+G, ... ------------------------------------------------------
+    const unsigned long long key = ld_gpu(&sa.ctl->gkey[par]);
+    const PreScan ps = pre_scan(key, false);
+    const int qb = ps.qb;
+    WeightSrc<real> ws{logw, nullptr, ps.gmax};
+    if (b == 0 && threadIdx.x == 0) sa.ctl->gkey[par ^ 1] = 0ull;
+    for (int t = b; t < sa.nt; t += G) {
+      wt wv[ITEMS];
+      ws.template load<ITEMS>((long long)t * TILE + threadIdx.x, TILE_THREADS, N, wv);
+      u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
+      wt mxv = (wt)0;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
+        acc2 = add128(acc2, WeightSrc<real>::fix_sq(wv[j], 1.0));
+        mxv = wv[j] > mxv ? wv[j] : mxv;
+      }
+      double mxw = (double)mxv;
+      acc = warp_sum128(acc);
+      acc2 = warp_sum128(acc2);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
+      __syncthreads();  // s_r / s_mxw of the previous tile have been read
+      if (lane == 0) { s_r[0][wid] = acc; s_r[1][wid] = acc2; s_mxw[wid] = mxw; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u128 t1 = s_r[0][0], t2 = s_r[1][0];
+        double m2 = s_mxw[0];
+        for (int w = 1; w < TILE_THREADS / 32; ++w) {
+          t1 = add128(t1, s_r[0][w]);
+          t2 = add128(t2, s_r[1][w]);
+          m2 = fmax(m2, s_mxw[w]);
+        }
+        sa.tile_sum[t] = t1;
+        sa.tile_q[t] = t2;
+        sa.tile_maxw[t] = m2;
+      }
+    }
+    grid_barrier(sa.ctl, sa.sc, target, G);
+
+    // ---- P3: totals once per block, then scan + search of the tiles b, b+G, ... -----------------------
+    {
+      u128 at = make_u128(0, 0), aq = make_u128(0, 0), ae = make_u128(0, 0);
+      for (int tt = threadIdx.x; tt < sa.nt; tt += TILE_THREADS) {
+        const u128 v = ld_gpu128(&sa.tile_sum[tt]);
+        at = add128(at, v);
+        if (tt < b) ae = add128(ae, v);
+        aq = add128(aq, ld_gpu128(&sa.tile_q[tt]));
+      }
+      at = warp_sum128(at);
+      aq = warp_sum128(aq);
+      ae = warp_sum128(ae);
+      if (lane == 0) { s_r[0][wid] = at; s_r[1][wid] = aq; s_r[2][wid] = ae; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u128 r0 = s_r[0][0], r1 = s_r[1][0], r2 = s_r[2][0];
+        for (int w = 1; w < TILE_THREADS / 32; ++w) {
+          r0 = add128(r0, s_r[0][w]);
+          r1 = add128(r1, s_r[1][w]);
+          r2 = add128(r2, s_r[2][w]);
+        }
+        sm.s_tot = r0;
+        sm.s_q = r1;
+        s_excl_run = r2;
+      }
+      __syncthreads();
+      const u128 tot = sm.s_tot, qsum = sm.s_q;
+      K3Ctl kc;
+      kc.parity = 0;
+      kc.obs_seq = 0;
+      kc.gstep = 0;
+      kc.inv_n = sa.inv_n;
+      kc.direct = 0;
+      kc.add_ll = 1;
+      kc.use_u_inj = 0;
+      kc.key0 = sa.key0;
+      kc.key1 = sa.key1;
+      kc.step = step;
+      kc.ll_steps = sa.ll_steps;
+      kc.ess_steps = sa.ess_steps;
+      kc.step_slot = s;
+      for (int t = b; t < sa.nt; t += G) {
+        const u128 excl = s_excl_run;
+        __syncthreads();  // everyone holds excl (and is done with the shared memory of the previous tile)
+        k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, tot, qsum, key, excl);
+        if (t + (int)G < sa.nt) {  // exclusive prefix of the block's next tile: add the tiles t .. t+G-1
+          u128 ad = make_u128(0, 0);
+          for (int tt = t + threadIdx.x; tt < t + (int)G; tt += TILE_THREADS) ad = add128(ad, ld_gpu128(&sa.tile_sum[tt]));
+          ad = warp_sum128(ad);
+          __syncthreads();
+          if (lane == 0) s_r[0][wid] = ad;
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            u128 r0 = s_excl_run;
+            for (int w = 0; w < TILE_THREADS / 32; ++w) r0 = add128(r0, s_r[0][w]);
+            s_excl_run = r0;
+          }
+          __syncthreads();
+        }
+      }
+      anc_valid = true;
+      ++n_obs;
+    }
+    grid_barrier(sa.ctl, sa.sc, target, G);
+  }
+}
 
 }  // namespace cssm

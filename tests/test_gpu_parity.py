@@ -259,3 +259,35 @@ def test_series_kernel_degenerate_weights_and_large_grid():
     np.testing.assert_array_equal(out[0][1], out[1][1])
     np.testing.assert_array_equal(out[0][2], out[1][2])
     np.testing.assert_array_equal(out[0][3], out[1][3])
+
+
+@pytest.mark.parametrize("name,N", [("c2", 300 * 512 + 77), ("c4", 300 * 512 + 77), ("c2", (1 << 18) + 6149), ("c5", (1 << 19) + 3)])
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+@pytest.mark.parametrize("kind", [SYS, STRAT])
+def test_series_multi_tile_kernel_equals_three_launch_path(name, N, dtype, kind):
+    """Mid-size clouds: more tiles than resident blocks, every block loops over several tiles in
+    each stage of the single-launch kernel (512- and 2048-particle tiles, compile-time and generic
+    latent dimension).  Same bits as the three-launch step."""
+    mod = ALL[name]()
+    orc = oracle.Oracle(mod)
+    T = 10
+    t, y, _ = orc.simulate(T, 0.1, 33)
+    has = np.ones(T, dtype=np.uint8)
+    has[[3, 4]] = 0
+    out = []
+    for mode in (_abi.SERIES_THREE_LAUNCH, _abi.SERIES_SINGLE_LAUNCH):
+        h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, seed=13)
+        h.series_mode(mode)
+        h.load_series(t, y, has)
+        ll, lls, ess = h.ll_resident(steps=True)
+        n_launch = h.last_launches()
+        x = h.get_particles()
+        ll2, ess2 = h.step(t[-1] + 0.1, float(y[-1]))
+        out.append((ll, lls, ess, x, ll2, ess2, n_launch))
+        h.close()
+    a, b = out
+    assert b[6] == 2 and a[6] > T
+    assert a[0] == b[0] and a[4] == b[4] and a[5] == b[5]
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
