@@ -352,6 +352,15 @@ def main():
         prof = h.profile_read()
         h.profile(0)
         value = n_total * T * args.steps / (ms * 1e-3)
+        if not sharded and wl_model != "c3":
+            # the step after the filter in the streaming examples (examples/Filtering.scala:29): getIntervals of the
+            # final cloud on the device (mean + 2(d+1) order statistics by radix select), not part of the timed region
+            h.intervals(float(t[-1]))
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(3):
+                h.intervals(float(t[-1]))
+            extra["get_intervals_ms"] = (time.perf_counter() - w0) / 3 * 1e3
 
         # ---- end to end through the public API: host observations in, log-likelihood out ----------
         from composablestatespacemodels_b200 import Filter, FilterLgcp, Data
@@ -400,8 +409,16 @@ def main():
             # what one observed step moves with the gather fused into the next propagate and no CDF written:
             # K1 2db+b+4, K2 b, K3 b+4
             real_bpp = k1_bpp + b + b + 4
+            traffic = None
+            try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same shape only)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+                if tr and tr["particles"] == n_local and args.dtype == "f32":
+                    traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": "k_propagate_weight (gather + propagate + weight, fused)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": k1_bpp * n_local,
                     "peak_source": peak_src, "algorithmic_bytes_per_particle": k1_bpp,
                     "avg_launch_ms": k1_ms / k1_n, "sampled_launches": k1_n,
                     "kernel_ms_per_launch": per_launch,

@@ -1627,6 +1627,82 @@ int cssm_filter_mean_state(cssm_filter_t* f, double* mean_out) {
   return CSSM_OK;
 }
 
+int cssm_filter_intervals(cssm_filter_t* f, double t, double interval, double* state_mean, double* state_lower,
+                          double* state_upper, double* gamma_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "no particles yet");
+  if (!state_mean || !state_lower || !state_upper || !gamma_out) return fail(CSSM_ERR_INVALID, "null output");
+  if (f->world > 1) return fail(CSSM_ERR_UNSUPPORTED, "intervals of a sharded cloud are not implemented");
+  const long long n = f->N;
+  // getCredibleInterval (model/ParticleFilter.scala:498-503): index = floor(interval * n), sorted(n - index - 1), sorted(index - 1)
+  const long long idx_s = (long long)std::floor(interval * (double)n);
+  const long long lo_s = n - idx_s - 1, hi_s = idx_s - 1;
+  // getOrderStatistic (:455-460): index = floor(n * interval), ordered(n - index), ordered(index)
+  const long long idx_e = (long long)std::floor((double)n * interval);
+  long long lo_e = n - idx_e, hi_e = idx_e;
+  if (idx_e >= n || idx_e < 1) return fail(CSSM_ERR_INVALID, "intervals: the order-statistic index is outside the cloud (the reference throws IndexOutOfBounds here)");
+  // decreasing link (BetaModel: exp(-x), model/Model.scala:345): ascending eta is descending gamma, the ranks mirror
+  if (f->model.obs_kind == CSSM_OBS_BETA) { lo_e = n - 1 - idx_e; hi_e = idx_e - 1; }
+  if (lo_s < 0 || lo_s >= n || hi_s < 0 || hi_s >= n || lo_e < 0 || lo_e >= n || hi_e < 0 || hi_e >= n)
+    return fail(CSSM_ERR_INVALID, "intervals: the order-statistic index is outside the cloud (the reference throws IndexOutOfBounds here)");
+  const int d = f->d, cols = d + 1;
+  // scratch: mean[d] | out[2*cols] | SelState[2*cols] | hist[cols*512 u32]
+  const size_t n_dbl = (size_t)d + 2 * cols + 2 * (2 * cols) + (size_t)cols * 256 + 8;
+  rc = ensure_scratch(f, n_dbl);
+  if (rc) return rc;
+  double* mean_dev = f->scratch;
+  double* out_dev = mean_dev + d;
+  SelState* sel_dev = reinterpret_cast<SelState*>(out_dev + 2 * cols);
+  unsigned* hist_dev = reinterpret_cast<unsigned*>(sel_dev + 2 * cols);
+  std::vector<SelState> sel((size_t)2 * cols);
+  for (int c = 0; c < cols; ++c) {
+    sel[2 * c] = SelState{0ull, c < d ? lo_s : lo_e};
+    sel[2 * c + 1] = SelState{0ull, c < d ? hi_s : hi_e};
+  }
+  CU(cudaMemsetAsync(mean_dev, 0, (size_t)d * sizeof(double), f->stream));
+  CU(cudaMemsetAsync(hist_dev, 0, (size_t)cols * 512 * sizeof(unsigned), f->stream));
+  CU(cudaMemcpyAsync(sel_dev, sel.data(), sel.size() * sizeof(SelState), cudaMemcpyHostToDevice, f->stream));
+  const int32_t* anc = f->anc_valid ? f->anc : nullptr;
+  const Peers pr = make_peers(f, f->cur);
+  StepHost h;
+  std::memset(&h, 0, sizeof(h));
+  f_coeffs(f->model, t, h.C);
+  const int gx = (int)std::min<long long>(nblk(n, 256), 148 * 8);
+  dim3 gmean((unsigned)std::min<long long>(nblk(n, 256), 1184), (unsigned)d), ghist((unsigned)gx, (unsigned)cols);
+  if (f->dtype == CSSM_F32) {
+    StepArgs<float> a;
+    to_args<float>(f->model, h, a);
+    k_mean_state<float><<<gmean, 256, 0, f->stream>>>(pr, anc, mean_dev, d, n, f->Ns);
+    for (int pass = 0; pass < 4; ++pass) {
+      k_select_hist<float><<<ghist, 256, 0, f->stream>>>(pr, anc, a, d, n, f->Ns, pass, sel_dev, hist_dev);
+      k_select_pick<<<2 * cols, 32, 0, f->stream>>>(sel_dev, hist_dev);
+    }
+    k_select_finish<float><<<1, 128, 0, f->stream>>>(sel_dev, out_dev, 2 * cols);
+  } else {
+    StepArgs<double> a;
+    to_args<double>(f->model, h, a);
+    k_mean_state<double><<<gmean, 256, 0, f->stream>>>(pr, anc, mean_dev, d, n, f->Ns);
+    for (int pass = 0; pass < 8; ++pass) {
+      k_select_hist<double><<<ghist, 256, 0, f->stream>>>(pr, anc, a, d, n, f->Ns, pass, sel_dev, hist_dev);
+      k_select_pick<<<2 * cols, 32, 0, f->stream>>>(sel_dev, hist_dev);
+    }
+    k_select_finish<double><<<1, 128, 0, f->stream>>>(sel_dev, out_dev, 2 * cols);
+  }
+  CU(cudaGetLastError());
+  std::vector<double> host((size_t)d + 2 * cols);
+  CU(cudaMemcpyAsync(host.data(), mean_dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  for (int k = 0; k < d; ++k) {
+    state_mean[k] = host[k];
+    state_lower[k] = host[d + 2 * k];
+    state_upper[k] = host[d + 2 * k + 1];
+  }
+  gamma_out[0] = host[d + 2 * d];
+  gamma_out[1] = host[d + 2 * d + 1];
+  return CSSM_OK;
+}
+
 int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t n_u, int32_t* ancestors_out, int device) {
   if (kind < 0 || kind > 2) return fail(CSSM_ERR_INVALID, "unknown resample kind");
   if (!w || !u || !ancestors_out || n <= 0 || n > 2147483647LL) return fail(CSSM_ERR_INVALID, "bad resample arguments");

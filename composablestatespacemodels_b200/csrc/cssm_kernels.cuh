@@ -1448,4 +1448,104 @@ k_mean_state(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, 
   if ((threadIdx.x & 31) == 0) atomicAdd(out + k, acc / (double)N);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Order statistics of the cloud without sorting it (ParticleFilter.getIntervals /
+// getCredibleInterval / getOrderStatistic, model/ParticleFilter.scala:415-424,455-460,490-505):
+// MSD radix select, 8 bits per pass, on the order-preserving integer image of the values.  Column
+// c < d is coordinate c of the resampled cloud, column d is gamma = f(x, t) = sum_k C[k] x[k]
+// (evaluated with the same fma chain as K1).  Every column carries TWO targets (lower / upper
+// rank); a pass histograms, per target, the next digit of the elements that match the digits
+// chosen so far, k_select_pick then fixes that digit.  The result is an element of the cloud,
+// bit for bit -- selection, unlike the reference's full sort, is O(N) per pass.
+// ---------------------------------------------------------------------------------------------
+struct SelState {
+  unsigned long long prefix;  // digits chosen so far (right-aligned)
+  long long rank;             // rank of the target among the elements that match the prefix
+};
+template <typename real> struct KeyOf;
+template <> struct KeyOf<float> {
+  typedef unsigned type;
+  static constexpr int BITS = 32;
+  __device__ __forceinline__ static unsigned key(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  }
+  __device__ __forceinline__ static double value(unsigned long long k) {
+    const unsigned kk = (unsigned)k;
+    return (double)__uint_as_float((kk & 0x80000000u) ? (kk & 0x7FFFFFFFu) : ~kk);
+  }
+};
+template <> struct KeyOf<double> {
+  typedef unsigned long long type;
+  static constexpr int BITS = 64;
+  __device__ __forceinline__ static unsigned long long key(double v) { return ord_key(v); }
+  __device__ __forceinline__ static double value(unsigned long long k) { return ord_unkey(k); }
+};
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+k_select_hist(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, const __grid_constant__ StepArgs<real> a, int d,
+              long long N, long long Ns, int pass, const SelState* __restrict__ sel, unsigned* __restrict__ hist) {
+  typedef typename KeyOf<real>::type key_t;
+  constexpr int BITS = KeyOf<real>::BITS;
+  __shared__ unsigned h[2][256];
+  const int c = blockIdx.y;  // column: coordinate c, or gamma when c == d
+  h[0][threadIdx.x] = 0u;
+  h[1][threadIdx.x] = 0u;
+  __syncthreads();
+  const int shift = BITS - 8 * (pass + 1);  // position of this pass's digit
+  const key_t p0 = (key_t)sel[2 * c].prefix, p1 = (key_t)sel[2 * c + 1].prefix;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;
+    if (anc) {
+      const unsigned g = (unsigned)anc[i];
+      const unsigned q = (pr.R > 1) ? owner_of(pr, g) : 0u;
+      src = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+    }
+    real v;
+    if (c < d) {
+      v = src[(long long)c * Ns];
+    } else {
+      v = (real)0;
+      for (int k = 0; k < d; ++k) v = r_fma<real>(a.C[k], src[(long long)k * Ns], v);
+    }
+    const key_t key = KeyOf<real>::key(v);
+    const key_t hi = (pass == 0) ? (key_t)0 : (key_t)(key >> (shift + 8));
+    const unsigned digit = (unsigned)(key >> shift) & 0xFFu;
+    if (hi == p0) atomicAdd(&h[0][digit], 1u);
+    if (hi == p1) atomicAdd(&h[1][digit], 1u);
+  }
+  __syncthreads();
+  unsigned* out = hist + (size_t)c * 512;
+  if (h[0][threadIdx.x]) atomicAdd(out + threadIdx.x, h[0][threadIdx.x]);
+  if (h[1][threadIdx.x]) atomicAdd(out + 256 + threadIdx.x, h[1][threadIdx.x]);
+}
+
+// one block of 32 threads per (column, target): the digit whose bin holds the target rank
+__global__ void __launch_bounds__(32) k_select_pick(SelState* __restrict__ sel, unsigned* __restrict__ hist) {
+  const int ct = blockIdx.x;  // 2*c + target
+  unsigned* hh = hist + (size_t)ct * 256;
+  if (threadIdx.x == 0) {
+    SelState st = sel[ct];
+    long long cum = 0;
+    int digit = 255;
+    for (int b = 0; b < 256; ++b) {
+      const long long n = (long long)hh[b];
+      if (st.rank < cum + n) { digit = b; break; }
+      cum += n;
+    }
+    st.prefix = (st.prefix << 8) | (unsigned long long)digit;
+    st.rank -= cum;
+    sel[ct] = st;
+  }
+  __syncwarp();
+  for (int b = threadIdx.x; b < 256; b += 32) hh[b] = 0u;  // ready for the next pass
+}
+
+template <typename real>
+__global__ void k_select_finish(const SelState* __restrict__ sel, double* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = KeyOf<real>::value(sel[i].prefix);
+}
+
 }  // namespace cssm

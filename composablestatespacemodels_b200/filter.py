@@ -31,6 +31,24 @@ class StateSpace:
         self.time, self.state = time, state
 
 
+class CredibleInterval:
+    """model/ParticleFilter.scala:20-22."""
+
+    def __init__(self, lower, upper):
+        self.lower, self.upper = lower, upper
+
+    def __repr__(self):
+        return f"{self.lower}, {self.upper}"
+
+
+class PfOut:
+    """model/ParticleFilter.scala:53-59."""
+
+    def __init__(self, time, observation, eta, etaIntervals, state, stateIntervals):
+        self.time, self.observation, self.eta, self.etaIntervals = time, observation, eta, etaIntervals
+        self.state, self.stateIntervals = state, stateIntervals
+
+
 class PfState:
     """model/ParticleFilter.scala:32-37.  `particles` is read from the device when asked for."""
 
@@ -236,6 +254,14 @@ class GpuFilterHandle:
         _abi.check(self._lib.cssm_filter_mean_state(self._h, _abi.dptr(m)))
         return m
 
+    def intervals(self, t, interval=0.975):
+        """Mean, per-coordinate credible intervals and the two order statistics of gamma = f(x, t) of
+        the current cloud, computed on the device (cssm_filter_intervals)."""
+        mean, lo, up, g = np.empty(self.d), np.empty(self.d), np.empty(self.d), np.empty(2)
+        _abi.check(self._lib.cssm_filter_intervals(self._h, float(t), float(interval), _abi.dptr(mean), _abi.dptr(lo),
+                                                   _abi.dptr(up), _abi.dptr(g)))
+        return dict(mean=mean, lower=lo, upper=up, gamma=(float(g[0]), float(g[1])))
+
 
 class ShardedGroup:
     """R shards of ONE filter inside one process, driven in lock-step by the cssm_group_* entry
@@ -404,6 +430,19 @@ class ParticleFilter:
     @staticmethod
     def likelihood(data, resample, n, **kw):
         return lambda mod: Filter(mod, resample, **kw).llFilter(data, n)
+
+    @staticmethod
+    def getIntervals(model, s, interval=0.975):
+        """model/ParticleFilter.scala:415-424: PfState -> PfOut (mean state, state intervals, eta = link(f(mean)),
+        eta intervals).  The cloud stays on the device: mean and order statistics come from
+        cssm_filter_intervals; the (monotone) link is applied here, in fp64, to the two order statistics of gamma."""
+        r = s._handle.intervals(s.t, interval)
+        lo, up = model.link(r["gamma"][0]), model.link(r["gamma"][1])
+        if lo > up:  # decreasing link (Beta: exp(-x)): ascending eta is descending gamma
+            lo, up = model.link(r["gamma"][1]), model.link(r["gamma"][0])
+        eta = model.link(model.f(r["mean"], s.t))
+        return PfOut(s.t, s.observation, eta, CredibleInterval(lo, up), r["mean"],
+                     [CredibleInterval(a, b) for a, b in zip(r["lower"], r["upper"])])
 
     @staticmethod
     def effectiveSampleSize(weights):

@@ -259,6 +259,20 @@ int cssm_filter_profile_read(cssm_filter_t* f, double* ms_sum_out, int64_t* coun
  * ---------------------------------------------------------------------------------------- */
 /* resampled particles after the last step, x_out[d][N] (SoA) */
 int cssm_filter_get_particles(cssm_filter_t* f, double* x_out);
+/* ParticleFilter.getIntervals (model/ParticleFilter.scala:415-424) of the current cloud, on the device
+ * (radix select, no sort, no N x d copy to the host):
+ *   state_mean[d]              meanState (:478-480)
+ *   state_lower/upper[d]       getCredibleInterval (:490-505): sorted(n - index - 1), sorted(index - 1),
+ *                              index = floor(interval * n), per coordinate -- elements of the cloud, bit for bit
+ *   gamma_out[2]               the order statistics ordered(n - index), ordered(index), index = floor(n * interval)
+ *                              (getOrderStatistic :455-460) of gamma_i = f(x_i, t).  The caller applies Model.link:
+ *                              eta_i = link(gamma_i) is what the reference orders, and every link of the reference is
+ *                              monotone (increasing; decreasing for the Beta model, for which the mirrored ranks
+ *                              n - 1 - index and index - 1 are returned, so that link(gamma_out[1]) and
+ *                              link(gamma_out[0]) are the reference's lower and upper eta).
+ * interval is 0.975 in the reference.  CSSM_ERR_INVALID where the reference would throw IndexOutOfBounds. */
+int cssm_filter_intervals(cssm_filter_t* f, double t, double interval, double* state_mean,
+                          double* state_lower, double* state_upper, double* gamma_out);
 /* Resampling.sampleOne of the current cloud, x_out[d] */
 int cssm_filter_sample_one(cssm_filter_t* f, double* x_out);
 /* PfState.ll / PfState.ess */

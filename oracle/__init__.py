@@ -64,6 +64,8 @@ def lib():
             "orc_filter_ll_many": ([MD, C.c_int64, C.c_int, C.c_int64, dp, dp, u8p, C.c_uint64, C.c_int, C.c_int, C.c_int, dp],
                                    None),
             "orc_simulate": ([MD, C.c_int64, C.c_double, C.c_uint64, dp, dp, dp], None),
+            "orc_link": ([MD, C.c_double], C.c_double),
+            "orc_intervals": ([MD, C.c_int64, dp, C.c_double, C.c_double, dp, dp, dp, dp], C.c_int),
         }
         for name, (args, res) in sig.items():
             fn = getattr(l, name)
@@ -158,6 +160,19 @@ class Oracle:
         self.L.orc_filter_ll_many(C.byref(self.desc), N, resample_kind, t.size, _d(t), _d(y),
                                   None if h is None else h.ctypes.data_as(u8p), seed, variant, R, threads, _d(out))
         return out
+
+    def intervals(self, x, t, interval=0.975):
+        """ParticleFilter.getIntervals of the cloud x[d][N]: dict(mean, lower, upper, eta=(mean, lower, upper))."""
+        x = f64(x)
+        N = x.shape[1]
+        mean, lo, up, eta = np.empty(self.d), np.empty(self.d), np.empty(self.d), np.empty(3)
+        rc = self.L.orc_intervals(C.byref(self.desc), N, _d(x), t, interval, _d(mean), _d(lo), _d(up), _d(eta))
+        if rc:
+            raise IndexError("order-statistic index outside the cloud")
+        return dict(mean=mean, lower=lo, upper=up, eta=tuple(eta))
+
+    def link(self, g):
+        return self.L.orc_link(C.byref(self.desc), float(g))
 
     def simulate(self, T, dt=0.1, seed=1):
         t, y, x = np.empty(T), np.empty(T), np.empty((T, self.d))

@@ -318,6 +318,49 @@ void orc_loglik(const cssm_model_desc_t* m, int64_t N, const double* gamma, doub
   for (int64_t i = 0; i < N; ++i) logw[i] = orc_loglik_1(m, gamma[i], y);
 }
 
+// Model.link (model/Model.scala:25, and the overrides :180,:268,:296,:318-322,:345)
+double orc_link(const cssm_model_desc_t* m, double g) {
+  switch (m->obs_kind) {
+    case CSSM_OBS_POISSON: case CSSM_OBS_NEGBIN: case CSSM_OBS_ZIP: return std::exp(g);
+    case CSSM_OBS_BERNOULLI: return (g > 6) ? 1.0 : (g < -6) ? 0.0 : 1.0 / (1 + std::exp(-g));
+    case CSSM_OBS_BETA: return std::exp(-g);
+    default: return g;
+  }
+}
+
+// ParticleFilter.getIntervals (model/ParticleFilter.scala:415-424) of a cloud x[d][N] at time t:
+// meanState (:478-480, weightedMean with unit weights :465-473), getallCredibleIntervals (:490-513:
+// per coordinate sorted(n - index - 1), sorted(index - 1), index = floor(interval * n)),
+// meanEta = link(f(stateMean, t)), getOrderStatistic of eta_i = link(f(x_i, t)) (:455-460:
+// ordered(n - index), ordered(index), index = floor(n * interval)).  eta[3] = {meanEta, lower, upper}.
+// Returns -1 where the reference would throw IndexOutOfBounds.
+int orc_intervals(const cssm_model_desc_t* m, int64_t N, const double* x, double t, double interval, double* mean,
+                  double* lower, double* upper, double* eta) {
+  const int d = orc_dim(m);
+  const int64_t idx_s = (int64_t)std::floor(interval * (double)N), idx_e = (int64_t)std::floor((double)N * interval);
+  if (N - idx_s - 1 < 0 || N - idx_s - 1 >= N || idx_s - 1 < 0 || idx_s - 1 >= N || N - idx_e < 0 || N - idx_e >= N || idx_e >= N)
+    return -1;
+  double wsum = 0.0;
+  for (int64_t i = 0; i < N; ++i) wsum = wsum + 1.0;
+  const double wn = 1.0 / wsum;
+  std::vector<double> col(N);
+  for (int k = 0; k < d; ++k) {
+    double acc = x[(int64_t)k * N] * wn;
+    for (int64_t i = 1; i < N; ++i) acc = acc + x[(int64_t)k * N + i] * wn;
+    mean[k] = acc;
+    for (int64_t i = 0; i < N; ++i) col[i] = x[(int64_t)k * N + i];
+    std::sort(col.begin(), col.end());
+    lower[k] = col[N - idx_s - 1];
+    upper[k] = col[idx_s - 1];
+  }
+  for (int64_t i = 0; i < N; ++i) col[i] = orc_link(m, f_one(m, N, x, i, t));
+  std::sort(col.begin(), col.end());
+  eta[0] = orc_link(m, f_one(m, 1, mean, 0, t));
+  eta[1] = col[N - idx_e];
+  eta[2] = col[idx_e];
+  return 0;
+}
+
 // a8  max, w1 = exp(w - max)  (model/ParticleFilter.scala:124-125)
 double orc_max(int64_t N, const double* w) {
   double mx = w[0];

@@ -291,3 +291,31 @@ def test_series_multi_tile_kernel_equals_three_launch_path(name, N, dtype, kind)
     np.testing.assert_array_equal(a[1], b[1])
     np.testing.assert_array_equal(a[2], b[2])
     np.testing.assert_array_equal(a[3], b[3])
+
+
+@pytest.mark.parametrize("name", ["c2", "c4", "bernoulli", "beta", "student_t"])
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+def test_intervals_on_device_match_the_sorted_cloud(name, dtype):
+    """ParticleFilter.getIntervals (model/ParticleFilter.scala:415-424) by radix select on the
+    device against the oracle's literal sort of the SAME cloud (read back from the device): state
+    intervals are elements of the cloud, bit for bit; mean and eta within the dtype tolerance."""
+    from composablestatespacemodels_b200 import Filter, Resampling, Data, ParticleFilter
+    mod = ALL[name]()
+    orc = oracle.Oracle(mod)
+    N, T = 3000, 6
+    t, y, _ = orc.simulate(T, 0.1, 17)
+    flt = Filter(mod, Resampling.systematicResampling, dtype=dtype, seed=9)
+    s = flt.initialiseState(N, t[0])
+    for k in range(T):
+        s = flt.stepFilter(s, Data(t[k], y[k]))
+    x = s.particles.T                                  # [d][N], what the device holds (as doubles)
+    ref = orc.intervals(x, s.t, 0.975)
+    out = ParticleFilter.getIntervals(mod, s)
+    np.testing.assert_array_equal([ci.lower for ci in out.stateIntervals], ref["lower"])
+    np.testing.assert_array_equal([ci.upper for ci in out.stateIntervals], ref["upper"])
+    tol = TOL[dtype]
+    rel_close(out.state, ref["mean"], 1e-12, "mean state")
+    rel_close([out.eta, out.etaIntervals.lower, out.etaIntervals.upper], ref["eta"], tol, "eta and its interval")
+    with pytest.raises(cs._abi.CssmError):
+        s._handle.intervals(s.t, 1.0)                  # index = n: the reference throws IndexOutOfBounds
+    flt.close()

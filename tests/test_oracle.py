@@ -95,6 +95,26 @@ def test_further_densities_against_scipy():
         np.testing.assert_allclose(o.loglik(g, y), stats.beta.logpdf(y, np.exp(-g), 1.0), rtol=1e-11, atol=1e-12)
 
 
+def test_intervals_are_the_literal_order_statistics():
+    """getIntervals / getCredibleInterval / getOrderStatistic (model/ParticleFilter.scala:415-424,455-460,490-505)."""
+    for name in ("c2", "beta", "bernoulli", "c4"):
+        mod = ALL[name]()
+        o = oracle.Oracle(mod)
+        rng = np.random.default_rng(1)
+        N, t = 1000, 0.7
+        x = 0.5 * rng.standard_normal((mod.dimension, N))
+        r = o.intervals(x, t)
+        idx = math.floor(0.975 * N)
+        xs = np.sort(x, axis=1)
+        np.testing.assert_array_equal(r["lower"], xs[:, N - idx - 1])
+        np.testing.assert_array_equal(r["upper"], xs[:, idx - 1])
+        np.testing.assert_allclose(r["mean"], x.mean(axis=1), rtol=1e-12, atol=1e-14)
+        eta = np.sort([mod.link(mod.f(x[:, i], t)) for i in range(N)])
+        np.testing.assert_allclose(r["eta"], [mod.link(mod.f(r["mean"], t)), eta[N - idx], eta[idx]], rtol=1e-12)
+    with pytest.raises(IndexError):
+        o.intervals(x, t, 1.0)
+
+
 def test_transitions_have_the_reference_moments():
     # OU exact transition: mean mu + (x - mu) e^{-phi dt}, variance sigma^2/(2 phi) (1 - e^{-2 phi dt})  (model/Sde.scala:139-150)
     m = c1()
