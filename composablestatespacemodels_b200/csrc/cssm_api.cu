@@ -448,7 +448,11 @@ int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
 #define K1_CASE(DD)                                                                                                    \
   e = launch(k_propagate_weight<real, DD>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, f->N, f->Ns, \
              slot0, f->key0, f->key1, cx.step, ctl)
-      if (f->d == 1) K1_CASE(1);
+      static const int k1_ppt = std::getenv("CSSM_K1_PPT") ? std::atoi(std::getenv("CSSM_K1_PPT")) : 0;
+      if (f->d == 7 && k1_ppt == 2 && sizeof(real) == 4) {
+        e = launch(k_propagate_weight<float, 7, 2>, nblk(f->N, 256 * 2), 256, f->stream, pdl, *reinterpret_cast<StepArgs<float>*>(&a), pr,
+                   (float*)xdst, anc, (float*)f->logw, io.zinj, f->N, f->Ns, slot0, f->key0, f->key1, cx.step, ctl);
+      } else if (f->d == 1) K1_CASE(1);
       else if (f->d == 2) K1_CASE(2);
       else if (f->d == 7) K1_CASE(7);
       else K1_CASE(0);

@@ -238,10 +238,16 @@ __device__ __forceinline__ void gate_wait(unsigned long long* gate, unsigned lon
   }
   __syncthreads();
 }
-__device__ __forceinline__ void push_progress(const Peers& pr, unsigned long long gstep_done) {
+// The first warp of a block publishes to the peers: lane q writes into rank q's memory, so the R
+// NVLink round trips of the release stores overlap instead of following one another (a serial loop
+// over 8 peers cost ~25 us per exchange, three times per observation).  `last` is lane 0's verdict
+// ("this was the last block of the launch"); all 32 lanes call.  Every rank's slot array gets the
+// flag, our own included: gate_wait polls all R slots alike.
+__device__ __forceinline__ bool warp_is_last(int last_lane0) { return __shfl_sync(0xffffffffu, last_lane0, 0) != 0; }
+__device__ __forceinline__ void push_progress_warp(const Peers& pr, unsigned long long gstep_done) {
   __threadfence_system();
-  // every rank's slot array gets the flag, our own included: gate_wait polls all R slots alike
-  for (int q = 0; q < pr.R; ++q) st_release_sys(&pr.xch[q][pr.rank].progress, gstep_done);
+  const int q = threadIdx.x & 31;
+  if (q < pr.R) st_release_sys(&pr.xch[q][pr.rank].progress, gstep_done);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -307,21 +313,30 @@ __device__ __forceinline__ void k1_tail(double mx, bool bad, int has_obs, const 
       if (s_bad) atomicOr(&sc->flags, FLAG_NAN_WEIGHT);
     }
   }
-  if (pr.R > 1 && threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long tk = atomicAdd(&sc->ticket1, 1ull);
-    if (tk % gridDim.x == gridDim.x - 1) {  // every block of this launch has contributed
+  if (pr.R > 1 && threadIdx.x < 32) {
+    int last = 0;
+    unsigned long long key = 0ull;
+    if (threadIdx.x == 0) {
       __threadfence();
+      const unsigned long long tk = atomicAdd(&sc->ticket1, 1ull);
+      if (tk % gridDim.x == gridDim.x - 1) {  // every block of this launch has contributed
+        __threadfence();
+        last = 1;
+        if (has_obs) key = ld_gpu(&sc->acc[ctl.parity].gmax_key);
+      }
+    }
+    if (warp_is_last(last)) {
       if (has_obs) {
-        const unsigned long long key = ld_gpu(&sc->acc[ctl.parity].gmax_key);
+        key = __shfl_sync(0xffffffffu, key, 0);
         __threadfence_system();
-        for (int q = 0; q < pr.R; ++q) {
+        const int q = threadIdx.x;
+        if (q < pr.R) {
           XchSlot* s = &pr.xch[q][pr.rank];
           st_relaxed_sys(&s->max_key[ctl.parity], key);
           st_release_sys(&s->max_seq[ctl.parity], ctl.obs_seq + 1);
         }
       } else {
-        push_progress(pr, ctl.gstep + 1);
+        push_progress_warp(pr, ctl.gstep + 1);
       }
     }
   }
@@ -487,13 +502,12 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
   }
 }
 
-template <typename real, int D>
-__global__ void __launch_bounds__(256, 4)
+template <typename real, int D, int PPT = VecOf<real>::PPT>
+__global__ void __launch_bounds__(256, PPT == 4 ? 4 : 6)
 k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
                    const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
                    long long N, long long Ns, unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
                    K1Ctl ctl) {
-  constexpr int PPT = VecOf<real>::PPT;
   griddep_wait();
   griddep_launch();
   if (pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
@@ -772,6 +786,8 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
     s_mxw[threadIdx.x >> 5] = mxw;
   }
   const u128 t = block_sum128(acc, s_w);  // contains the __syncthreads that publishes s_w2 / s_mxw
+  int pub = 0;
+  u128 pub_tot = make_u128(0, 0), pub_q = make_u128(0, 0);
   if (threadIdx.x == 0) {
     u128 t2 = s_w2[0];
     double m2 = s_mxw[0];
@@ -798,17 +814,26 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
       if (pr.R > 1 && tk2 % (unsigned long long)tb.ns == (unsigned long long)tb.ns - 1) {
         // last block of the grid: all-gather of (sum w, sum w^2) by direct stores into the peers
         __threadfence();
-        const u128 tot = ld_gpu128(&A->tot), qq = ld_gpu128(&A->q);
-        __threadfence_system();
-        for (int q = 0; q < pr.R; ++q) {
-          XchSlot* s = &pr.xch[q][pr.rank];
-          st_relaxed_sys(&s->tot_lo[parity], tot.lo);
-          st_relaxed_sys(&s->tot_hi[parity], tot.hi);
-          st_relaxed_sys(&s->q_lo[parity], qq.lo);
-          st_relaxed_sys(&s->q_hi[parity], qq.hi);
-          st_release_sys(&s->sum_seq[parity], obs_seq + 1);
-        }
+        pub_tot = ld_gpu128(&A->tot);
+        pub_q = ld_gpu128(&A->q);
+        pub = 1;
       }
+    }
+  }
+  if (pr.R > 1 && threadIdx.x < 32 && warp_is_last(pub)) {  // lane q -> rank q, see push_progress_warp
+    pub_tot.lo = __shfl_sync(0xffffffffu, pub_tot.lo, 0);
+    pub_tot.hi = __shfl_sync(0xffffffffu, pub_tot.hi, 0);
+    pub_q.lo = __shfl_sync(0xffffffffu, pub_q.lo, 0);
+    pub_q.hi = __shfl_sync(0xffffffffu, pub_q.hi, 0);
+    __threadfence_system();
+    const int q = threadIdx.x;
+    if (q < pr.R) {
+      XchSlot* s = &pr.xch[q][pr.rank];
+      st_relaxed_sys(&s->tot_lo[parity], pub_tot.lo);
+      st_relaxed_sys(&s->tot_hi[parity], pub_tot.hi);
+      st_relaxed_sys(&s->q_lo[parity], pub_q.lo);
+      st_relaxed_sys(&s->q_hi[parity], pub_q.hi);
+      st_release_sys(&s->sum_seq[parity], obs_seq + 1);
     }
   }
 }
@@ -1346,10 +1371,14 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   if (pr.R > 1) {  // "resampling done": the last block tells the peers this step is complete
     if (wrote_remote) __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned long long tk = atomicAdd(&sc->ticket3, 1ull);
-      if (tk % gridDim.x == gridDim.x - 1) push_progress(pr, ctl.gstep + 1);
+    if (threadIdx.x < 32) {
+      int last = 0;
+      if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long tk = atomicAdd(&sc->ticket3, 1ull);
+        last = (tk % gridDim.x == gridDim.x - 1) ? 1 : 0;
+      }
+      if (warp_is_last(last)) push_progress_warp(pr, ctl.gstep + 1);
     }
   }
 }

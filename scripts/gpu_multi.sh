@@ -3,7 +3,7 @@
 N=${1:-2}; TAG=${2:-cur}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/${TAG}_topo.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_sharded.py -m gpu -q -k multiprocess > gpurun_out/${TAG}_pytest_mp.log 2>&1; echo "rc=$?" >> gpurun_out/${TAG}_pytest_mp.log
+timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q > gpurun_out/${TAG}_pytest_mp.log 2>&1; echo "rc=$?" >> gpurun_out/${TAG}_pytest_mp.log
 tail -3 gpurun_out/${TAG}_pytest_mp.log
 for wl in c5 target c4; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
