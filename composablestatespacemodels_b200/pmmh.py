@@ -92,3 +92,39 @@ class MetropolisHastings:
 
 class ParticleMetropolisHastings(MetropolisHastings):
     """model/PMMH.scala:114-123"""
+
+
+class ApproxPMMH(MetropolisHastings):
+    """model/PMMH.scala:128-153: the likelihood of the CURRENT parameters is re-estimated in every
+    iteration (two filter runs per step); on rejection the chain keeps the re-estimated value."""
+
+    def mhStep(self, s):
+        propParams = self.proposal(s.params)
+        state = self.pf(propParams)
+        oldState = self.pf(s.params)
+        a = (state[0] + self.logTransition(propParams, s.params) + self.prior(propParams)
+             - self.logTransition(s.params, propParams) - oldState[0] - self.prior(s.params))
+        u = self.rng.random()
+        if math.log(u) < a:
+            return MetropState(state[0], propParams, state[1][-1], s.accepted + 1)
+        return MetropState(oldState[0], s.params, oldState[1][-1], s.accepted)
+
+
+def approxPmmh(initP, proposal, logTransition, prior, rng=None):
+    """model/PMMH.scala:169-175."""
+    return lambda pf: ApproxPMMH(initP, proposal, logTransition, prior, pf, rng).iters()
+
+
+def pmmhStep(pos, proposal, rng=None):
+    """model/PMMH.scala:177-191: one step of a Metropolis chain on (ll, parameters) with a symmetric proposal."""
+    rng = rng if rng is not None else np.random.default_rng()
+
+    def step(s):
+        prop = proposal(s[1])
+        ll = pos(prop)
+        return (ll, prop) if math.log(rng.random()) < ll - s[0] else s
+    return step
+
+
+MetropolisHastings.approxPmmh = staticmethod(approxPmmh)
+MetropolisHastings.pmmhStep = staticmethod(pmmhStep)

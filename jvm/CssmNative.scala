@@ -4,9 +4,10 @@ package com.github.jonnylaw.gpu
 object CssmNative {
   System.loadLibrary("cssm_jni")   // which links libcssm_gpu.so
   @native def filterCreate(kinds: Array[Int], params: Array[Double], obsKind: Int, hasScale: Boolean, scale: Double,
-    stepMode: Int, precision: Int, n: Long, resampleKind: Int, dtype: Int, device: Int, seed: Long, streamId: Long): Long
+    stepMode: Int, precision: Int, obsDf: Int, n: Long, resampleKind: Int, dtype: Int, device: Int, seed: Long,
+    streamId: Long): Long
   @native def filterSetParams(h: Long, kinds: Array[Int], params: Array[Double], obsKind: Int, hasScale: Boolean,
-    scale: Double, stepMode: Int, precision: Int): Unit
+    scale: Double, stepMode: Int, precision: Int, obsDf: Int): Unit
   @native def filterDestroy(h: Long): Unit
   @native def filterInit(h: Long, t0: Double): Unit
   @native def filterInitState(h: Long, t0: Double, x0: Array[Double]): Unit
@@ -14,5 +15,9 @@ object CssmNative {
   @native def filterLl(h: Long, t: Array[Double], y: Array[Double], hasObs: Array[Byte]): Double
   @native def filterRun(h: Long, t: Array[Double], y: Array[Double], hasObs: Array[Byte], statesOut: Array[Double]): Double
   @native def filterGetParticles(h: Long, out: Array[Double]): Unit
+  @native def filterSeriesMode(h: Long, mode: Int): Unit
+  /** out = mean[d] | lower[d] | upper[d] | gammaLower, gammaUpper (ParticleFilter.getIntervals on the device) */
+  @native def filterIntervals(h: Long, t: Double, interval: Double, d: Int, out: Array[Double]): Unit
+  @native def filterSampleOne(h: Long, out: Array[Double]): Unit
   @native def resample(kind: Int, w: Array[Double], u: Array[Double], anc: Array[Int], device: Int): Unit
 }

@@ -13,7 +13,7 @@ import com.github.jonnylaw.gpu.CssmNative
 
 /** Flat description of a parameterised model: what include/cssm.h calls cssm_model_desc_t. */
 final case class GpuDesc(kinds: Array[Int], params: Array[Double], obsKind: Int, scale: Option[Double],
-  stepMode: Int = 0, precision: Int = 0)
+  stepMode: Int = 0, precision: Int = 0, obsDf: Int = 0)
 
 object GpuDesc {
   private def leafOf(sde: Sde): (Array[Int], Array[Array[Double]]) = sde match {
@@ -32,6 +32,9 @@ object GpuDesc {
     case SeasonalModel(per, h, s, p)   => (2, 1, per, h, p.scale, s)
     case BernoulliModel(s, p)          => (3, 0, 0, 0, p.scale, s)
     case LogGaussianCox(s, p)          => (4, 0, 0, 0, p.scale, s)
+    case StudentsTModel(s, _, p)       => (5, 0, 0, 0, p.scale, s)   // df travels in GpuDesc.obsDf
+    case ZeroInflatedPoisson(s, p)     => (6, 0, 0, 0, p.scale, s)
+    case BetaModel(s, p)               => (7, 0, 0, 0, p.scale, s)
   }
   /** leaves in Tree.flatten order; `models` is the list of un-composed models, left to right */
   def apply(models: List[Model], precision: Int = 0): GpuDesc = {
@@ -39,7 +42,8 @@ object GpuDesc {
     val leaves = singles.map { case (_, f, per, h, _, s) => val (k, p) = leafOf(s); (Array(k(0), k(1), f, per, h), p) }
     val d = leaves.map(_._1(1)).sum
     val params = (0 until 5).toArray.flatMap(i => leaves.flatMap(_._2(i)))   // m0 | c0 | phi | mu | sigma
-    GpuDesc(leaves.flatMap(_._1).toArray, params, singles.head._1, singles.head._5, 0, precision)
+    val df = models.head match { case StudentsTModel(_, df, _) => df; case _ => 0 }
+    GpuDesc(leaves.flatMap(_._1).toArray, params, singles.head._1, singles.head._5, 0, precision, df)
   }
 }
 
@@ -57,7 +61,8 @@ final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, p
     if (handle == 0L || n != particles) {
       close()
       handle = CssmNative.filterCreate(desc.kinds, desc.params, desc.obsKind, desc.scale.isDefined,
-        desc.scale.getOrElse(0.0), desc.stepMode, desc.precision, particles.toLong, resampleKind, dtype, device, seed, 0L)
+        desc.scale.getOrElse(0.0), desc.stepMode, desc.precision, desc.obsDf, particles.toLong, resampleKind, dtype, device,
+        seed, 0L)
       n = particles
     }
     handle

@@ -23,8 +23,8 @@ static int check(JNIEnv* env, int status) {
 /* leaves arrive flattened: kinds[n_leaves*5] = (sde_kind, dim, f_kind, period, harmonics) per leaf and
  * params[5 * d] = m0 | c0 | phi | mu | sigma, each of total length d in leaf order */
 static void build_desc(JNIEnv* env, jintArray kinds, jdoubleArray params, jint obs_kind, jboolean has_scale,
-                       jdouble scale, jint step_mode, jint precision, cssm_model_desc_t* desc, cssm_leaf_t** leaves_out,
-                       jint** k_out, jdouble** p_out) {
+                       jdouble scale, jint step_mode, jint precision, jint obs_df, cssm_model_desc_t* desc,
+                       cssm_leaf_t** leaves_out, jint** k_out, jdouble** p_out) {
   jsize nk = (*env)->GetArrayLength(env, kinds) / 5;
   jint* k = (*env)->GetIntArrayElements(env, kinds, NULL);
   jdouble* p = (*env)->GetDoubleArrayElements(env, params, NULL);
@@ -40,14 +40,16 @@ static void build_desc(JNIEnv* env, jintArray kinds, jdoubleArray params, jint o
   }
   desc->n_leaves = (int32_t)nk; desc->leaves = leaves; desc->obs_kind = obs_kind; desc->has_scale = has_scale;
   desc->scale = scale; desc->step_mode = step_mode; desc->lgcp_precision = precision;
+  desc->obs_df = obs_df; desc->reserved = 0; /* StudentsTModel.df, model/Model.scala:144 */
   *leaves_out = leaves; *k_out = k; *p_out = p;
 }
 
 JNIEXPORT jlong JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterCreate(
     JNIEnv* env, jobject self, jintArray kinds, jdoubleArray params, jint obs_kind, jboolean has_scale, jdouble scale,
-    jint step_mode, jint precision, jlong n, jint resample_kind, jint dtype, jint device, jlong seed, jlong stream_id) {
+    jint step_mode, jint precision, jint obs_df, jlong n, jint resample_kind, jint dtype, jint device, jlong seed,
+    jlong stream_id) {
   cssm_model_desc_t desc; cssm_leaf_t* leaves; jint* k; jdouble* p; cssm_filter_t* f = NULL;
-  build_desc(env, kinds, params, obs_kind, has_scale, scale, step_mode, precision, &desc, &leaves, &k, &p);
+  build_desc(env, kinds, params, obs_kind, has_scale, scale, step_mode, precision, obs_df, &desc, &leaves, &k, &p);
   int rc = cssm_filter_create(&desc, n, resample_kind, dtype, device, (uint64_t)seed, (uint64_t)stream_id, &f);
   free(leaves);
   (*env)->ReleaseIntArrayElements(env, kinds, k, JNI_ABORT);
@@ -58,9 +60,9 @@ JNIEXPORT jlong JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterCrea
 
 JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterSetParams(
     JNIEnv* env, jobject self, jlong h, jintArray kinds, jdoubleArray params, jint obs_kind, jboolean has_scale,
-    jdouble scale, jint step_mode, jint precision) {
+    jdouble scale, jint step_mode, jint precision, jint obs_df) {
   cssm_model_desc_t desc; cssm_leaf_t* leaves; jint* k; jdouble* p;
-  build_desc(env, kinds, params, obs_kind, has_scale, scale, step_mode, precision, &desc, &leaves, &k, &p);
+  build_desc(env, kinds, params, obs_kind, has_scale, scale, step_mode, precision, obs_df, &desc, &leaves, &k, &p);
   int rc = cssm_filter_set_params((cssm_filter_t*)(intptr_t)h, &desc);
   free(leaves);
   (*env)->ReleaseIntArrayElements(env, kinds, k, JNI_ABORT);
@@ -138,5 +140,25 @@ JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_resample(
   (*env)->ReleaseDoubleArrayElements(env, w, wp, JNI_ABORT);
   (*env)->ReleaseDoubleArrayElements(env, u, up, JNI_ABORT);
   (*env)->ReleaseIntArrayElements(env, anc, ap, 0);
+  check(env, rc);
+}
+
+/* cssm_filter_series_mode: 0 auto, 1 three launches per observation, 2 one cooperative launch per llFilter */
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterSeriesMode(JNIEnv* env, jobject self, jlong h, jint mode) {
+  check(env, cssm_filter_series_mode((cssm_filter_t*)(intptr_t)h, mode));
+}
+/* ParticleFilter.getIntervals on the device: out = mean[d] | lower[d] | upper[d] | gamma_lower, gamma_upper */
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterIntervals(
+    JNIEnv* env, jobject self, jlong h, jdouble t, jdouble interval, jint d, jdoubleArray out) {
+  jdouble* p = (*env)->GetDoubleArrayElements(env, out, NULL);
+  int rc = cssm_filter_intervals((cssm_filter_t*)(intptr_t)h, t, interval, p, p + d, p + 2 * d, p + 3 * d);
+  (*env)->ReleaseDoubleArrayElements(env, out, p, 0);
+  check(env, rc);
+}
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterSampleOne(JNIEnv* env, jobject self, jlong h,
+                                                                                      jdoubleArray out) {
+  jdouble* p = (*env)->GetDoubleArrayElements(env, out, NULL);
+  int rc = cssm_filter_sample_one((cssm_filter_t*)(intptr_t)h, p);
+  (*env)->ReleaseDoubleArrayElements(env, out, p, 0);
   check(env, rc);
 }

@@ -98,3 +98,25 @@ def test_simulator_is_deterministic_and_shaped():
     t2, y2, _ = simulate.simRegular(c2(), 0.1, 50, seed=3)
     assert np.array_equal(y, y2) and x.shape == (50, 7) and np.allclose(np.diff(t), 0.1)
     assert np.all(y >= 0) and np.all(y == np.floor(y))
+
+
+def test_approx_pmmh_reestimates_the_current_likelihood():
+    """model/PMMH.scala:128-153 with a fake filter: two filter calls per step, and a rejected
+    proposal still replaces the stored likelihood by the re-estimate."""
+    from composablestatespacemodels_b200.pmmh import ApproxPMMH, pmmhStep
+    calls = []
+
+    def pf(p):
+        calls.append(p)
+        return (-10.0 - 100.0 * abs(p) - 0.001 * len(calls), [("state", len(calls))])
+
+    rng = np.random.default_rng(3)
+    mh = ApproxPMMH(0.0, lambda p: p + 5.0, lambda a, b: 0.0, lambda p: 0.0, pf, rng)
+    it = mh.iters()
+    s1 = next(it)
+    assert len(calls) == 2 and calls == [5.0, 0.0]
+    assert s1.accepted == 0 and s1.params == 0.0 and s1.ll == -10.0 - 0.002 and s1.state == ("state", 2)
+    s2 = next(it)
+    assert len(calls) == 4 and s2.ll == -10.0 - 0.004
+    step = pmmhStep(lambda p: -abs(p), lambda p: p * 0.5, rng)
+    assert step((-4.0, 4.0)) == (-2.0, 2.0)
