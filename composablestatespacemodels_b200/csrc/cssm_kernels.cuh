@@ -881,6 +881,21 @@ struct KFun {
   }
   // the same count minus `lo` (as a double, lo <= count), clamped to [0, n_rel]: 32-bit arithmetic
   __device__ __forceinline__ int count_rel(double P, double scale, long long N, long long lo, double lo_d, int n_rel) const {
+    if (KIND == CSSM_RESAMPLE_SYSTEMATIC) {
+      // y = P*scale - (u + lo) in one fma; the count minus lo is floor(y) + 1 unless y is within 1e-5 of an
+      // integer, which is the case exactly when the floors of y - 1e-5 and y + 1e-5 differ.  The conversions
+      // saturate, the clamp below absorbs that.  (u + lo is the same for every particle of the thread.)
+      const double y = __fma_rn(P, scale, -__dadd_rn(u, lo_d));
+      const int a = __double2int_rd(__dadd_rn(y, -1e-5)), b = __double2int_rd(__dadd_rn(y, 1e-5));
+      int c;
+      if (a != b) {
+        const long long d = count_le(P, N) - lo;
+        c = (int)(d > 0x7FFFFFFFll ? 0x7FFFFFFFll : (d < -0x7FFFFFFFll ? -0x7FFFFFFFll : d));
+      } else {
+        c = (a == 0x7FFFFFFF) ? a : a + 1;
+      }
+      return min(max(c, 0), n_rel);
+    }
     const double x = (KIND == CSSM_RESAMPLE_SYSTEMATIC) ? __dsub_rn(__dmul_rn(P, scale), u) : __dmul_rn(P, scale);
     const double fl = floor(x);
     const double fr = __dsub_rn(x, fl);
@@ -1217,20 +1232,40 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
       // copy-out: the duplicate-key rule per output, then a coalesced store
       const bool novanish = sm.s_novanish != 0;  // written before the barriers of this pass
       const int n_w = min(WIN, n_out - w0);
-      for (int o = threadIdx.x; o < n_w; o += TILE_THREADS) {
-        int jt = s_res[o];
-        // TreeMap: a duplicated key keeps the last particle inserted
-        if (!novanish)
+      int jts[PER];
+      // all the shared-memory reads of the thread's PER outputs first, then the (rare) slow path, then the stores
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int o = threadIdx.x + k * TILE_THREADS;
+        int jt = s_res[min(o, WIN - 1)];
+        jt = (o < n_w) ? jt : 0;
+        bool mayv = false;
+        if (!novanish) {
+          // TreeMap: a duplicated key keeps the last particle inserted.  First the cheap necessary condition
+          // (next weight at most 2^-52 of the cumulative value), branch-free
+          const int jn = min(jt + 1, tile_n - 1);
+          mayv = (o < n_w) && (jt + 1 < tile_n) && !(Ws[phys<ITEMS>(jn)] > Ps[phys<ITEMS>(jt)] * 2.220446049250313e-16);
+        }
+        if (mayv)
           while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
-        const long long i = lo + w0 + o;
-        if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
-        const int32_t val = (int32_t)(gbase + jt);
-        if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
-          const unsigned q = owner_of(pr, (unsigned)i);
-          pr.anc[q][i - (long long)q * N] = val;
-          wrote_remote |= (q != pr.rank);
-        } else {
-          pr.anc[0][i] = val;
+        jts[k] = jt;
+      }
+      int32_t* const out_local = pr.anc[pr.rank] + (lo + w0 - (long long)pr.rank * N);  // R == 1: plain coalesced stores
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int o = threadIdx.x + k * TILE_THREADS;
+        if (o < n_w) {
+          const int jt = jts[k];
+          const long long i = lo + w0 + o;
+          if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
+          const int32_t val = (int32_t)(gbase + jt);
+          if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+            const unsigned q = owner_of(pr, (unsigned)i);
+            pr.anc[q][i - (long long)q * N] = val;
+            wrote_remote |= (q != pr.rank);
+          } else {
+            out_local[o] = val;
+          }
         }
       }
       __syncthreads();
