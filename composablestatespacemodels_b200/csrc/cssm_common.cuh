@@ -196,15 +196,14 @@ __device__ __forceinline__ unsigned long long shr64c(unsigned long long x, int n
   asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n));
   return r;
 }
-// floor(w*w * 2^48) of an fp32 weight (the ESS accumulator of F32 filters; fits 64 bits):
-// w^2 = m^2 * 2^(2(e-150)) exactly, m^2 < 2^48; branch-free
+// floor(w*w * 2^48) of an fp32 weight 0 <= w <= 1 (the ESS accumulator of F32 filters; fits 64 bits).
+// (double)w * 2^24 and its square are exact in fp64 (48-bit product), the truncating conversion is
+// the floor: the same integer as m^2 * 2^(2(e-150)+48) assembled from the mantissa, but on the
+// conversion / fp64 pipes that the weight pass leaves idle instead of a dozen integer instructions.
+// NaN, zero and subnormal weights give 0.
 __device__ __forceinline__ unsigned long long fix_sq48_f32(float w) {
-  const unsigned b = __float_as_uint(w);
-  const int e = (int)(b >> 23) & 0xff;
-  const unsigned m = (e == 0 || e == 255) ? 0u : ((b & 0x7FFFFFu) | 0x800000u);
-  const unsigned long long m2 = (unsigned long long)m * m;
-  const int s = 2 * e - 252;  // in [-250, 2]
-  return shl64c(m2, s) | shr64c(m2, -s);
+  const double a = __dmul_rn((double)w, 16777216.0);
+  return __double2ull_rz(__dmul_rn(a, a));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -626,7 +626,17 @@ template <> struct WeightSrc<float> {
   __device__ __forceinline__ float weight(float lw) const { return expf_det(__fsub_rn(lw, (float)gmax)); }
   __device__ __forceinline__ float operator()(long long idx) const { return weight(logw[idx]); }
   __device__ __forceinline__ static u128 fix(float w, int) { return fix_f32(w); }
-  __device__ __forceinline__ static u128 fix_sq(float w, double) { return make_u128(fix_sq48_f32(w), 0); }
+  // sum of squares: quantum 2^-48, a whole block's partial sum stays below 2^64 -> 64-bit adds and shuffles
+  __device__ __forceinline__ static void acc_sq(u128& a, float w, double) { a.lo += fix_sq48_f32(w); }
+  __device__ __forceinline__ static u128 warp_sum_sq(u128 a) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) a.lo += __shfl_xor_sync(0xffffffffu, a.lo, m);
+    return make_u128(a.lo, 0);
+  }
+  // non-negative floats order as their bit patterns: one REDUX instead of five shuffle rounds
+  __device__ __forceinline__ static double warp_max(float w) {
+    return (double)__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(w)));
+  }
   // weights of ITEMS elements base, base+stride, ...: loads first, then the arithmetic
   template <int ITEMS>
   __device__ __forceinline__ void load(long long base, int stride, long long N, float* wv) const {
@@ -661,9 +671,15 @@ template <> struct WeightSrc<double> {
   __device__ __forceinline__ double operator()(long long idx) const { return direct ? direct[idx] : weight(logw[idx]); }
   __device__ __forceinline__ static u128 fix(double w, int qb) { return fix_fast(w, qb); }
   // direct weights are pre-scaled to <= 1 by q2scale = 2^-(96-qb) before squaring
-  __device__ __forceinline__ static u128 fix_sq(double w, double q2scale) {
+  __device__ __forceinline__ static void acc_sq(u128& a, double w, double q2scale) {
     const double ws = __dmul_rn(w, q2scale);
-    return fix_fast(__dmul_rn(ws, ws), 96);
+    a = add128(a, fix_fast(__dmul_rn(ws, ws), 96));
+  }
+  __device__ __forceinline__ static u128 warp_sum_sq(u128 a) { return warp_sum128(a); }
+  __device__ __forceinline__ static double warp_max(double w) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, m));
+    return w;
   }
   template <int ITEMS>
   __device__ __forceinline__ void load(long long base, int stride, long long N, double* wv) const {
@@ -773,13 +789,11 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
-    acc2 = add128(acc2, WeightSrc<real>::fix_sq(wv[j], q2scale));
+    WeightSrc<real>::acc_sq(acc2, wv[j], q2scale);
     mxv = wv[j] > mxv ? wv[j] : mxv;
   }
-  double mxw = (double)mxv;
-  acc2 = warp_sum128(acc2);
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
+  const double mxw = WeightSrc<real>::warp_max(mxv);
+  acc2 = WeightSrc<real>::warp_sum_sq(acc2);
   __shared__ u128 s_w2[TILE_THREADS / 32];
   if ((threadIdx.x & 31) == 0) {
     s_w2[threadIdx.x >> 5] = acc2;

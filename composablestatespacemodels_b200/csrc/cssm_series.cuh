@@ -207,14 +207,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
-        acc2 = add128(acc2, WeightSrc<real>::fix_sq(wv[j], 1.0));
+        WeightSrc<real>::acc_sq(acc2, wv[j], 1.0);
         mxv = wv[j] > mxv ? wv[j] : mxv;
       }
-      double mxw = (double)mxv;
+      const double mxw = WeightSrc<real>::warp_max(mxv);
       acc = warp_sum128(acc);
-      acc2 = warp_sum128(acc2);
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
+      acc2 = WeightSrc<real>::warp_sum_sq(acc2);
       if (lane == 0) { s_r[0][wid] = acc; s_r[1][wid] = acc2; s_mxw[wid] = mxw; }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -402,14 +400,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_series_multi(const __grid_c
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
-        acc2 = add128(acc2, WeightSrc<real>::fix_sq(wv[j], 1.0));
+        WeightSrc<real>::acc_sq(acc2, wv[j], 1.0);
         mxv = wv[j] > mxv ? wv[j] : mxv;
       }
-      double mxw = (double)mxv;
+      const double mxw = WeightSrc<real>::warp_max(mxv);
       acc = warp_sum128(acc);
-      acc2 = warp_sum128(acc2);
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) mxw = fmax(mxw, __shfl_xor_sync(0xffffffffu, mxw, m));
+      acc2 = WeightSrc<real>::warp_sum_sq(acc2);
       __syncthreads();  // s_r / s_mxw of the previous tile have been read
       if (lane == 0) { s_r[0][wid] = acc; s_r[1][wid] = acc2; s_mxw[wid] = mxw; }
       __syncthreads();
