@@ -11,6 +11,7 @@
 
 #include "cssm_kernels.cuh"
 #include "cssm_series.cuh"
+#include "cssm_forecast.cuh"
 
 using namespace cssm;
 
@@ -243,6 +244,11 @@ struct cssm_filter {
   bool series_use_multi = false;
   bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
+  // forecast cloud (cssm_forecast.cuh): d + 4 columns [x1 | gamma | eta | obs | obs2], filter dtype
+  void* fc = nullptr;
+  bool fc_valid = false;
+  double fc_t = 0.0;
+  uint32_t fc_ctr = 0;
   float last_ms = 0.f;
   // per-kernel-class device timing (CUDA events on the launching stream), sampled every prof_stride steps
   int prof_stride = 0;
@@ -953,6 +959,71 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
 
 }  // namespace
 
+// ---- forecast (cssm_forecast.cuh) ---------------------------------------------------------------
+namespace {
+template <typename real>
+int forecast_impl(cssm_filter* f, double t, double interval, int chain, bool summarise, std::vector<double>& host) {
+  const int d = f->d, cols = d + 4;
+  const long long n = f->N;
+  if (!f->fc) CU(cudaMalloc(&f->fc, (size_t)cols * f->Ns * sizeof(real)));
+  const double t_from = chain ? f->fc_t : f->t_cur;
+  StepHost h;
+  std::memset(&h, 0, sizeof(h));
+  transition_consts(f->model, t - t_from, h);
+  f_coeffs(f->model, t, h.C);
+  StepArgs<real> a;
+  to_args<real>(f->model, h, a);
+  const Peers pr = make_peers(f, f->cur);
+  const int32_t* anc = f->anc_valid ? f->anc : nullptr;
+  ObsDraw od{f->model.obs_kind, f->model.obs_df, f->model.has_scale, f->model.scale};
+  k_forecast<real><<<nblk(n, 256), 256, 0, f->stream>>>(a, pr, anc, (real*)f->fc, chain, od, n, f->Ns, f->key0, f->key1, f->fc_ctr++);
+  f->launches++;
+  CU(cudaGetLastError());
+  f->fc_valid = true;
+  f->fc_t = t;
+  if (!summarise) return CSSM_OK;
+  // getCredibleInterval ranks for the state, getOrderStatistic ranks for eta and the observations (see cssm_filter_intervals)
+  const long long idx = (long long)std::floor(interval * (double)n);
+  const long long lo_s = n - idx - 1, hi_s = idx - 1, lo_e = n - idx, hi_e = idx;
+  if (lo_s < 0 || lo_s >= n || hi_s < 0 || hi_s >= n || lo_e < 0 || lo_e >= n || hi_e < 0 || hi_e >= n)
+    return fail(CSSM_ERR_INVALID, "forecast: the order-statistic index is outside the cloud (the reference throws IndexOutOfBounds here)");
+  // scratch: mean[cols] | out[2*cols] | SelState[2*cols] | hist[cols*512 u32]
+  int rc = ensure_scratch(f, (size_t)cols + 2 * cols + 2 * (2 * cols) + (size_t)cols * 256 + 8);
+  if (rc) return rc;
+  double* mean_dev = f->scratch;
+  double* out_dev = mean_dev + cols;
+  SelState* sel_dev = reinterpret_cast<SelState*>(out_dev + 2 * cols);
+  unsigned* hist_dev = reinterpret_cast<unsigned*>(sel_dev + 2 * cols);
+  std::vector<SelState> sel((size_t)2 * cols);
+  for (int c = 0; c < cols; ++c) {
+    sel[2 * c] = SelState{0ull, c < d ? lo_s : lo_e};
+    sel[2 * c + 1] = SelState{0ull, c < d ? hi_s : hi_e};
+  }
+  CU(cudaMemsetAsync(mean_dev, 0, (size_t)cols * sizeof(double), f->stream));
+  CU(cudaMemsetAsync(hist_dev, 0, (size_t)cols * 512 * sizeof(unsigned), f->stream));
+  CU(cudaMemcpyAsync(sel_dev, sel.data(), sel.size() * sizeof(SelState), cudaMemcpyHostToDevice, f->stream));
+  Peers pc;  // the forecast cloud as a plain single-rank cloud of `cols` coordinates
+  std::memset(&pc, 0, sizeof(pc));
+  pc.R = 1; pc.rank = 0; pc.Nl = n; pc.inv_nl = 1.0f / (float)n;
+  pc.x[0] = f->fc;
+  const int gx = (int)std::min<long long>(nblk(n, 256), 148 * 8);
+  dim3 gmean((unsigned)std::min<long long>(nblk(n, 256), 1184), (unsigned)cols), ghist((unsigned)gx, (unsigned)cols);
+  k_mean_state<real><<<gmean, 256, 0, f->stream>>>(pc, nullptr, mean_dev, cols, n, f->Ns);
+  const int passes = (int)sizeof(real) == 4 ? 4 : 8;
+  for (int pass = 0; pass < passes; ++pass) {
+    k_select_hist<real><<<ghist, 256, 0, f->stream>>>(pc, nullptr, a, cols, n, f->Ns, pass, sel_dev, hist_dev);
+    k_select_pick<<<2 * cols, 32, 0, f->stream>>>(sel_dev, hist_dev);
+  }
+  k_select_finish<real><<<1, 128, 0, f->stream>>>(sel_dev, out_dev, 2 * cols);
+  f->launches += 2 + 2 * passes;
+  CU(cudaGetLastError());
+  host.resize((size_t)cols + 2 * cols);
+  CU(cudaMemcpyAsync(host.data(), mean_dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  return CSSM_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int cssm_version(void) { return CSSM_VERSION; }
@@ -1097,7 +1168,7 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
                   f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl,
-                  f->recs};
+                  f->recs, f->fc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (f->ev0) cudaEventDestroy(f->ev0);
@@ -1704,6 +1775,53 @@ int cssm_filter_intervals(cssm_filter_t* f, double t, double interval, double* s
   }
   gamma_out[0] = host[d + 2 * d];
   gamma_out[1] = host[d + 2 * d + 1];
+  return CSSM_OK;
+}
+
+int cssm_filter_forecast(cssm_filter_t* f, double t, double interval, int chain, double* state_mean, double* state_lower,
+                         double* state_upper, double* eta_out, double* obs_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->initialised) return fail(CSSM_ERR_STATE, "no particles yet");
+  if (f->world > 1) return fail(CSSM_ERR_UNSUPPORTED, "forecast of a sharded cloud is not implemented");
+  if (f->model.obs_kind == CSSM_OBS_LGCP) return fail(CSSM_ERR_UNSUPPORTED, "LGCP has no observation distribution (`???` in the reference)");
+  if (chain && !f->fc_valid) return fail(CSSM_ERR_STATE, "forecast: nothing to continue from");
+  const double t_from = chain ? f->fc_t : f->t_cur;
+  if (!(t >= t_from)) return fail(CSSM_ERR_INVALID, "forecast: the forecast time lies before the cloud");
+  const bool summarise = state_mean || state_lower || state_upper || eta_out || obs_out;
+  std::vector<double> host;
+  rc = (f->dtype == CSSM_F32) ? forecast_impl<float>(f, t, interval, chain, summarise, host)
+                              : forecast_impl<double>(f, t, interval, chain, summarise, host);
+  if (rc || !summarise) return rc;
+  const int d = f->d, cols = d + 4;
+  for (int k = 0; k < d; ++k) {
+    if (state_mean) state_mean[k] = host[k];
+    if (state_lower) state_lower[k] = host[cols + 2 * k];
+    if (state_upper) state_upper[k] = host[cols + 2 * k + 1];
+  }
+  if (eta_out) { eta_out[0] = host[d + 1]; eta_out[1] = host[cols + 2 * (d + 1)]; eta_out[2] = host[cols + 2 * (d + 1) + 1]; }
+  if (obs_out) { obs_out[0] = host[d + 3]; obs_out[1] = host[cols + 2 * (d + 3)]; obs_out[2] = host[cols + 2 * (d + 3) + 1]; }
+  return CSSM_OK;
+}
+
+int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_out, double* eta_out, double* obs_out,
+                               double* obs2_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (!f->fc_valid) return fail(CSSM_ERR_STATE, "no forecast yet");
+  const long long n = f->N;
+  rc = ensure_scratch(f, (size_t)n);
+  if (rc) return rc;
+  const int d = f->d;
+  for (int c = 0; c < d + 4; ++c) {
+    double* dst = c < d ? (x_out ? x_out + (size_t)c * n : nullptr) : c == d ? gamma_out : c == d + 1 ? eta_out : c == d + 2 ? obs_out : obs2_out;
+    if (!dst) continue;
+    if (f->dtype == CSSM_F32) k_to_double<float><<<nblk(n, 256), 256, 0, f->stream>>>((const float*)f->fc + (size_t)c * f->Ns, f->scratch, n);
+    else k_to_double<double><<<nblk(n, 256), 256, 0, f->stream>>>((const double*)f->fc + (size_t)c * f->Ns, f->scratch, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst, f->scratch, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+  }
   return CSSM_OK;
 }
 

@@ -49,6 +49,22 @@ class PfOut:
         self.state, self.stateIntervals = state, stateIntervals
 
 
+class ForecastOut:
+    """model/ParticleFilter.scala:71-78."""
+
+    def __init__(self, t, obs, obsIntervals, eta, etaIntervals, state, stateIntervals):
+        self.t, self.obs, self.obsIntervals, self.eta, self.etaIntervals = t, obs, obsIntervals, eta, etaIntervals
+        self.state, self.stateIntervals = state, stateIntervals
+
+
+class ObservationWithState:
+    """model/Data.scala:27-36: one forecast / simulated datum.  In a forecast of N particles every field but `t` is
+    an array over the particles (sdeState: [N, d])."""
+
+    def __init__(self, t, observation, eta, gamma, sdeState):
+        self.t, self.observation, self.eta, self.gamma, self.sdeState = t, observation, eta, gamma, sdeState
+
+
 class PfState:
     """model/ParticleFilter.scala:32-37.  `particles` is read from the device when asked for."""
 
@@ -263,6 +279,28 @@ class GpuFilterHandle:
         return dict(mean=mean, lower=lo, upper=up, gamma=(float(g[0]), float(g[1])))
 
 
+    def forecast(self, t, interval=0.975, chain=False, summarise=True):
+        """getForecast / getMeanForecast (model/ParticleFilter.scala:368-412) on the device: every particle advanced
+        to `t` (the filter itself is not touched), eta and two observation draws per particle; with `summarise` the
+        means and credible intervals of cssm_filter_forecast.  `chain`: continue from the previous forecast cloud
+        (SimulateData.forecast, model/Data.scala:202-217)."""
+        if not summarise:
+            _abi.check(self._lib.cssm_filter_forecast(self._h, float(t), float(interval), int(bool(chain)), None, None, None,
+                                                      None, None))
+            return None
+        mean, lo, up, eta, obs = np.empty(self.d), np.empty(self.d), np.empty(self.d), np.empty(3), np.empty(3)
+        _abi.check(self._lib.cssm_filter_forecast(self._h, float(t), float(interval), int(bool(chain)), _abi.dptr(mean),
+                                                  _abi.dptr(lo), _abi.dptr(up), _abi.dptr(eta), _abi.dptr(obs)))
+        return dict(mean=mean, lower=lo, upper=up, eta=tuple(eta), obs=tuple(obs))
+
+    def forecast_cloud(self):
+        """The last forecast cloud: x [d, N], gamma, eta, obs, obs2 [N]."""
+        x, g, e, o, o2 = np.empty((self.d, self.n)), np.empty(self.n), np.empty(self.n), np.empty(self.n), np.empty(self.n)
+        _abi.check(self._lib.cssm_filter_forecast_cloud(self._h, _abi.dptr(x), _abi.dptr(g), _abi.dptr(e), _abi.dptr(o),
+                                                        _abi.dptr(o2)))
+        return dict(x=x, gamma=g, eta=e, obs=o, obs2=o2)
+
+
 class ShardedGroup:
     """R shards of ONE filter inside one process, driven in lock-step by the cssm_group_* entry
     points: virtual ranks on one GPU (devices all equal) or one process over several GPUs.  This
@@ -443,6 +481,23 @@ class ParticleFilter:
         eta = model.link(model.f(r["mean"], s.t))
         return PfOut(s.t, s.observation, eta, CredibleInterval(lo, up), r["mean"],
                      [CredibleInterval(a, b) for a, b in zip(r["lower"], r["upper"])])
+
+    @staticmethod
+    def getForecast(s, mod, t):
+        """model/ParticleFilter.scala:368-383: the particles of `s` advanced to `t` with eta and a drawn observation
+        each, as ONE ObservationWithState whose fields are arrays over the particles (the reference returns a
+        Vector of N of them)."""
+        s._handle.forecast(t, summarise=False)
+        c = s._handle.forecast_cloud()
+        return ObservationWithState(t, c["obs"], c["eta"], c["gamma"], c["x"].T.copy())
+
+    @staticmethod
+    def getMeanForecast(s, mod, t, interval):
+        """model/ParticleFilter.scala:394-412 -> ForecastOut; nothing but the 3(d + 2) summary numbers leaves the device."""
+        r = s._handle.forecast(t, interval)
+        return ForecastOut(t, r["obs"][0], CredibleInterval(r["obs"][1], r["obs"][2]), r["eta"][0],
+                           CredibleInterval(r["eta"][1], r["eta"][2]), r["mean"],
+                           [CredibleInterval(a, b) for a, b in zip(r["lower"], r["upper"])])
 
     @staticmethod
     def effectiveSampleSize(weights):

@@ -273,6 +273,25 @@ int cssm_filter_get_particles(cssm_filter_t* f, double* x_out);
  * interval is 0.975 in the reference.  CSSM_ERR_INVALID where the reference would throw IndexOutOfBounds. */
 int cssm_filter_intervals(cssm_filter_t* f, double t, double interval, double* state_mean,
                           double* state_lower, double* state_upper, double* gamma_out);
+/* ParticleFilter.getForecast / getMeanForecast (model/ParticleFilter.scala:368-412) and one step of
+ * SimulateData.forecast (model/Data.scala:186-217), on the device.  Every particle of the current (resampled)
+ * cloud is advanced to time t without touching the filter -- x1 = stepFunction(t - s.t)(x).draw, gamma = f(x1, t),
+ * eta = link(gamma) -- and two observations are drawn from Model.observation(gamma) (getForecast's, and the second
+ * draw getMeanForecast summarises); the result is kept in a forecast cloud next to the filter's own.
+ *   chain != 0     continue from the previous forecast cloud instead (Data.forecast's scan over times)
+ *   state_mean[d], state_lower[d], state_upper[d]   meanState and getallCredibleIntervals of x1 (:398-399)
+ *   eta_out[3]     mean(eta) and getOrderStatistic(eta, interval): mean, lower, upper (:400-401)
+ *   obs_out[3]     the same for the second observation draw (:402-404)
+ * All five outputs NULL: only the forecast cloud is produced (read it with cssm_filter_forecast_cloud).
+ * Samplers: Poisson (CDF inversion / Hoermann's PTRS), Gamma (Marsaglia-Tsang), Student's t, Beta, Bernoulli, Normal
+ * from the filter's Philox stream; the reference's Breeze RNG streams are not reproduced.  LGCP: CSSM_ERR_UNSUPPORTED
+ * (`observation = ???`, model/Model.scala:364). */
+int cssm_filter_forecast(cssm_filter_t* f, double t, double interval, int chain, double* state_mean,
+                         double* state_lower, double* state_upper, double* eta_out, double* obs_out);
+/* the last forecast cloud: x_out[d][N], gamma_out[N], eta_out[N], obs_out[N] (getForecast's draw), obs2_out[N] (the draw
+ * getMeanForecast summarises); NULL to skip */
+int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_out, double* eta_out,
+                               double* obs_out, double* obs2_out);
 /* Resampling.sampleOne of the current cloud, x_out[d] */
 int cssm_filter_sample_one(cssm_filter_t* f, double* x_out);
 /* PfState.ll / PfState.ess */

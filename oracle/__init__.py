@@ -171,6 +171,51 @@ class Oracle:
             raise IndexError("order-statistic index outside the cloud")
         return dict(mean=mean, lower=lo, upper=up, eta=tuple(eta))
 
+    def observation(self, gamma, rng):
+        """Model.observation(gamma).draw for every element of gamma (model/Model.scala:145-149,169-178,209-213,
+        242-246,267,282-290,316,340-341), with NumPy's samplers."""
+        m, k = self.mod, self.mod.obs_kind
+        g = f64(gamma)
+        if k == _abi.OBS_POISSON:
+            return rng.poisson(np.exp(g)).astype(np.float64)
+        if k == _abi.OBS_NEGBIN:
+            size = np.exp(m.scale)
+            mu = np.exp(g)
+            prob = mu / (size + mu)
+            return rng.poisson(rng.gamma(size, prob / (1 - prob))).astype(np.float64)
+        if k == _abi.OBS_NORMAL:
+            return rng.normal(g, np.exp(m.scale))
+        if k == _abi.OBS_BERNOULLI:
+            return (rng.random(g.size) < np.array([self.link(v) for v in g])).astype(np.float64)
+        if k == _abi.OBS_STUDENT_T:
+            return rng.standard_t(m.df, g.size) * np.exp(m.scale) + g
+        if k == _abi.OBS_ZIP:
+            p = np.exp(m.scale) / (1 + np.exp(m.scale))
+            u, nz = rng.random(g.size), rng.poisson(np.exp(g))
+            return np.where(u < p, 0.0, nz.astype(np.float64))
+        if k == _abi.OBS_BETA:
+            return rng.beta(np.exp(-g), m.scale)
+        raise NotImplementedError("observation = ??? (model/Model.scala:364)")
+
+    def forecast(self, x, t_from, t, rng, interval=0.975):
+        """ParticleFilter.getForecast + getMeanForecast (model/ParticleFilter.scala:368-412) of the cloud x[d][N]."""
+        x = f64(x)
+        N = x.shape[1]
+        x1 = self.propagate(x, rng.standard_normal(x.shape), t - t_from)
+        gamma = self.f(x1, t)
+        eta = np.array([self.link(v) for v in gamma])
+        obs = self.observation(gamma, rng)
+        obs2 = self.observation(gamma, rng)
+        idx = int(np.floor(interval * N))
+
+        def order_stat(v):  # getOrderStatistic :455-460
+            o = np.sort(v)
+            return float(o[N - idx]), float(o[idx])
+
+        xs = np.sort(x1, axis=1)  # getCredibleInterval :498-503
+        return dict(x=x1, gamma=gamma, eta=eta, obs=obs, mean=x1.mean(axis=1), lower=xs[:, N - idx - 1], upper=xs[:, idx - 1],
+                    eta_summary=(float(eta.mean()),) + order_stat(eta), obs_summary=(float(obs2.mean()),) + order_stat(obs2))
+
     def link(self, g):
         return self.L.orc_link(C.byref(self.desc), float(g))
 

@@ -77,5 +77,11 @@ def beta_bm():
     return Model.beta(Sde.brownianMotion(1))(Parameters(2.0, SdeParameter.brownianParameter([0.3], [0.2], [0.05])))
 
 
+def poisson_big():
+    """Poisson observations with a mean around 60 (the transformed-rejection branch of the forecast sampler)."""
+    return Model.poisson(Sde.ouProcess(1))(Parameters(None, SdeParameter.ouParameter([4.0], [0.05], [0.2], [4.1], [0.1])))
+
+
 ALL = {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "bernoulli": bernoulli_bm, "normal_genbm": normal_genbm,
        "student_t": student_ou, "zip": zip_seasonal, "beta": beta_bm}
+EXTRA = {"poisson_big": poisson_big}

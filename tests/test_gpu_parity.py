@@ -7,7 +7,7 @@ import pytest
 import composablestatespacemodels_b200 as cs
 from composablestatespacemodels_b200 import _abi
 import oracle
-from configs import ALL, SYS, STRAT, MULTI, c1, c2, c3, c5
+from configs import ALL, EXTRA, SYS, STRAT, MULTI, c1, c2, c3, c5
 
 pytestmark = pytest.mark.gpu
 
@@ -318,4 +318,126 @@ def test_intervals_on_device_match_the_sorted_cloud(name, dtype):
     rel_close([out.eta, out.etaIntervals.lower, out.etaIntervals.upper], ref["eta"], tol, "eta and its interval")
     with pytest.raises(cs._abi.CssmError):
         s._handle.intervals(s.t, 1.0)                  # index = n: the reference throws IndexOutOfBounds
+    flt.close()
+
+
+FORECAST_MODELS = ["c1", "c2", "c4", "c5", "bernoulli", "student_t", "zip", "beta"]
+
+
+def _filtered(mod, N, dtype, T=4, seed=9):
+    from composablestatespacemodels_b200 import Filter, Resampling, Data
+    orc = oracle.Oracle(mod)
+    t, y, _ = orc.simulate(T, 0.1, 17)
+    flt = Filter(mod, Resampling.systematicResampling, dtype=dtype, seed=seed)
+    s = flt.initialiseState(N, t[0])
+    for k in range(T):
+        s = flt.stepFilter(s, Data(t[k], y[k]))
+    return flt, s, orc
+
+
+@pytest.mark.parametrize("name", FORECAST_MODELS)
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+def test_forecast_summaries_match_the_forecast_cloud(name, dtype):
+    """cssm_filter_forecast (getMeanForecast, model/ParticleFilter.scala:394-412): the summaries computed on
+    the device against a literal sort of the forecast cloud read back from it -- intervals are elements of
+    the cloud, bit for bit; and the cloud is self-consistent: gamma = f(x1, t), eta = link(gamma), observations
+    in the support of the model's distribution.  The filter's own cloud is not touched."""
+    mod = ALL[name]()
+    N = 4000
+    flt, s, orc = _filtered(mod, N, dtype)
+    tol = TOL[dtype]
+    before = s.particles
+    tf = s.t + 0.35
+    r = s._handle.forecast(tf, 0.975)
+    c = s._handle.forecast_cloud()
+    np.testing.assert_array_equal(s.particles, before)
+    idx = int(np.floor(0.975 * N))
+    xs = np.sort(c["x"], axis=1)
+    np.testing.assert_array_equal(r["lower"], xs[:, N - idx - 1])
+    np.testing.assert_array_equal(r["upper"], xs[:, idx - 1])
+    rel_close(r["mean"], c["x"].mean(axis=1), 1e-9, "forecast mean state")
+    for key, col in (("eta", "eta"), ("obs", "obs2")):
+        o = np.sort(c[col])
+        assert r[key][1] == o[N - idx] and r[key][2] == o[idx], key
+        rel_close(r[key][0], c[col].mean(), 1e-9, f"mean {key}")
+    rel_close(c["gamma"], orc.f(c["x"], tf), tol, "gamma = f(x1, t)")
+    rel_close(c["eta"], [orc.link(g) for g in c["gamma"]], tol, "eta = link(gamma)")
+    for col in ("obs", "obs2"):
+        o = c[col]
+        assert np.all(np.isfinite(o))
+        if name in ("c1", "c2", "c4", "zip"):
+            assert np.all(o >= 0) and np.all(o == np.floor(o))
+        if name == "bernoulli":
+            assert set(np.unique(o)) <= {0.0, 1.0}
+        if name == "beta":
+            assert np.all((o >= 0) & (o <= 1))
+    assert not np.array_equal(c["obs"], c["obs2"])
+    with pytest.raises(cs._abi.CssmError):
+        s._handle.forecast(s.t - 1.0)
+    flt.close()
+
+
+@pytest.mark.parametrize("name", FORECAST_MODELS + ["poisson_big"])
+def test_forecast_agrees_with_the_oracle_in_distribution(name):
+    """getForecast / getMeanForecast against the oracle's NumPy restatement started from the SAME filtering cloud:
+    independent RNG streams, so means agree within 6 standard errors and every interval end point lies between the
+    oracle's empirical quantiles at p -+ 6 sd of an empirical CDF value."""
+    from composablestatespacemodels_b200 import ParticleFilter
+    mod = {**ALL, **EXTRA}[name]()
+    N = 200000
+    flt, s, orc = _filtered(mod, N, _abi.F32)
+    x = s.particles.T
+    tf = s.t + 0.5
+    out = ParticleFilter.getMeanForecast(s, mod, tf, 0.975)
+    cloud = ParticleFilter.getForecast(s, mod, tf)
+    assert cloud.sdeState.shape == (N, mod.dimension)
+    rng = np.random.default_rng(5)
+    ref = orc.forecast(x, s.t, tf, rng, 0.975)
+    ref2 = orc.forecast(x, s.t, tf, rng, 0.975)   # a second oracle run gauges the Monte-Carlo error itself
+
+    def close_mean(a, sample, what):
+        se = np.std(sample) * np.sqrt(2.0 / N) + 1e-12
+        assert abs(a - np.mean(sample)) <= 6 * se, f"{what}: {a} vs {np.mean(sample)} (se {se})"
+
+    def within_quantiles(q, sample, p, what):
+        dlt = 6 * np.sqrt(2 * p * (1 - p) / N)
+        lo, hi = np.quantile(sample, max(p - dlt, 0.0), method="lower"), np.quantile(sample, min(p + dlt, 1.0), method="higher")
+        assert lo <= q <= hi, f"{what}: {q} outside [{lo}, {hi}]"
+
+    for k in range(mod.dimension):
+        close_mean(out.state[k], ref["x"][k], f"state mean {k}")
+        within_quantiles(out.stateIntervals[k].lower, ref["x"][k], 0.025, f"state lower {k}")
+        within_quantiles(out.stateIntervals[k].upper, ref["x"][k], 0.975, f"state upper {k}")
+    close_mean(out.eta, ref["eta"], "mean eta")
+    within_quantiles(out.etaIntervals.lower, ref["eta"], 0.025, "eta lower")
+    within_quantiles(out.etaIntervals.upper, ref["eta"], 0.975, "eta upper")
+    close_mean(out.obs, ref["obs"], "mean observation")
+    within_quantiles(out.obsIntervals.lower, ref["obs"], 0.025, "observation lower")
+    within_quantiles(out.obsIntervals.upper, ref["obs"], 0.975, "observation upper")
+    # the observation distribution beyond its mean: variance, and P(obs == 0) for the count models
+    vg, vr, vr2 = np.var(cloud.observation), np.var(ref["obs"]), np.var(ref2["obs"])
+    assert abs(vg - vr) <= 8 * abs(vr - vr2) + 0.03 * vr, (vg, vr, vr2)
+    if name in ("c1", "c2", "c4", "zip", "poisson_big"):
+        p0g, p0r = np.mean(cloud.observation == 0), np.mean(ref["obs"] == 0)
+        assert abs(p0g - p0r) <= 6 * np.sqrt(2 * max(p0r, 1e-4) / N), (p0g, p0r)
+    flt.close()
+
+
+def test_forecast_chain_continues_from_the_forecast_cloud():
+    """SimulateData.forecast (model/Data.scala:202-217) scans simStep over the forecast times: chain=True advances the
+    forecast cloud itself.  Two chained steps of 0.3 and 0.4 agree in distribution with one step of 0.7 (the exact
+    OU / Brownian transitions compose)."""
+    mod = ALL["c5"]()
+    N = 200000
+    flt, s, orc = _filtered(mod, N, _abi.F32)
+    h = s._handle
+    one = h.forecast(s.t + 0.7, 0.975)
+    h.forecast(s.t + 0.3, summarise=False)
+    two = h.forecast(s.t + 0.7, 0.975, chain=True)
+    c = h.forecast_cloud()
+    sd = c["x"].std(axis=1)
+    assert np.all(np.abs(one["mean"] - two["mean"]) <= 6 * sd * np.sqrt(2.0 / N))
+    assert np.all(np.abs(one["upper"] - two["upper"]) <= 0.05 * sd + 1e-6)
+    assert np.all(np.abs(one["lower"] - two["lower"]) <= 0.05 * sd + 1e-6)
+    assert abs(one["obs"][0] - two["obs"][0]) <= 6 * c["obs2"].std() * np.sqrt(2.0 / N)
     flt.close()

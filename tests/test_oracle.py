@@ -304,3 +304,30 @@ def test_euler_maruyama_definition():
     ob = oracle.Oracle(mb)
     xb = np.zeros((2, 1))
     np.testing.assert_allclose(ob.propagate(xb, np.zeros((2, 1)), 0.25), np.full((2, 1), 0.25))
+
+
+def test_oracle_forecast_moments():
+    """Oracle.forecast (getForecast / getMeanForecast restated with NumPy samplers): law of total variance of the
+    drawn observations, and the interval ranks of getCredibleInterval / getOrderStatistic."""
+    import oracle
+    from configs import c5, c1
+    rng = np.random.default_rng(3)
+    N = 100000
+    for make, kind in ((c5, "normal"), (c1, "poisson")):
+        mod = make()
+        orc = oracle.Oracle(mod)
+        x = orc.init_state(rng.standard_normal((mod.dimension, N)))
+        r = orc.forecast(x, 0.0, 0.4, rng, 0.975)
+        g, eta, obs = r["gamma"], r["eta"], r["obs"]
+        if kind == "normal":
+            np.testing.assert_allclose(eta, g)
+            assert abs(obs.var() - (g.var() + np.exp(mod.scale) ** 2)) < 0.05 * obs.var()
+        else:
+            np.testing.assert_allclose(eta, np.exp(g))
+            assert abs(obs.var() - (eta.mean() + eta.var())) < 0.05 * obs.var()
+        assert abs(obs.mean() - eta.mean()) < 6 * obs.std() / np.sqrt(N)
+        idx = int(np.floor(0.975 * N))
+        xs = np.sort(r["x"][0])
+        assert r["lower"][0] == xs[N - idx - 1] and r["upper"][0] == xs[idx - 1]
+        es = np.sort(eta)
+        assert r["eta_summary"][1] == es[N - idx] and r["eta_summary"][2] == es[idx]
