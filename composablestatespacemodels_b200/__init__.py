@@ -14,13 +14,13 @@ from . import model as Model
 from .model import UnparamModel
 from .resampling import Resampling
 from .filter import (Data, TimedObservation, StateSpace, PfState, PfOut, ForecastOut, ObservationWithState, CredibleInterval,
-                     Filter, FilterLgcp, FilterInit, ParticleFilter,
+                     Filter, FilterLgcp, FilterInit, FilterInterpolate, PfStateInterpolate, ParticleFilter,
                      GpuFilterHandle, ShardedGroup)
 from .pmmh import MetropolisHastings, ParticleMetropolisHastings, MetropState, GpuBootstrapFilter
 
 F32, F64 = _abi.F32, _abi.F64
 __all__ = ["Tree", "Leaf", "Branch", "Sde", "SdeParameter", "BrownianParameter", "GenBrownianParameter", "OuParameter",
            "ParamNode", "Parameters", "flattenParams", "perturb", "perturbMvn", "Model", "UnparamModel", "Resampling",
-           "Data", "TimedObservation", "StateSpace", "PfState", "PfOut", "ForecastOut", "ObservationWithState", "CredibleInterval", "Filter", "FilterLgcp", "FilterInit", "ParticleFilter",
+           "Data", "TimedObservation", "StateSpace", "PfState", "PfOut", "ForecastOut", "ObservationWithState", "CredibleInterval", "Filter", "FilterLgcp", "FilterInit", "FilterInterpolate", "PfStateInterpolate", "ParticleFilter",
            "GpuFilterHandle", "ShardedGroup", "MetropolisHastings", "ParticleMetropolisHastings", "MetropState", "GpuBootstrapFilter",
            "F32", "F64"]

@@ -109,6 +109,9 @@ _SIGNATURES = {
     "cssm_filter_forecast": [_FILTER, C.c_double, C.c_double, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                              c_double_p],
     "cssm_filter_forecast_cloud": [_FILTER, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p],
+    "cssm_filter_paths_enable": [_FILTER, C.c_int64],
+    "cssm_filter_paths_len": [_FILTER, c_int64_p],
+    "cssm_filter_get_paths": [_FILTER, c_int32_p, C.c_int64, c_double_p],
     "cssm_resample": [C.c_int, c_double_p, C.c_int64, c_double_p, C.c_int64, c_int32_p, C.c_int],
     "cssm_filter_init_injected": [_FILTER, C.c_double, c_double_p],
     "cssm_filter_step_injected": [_FILTER, C.c_double, C.c_int, C.c_double, c_double_p, c_double_p,

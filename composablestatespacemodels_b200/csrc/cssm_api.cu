@@ -245,6 +245,12 @@ struct cssm_filter {
   bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
   // forecast cloud (cssm_forecast.cuh): d + 4 columns [x1 | gamma | eta | obs | obs2], filter dtype
+  // path storage (FilterInterpolate): px = (paths_cap + 1) propagated clouds, panc = paths_cap ancestor vectors
+  void* px = nullptr;
+  int32_t* panc = nullptr;
+  uint8_t* pres_dev = nullptr;
+  long long paths_cap = 0, paths_len = -1;  // paths_len = recorded steps; -1: nothing recorded (no init since enable)
+  std::vector<uint8_t> pres;                // per recorded step: did it resample?
   void* fc = nullptr;
   bool fc_valid = false;
   double fc_t = 0.0;
@@ -364,6 +370,12 @@ int do_init(cssm_filter* f, double t0, const double* zinj_dev, const double* x0)
   f->anc_valid = false;
   f->initialised = true;
   f->t_cur = t0;
+  if (f->paths_cap > 0) {  // FilterInterpolate: the initial cloud is element 0 of every path
+    const size_t cloud = (size_t)f->d * f->Ns * (f->dtype == CSSM_F32 ? 4 : 8);
+    CU(cudaMemcpyAsync(f->px, f->x[f->cur], cloud, cudaMemcpyDeviceToDevice, f->stream));
+    f->paths_len = 0;
+    f->pres.clear();
+  }
   return CSSM_OK;
 }
 
@@ -642,9 +654,20 @@ int run_one_step(cssm_filter* f, double t, int has_obs, double y, const StepIO& 
   const void* ctab;
   int rc = prepare_one_step(f, t, has_obs, y, h, n_sub, delta, ctab);
   if (rc) return rc;
+  if (f->paths_cap > 0 && f->paths_len >= f->paths_cap) return fail(CSSM_ERR_STATE, "path storage is full (cssm_filter_paths_enable)");
   rc = (f->dtype == CSSM_F32) ? launch_step<float>(f, h, n_sub, ctab, delta, io) : launch_step<double>(f, h, n_sub, ctab, delta, io);
   if (rc) return rc;
   f->t_cur = t;
+  if (f->paths_cap > 0 && f->paths_len >= 0) {  // FilterInterpolate: keep the propagated cloud and the ancestors of this step
+    const size_t cloud = (size_t)f->d * f->Ns * (f->dtype == CSSM_F32 ? 4 : 8);
+    const bool resampled = f->anc_valid;
+    CU(cudaMemcpyAsync((char*)f->px + (size_t)(f->paths_len + 1) * cloud, f->x[f->cur], cloud, cudaMemcpyDeviceToDevice, f->stream));
+    if (resampled)
+      CU(cudaMemcpyAsync(f->panc + (size_t)f->paths_len * f->N, f->anc, (size_t)f->N * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                         f->stream));
+    f->pres.push_back(resampled ? 1 : 0);
+    f->paths_len++;
+  }
   return CSSM_OK;
 }
 
@@ -1168,7 +1191,7 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
                   f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl,
-                  f->recs, f->fc};
+                  f->recs, f->fc, f->px, f->panc, f->pres_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (f->ev0) cudaEventDestroy(f->ev0);
@@ -1822,6 +1845,63 @@ int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_ou
     CU(cudaMemcpyAsync(dst, f->scratch, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
     CU(cudaStreamSynchronize(f->stream));
   }
+  return CSSM_OK;
+}
+
+int cssm_filter_paths_enable(cssm_filter_t* f, int64_t max_steps) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (max_steps < 0) return fail(CSSM_ERR_INVALID, "negative path capacity");
+  if (f->world > 1) return fail(CSSM_ERR_UNSUPPORTED, "path storage of a sharded cloud is not implemented");
+  CU(cudaStreamSynchronize(f->stream));
+  if (f->px) cudaFree(f->px);
+  if (f->panc) cudaFree(f->panc);
+  if (f->pres_dev) cudaFree(f->pres_dev);
+  f->px = nullptr; f->panc = nullptr; f->pres_dev = nullptr;
+  f->paths_cap = 0; f->paths_len = -1; f->pres.clear();
+  if (max_steps == 0) return CSSM_OK;
+  const size_t cloud = (size_t)f->d * f->Ns * (f->dtype == CSSM_F32 ? 4 : 8);
+  CU(cudaMalloc(&f->px, (size_t)(max_steps + 1) * cloud));
+  CU(cudaMalloc(&f->panc, (size_t)max_steps * f->N * sizeof(int32_t)));
+  CU(cudaMalloc(&f->pres_dev, (size_t)max_steps));
+  f->paths_cap = max_steps;
+  return CSSM_OK;
+}
+
+int cssm_filter_paths_len(const cssm_filter_t* f, int64_t* len_out) {
+  if (!f || !len_out) return fail(CSSM_ERR_INVALID, "null argument");
+  *len_out = f->paths_len;
+  return CSSM_OK;
+}
+
+int cssm_filter_get_paths(cssm_filter_t* f, const int32_t* idx, int64_t n_idx, double* out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  if (f->paths_cap <= 0 || f->paths_len < 0) return fail(CSSM_ERR_STATE, "no paths recorded (cssm_filter_paths_enable, then initialise)");
+  if (!out || n_idx <= 0 || n_idx > f->N) return fail(CSSM_ERR_INVALID, "bad path request");
+  if (idx)
+    for (int64_t i = 0; i < n_idx; ++i)
+      if (idx[i] < 0 || idx[i] >= f->N) return fail(CSSM_ERR_INVALID, "path index outside the cloud");
+  const int len = (int)f->paths_len;
+  const size_t n_out = (size_t)n_idx * (size_t)(len + 1) * (size_t)f->d;
+  const size_t idx_dbl = ((size_t)n_idx * sizeof(int32_t) + 7) / 8;
+  rc = ensure_scratch(f, n_out + idx_dbl + 1);
+  if (rc) return rc;
+  int32_t* idx_dev = nullptr;
+  if (idx) {
+    idx_dev = reinterpret_cast<int32_t*>(f->scratch + n_out);
+    CU(cudaMemcpyAsync(idx_dev, idx, (size_t)n_idx * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+  }
+  if (len > 0) CU(cudaMemcpyAsync(f->pres_dev, f->pres.data(), (size_t)len, cudaMemcpyHostToDevice, f->stream));
+  if (f->dtype == CSSM_F32)
+    k_paths<float><<<nblk(n_idx, 256), 256, 0, f->stream>>>((const float*)f->px, f->panc, f->pres_dev, len, f->N, f->Ns, f->d, idx_dev,
+                                                             n_idx, f->scratch);
+  else
+    k_paths<double><<<nblk(n_idx, 256), 256, 0, f->stream>>>((const double*)f->px, f->panc, f->pres_dev, len, f->N, f->Ns, f->d, idx_dev,
+                                                              n_idx, f->scratch);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, f->scratch, n_out * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
   return CSSM_OK;
 }
 

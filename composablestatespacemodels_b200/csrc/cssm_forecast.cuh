@@ -184,4 +184,26 @@ k_forecast(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Pee
   fc[(long long)(d + 3) * Ns + i] = (real)sample_observation(g, od, gd);
 }
 
+// ---------------------------------------------------------------------------------------------
+// FilterInterpolate (model/ParticleFilter.scala:273-311): every particle is a PATH (List[State], newest first) and
+// an observed step resamples whole paths.  The device keeps the propagated cloud of every step, px[s] (s = 0 is
+// the initial cloud), and the ancestors of every resampling, panc[s-1]; a path is read back by walking the
+// ancestor tree from the newest step to the oldest.  out[p][s][k], s = 0 .. len (oldest state first).
+// ---------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256)
+k_paths(const real* __restrict__ px, const int32_t* __restrict__ panc, const uint8_t* __restrict__ resampled, int len, long long N,
+        long long Ns, int d, const int32_t* __restrict__ idx, long long n_idx, double* __restrict__ out) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_idx) return;
+  long long j = idx ? (long long)idx[p] : p;
+  const size_t cloud = (size_t)d * (size_t)Ns;
+  for (int s = len; s >= 0; --s) {
+    if (s > 0 && resampled[s - 1]) j = panc[(size_t)(s - 1) * (size_t)N + j];
+    const real* x = px + (size_t)s * cloud + j;
+    double* o = out + ((size_t)p * (size_t)(len + 1) + (size_t)s) * (size_t)d;
+    for (int k = 0; k < d; ++k) o[k] = (double)x[(size_t)k * Ns];
+  }
+}
+
 }  // namespace cssm

@@ -78,6 +78,24 @@ class PfState:
         return self._handle.get_particles().T.copy()
 
 
+class PfStateInterpolate:
+    """model/ParticleFilter.scala:39-44: the particles are paths.  `particles` reads them from the device when asked
+    for: an array [N, len, d] with the NEWEST state first (the reference's List[State] conses new states at the head)."""
+
+    def __init__(self, t, observation, handle, ll, ess, reverse=False):
+        self.t, self.observation, self.ll, self.ess = t, observation, ll, ess
+        self._handle, self._reverse = handle, reverse
+
+    def paths(self, indices=None):
+        """Paths of the given particles (all by default), [n, len, d], OLDEST state first."""
+        return self._handle.get_paths(indices)
+
+    @property
+    def particles(self):
+        p = self._handle.get_paths()[:, ::-1, :]
+        return p[::-1] if self._reverse else p
+
+
 class GpuFilterHandle:
     """Owner of one cssm_filter_t (AutoCloseable on the JVM side)."""
 
@@ -279,6 +297,27 @@ class GpuFilterHandle:
         return dict(mean=mean, lower=lo, upper=up, gamma=(float(g[0]), float(g[1])))
 
 
+    # ---- paths (FilterInterpolate) ------------------------------------------------------------
+    def paths_enable(self, max_steps):
+        _abi.check(self._lib.cssm_filter_paths_enable(self._h, int(max_steps)))
+
+    def paths_len(self):
+        n = C.c_int64()
+        _abi.check(self._lib.cssm_filter_paths_len(self._h, C.byref(n)))
+        return n.value
+
+    def get_paths(self, indices=None):
+        """[n, len + 1, d], oldest state first, of the particles `indices` (all by default) of the current cloud."""
+        ln = self.paths_len()
+        if ln < 0:
+            raise _abi.CssmError(-5, "no paths recorded")
+        idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+        n = self.n if idx is None else idx.size
+        out = np.empty((n, ln + 1, self.d))
+        _abi.check(self._lib.cssm_filter_get_paths(self._h, None if idx is None else idx.ctypes.data_as(_abi.c_int32_p), n,
+                                                   _abi.dptr(out)))
+        return out
+
     def forecast(self, t, interval=0.975, chain=False, summarise=True):
         """getForecast / getMeanForecast (model/ParticleFilter.scala:368-412) on the device: every particle advanced
         to `t` (the filter itself is not touched), eta and two observation draws per particle; with `summarise` the
@@ -448,6 +487,54 @@ class FilterInit(_ParticleFilterBase):
         h = self._get(particles)
         h.init_state(t0, self.initState)
         return PfState(t0, None, h, 0.0, particles)
+
+
+class FilterInterpolate:
+    """model/ParticleFilter.scala:273-311: the particle filter whose particles are whole paths -- an unobserved datum
+    extends every path, an observed one resamples the paths.  The device keeps the propagated cloud of every step and
+    the ancestors of every resampling (cssm_filter_paths_enable); a path is materialised by a walk through the
+    ancestor tree only when `particles` / `paths` is read.  `max_steps` bounds the stored history."""
+
+    def __init__(self, mod, resample, max_steps=1024, dtype=_abi.F32, device=0, seed=0, stream_id=0):
+        self.mod, self.resample, self.max_steps = mod, resample, int(max_steps)
+        self.resample_kind = Resampling.kind_of(resample)
+        self.dtype, self.device, self.seed, self.stream_id = dtype, device, seed, stream_id
+        self._handle = None
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
+    def initialise(self, particles, t0):
+        """x0 = mod.sde.initialState.sample(particles) map (_ :: Nil); ll = 0, ess = 0 (sic, :302-303)"""
+        if self._handle is None or self._handle.n != particles:
+            self.close()
+            self._handle = GpuFilterHandle(self.mod, self.resample_kind, particles, self.dtype, self.device, self.seed,
+                                           self.stream_id)
+            self._handle.paths_enable(self.max_steps)
+        self._handle.init(t0)
+        return PfStateInterpolate(t0, None, self._handle, 0.0, 0)
+
+    def stepInterpolate(self, s, y):
+        """model/ParticleFilter.scala:281-298"""
+        h = s._handle
+        ll, ess = h.step(y.t, y.observation)
+        if y.observation is None:
+            ll, ess = s.ll, s.ess
+        return PfStateInterpolate(y.t, y.observation, h, ll, ess)
+
+    def filterInterpolate(self, t0, particles):
+        """model/ParticleFilter.scala:300-310: Flow[Data].scan(init)(stepInterpolate).map(s => s.copy(particles =
+        s.particles.reverse)) as a generator transformer -- the emitted states list their particles in reverse order,
+        as the reference's do."""
+        def flow(source):
+            s = self.initialise(particles, t0)
+            yield PfStateInterpolate(s.t, s.observation, s._handle, s.ll, s.ess, reverse=True)
+            for y in source:
+                s = self.stepInterpolate(s, y)
+                yield PfStateInterpolate(s.t, s.observation, s._handle, s.ll, s.ess, reverse=True)
+        return flow
 
 
 class ParticleFilter:

@@ -292,6 +292,17 @@ int cssm_filter_forecast(cssm_filter_t* f, double t, double interval, int chain,
  * getMeanForecast summarises); NULL to skip */
 int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_out, double* eta_out,
                                double* obs_out, double* obs2_out);
+/* FilterInterpolate (model/ParticleFilter.scala:273-311): particles are PATHS and an observed step resamples whole
+ * paths.  With path storage enabled the streaming entry points (cssm_filter_init*, cssm_filter_step, cssm_filter_step_injected)
+ * keep the propagated cloud of every step and the ancestors of every resampling on the device (max_steps + 1 clouds);
+ * a step beyond max_steps fails with CSSM_ERR_STATE.  max_steps == 0 frees the storage.  The whole-series calls
+ * (cssm_filter_ll, _run, _ll_resident) do not record. */
+int cssm_filter_paths_enable(cssm_filter_t* f, int64_t max_steps);
+/* steps recorded since the last initialisation (a path has len + 1 states); -1: nothing recorded */
+int cssm_filter_paths_len(const cssm_filter_t* f, int64_t* len_out);
+/* the paths of the particles idx[0..n_idx) of the current (resampled) cloud -- idx NULL: particles 0..n_idx-1 --
+ * by a walk through the ancestor tree: out[n_idx][len + 1][d], OLDEST state first (the reference's List is newest first) */
+int cssm_filter_get_paths(cssm_filter_t* f, const int32_t* idx, int64_t n_idx, double* out);
 /* Resampling.sampleOne of the current cloud, x_out[d] */
 int cssm_filter_sample_one(cssm_filter_t* f, double* x_out);
 /* PfState.ll / PfState.ess */

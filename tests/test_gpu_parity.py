@@ -441,3 +441,68 @@ def test_forecast_chain_continues_from_the_forecast_cloud():
     assert np.all(np.abs(one["lower"] - two["lower"]) <= 0.05 * sd + 1e-6)
     assert abs(one["obs"][0] - two["obs"][0]) <= 6 * c["obs2"].std() * np.sqrt(2.0 / N)
     flt.close()
+
+
+@pytest.mark.parametrize("name,kind", [("c2", SYS), ("c4", STRAT), ("c1", MULTI)])
+@pytest.mark.parametrize("dtype", [_abi.F64, _abi.F32])
+def test_path_storage_follows_the_list_semantics_of_filter_interpolate(name, kind, dtype):
+    """FilterInterpolate.stepInterpolate (model/ParticleFilter.scala:281-298): `x.head` is advanced and consed onto
+    the path; an observed step resamples the PATHS, an unobserved one does not.  The lists are built here literally
+    from what every device step returned (propagated cloud, ancestors) and compared, bit for bit, with the paths the
+    device reads out of its ancestor tree."""
+    mod = ALL[name]()
+    orc = oracle.Oracle(mod)
+    N, T, d = 1500, 7, mod.dimension
+    missing = (2, 5)
+    rng = np.random.default_rng(4)
+    t, y, _ = orc.simulate(T, 0.1, 21)
+    h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, seed=3)
+    with pytest.raises(cs._abi.CssmError):
+        h.get_paths()
+    h.paths_enable(T)
+    h.init_injected(t[0], rng.standard_normal((d, N)))
+    x0 = h.get_particles()
+    paths = [[x0[:, i]] for i in range(N)]                      # newest first, like List[State]
+    np.testing.assert_array_equal(h.get_paths()[:, 0, :], x0.T)
+    for s in range(T):
+        obs = None if s in missing else float(y[s])
+        g = h.step_injected(t[s], obs, rng.standard_normal((d, N)), rng.random(1 if kind == SYS else N))
+        x1 = [[g["x_prop"][:, i]] + paths[i] for i in range(N)]
+        paths = x1 if obs is None else [x1[a] for a in g["anc"]]
+        assert h.paths_len() == s + 1
+    got = h.get_paths()                                          # [N, T + 1, d], oldest first
+    want = np.array([p[::-1] for p in paths])
+    np.testing.assert_array_equal(got, want)
+    some = np.array([N - 1, 0, 17, 17, 3])
+    np.testing.assert_array_equal(h.get_paths(some), want[some])
+    np.testing.assert_array_equal(got[:, -1, :], h.get_particles().T)
+    with pytest.raises(cs._abi.CssmError):                       # the storage holds T steps
+        h.step(t[-1] + 0.1, 1.0)
+    h.close()
+
+
+def test_filter_interpolate_host_mirror():
+    """FilterInterpolate.filterInterpolate (model/ParticleFilter.scala:300-310) as a generator transformer: same
+    log-likelihood as the plain filter with the same seed, paths grow by one state per datum, the emitted states
+    list their particles in reverse order (`s.particles.reverse`)."""
+    from composablestatespacemodels_b200 import Filter, FilterInterpolate, Resampling, Data
+    mod = ALL["c2"]()
+    orc = oracle.Oracle(mod)
+    T, N = 6, 2000
+    t, y, _ = orc.simulate(T, 0.1, 5)
+    data = [Data(t[k], None if k == 3 else y[k]) for k in range(T)]
+    fi = FilterInterpolate(mod, Resampling.systematicResampling, max_steps=T, dtype=_abi.F32, seed=7)
+    states = list(fi.filterInterpolate(t[0], N)(data))
+    assert len(states) == T + 1 and states[0].ess == 0 and states[0].ll == 0.0
+    last = states[-1]
+    p = last.particles
+    assert p.shape == (N, T + 1, mod.dimension)
+    np.testing.assert_array_equal(p[::-1, 0, :], last._handle.get_particles().T)   # newest state first, particles reversed
+    assert states[4].ll == states[3].ll and states[4].ess == states[3].ess           # the unobserved datum
+    flt = Filter(mod, Resampling.systematicResampling, dtype=_abi.F32, seed=7)
+    s = flt.initialiseState(N, t[0])
+    for dd in data:
+        s = flt.stepFilter(s, dd)
+    assert s.ll == last.ll
+    fi.close()
+    flt.close()
