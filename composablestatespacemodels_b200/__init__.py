@@ -16,11 +16,14 @@ from .resampling import Resampling
 from .filter import (Data, TimedObservation, StateSpace, PfState, PfOut, ForecastOut, ObservationWithState, CredibleInterval,
                      Filter, FilterLgcp, FilterInit, FilterInterpolate, PfStateInterpolate, ParticleFilter,
                      GpuFilterHandle, ShardedGroup)
-from .pmmh import MetropolisHastings, ParticleMetropolisHastings, MetropState, GpuBootstrapFilter
+from .pmmh import (MetropolisHastings, ParticleMetropolisHastings, ApproxPMMH, approxPmmh, pmmhStep, MetropState,
+                   GpuBootstrapFilter)
+from . import streaming as Streaming
 
 F32, F64 = _abi.F32, _abi.F64
 __all__ = ["Tree", "Leaf", "Branch", "Sde", "SdeParameter", "BrownianParameter", "GenBrownianParameter", "OuParameter",
            "ParamNode", "Parameters", "flattenParams", "perturb", "perturbMvn", "Model", "UnparamModel", "Resampling",
            "Data", "TimedObservation", "StateSpace", "PfState", "PfOut", "ForecastOut", "ObservationWithState", "CredibleInterval", "Filter", "FilterLgcp", "FilterInit", "FilterInterpolate", "PfStateInterpolate", "ParticleFilter",
-           "GpuFilterHandle", "ShardedGroup", "MetropolisHastings", "ParticleMetropolisHastings", "MetropState", "GpuBootstrapFilter",
+           "GpuFilterHandle", "ShardedGroup", "MetropolisHastings", "ParticleMetropolisHastings", "ApproxPMMH", "approxPmmh", "pmmhStep", "MetropState",
+           "GpuBootstrapFilter", "Streaming",
            "F32", "F64"]

@@ -506,3 +506,22 @@ def test_filter_interpolate_host_mirror():
     assert s.ll == last.ll
     fi.close()
     flt.close()
+
+
+def test_pilot_run_variances():
+    """Streaming.pilotRun (model/Streaming.scala:19-41): the variance of the log-likelihood estimate per particle
+    count falls roughly like 1/n and agrees with the oracle's own repeated filters within the F-distribution's
+    99.9 % range for 40 repetitions each."""
+    from composablestatespacemodels_b200 import Streaming, Resampling, Data
+    mod = ALL["c1"]()
+    orc = oracle.Oracle(mod)
+    T, R = 60, 40
+    t, y, _ = orc.simulate(T, 0.1, 3)
+    data = [Data(a, b) for a, b in zip(t, y)]
+    res = Streaming.pilotRun(data, mod, Resampling.systematicResampling, [100, 1600], R, dtype=_abi.F32, seed=11)
+    assert [n for n, _ in res] == [100, 1600]
+    v = dict(res)
+    assert v[100] > 3 * v[1600] > 0
+    for n in (100, 1600):
+        ref = np.var(orc.filter_ll_many(n, SYS, t, y, seed=5, R=R, threads=4), ddof=1)
+        assert ref / 3.2 < v[n] < ref * 3.2, (n, v[n], ref)
