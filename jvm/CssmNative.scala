@@ -19,5 +19,13 @@ object CssmNative {
   /** out = mean[d] | lower[d] | upper[d] | gammaLower, gammaUpper (ParticleFilter.getIntervals on the device) */
   @native def filterIntervals(h: Long, t: Double, interval: Double, d: Int, out: Array[Double]): Unit
   @native def filterSampleOne(h: Long, out: Array[Double]): Unit
+  /** out = mean[d] | lower[d] | upper[d] | eta mean, lower, upper | obs mean, lower, upper (getMeanForecast on the device) */
+  @native def filterForecast(h: Long, t: Double, interval: Double, chain: Boolean, d: Int, out: Array[Double]): Unit
+  /** out = x[d*N] | gamma[N] | eta[N] | obs[N] (getForecast) */
+  @native def filterForecastCloud(h: Long, d: Int, n: Long, out: Array[Double]): Unit
+  @native def filterPathsEnable(h: Long, maxSteps: Long): Unit
+  @native def filterPathsLen(h: Long): Long
+  /** out[idx.length][len + 1][d], oldest state first (FilterInterpolate) */
+  @native def filterGetPaths(h: Long, idx: Array[Int], out: Array[Double]): Unit
   @native def resample(kind: Int, w: Array[Double], u: Array[Double], anc: Array[Int], device: Int): Unit
 }

@@ -110,6 +110,30 @@ final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, p
       StateSpace(t, dims.map { dim => val v = DenseVector(states.slice(off, off + dim)); off += dim; Tree.leaf(v): State }
         .reduceLeft(_ +++ _)) })
   }
+  private def toState(v: Array[Double], from: Int): State = {
+    var off = from
+    dims.map { dim => val x = DenseVector(v.slice(off, off + dim)); off += dim; Tree.leaf(x): State }.reduceLeft(_ +++ _)
+  }
+  /** ParticleFilter.getMeanForecast (model/ParticleFilter.scala:394-412) of the handle's current cloud, on the device:
+    * only the 3(d + 2) summary numbers cross the boundary.  `chain` continues from the previous forecast cloud
+    * (SimulateData.forecast, model/Data.scala:202-217). */
+  def getMeanForecast(t: Time, interval: Double, chain: Boolean = false): ForecastOut[State] = {
+    val d = dims.sum
+    val o = new Array[Double](3 * d + 6)
+    CssmNative.filterForecast(handle, t, interval, chain, d, o)
+    ForecastOut(t, o(3 * d + 3), CredibleInterval(o(3 * d + 4), o(3 * d + 5)), o(3 * d), CredibleInterval(o(3 * d + 1), o(3 * d + 2)),
+      toState(o, 0), (0 until d).map(k => CredibleInterval(o(d + k), o(2 * d + k))))
+  }
+  /** FilterInterpolate (model/ParticleFilter.scala:273-311): enable before initialiseState; `paths(idx)` returns the paths
+    * of the given particles, newest state first like the reference's List[State]. */
+  def enablePaths(maxSteps: Int): Unit = CssmNative.filterPathsEnable(handle, maxSteps.toLong)
+  def paths(idx: Array[Int]): Vector[List[State]] = {
+    val d = dims.sum
+    val len = CssmNative.filterPathsLen(handle).toInt + 1
+    val flat = new Array[Double](idx.length * len * d)
+    CssmNative.filterGetPaths(handle, idx, flat)
+    Vector.tabulate(idx.length)(p => List.tabulate(len)(s => toState(flat, (p * len + (len - 1 - s)) * d)))
+  }
   override def filterStream(t0: Time, particles: Int): Flow[Data, PfState[State], NotUsed] =
     Flow[Data].scan(initialiseState(particles, t0))(stepFilter)           // same shape as model/ParticleFilter.scala:163-166
 }

@@ -162,3 +162,42 @@ JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterSampl
   (*env)->ReleaseDoubleArrayElements(env, out, p, 0);
   check(env, rc);
 }
+/* ParticleFilter.getMeanForecast on the device: out = mean[d] | lower[d] | upper[d] | eta mean, lower, upper | obs mean,
+ * lower, upper; chain: continue from the previous forecast cloud (SimulateData.forecast) */
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterForecast(
+    JNIEnv* env, jobject self, jlong h, jdouble t, jdouble interval, jboolean chain, jint d, jdoubleArray out) {
+  jdouble* p = (*env)->GetDoubleArrayElements(env, out, NULL);
+  int rc = cssm_filter_forecast((cssm_filter_t*)(intptr_t)h, t, interval, chain ? 1 : 0, p, p + d, p + 2 * d, p + 3 * d, p + 3 * d + 3);
+  (*env)->ReleaseDoubleArrayElements(env, out, p, 0);
+  check(env, rc);
+}
+/* ParticleFilter.getForecast: the forecast cloud, x[d*N] | gamma[N] | eta[N] | obs[N] */
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterForecastCloud(JNIEnv* env, jobject self, jlong h, jint d,
+                                                                                          jlong n, jdoubleArray out) {
+  jdouble* p = (*env)->GetDoubleArrayElements(env, out, NULL);
+  int rc = cssm_filter_forecast_cloud((cssm_filter_t*)(intptr_t)h, p, p + (size_t)d * n, p + (size_t)(d + 1) * n,
+                                      p + (size_t)(d + 2) * n, NULL);
+  (*env)->ReleaseDoubleArrayElements(env, out, p, 0);
+  check(env, rc);
+}
+/* FilterInterpolate: path storage */
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterPathsEnable(JNIEnv* env, jobject self, jlong h,
+                                                                                        jlong maxSteps) {
+  check(env, cssm_filter_paths_enable((cssm_filter_t*)(intptr_t)h, maxSteps));
+}
+JNIEXPORT jlong JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterPathsLen(JNIEnv* env, jobject self, jlong h) {
+  int64_t n = -1;
+  check(env, cssm_filter_paths_len((const cssm_filter_t*)(intptr_t)h, &n));
+  return n;
+}
+/* out[idx.length][len + 1][d], oldest state first */
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterGetPaths(JNIEnv* env, jobject self, jlong h,
+                                                                                     jintArray idx, jdoubleArray out) {
+  jsize n = (*env)->GetArrayLength(env, idx);
+  jint* ip = (*env)->GetIntArrayElements(env, idx, NULL);
+  jdouble* p = (*env)->GetDoubleArrayElements(env, out, NULL);
+  int rc = cssm_filter_get_paths((cssm_filter_t*)(intptr_t)h, (const int32_t*)ip, n, p);
+  (*env)->ReleaseIntArrayElements(env, idx, ip, JNI_ABORT);
+  (*env)->ReleaseDoubleArrayElements(env, out, p, 0);
+  check(env, rc);
+}
