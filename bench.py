@@ -224,6 +224,8 @@ def main():
     ap.add_argument("--obs", type=int, default=0, help="override number of observations")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tie-first", action="store_true",
+                    help="informational: CSSM_TIE_FIRST (textbook inverse CDF) instead of the reference's TreeMap rule")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.particles:
@@ -284,6 +286,8 @@ def main():
         h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, device=local, seed=2, stream_id=rank)
         n_local, n_total = N, N * world
     h.set_stream(stream.cuda_stream)
+    if args.tie_first:
+        h.set_tie_rule(_abi.TIE_FIRST)
     h.load_series(t, y)  # inputs resident in HBM before the timed region
 
     sampler = ClockSampler(local)
@@ -467,6 +471,7 @@ def main():
                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                "config": {"workload": desc, "particles_per_gpu": n_local, "particles_total": n_total, "observations": T,
                           "latent_dim": d, "resampler": resampler,
+                          "tie_rule": "first index (NOT the reference's rule)" if args.tie_first else "reference (TreeMap: last particle of a repeated key)",
                           "l2": "working set %.0f MB per GPU %s the 126 MB L2, no flush" % (
                               ws_bytes / 1e6, "exceeds" if ws_bytes > 126e6 else "is below"),
                           "parallelism": par},

@@ -244,6 +244,7 @@ struct cssm_filter {
   bool series_use_multi = false;
   bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
+  int tie_first = 0;  // CSSM_TIE_FIRST instead of the reference's TreeMap rule (cssm_filter_set_tie_rule)
   // forecast cloud (cssm_forecast.cuh): d + 4 columns [x1 | gamma | eta | obs | obs2], filter dtype
   // path storage (FilterInterpolate): px = (paths_cap + 1) propagated clouds, panc = paths_cap ancestor vectors
   void* px = nullptr;
@@ -532,7 +533,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   ctl.parity = cx.parity; ctl.obs_seq = f->obs_seq; ctl.gstep = f->gstep;
   const long long Ng = f->N * (long long)pr.R;
   ctl.inv_n = ((Ng & (Ng - 1)) == 0) ? 1.0 / (double)Ng : 0.0;
-  ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj;
+  ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj; ctl.tie_first = f->tie_first;
   ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
   ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
   const bool strat = f->resample_kind == CSSM_RESAMPLE_STRATIFIED;
@@ -810,6 +811,7 @@ int run_series_single_launch(cssm_filter* f) {
   sa.N = f->N; sa.Ns = f->Ns; sa.T = (int)T; sa.d = f->d; sa.nt = f->nt; sa.obs_kind = f->model.obs_kind;
   sa.key0 = f->key0; sa.key1 = f->key1; sa.step0 = f->step_ctr;
   sa.inv_n = ((f->N & (f->N - 1)) == 0) ? 1.0 / (double)f->N : 0.0;
+  sa.tie_first = f->tie_first;
   sa.pr[0] = make_peers(f, f->cur);
   sa.pr[1] = make_peers(f, f->cur ^ 1);
   static const bool debug_stamps = std::getenv("CSSM_SERIES_DEBUG") != nullptr;
@@ -1845,6 +1847,13 @@ int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_ou
     CU(cudaMemcpyAsync(dst, f->scratch, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
     CU(cudaStreamSynchronize(f->stream));
   }
+  return CSSM_OK;
+}
+
+int cssm_filter_set_tie_rule(cssm_filter_t* f, int rule) {
+  if (!f) return fail(CSSM_ERR_INVALID, "null filter handle");
+  if (rule != CSSM_TIE_REFERENCE && rule != CSSM_TIE_FIRST) return fail(CSSM_ERR_INVALID, "unknown tie rule");
+  f->tie_first = rule == CSSM_TIE_FIRST ? 1 : 0;
   return CSSM_OK;
 }
 

@@ -1028,6 +1028,7 @@ struct K3Ctl {
   double inv_n;         // 1 / (number of outputs) when that is a power of two, else 0
   int direct;           // cssm_resample: caller weights, no ll update
   int add_ll, use_u_inj;
+  int tie_first;        // CSSM_TIE_FIRST: plain inverse CDF (first index with C_j >= k), no TreeMap duplicate-key rule
   uint32_t key0, key1, step;
   double* ll_steps;
   int* ess_steps;
@@ -1196,12 +1197,12 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     unsigned mm = sm.s_minw[0];
 #pragma unroll
     for (int w = 1; w < TILE_THREADS / 32; ++w) mm = min(mm, sm.s_minw[w]);
-    sm.s_novanish = ((double)__uint_as_float(mm) > c_end * 2.220446049250313e-16) ? 1 : 0;
+    sm.s_novanish = (ctl.tie_first || (double)__uint_as_float(mm) > c_end * 2.220446049250313e-16) ? 1 : 0;
   }
   const int n_out = s_cnt[TILE_THREADS - 1];
   const long long hi = lo + n_out;
   // does the run of repeated keys at the end of this tile continue into the next tile?
-  const bool cont = !last_tile && vanishes(c_end, s_wnext, total);
+  const bool cont = !ctl.tie_first && !last_tile && vanishes(c_end, s_wnext, total);
   if (last_tile && threadIdx.x == 0 && kf(Ng - 1) > c_end) atomicOr(&sc->flags, FLAG_CLAMPED);  // reference would throw (m.head)
 
   // ---- expansion, WIN outputs per pass: every particle with offspring drops its local index at the

@@ -54,6 +54,7 @@ struct SeriesArgs {
   int T, d, nt, obs_kind;
   uint32_t key0, key1, step0;   // Philox step counter of the first step
   double inv_n;                 // 1/N when N is a power of two, else 0
+  int tie_first;                // K3Ctl::tie_first
   unsigned long long* dbg;      // NULL, or 8 cycle counters of block 0 (CSSM_SERIES_DEBUG): P1 B1 P2 B2 P3 B3 head
   Peers pr[2];                  // the (single-rank) topology with x[0] = the cloud read in even / odd steps: kept in
                                 // the kernel's constant bank instead of a 400-byte struct in local memory
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
       kc.direct = 0;
       kc.add_ll = 1;
       kc.use_u_inj = 0;
+      kc.tie_first = sa.tie_first;
       kc.key0 = sa.key0;
       kc.key1 = sa.key1;
       kc.step = step;
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_series_multi(const __grid_c
       kc.direct = 0;
       kc.add_ll = 1;
       kc.use_u_inj = 0;
+      kc.tie_first = sa.tie_first;
       kc.key0 = sa.key0;
       kc.key1 = sa.key1;
       kc.step = step;

@@ -150,6 +150,11 @@ class GpuFilterHandle:
     def reseed(self, seed, stream_id=0):
         _abi.check(self._lib.cssm_filter_reseed(self._h, seed, stream_id))
 
+    def set_tie_rule(self, rule):
+        """_abi.TIE_REFERENCE (default: the reference's TreeMap rule, a repeated cumulative weight selects the last
+        particle inserted) or _abi.TIE_FIRST (textbook inverse CDF; see include/cssm.h)."""
+        _abi.check(self._lib.cssm_filter_set_tie_rule(self._h, int(rule)))
+
     def set_stream(self, cuda_stream):
         _abi.check(self._lib.cssm_filter_set_stream(self._h, cuda_stream))
 

@@ -64,6 +64,15 @@ typedef enum { CSSM_STEP_EXACT = 0, CSSM_STEP_EULER = 1 } cssm_step_mode;
 /* model/Resampling.scala:63-96 */
 typedef enum { CSSM_RESAMPLE_SYSTEMATIC = 0, CSSM_RESAMPLE_STRATIFIED = 1, CSSM_RESAMPLE_MULTINOMIAL = 2 } cssm_resample_kind;
 typedef enum { CSSM_F32 = 0, CSSM_F64 = 1 } cssm_dtype;
+/* which particle an output takes when cumulative weights repeat (a weight too small to change the running sum):
+ *   CSSM_TIE_REFERENCE  the reference: `tree ++ (cumulative sums zip items)` keeps the LAST particle inserted under a
+ *                       repeated key (model/Resampling.scala:52-58), so the offspring of a particle go to the last particle
+ *                       of the run of vanishing weights that follows it.  Default; ancestors bit-exact with the reference.
+ *   CSSM_TIE_FIRST      the textbook inverse CDF: the FIRST index whose cumulative weight reaches k.  Not the reference's
+ *                       result: with 2^20+ particles and degenerate weights the reference's rule hands about 1 % of the
+ *                       offspring per step to particles of negligible weight and the log-likelihood estimate drifts down
+ *                       like log N (measured: DESIGN.md section 2a); this rule does not. */
+typedef enum { CSSM_TIE_REFERENCE = 0, CSSM_TIE_FIRST = 1 } cssm_tie_rule;
 
 /*
  * One leaf of the composed model = one (Model, Sde) pair of the reference.
@@ -292,6 +301,9 @@ int cssm_filter_forecast(cssm_filter_t* f, double t, double interval, int chain,
  * getMeanForecast summarises); NULL to skip */
 int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_out, double* eta_out,
                                double* obs_out, double* obs2_out);
+/* the rule for repeated cumulative weights in systematic / stratified resampling (cssm_tie_rule); for a sharded filter
+ * set the same rule on every shard */
+int cssm_filter_set_tie_rule(cssm_filter_t* f, int rule);
 /* FilterInterpolate (model/ParticleFilter.scala:273-311): particles are PATHS and an observed step resamples whole
  * paths.  With path storage enabled the streaming entry points (cssm_filter_init*, cssm_filter_step, cssm_filter_step_injected)
  * keep the propagated cloud of every step and the ancestors of every resampling on the device (max_steps + 1 clouds);

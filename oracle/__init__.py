@@ -15,6 +15,7 @@ from composablestatespacemodels_b200 import _abi  # descriptor struct definition
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libcssm_oracle.so")
 ORDER_REFERENCE, ORDER_DEVICE, ORDER_DEVICE_F32 = 0, 1, 2
+TIE_FIRST = 8  # flag on the order of resample(): textbook inverse CDF, no TreeMap duplicate-key rule (not the reference)
 
 
 def device_order(dtype):

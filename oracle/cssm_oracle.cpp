@@ -442,8 +442,12 @@ void orc_ll_ess(int64_t N, const double* w1, double mx, int order, double* ll_in
 //   multinomial (:92-96): N independent Multinomial(w).draw; Breeze 1.0's first draw walks
 //   prob = u*sum; for i: prob -= w_i; if (prob <= 0) return i.
 //   ancestors are int32 indices into the input vector.
+//   order | ORC_TIE_FIRST (8): the textbook inverse CDF instead (first index whose cumulative weight reaches k, no
+//   duplicate-key rule) -- NOT the reference; the checker of the library's CSSM_TIE_FIRST option.
 int orc_resample(int kind, int order, int64_t N, const double* w, const double* u, int32_t* anc,
                  int64_t* n_clamped) {
+  const bool tie_first = (order & 8) != 0;
+  order &= 7;
   int64_t clamped = 0;
   if (kind == CSSM_RESAMPLE_MULTINOMIAL) {
     if (order == ORC_ORDER_REFERENCE) {
@@ -493,7 +497,7 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
       // device applies that same test to its own C_j = fl(P_j / total), so a run of vanishing
       // weights is skipped as a whole in both orders.
       int64_t jj = j;
-      while (jj + 1 < N) {
+      while (!tie_first && jj + 1 < N) {
         volatile double c = P[jj] / total;
         volatile double wn = w[jj + 1] / total;
         volatile double nx = c + wn;
@@ -522,7 +526,7 @@ int orc_resample(int kind, int order, int64_t N, const double* w, const double* 
     if (j >= N) { anc[i] = (int32_t)(N - 1); ++clamped; continue; }
     // duplicate key: last insert wins (model/Resampling.scala:55-57)
     int64_t jj = j;
-    while (jj + 1 < N && C[jj + 1] == C[jj]) ++jj;
+    while (!tie_first && jj + 1 < N && C[jj + 1] == C[jj]) ++jj;
     anc[i] = (int32_t)jj;
   }
   if (n_clamped) *n_clamped = clamped;

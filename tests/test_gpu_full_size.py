@@ -1,0 +1,123 @@
+"""GPU tests at BASELINE.json's full sizes, through properties that do not need the CPU oracle to finish a 2^24
+particle run: an exact known answer (the Kalman-filter likelihood of the Normal compositions), the defining
+property of systematic resampling (every offspring count within one of n*w/W), sortedness, determinism and
+independence of the launch geometry."""
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy import special
+
+import composablestatespacemodels_b200 as cs
+from composablestatespacemodels_b200 import _abi
+import oracle
+from configs import SYS, STRAT, c2, c5
+from test_oracle import kalman_loglik
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype,N", [(_abi.F64, 1 << 18), (_abi.F32, 1 << 18), (_abi.F32, 1 << 24)])
+def test_log_likelihood_against_the_exact_kalman_filter(dtype, N):
+    """Normal + seasonal + OU (BASELINE configs[4]'s model) is linear-Gaussian: its marginal likelihood is known
+    exactly.  The particle estimate exp(ll_hat) is unbiased, so on the likelihood scale independent Philox runs agree
+    with it within Monte-Carlo error (north_star: "independent-RNG runs must agree within Monte Carlo standard
+    error") -- and at 2^24 particles (the target cloud size) the estimate itself is within 0.02 of the exact value."""
+    mod = c5()
+    orc = oracle.Oracle(mod)
+    T, R = 40, 6
+    t, y, _ = orc.simulate(T, 0.1, 5)
+    exact = kalman_loglik(mod, t, y)
+    h = cs.GpuFilterHandle(mod, SYS, N, dtype=dtype, seed=21)
+    h.load_series(t, y)
+    est = np.array([h.ll_resident() for _ in range(R)])
+    h.close()
+    assert np.all(np.isfinite(est))
+    lm = special.logsumexp(est) - math.log(R)
+    se = np.std(np.exp(est - exact)) / math.sqrt(R)
+    assert abs(math.exp(lm - exact) - 1) < 5 * se + 0.02, (est, exact)
+    if N == 1 << 24:
+        assert np.max(np.abs(est - exact)) < 0.02, (est, exact)
+
+
+@pytest.mark.parametrize("kind", [SYS, STRAT])
+def test_full_size_resampling_properties(kind):
+    """cssm_resample at 2^24 weights: ancestors sorted, inside the cloud, and (systematic) every particle's number
+    of offspring follows n*w/W (cumulatively within one), with the reference's repeated-key quirk."""
+    from composablestatespacemodels_b200.resampling import ancestors
+    n = 1 << 24
+    rng = np.random.default_rng(12)
+    w = np.exp(rng.normal(0.0, 2.0, n))
+    w[rng.integers(0, n, 1000)] = 0.0
+    u = rng.random(1 if kind == SYS else n)
+    anc = ancestors(kind, w, u)
+    assert anc.shape == (n,) and anc.min() >= 0 and anc.max() < n
+    assert np.all(np.diff(anc) >= 0)
+    counts = np.bincount(anc, minlength=n)
+    # the defining property, on the cumulative counts: #{k_i <= C_j} is within one of n * C_j.  It is read where a
+    # TreeMap key is not repeated: a zero weight repeats the key of its predecessor and the LAST particle of such a run
+    # takes the run's offspring (model/Resampling.scala:55-57) -- the reference's quirk, kept
+    nxt_zero = np.append(w[1:] == 0.0, False)
+    cc, ce = np.cumsum(counts), np.cumsum(w) * (n / w.sum())
+    assert np.all(np.abs(cc - ce)[~nxt_zero] <= 1.0 + 1e-3)
+    assert cc[-1] == n
+    assert np.all(counts[(w == 0.0) & nxt_zero] == 0)           # inside a run of zeros: nothing
+    heirs = (w == 0.0) & ~nxt_zero                               # the last zero of a run inherits its predecessor's offspring
+    assert counts[heirs].sum() > 0
+    # and bit for bit against the oracle's sequential search (a plain loop over the 2^24 weights: about a second)
+    np.testing.assert_array_equal(anc, oracle.resample(kind, w, u))
+
+
+def test_full_size_filter_is_deterministic_and_geometry_independent(monkeypatch):
+    """2^24 particles x 12 observations of the target model: the same seed gives the same bits twice, and the same
+    bits again with 512-particle tiles instead of 2048 (exact integer sums: no result depends on the tiling)."""
+    mod = c2()
+    orc = oracle.Oracle(mod)
+    t, y, _ = orc.simulate(12, 0.1, 1)
+    N = 1 << 24
+
+    def run():
+        h = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F32, seed=4)
+        h.load_series(t, y)
+        ll, lls, ess = h.ll_resident(steps=True)
+        m = h.mean_state()
+        h.close()
+        return ll, lls, ess, m
+
+    a = run()
+    b = run()
+    monkeypatch.setenv("CSSM_TILE_ITEMS", "2")
+    c = run()
+    for other in (b, c):
+        assert a[0] == other[0]
+        np.testing.assert_array_equal(a[1], other[1])
+        np.testing.assert_array_equal(a[2], other[2])
+        np.testing.assert_allclose(a[3], other[3], rtol=1e-12)   # meanState: fp64 atomics, the order of the adds varies
+    assert np.isfinite(a[0]) and np.all(a[2] >= 1) and np.all(a[2] <= N)
+
+
+def test_tie_rule_and_the_drift_of_the_reference_estimate():
+    """What the reference's TreeMap rule does at GPU cloud sizes: under a repeated cumulative
+    weight the LAST particle wins (model/Resampling.scala:52-58), so offspring of good particles land on particles of
+    negligible weight; with the degenerate weights of the 7-dimensional Poisson model the log-likelihood estimate
+    drifts DOWN as the cloud grows.  The library reproduces that by default (ancestors bit-exact with the oracle's
+    restatement); CSSM_TIE_FIRST, the textbook rule, gives estimates that agree across cloud sizes."""
+    mod = c2()
+    orc = oracle.Oracle(mod)
+    t, y, _ = orc.simulate(12, 0.1, 1)
+
+    def est(N, rule, R=4):
+        h = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F32, seed=4)
+        h.set_tie_rule(rule)
+        h.load_series(t, y)
+        v = np.array([h.ll_resident() for _ in range(R)])
+        h.close()
+        return v
+
+    first_small, first_big = est(1 << 18, _abi.TIE_FIRST, 8), est(1 << 24, _abi.TIE_FIRST)
+    ref_small, ref_big = est(1 << 18, _abi.TIE_REFERENCE, 8), est(1 << 24, _abi.TIE_REFERENCE)
+    se = first_small.std(ddof=1) / math.sqrt(8)
+    assert abs(first_small.mean() - first_big.mean()) < 6 * se + 0.01, (first_small, first_big)
+    assert ref_big.mean() < ref_small.mean() - 0.05, (ref_small, ref_big)        # the reference rule: measured -0.12
+    assert ref_big.mean() < first_big.mean() - 0.05

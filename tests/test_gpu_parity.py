@@ -21,7 +21,7 @@ def rel_close(a, b, tol, what):
     assert err <= tol, f"{what}: max relative error {err:.3e} > {tol:.1e}"
 
 
-def run_steps(mod, N, T, kind, dtype, seed=0, missing=()):
+def run_steps(mod, N, T, kind, dtype, seed=0, missing=(), tie_first=False):
     """T stepFilters with injected noise on the GPU; each stage checked against the oracle fed
     with the device's own output of the previous stage (so every comparison is like for like)."""
     rng = np.random.default_rng(seed)
@@ -29,8 +29,11 @@ def run_steps(mod, N, T, kind, dtype, seed=0, missing=()):
     d = mod.dimension
     t, y, _ = orc.simulate(T, 0.1, seed + 11)
     h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, seed=3)
+    if tie_first:
+        h.set_tie_rule(_abi.TIE_FIRST)
     tol = TOL[dtype]
     DEV = oracle.device_order(dtype)   # F32 filters evaluate w1 = exp(logw - max) in fp32
+    TIE = oracle.TIE_FIRST if tie_first else 0
     z0 = rng.standard_normal((d, N))
     h.init_injected(t[0], z0)
     x = h.get_particles()
@@ -60,10 +63,10 @@ def run_steps(mod, N, T, kind, dtype, seed=0, missing=()):
         ll_ref += incr
         assert g["ess"] == ess
         rel_close(g["ll"], ll_ref, 1e-12, f"step {s} log-likelihood")
-        anc = oracle.resample(kind, w1, u, DEV)
+        anc = oracle.resample(kind, w1, u, DEV | TIE)
         np.testing.assert_array_equal(g["anc"], anc)
         # the reference-order (sequential fp64) restatement agrees except for last-ulp ties
-        anc_ref = oracle.resample(kind, oracle.w1(g["logw"], mx, oracle.ORDER_REFERENCE), u, oracle.ORDER_REFERENCE)
+        anc_ref = oracle.resample(kind, oracle.w1(g["logw"], mx, oracle.ORDER_REFERENCE), u, oracle.ORDER_REFERENCE | TIE)
         assert np.mean(anc_ref != anc) <= 2e-3
         # stage 3: gather
         x = h.get_particles()
@@ -98,6 +101,14 @@ def test_step_parity_large_tiles(monkeypatch):
     run_steps(c2(), 4100, 3, STRAT, _abi.F64, seed=9)
     monkeypatch.setenv("CSSM_PDL", "0")  # and without programmatic dependent launch
     run_steps(c2(), 3000, 3, SYS, _abi.F32, seed=10)
+
+
+def test_step_parity_tie_first_option():
+    """CSSM_TIE_FIRST (textbook inverse CDF, NOT the reference's TreeMap rule) against the oracle's restatement of it;
+    the degenerate Poisson clouds are where the two rules differ."""
+    run_steps(c2(), 6000, 4, SYS, _abi.F32, seed=12, tie_first=True)
+    run_steps(c2(), 3000, 4, STRAT, _abi.F64, seed=13, tie_first=True)
+    run_steps(ALL["bernoulli"](), 2500, 3, SYS, _abi.F64, seed=14, tie_first=True)
 
 
 def test_step_parity_euler():
