@@ -75,3 +75,37 @@ class Resampling:
         """model/Resampling.scala:21-24 (host helper)"""
         prob = np.asarray(prob, dtype=np.float64)
         return prob / prob.sum()
+
+    # ---- the small host helpers of model/Resampling.scala (used around the filter, never on N-sized clouds) ----
+    @staticmethod
+    def indentity(samples, weights):
+        """model/Resampling.scala:29 (sic)"""
+        return samples
+
+    @staticmethod
+    def expNormalise(prob):
+        """model/Resampling.scala:102-108"""
+        prob = np.asarray(prob, dtype=np.float64)
+        w1 = np.exp(prob - prob.max())
+        return w1 / w1.sum()
+
+    @staticmethod
+    def cumSum(l):
+        """model/Resampling.scala:113-115: scanLeft from zero, n + 1 values"""
+        return np.concatenate([[0.0], np.cumsum(np.asarray(l, dtype=np.float64))])
+
+    @staticmethod
+    def empDist(w):
+        """model/Resampling.scala:120-122"""
+        return Resampling.cumSum(Resampling.normalise(w))
+
+    @staticmethod
+    def sampleOne(s):
+        """model/Resampling.scala:151-154"""
+        return s[int(_rng.integers(0, len(s)))]
+
+    @staticmethod
+    def sampleMany(n, s):
+        """model/Resampling.scala:159-162: uniformly without replacement"""
+        idx = _rng.permutation(len(s))[:n]
+        return _take(s, idx)

@@ -120,3 +120,19 @@ def test_approx_pmmh_reestimates_the_current_likelihood():
     assert len(calls) == 4 and s2.ll == -10.0 - 0.004
     step = pmmhStep(lambda p: -abs(p), lambda p: p * 0.5, rng)
     assert step((-4.0, 4.0)) == (-2.0, 2.0)
+
+
+def test_resampling_host_helpers():
+    """model/Resampling.scala:29,102-122,151-162"""
+    from composablestatespacemodels_b200 import Resampling
+    import numpy as np
+    lw = np.array([-1000.0, -1001.0, -1002.0])
+    en = Resampling.expNormalise(lw)
+    assert abs(en.sum() - 1) < 1e-15 and en[0] > en[1] > en[2] > 0
+    np.testing.assert_allclose(Resampling.cumSum([1, 2, 3]), [0, 1, 3, 6])
+    np.testing.assert_allclose(Resampling.empDist([1, 1, 2]), [0, 0.25, 0.5, 1.0])
+    assert Resampling.indentity([1, 2], [0.5, 0.5]) == [1, 2]
+    s = list(range(10))
+    assert Resampling.sampleOne(s) in s
+    m = Resampling.sampleMany(4, s)
+    assert len(m) == 4 and len(set(m)) == 4
