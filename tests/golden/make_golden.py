@@ -179,6 +179,17 @@ def find_all(ks, keys, m):
     return out, clamped
 
 
+def first_index(w, ks):
+    """NOT the reference: the textbook inverse CDF on the same cumulative sums, first index whose cumulative
+    weight reaches k (no key is overwritten).  Golden values for the library's CSSM_TIE_FIRST option."""
+    total = fold_sum(w)
+    cum, acc = [], 0.0
+    for a in w:
+        acc = acc + a / total
+        cum.append(acc)
+    return [min(bisect.bisect_left(cum, k), len(w) - 1) for k in ks]
+
+
 def systematic(w, u):  # :63-72
     n = len(w)
     keys, m = tree_ecdf(w)
@@ -374,7 +385,9 @@ def resample_cases():
             a_sys, c1 = systematic(w, u)
             a_str, c2 = stratified(w, us)
             out.append(dict(name=name, w=w, u=u, us=us, anc_systematic=a_sys, anc_stratified=a_str,
-                            anc_multinomial=multinomial(w, us), clamped=[c1, c2]))
+                            anc_multinomial=multinomial(w, us), clamped=[c1, c2],
+                            anc_systematic_first=first_index(w, [(u + i) / n for i in range(n)]),
+                            anc_stratified_first=first_index(w, [(i + us[i]) / n for i in range(n)])))
     return out
 
 
