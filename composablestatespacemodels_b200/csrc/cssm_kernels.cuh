@@ -570,7 +570,28 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
     real zb[PC];
     int zpos = PC;
     uint32_t ncall = 0;
-    for (long long s = 0; s < n_sub; ++s) {
+    long long s_first = 0;
+    if (DP == 1 && zinj == nullptr) {
+      // One coordinate (the LGCP of BASELINE configs[2]): Philox call c feeds the sub-steps c*PC .. c*PC+PC-1, so
+      // the loop runs call by call with the PC sub-steps unrolled -- no position counter, no select chain, no
+      // branch per sub-step.  The same operations in the same order as the general loop below: same bits.
+      const real A = a.A[0], Dc = a.D[0], S = a.S[0];
+      real xx = x[0];
+      const long long n_full = n_sub - (n_sub % PC);
+      for (long long s = 0; s < n_full; s += PC) {
+        Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | ncall, key0, key1, zb);
+        ++ncall;
+#pragma unroll
+        for (int q = 0; q < PC; ++q) {
+          xx = r_fma<real>(S, zb[q], r_fma<real>(A, xx, Dc));
+          const real cc = ctab ? ctab[s + q] : a.C[0];
+          hz += r_exp<real>(r_fma<real>(cc, xx, (real)0)) * delta;
+        }
+      }
+      x[0] = xx;
+      s_first = n_full;  // the last n_sub % PC sub-steps take the general loop (zpos == PC: it draws call `ncall`)
+    }
+    for (long long s = s_first; s < n_sub; ++s) {
       real gs = (real)0;
 #pragma unroll
       for (int k = 0; k < DP; ++k) {

@@ -536,3 +536,25 @@ def test_pilot_run_variances():
     for n in (100, 1600):
         ref = np.var(orc.filter_ll_many(n, SYS, t, y, seed=5, R=R, threads=4), ddof=1)
         assert ref / 3.2 < v[n] < ref * 3.2, (n, v[n], ref)
+
+
+@pytest.mark.parametrize("dtype", [_abi.F32, _abi.F64])
+def test_lgcp_philox_runs_agree_with_the_oracle(dtype):
+    """FilterLgcp with the device's own noise (Philox, the call-by-call unrolled sub-step loop and its tail) against
+    the oracle's independent runs of the same filter: the log-likelihood estimates agree within Monte-Carlo error
+    (event gaps of 7, 13, 20 ... sub-steps, so full Philox calls and partial ones both occur)."""
+    from composablestatespacemodels_b200 import FilterLgcp, Resampling, Data
+    mod = c3(precision=2)
+    orc = oracle.Oracle(mod)
+    gaps = np.array([0.07, 0.13, 0.2, 0.05, 0.11, 0.3, 0.02, 0.09, 0.16, 0.04])
+    t = np.concatenate([[0.0], np.cumsum(gaps)])
+    y = np.ones_like(t)
+    N, R = 20000, 8
+    flt = FilterLgcp(mod, Resampling.stratifiedResampling, 2, dtype=dtype, seed=31)
+    data = [Data(a, 1.0) for a in t]
+    gpu = np.array([flt.llFilter(data, N) for _ in range(R)])
+    flt.close()
+    cpu = orc.filter_ll_many(N, STRAT, t, y, seed=9, R=R, threads=4)
+    se = np.sqrt(gpu.var(ddof=1) / R + cpu.var(ddof=1) / R)
+    assert np.all(np.isfinite(gpu))
+    assert abs(gpu.mean() - cpu.mean()) < 5 * se + 2e-3, (gpu, cpu)
