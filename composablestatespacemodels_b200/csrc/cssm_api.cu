@@ -852,7 +852,16 @@ int run_series_single_launch(cssm_filter* f) {
 }
 
 // init + T steps on the loaded series; optionally one sampled particle per time (filter, :152-158)
+int run_series_impl(cssm_filter* f, bool sample_states);
 int run_series(cssm_filter* f, bool sample_states) {
+  const int rc = run_series_impl(f, sample_states);
+  if (f->paths_cap > 0) {  // the whole-series calls do not record paths: what was recorded no longer describes the cloud
+    f->paths_len = -1;
+    f->pres.clear();
+  }
+  return rc;
+}
+int run_series_impl(cssm_filter* f, bool sample_states) {
   const size_t T = f->series.size();
   int rc = ensure_steps_cap(f, T);
   if (rc) return rc;

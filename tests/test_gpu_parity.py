@@ -489,6 +489,12 @@ def test_path_storage_follows_the_list_semantics_of_filter_interpolate(name, kin
     np.testing.assert_array_equal(got[:, -1, :], h.get_particles().T)
     with pytest.raises(cs._abi.CssmError):                       # the storage holds T steps
         h.step(t[-1] + 0.1, 1.0)
+    h.ll_arrays(t, y)                                            # a whole-series call does not record ...
+    assert h.paths_len() == -1                                   # ... and invalidates what was recorded
+    with pytest.raises(cs._abi.CssmError):
+        h.get_paths()
+    h.init(t[0])                                                 # recording restarts with the next initialisation
+    assert h.paths_len() == 0
     h.close()
 
 
