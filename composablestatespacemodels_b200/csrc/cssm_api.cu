@@ -208,7 +208,7 @@ struct cssm_filter {
   int32_t* anc = nullptr;  // GLOBAL particle indices of the last resampling (offspring slots of this rank)
   bool anc_valid = false, initialised = false;
   FilterScalars* sc = nullptr;
-  SumTables tb = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+  SumTables tb = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
   XchSlot* xch = nullptr;  // [MAXR] written by the peers (sharded filters)
   double* ubuf = nullptr;   // uniforms (stratified / multinomial, injected): one per GLOBAL output
   double* cdf = nullptr;    // N cumulative values (multinomial)
@@ -244,6 +244,7 @@ struct cssm_filter {
   bool series_use_multi = false;
   bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
+  int flat_max_nt = 1024;  // clouds of at most this many tiles: K2 without atomics, K3 adds the tile sums itself (CSSM_FLAT_MAX_NT)
   int tie_first = 0;  // CSSM_TIE_FIRST instead of the reference's TreeMap rule (cssm_filter_set_tie_rule)
   // forecast cloud (cssm_forecast.cuh): d + 4 columns [x1 | gamma | eta | obs | obs2], filter dtype
   // path storage (FilterInterpolate): px = (paths_cap + 1) propagated clouds, panc = paths_cap ancestor vectors
@@ -486,6 +487,13 @@ int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
   return CSSM_OK;
 }
 
+// the sum tables of one step: single-rank clouds of few tiles run flat (ns = 0, see SumTables)
+inline SumTables step_tables(const cssm_filter* f) {
+  SumTables tb = f->tb;
+  if (f->world == 1 && f->nt <= f->flat_max_nt) tb.ns = 0;
+  return tb;
+}
+
 // ---- K2: exact weight sums ----------------------------------------------------------------------
 template <typename real>
 int step_phase2(cssm_filter* f, StepCtx& cx) {
@@ -497,10 +505,10 @@ int step_phase2(cssm_filter* f, StepCtx& cx) {
     ProfScope ps_(f, CLS_SUMS, cx.prof);
     if (f->items == 8)
       e = launch(k_weight_sums<real, 8>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
-                 f->sc, cx.parity, f->obs_seq, f->tb, pr);
+                 f->sc, cx.parity, f->obs_seq, step_tables(f), pr);
     else
       e = launch(k_weight_sums<real, 2>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
-                 f->sc, cx.parity, f->obs_seq, f->tb, pr);
+                 f->sc, cx.parity, f->obs_seq, step_tables(f), pr);
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K2: ") + cudaGetErrorString(e));
   f->launches++;
@@ -544,7 +552,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
     ProfScope ps_(f, CLS_SEARCH, cx.prof);
 #define K3_CASE(IT, KD)                                                                                                 \
   e = launch(k_scan_search<real, IT, KD>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, \
-             f->N, f->sc, f->tb, pr, ctl, ua, cdf)
+             f->N, f->sc, step_tables(f), pr, ctl, ua, cdf)
     if (f->items == 8) { if (strat) K3_CASE(8, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(8, CSSM_RESAMPLE_SYSTEMATIC); }
     else { if (strat) K3_CASE(2, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(2, CSSM_RESAMPLE_SYSTEMATIC); }
 #undef K3_CASE
@@ -972,6 +980,8 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   ALLOC(f->series_ctl, sizeof(SeriesCtl));
 #undef ALLOC
   f->tb.nt = f->nt; f->tb.ns = f->ns;
+  f->tb.tile_q = f->tile_q;
+  if (const char* e = std::getenv("CSSM_FLAT_MAX_NT")) f->flat_max_nt = std::atoi(e);
   cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz);
   cudaMemset(f->x[1], 0, (size_t)f->d * f->Ns * esz);
   cudaMemset(f->logw, 0, (size_t)(f->Ns + tile) * esz);
@@ -1941,7 +1951,7 @@ int cssm_resample(int kind, const double* w, int64_t n, const double* u, int64_t
   int32_t* danc = nullptr;
   FilterScalars* sc = nullptr;
   XchSlot* xch = nullptr;
-  SumTables tb = {nullptr, nullptr, nullptr, nullptr, nullptr, nt, ns};
+  SumTables tb = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nt, ns};
   cudaStream_t st = nullptr;
   int status = CSSM_OK;
 #define RCU(call)                                                                                  \

@@ -748,6 +748,8 @@ __device__ __forceinline__ PreScan pre_scan(unsigned long long gmax_key, bool di
 // per-filter tables of the weight pass
 struct SumTables {
   u128* tile_sum;             // [nt]   exact sum of fix(w) over the tile
+  u128* tile_q;               // [nt]   exact sum of fix(w^2) over the tile (flat mode, ns == 0: no super tiles, no atomics --
+                              //        every block of K3 adds the tile sums itself; clouds of at most a few thousand tiles)
   double* tile_maxw;          // [nt]   max weight of the tile
   u128* super_sum;            // [2][ns] by observed-step parity, zeroed for the next step by K3
   u128* super_q;              // [2][ns]
@@ -832,6 +834,10 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
     }
     tb.tile_sum[blockIdx.x] = t;
     tb.tile_maxw[blockIdx.x] = m2;
+    if (tb.ns == 0) {  // flat mode: the tile sums are all K3 needs, no atomics and no dependent round trips at the tail
+      tb.tile_q[blockIdx.x] = t2;
+      return;
+    }
     const int sidx = blockIdx.x / SUPER;
     u128* ssum = tb.super_sum + (size_t)parity * tb.ns + sidx;
     u128* ssq = tb.super_q + (size_t)parity * tb.ns + sidx;
@@ -1425,6 +1431,35 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     s_key = A->gmax_key;
     s_excl = make_u128(0, 0);
   }
+  if (tb.ns == 0) {
+    // flat mode (single rank): totals and the exclusive prefix straight from the tile sums
+    u128 at = make_u128(0, 0), aq = make_u128(0, 0), ae = make_u128(0, 0);
+    for (int tt = threadIdx.x; tt < tb.nt; tt += TILE_THREADS) {
+      const u128 v = tb.tile_sum[tt];
+      at = add128(at, v);
+      if (tt < t) ae = add128(ae, v);
+    }
+    at = warp_sum128(at);
+    ae = warp_sum128(ae);
+    if (t == 0) {  // the sum of squares only feeds the ESS, which block 0 computes
+      for (int tt = threadIdx.x; tt < tb.nt; tt += TILE_THREADS) aq = add128(aq, tb.tile_q[tt]);
+      aq = warp_sum128(aq);
+    }
+    __shared__ u128 s_r3[3][TILE_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { s_r3[0][threadIdx.x >> 5] = at; s_r3[1][threadIdx.x >> 5] = aq; s_r3[2][threadIdx.x >> 5] = ae; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u128 r0 = s_r3[0][0], r1 = s_r3[1][0], r2 = s_r3[2][0];
+      for (int w = 1; w < TILE_THREADS / 32; ++w) {
+        r0 = add128(r0, s_r3[0][w]);
+        r1 = add128(r1, s_r3[1][w]);
+        r2 = add128(r2, s_r3[2][w]);
+      }
+      s_tot = r0;
+      s_q = r1;
+      s_excl = r2;
+    }
+  } else
   // ---- exact sum of everything before this tile: whole super tiles + the tiles of this super ----
   {
     const int sidx = t / SUPER;

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
   SumTables tb;
   tb.tile_sum = sa.tile_sum;
   tb.tile_maxw = sa.tile_maxw;
+  tb.tile_q = sa.tile_q;
   tb.super_sum = nullptr;
   tb.super_q = nullptr;
   tb.super_ticket = nullptr;
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_series_multi(const __grid_c
   SumTables tb;
   tb.tile_sum = sa.tile_sum;
   tb.tile_maxw = sa.tile_maxw;
+  tb.tile_q = sa.tile_q;
   tb.super_sum = nullptr;
   tb.super_q = nullptr;
   tb.super_ticket = nullptr;

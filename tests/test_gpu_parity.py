@@ -111,6 +111,15 @@ def test_step_parity_tie_first_option():
     run_steps(ALL["bernoulli"](), 2500, 3, SYS, _abi.F64, seed=14, tie_first=True)
 
 
+def test_step_parity_two_level_sums_on_a_small_cloud(monkeypatch):
+    """Clouds of at most 1024 tiles run K2 / K3 "flat" (no super tiles, no atomics); CSSM_FLAT_MAX_NT=0 forces the
+    two-level tables of the large clouds onto a small one: same bits either way."""
+    monkeypatch.setenv("CSSM_FLAT_MAX_NT", "0")
+    run_steps(c2(), 5000, 3, SYS, _abi.F32, seed=15)
+    run_steps(c2(), 2300, 3, STRAT, _abi.F64, seed=16)
+    run_steps(c2(), 2300, 3, MULTI, _abi.F64, seed=17)
+
+
 def test_step_parity_euler():
     run_steps(c2().withStepMode(_abi.STEP_EULER), 1500, 4, SYS, _abi.F64, seed=6)
     run_steps(ALL["c4"]().withStepMode(_abi.STEP_EULER), 1500, 4, SYS, _abi.F32, seed=7)
