@@ -244,7 +244,7 @@ struct cssm_filter {
   bool series_use_multi = false;
   bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
-  int flat_max_nt = 1024;  // clouds of at most this many tiles: K2 without atomics, K3 adds the tile sums itself (CSSM_FLAT_MAX_NT)
+  int flat_max_nt = 2048;  // clouds of at most this many tiles: K2 without atomics, K3 adds the tile sums itself (CSSM_FLAT_MAX_NT)
   int tie_first = 0;  // CSSM_TIE_FIRST instead of the reference's TreeMap rule (cssm_filter_set_tie_rule)
   // forecast cloud (cssm_forecast.cuh): d + 4 columns [x1 | gamma | eta | obs | obs2], filter dtype
   // path storage (FilterInterpolate): px = (paths_cap + 1) propagated clouds, panc = paths_cap ancestor vectors
