@@ -48,9 +48,13 @@ object GpuDesc {
 }
 
 /** trait ParticleFilter[State] (model/ParticleFilter.scala:96-167) with the particle work on the GPU.
-  * `particles` of the returned PfState is materialised from device memory (Vector[State] in Tree.flatten order). */
+  * `PfState.particles` is a strict `Vector[State]` in the reference, and `Vector` cannot be subclassed, so a lazy view
+  * is not possible: with `materialise = true` every returned PfState carries the cloud (an N x d copy from the device per
+  * step, what the reference's own callers see); with `materialise = false` (default) `particles` is empty and the cloud
+  * stays on the device -- read it with `particles()`, summarise it with `intervals` / `getMeanForecast` below.  ll and ess
+  * are always filled. */
 final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, precision: Int = 0,
-  dtype: Int = 0, device: Int = 0, seed: Long = 0L) extends ParticleFilter[State] with AutoCloseable {
+  dtype: Int = 0, device: Int = 0, seed: Long = 0L, materialise: Boolean = false) extends ParticleFilter[State] with AutoCloseable {
 
   private val desc = GpuDesc(models, precision)
   private var handle: Long = 0L
@@ -76,6 +80,9 @@ final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, p
   def f(s: State, t: Time) = mod.f(s, t)
   def resample: Resample[State] = (p, w) => GpuResample(resampleKind, device)(p, w)
 
+  /** the current (resampled) cloud, copied out of device memory */
+  def particles(): Vector[State] = cloud()
+  private def held(): Vector[State] = if (materialise) cloud() else Vector.empty
   private def cloud(): Vector[State] = {
     val d = dims.sum
     val flat = new Array[Double](d * n)
@@ -89,12 +96,12 @@ final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, p
 
   override def initialiseState(particles: Int, t0: Time): PfState[State] = {
     CssmNative.filterInit(ensure(particles), t0)
-    PfState(t0, None, LazyCloud(() => cloud()), 0.0, particles)
+    PfState(t0, None, held(), 0.0, particles)
   }
   override def stepFilter(s: PfState[State], y: Data): PfState[State] = {
     val ess = new Array[Int](1)
     val ll = CssmNative.filterStep(handle, y.t, y.observation.isDefined, y.observation.getOrElse(0.0), ess)
-    PfState(y.t, y.observation, LazyCloud(() => cloud()), ll, ess(0))
+    PfState(y.t, y.observation, held(), ll, ess(0))
   }
   override def llFilter(data: Vector[Data], particles: Int): LogLikelihood =
     CssmNative.filterLl(ensure(particles), data.map(_.t).toArray, data.map(_.observation.getOrElse(0.0)).toArray,
@@ -113,6 +120,15 @@ final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, p
   private def toState(v: Array[Double], from: Int): State = {
     var off = from
     dims.map { dim => val x = DenseVector(v.slice(off, off + dim)); off += dim; Tree.leaf(x): State }.reduceLeft(_ +++ _)
+  }
+  /** ParticleFilter.getIntervals (model/ParticleFilter.scala:415-424) of the handle's current cloud, on the device */
+  def intervals(s: PfState[State], interval: Double = 0.975): PfOut[State] = {
+    val d = dims.sum
+    val o = new Array[Double](3 * d + 2)
+    CssmNative.filterIntervals(handle, s.t, interval, d, o)
+    val (lo, up) = (mod.link(o(3 * d)), mod.link(o(3 * d + 1)))
+    PfOut(s.t, s.observation, mod.link(mod.f(toState(o, 0), s.t)), CredibleInterval(math.min(lo, up), math.max(lo, up)),
+      toState(o, 0), (0 until d).map(k => CredibleInterval(o(d + k), o(2 * d + k))))
   }
   /** ParticleFilter.getMeanForecast (model/ParticleFilter.scala:394-412) of the handle's current cloud, on the device:
     * only the 3(d + 2) summary numbers cross the boundary.  `chain` continues from the previous forecast cloud
@@ -136,12 +152,6 @@ final case class FilterGpu(models: List[Model], mod: Model, resampleKind: Int, p
   }
   override def filterStream(t0: Time, particles: Int): Flow[Data, PfState[State], NotUsed] =
     Flow[Data].scan(initialiseState(particles, t0))(stepFilter)           // same shape as model/ParticleFilter.scala:163-166
-}
-
-/** Vector whose elements are fetched from the device on first access */
-object LazyCloud { def apply(get: () => Vector[State]): Vector[State] = new scala.collection.immutable.VectorBuilder[State]().result() match {
-  case _ => lazyVector(get) }
-  private def lazyVector(get: () => Vector[State]): Vector[State] = get()   // simplest form: materialise when the PfState is built lazily by the caller
 }
 
 /** Resample[A] backed by cssm_resample: uniforms from scala.util.Random as in model/Resampling.scala:66,83 */
