@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcssm_gpu.so")
+# CSSM_LIB: an alternative build of the SAME library (tuning experiments with other launch bounds); default: the in-tree build
+LIB_PATH = os.environ.get("CSSM_LIB") or os.path.join(_HERE, "csrc", "libcssm_gpu.so")
 
 # enums (include/cssm.h)
 SDE_BROWNIAN, SDE_GEN_BROWNIAN, SDE_OU = 0, 1, 2

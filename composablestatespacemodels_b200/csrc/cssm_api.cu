@@ -525,6 +525,10 @@ void k3_carveout_once() {
   cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
   cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
   cudaGetLastError();
   done = true;
 }
@@ -550,9 +554,12 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   cudaError_t e;
   {
     ProfScope ps_(f, CLS_SEARCH, cx.prof);
+    const SumTables tbs = step_tables(f);
 #define K3_CASE(IT, KD)                                                                                                 \
-  e = launch(k_scan_search<real, IT, KD>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, \
-             f->N, f->sc, step_tables(f), pr, ctl, ua, cdf)
+  e = tbs.ns == 0 ? launch(k_scan_search<real, IT, KD, true>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw,  \
+                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)                                  \
+                  : launch(k_scan_search<real, IT, KD, false>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
+                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)
     if (f->items == 8) { if (strat) K3_CASE(8, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(8, CSSM_RESAMPLE_SYSTEMATIC); }
     else { if (strat) K3_CASE(2, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(2, CSSM_RESAMPLE_SYSTEMATIC); }
 #undef K3_CASE

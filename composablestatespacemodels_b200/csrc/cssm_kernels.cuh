@@ -502,8 +502,11 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
   }
 }
 
+#ifndef CSSM_K1_MINBLOCKS
+#define CSSM_K1_MINBLOCKS 4
+#endif
 template <typename real, int D, int PPT = VecOf<real>::PPT>
-__global__ void __launch_bounds__(256, PPT == 4 ? 4 : 6)
+__global__ void __launch_bounds__(256, PPT == 4 ? CSSM_K1_MINBLOCKS : 6)
 k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
                    const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
                    long long N, long long Ns, unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
@@ -1387,7 +1390,9 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
 #ifndef CSSM_K3_MINBLOCKS
 #define CSSM_K3_MINBLOCKS 4
 #endif
-template <typename real, int ITEMS, int KIND>
+// FLAT: the sum tables have no super tiles (SumTables::ns == 0, single rank) -- a separate instantiation, so that the
+// two-level kernel of the large clouds keeps its register allocation
+template <typename real, int ITEMS, int KIND, bool FLAT = false>
 __global__ void __launch_bounds__(TILE_THREADS, CSSM_K3_MINBLOCKS)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
@@ -1431,7 +1436,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     s_key = A->gmax_key;
     s_excl = make_u128(0, 0);
   }
-  if (tb.ns == 0) {
+  if (FLAT) {
     // flat mode (single rank): totals and the exclusive prefix straight from the tile sums
     u128 at = make_u128(0, 0), aq = make_u128(0, 0), ae = make_u128(0, 0);
     for (int tt = threadIdx.x; tt < tb.nt; tt += TILE_THREADS) {
