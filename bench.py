@@ -196,7 +196,8 @@ def run_reference(args, wl, wl_name):
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_baseline(wl_model, resampler, T, budget_s=max(2.0, 20.0 / max(1, args.steps)), threads=cores, pmmh=pmmh)
+        budget = float(os.environ.get("CSSM_BENCH_BUDGET_S", max(2.0, 20.0 / max(1, args.steps))))  # tests shrink it
+        last = cpu_baseline(wl_model, resampler, T, budget_s=budget, threads=cores, pmmh=pmmh)
         if i >= args.warmup:
             vals.append(last["value"])
     v = float(np.mean(vals))

@@ -136,3 +136,29 @@ def test_resampling_host_helpers():
     assert Resampling.sampleOne(s) in s
     m = Resampling.sampleMany(4, s)
     assert len(m) == 4 and len(set(m)) == 4
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement on the host cores, no GPU involved) prints one JSON line with
+    the keys of the bench contract; rank != 0 of a multi-process launch prints nothing and exits 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CSSM_BENCH_BUDGET_S="0.3")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "scaling", "dtype", "data", "config",
+              "impl", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["value"] > 0 and j["gpu_launches"] == 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["sample"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
