@@ -427,6 +427,11 @@ def main():
                     "peak_source": peak_src, "algorithmic_bytes_per_particle": k1_bpp,
                     "avg_launch_ms": k1_ms / k1_n, "sampled_launches": k1_n,
                     "kernel_ms_per_launch": per_launch,
+                    # scan / search / gather throughput of the resampling stage (north_star): particles per second through
+                    # K2 (exp + exact sums) and K3 (CDF scan + ancestor search); the gather is fused into K1's load
+                    "resampling": {"weight_sums_particles_per_s": n_local / (per_launch["weight_sums"] * 1e-3) if per_launch["weight_sums"] else None,
+                                   "scan_search_particles_per_s": n_local / (per_launch["scan_search"] * 1e-3) if per_launch["scan_search"] else None,
+                                   "bytes_per_particle": {"weight_sums": b, "scan_search": b + 4}},
                     "whole_step": {"bytes_per_particle_fused": real_bpp,
                                    "achieved_gbs_fused": real_bpp * n_local / (tot * 1e-3) / 1e9 if tot else None,
                                    "frac_fused": real_bpp * n_local / (tot * 1e-3) / 1e9 / peak if tot else None,
