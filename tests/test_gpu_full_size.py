@@ -121,3 +121,32 @@ def test_tie_rule_and_the_drift_of_the_reference_estimate():
     assert abs(first_small.mean() - first_big.mean()) < 6 * se + 0.01, (first_small, first_big)
     assert ref_big.mean() < ref_small.mean() - 0.05, (ref_small, ref_big)        # the reference rule: measured -0.12
     assert ref_big.mean() < first_big.mean() - 0.05
+
+
+def test_bench_line_carries_the_contract_keys():
+    """bench.py on a small workload (c1, one cooperative launch per llFilter): one JSON line with the keys the bench
+    contract names -- roofline (bound, achieved, peak, unit, frac, traffic), e2e with the bytes copied per step,
+    gpu_launches, clocks -- and a log-likelihood that is a number."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "c1", "--steps", "2", "--warmup", "3", "--no-cpu"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in j, k
+    assert j["n_gpus"] == 1 and j["steps"] == 2 and j["warmup"] == 3 and j["value"] > 0 and j["gpu_launches"] > 0
+    assert "workload" in j["config"] and "model" not in j["config"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in j["roofline"], k
+    assert abs(j["roofline"]["frac"] - j["roofline"]["achieved"] / j["roofline"]["peak"]) < 1e-12
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in j["e2e"], k
+    assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert math.isfinite(j["log_likelihood_mean"])
