@@ -372,6 +372,7 @@ int do_init(cssm_filter* f, double t0, const double* zinj_dev, const double* x0)
   f->anc_valid = false;
   f->initialised = true;
   f->t_cur = t0;
+  f->fc_valid = false;  // a forecast cloud does not outlive the filtering cloud it was drawn from
   if (f->paths_cap > 0) {  // FilterInterpolate: the initial cloud is element 0 of every path
     const size_t cloud = (size_t)f->d * f->Ns * (f->dtype == CSSM_F32 ? 4 : 8);
     CU(cudaMemcpyAsync(f->px, f->x[f->cur], cloud, cudaMemcpyDeviceToDevice, f->stream));
@@ -674,6 +675,7 @@ int run_one_step(cssm_filter* f, double t, int has_obs, double y, const StepIO& 
   rc = (f->dtype == CSSM_F32) ? launch_step<float>(f, h, n_sub, ctab, delta, io) : launch_step<double>(f, h, n_sub, ctab, delta, io);
   if (rc) return rc;
   f->t_cur = t;
+  f->fc_valid = false;
   if (f->paths_cap > 0 && f->paths_len >= 0) {  // FilterInterpolate: keep the propagated cloud and the ancestors of this step
     const size_t cloud = (size_t)f->d * f->Ns * (f->dtype == CSSM_F32 ? 4 : 8);
     const bool resampled = f->anc_valid;
@@ -870,6 +872,7 @@ int run_series_single_launch(cssm_filter* f) {
 int run_series_impl(cssm_filter* f, bool sample_states);
 int run_series(cssm_filter* f, bool sample_states) {
   const int rc = run_series_impl(f, sample_states);
+  f->fc_valid = false;
   if (f->paths_cap > 0) {  // the whole-series calls do not record paths: what was recorded no longer describes the cloud
     f->paths_len = -1;
     f->pres.clear();

@@ -287,7 +287,8 @@ int cssm_filter_intervals(cssm_filter_t* f, double t, double interval, double* s
  * cloud is advanced to time t without touching the filter -- x1 = stepFunction(t - s.t)(x).draw, gamma = f(x1, t),
  * eta = link(gamma) -- and two observations are drawn from Model.observation(gamma) (getForecast's, and the second
  * draw getMeanForecast summarises); the result is kept in a forecast cloud next to the filter's own.
- *   chain != 0     continue from the previous forecast cloud instead (Data.forecast's scan over times)
+ *   chain != 0     continue from the previous forecast cloud instead (Data.forecast's scan over times); the forecast
+ *                  cloud is dropped by every filter step / initialisation (CSSM_ERR_STATE if there is none)
  *   state_mean[d], state_lower[d], state_upper[d]   meanState and getallCredibleIntervals of x1 (:398-399)
  *   eta_out[3]     mean(eta) and getOrderStatistic(eta, interval): mean, lower, upper (:400-401)
  *   obs_out[3]     the same for the second observation draw (:402-404)

@@ -460,6 +460,9 @@ def test_forecast_chain_continues_from_the_forecast_cloud():
     assert np.all(np.abs(one["upper"] - two["upper"]) <= 0.05 * sd + 1e-6)
     assert np.all(np.abs(one["lower"] - two["lower"]) <= 0.05 * sd + 1e-6)
     assert abs(one["obs"][0] - two["obs"][0]) <= 6 * c["obs2"].std() * np.sqrt(2.0 / N)
+    h.step(s.t + 0.1, 0.3)                                       # the filter moves on: the forecast cloud is dropped
+    with pytest.raises(cs._abi.CssmError):
+        h.forecast(s.t + 0.9, 0.975, chain=True)
     flt.close()
 
 
