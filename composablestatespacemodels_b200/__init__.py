@@ -15,9 +15,9 @@ from .model import UnparamModel
 from .resampling import Resampling
 from .filter import (Data, TimedObservation, StateSpace, PfState, PfOut, ForecastOut, ObservationWithState, CredibleInterval,
                      Filter, FilterLgcp, FilterInit, FilterInterpolate, PfStateInterpolate, ParticleFilter,
-                     GpuFilterHandle, ShardedGroup)
+                     GpuFilterHandle, ShardedGroup, StaleStateError)
 from .pmmh import (MetropolisHastings, ParticleMetropolisHastings, ApproxPMMH, approxPmmh, pmmhStep, MetropState,
-                   GpuBootstrapFilter)
+                   GpuBootstrapFilter, runChains)
 from . import streaming as Streaming
 
 F32, F64 = _abi.F32, _abi.F64
@@ -25,5 +25,5 @@ __all__ = ["Tree", "Leaf", "Branch", "Sde", "SdeParameter", "BrownianParameter",
            "ParamNode", "Parameters", "flattenParams", "perturb", "perturbMvn", "Model", "UnparamModel", "Resampling",
            "Data", "TimedObservation", "StateSpace", "PfState", "PfOut", "ForecastOut", "ObservationWithState", "CredibleInterval", "Filter", "FilterLgcp", "FilterInit", "FilterInterpolate", "PfStateInterpolate", "ParticleFilter",
            "GpuFilterHandle", "ShardedGroup", "MetropolisHastings", "ParticleMetropolisHastings", "ApproxPMMH", "approxPmmh", "pmmhStep", "MetropState",
-           "GpuBootstrapFilter", "Streaming",
+           "GpuBootstrapFilter", "runChains", "StaleStateError", "Streaming",
            "F32", "F64"]

@@ -97,6 +97,7 @@ _SIGNATURES = {
     "cssm_filter_ll": [_FILTER, c_double_p, c_double_p, c_uint8_p, C.c_int64, c_double_p],
     "cssm_filter_load_series": [_FILTER, c_double_p, c_double_p, c_uint8_p, C.c_int64],
     "cssm_filter_ll_resident": [_FILTER, c_double_p, c_double_p, c_int32_p],
+    "cssm_filter_series_len": [_FILTER, c_int64_p],
     "cssm_filter_run": [_FILTER, c_double_p, c_double_p, c_uint8_p, C.c_int64, c_double_p, c_double_p],
     "cssm_filter_last_elapsed_ms": [_FILTER, C.POINTER(C.c_float)],
     "cssm_filter_last_launches": [_FILTER, c_int64_p],

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 
 #include "cssm_kernels.cuh"
 #include "cssm_series.cuh"
@@ -258,6 +259,12 @@ struct cssm_filter {
   double fc_t = 0.0;
   uint32_t fc_ctr = 0;
   float last_ms = 0.f;
+  // pinned staging of the small tables a PMMH iteration rebuilds (records, LGCP coefficients): asynchronous copies, the
+  // buffer is reused only after the previous copy out of it has completed (pin_ev)
+  void* pin = nullptr;
+  size_t pin_cap = 0;
+  cudaEvent_t pin_ev = nullptr;
+  bool pin_pending = false;
   // per-kernel-class device timing (CUDA events on the launching stream), sampled every prof_stride steps
   int prof_stride = 0;
   std::vector<cudaEvent_t> prof_ev;  // pairs
@@ -282,6 +289,31 @@ int ensure_scratch(cssm_filter* f, size_t n) {
   f->scratch = nullptr; f->scratch_n = 0;
   CU(cudaMalloc(&f->scratch, n * sizeof(double)));
   f->scratch_n = n;
+  return CSSM_OK;
+}
+
+// `bytes` of pinned host memory whose previous contents have left for the device
+int pin_reserve(cssm_filter* f, size_t bytes, void** out) {
+  if (f->pin_pending) {
+    CU(cudaEventSynchronize(f->pin_ev));
+    f->pin_pending = false;
+  }
+  if (bytes > f->pin_cap) {
+    if (f->pin) cudaFreeHost(f->pin);
+    f->pin = nullptr; f->pin_cap = 0;
+    const size_t cap = std::max<size_t>(bytes, 1 << 16);
+    CU(cudaMallocHost(&f->pin, cap));
+    f->pin_cap = cap;
+  }
+  if (!f->pin_ev) CU(cudaEventCreateWithFlags(&f->pin_ev, cudaEventDisableTiming));
+  *out = f->pin;
+  return CSSM_OK;
+}
+// asynchronous copy of the staged bytes; no host wait
+int pin_send(cssm_filter* f, void* dst, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, f->pin, bytes, cudaMemcpyHostToDevice, f->stream));
+  CU(cudaEventRecord(f->pin_ev, f->stream));
+  f->pin_pending = true;
   return CSSM_OK;
 }
 
@@ -518,27 +550,31 @@ int step_phase2(cssm_filter* f, StepCtx& cx) {
 
 // K3 keeps two padded tiles of doubles in shared memory (37 KB per block with 2048-particle tiles):
 // prefer the large shared-memory carveout so that four blocks fit an SM
+// The attribute is per device and per kernel instantiation: one std::call_once per (real, device), so that handles on
+// several devices of one process (ShardedGroup, one thread per GPU) each get it, and concurrent first calls are safe.
+constexpr int MAX_DEVICES = 64;
 template <typename real>
-void k3_carveout_once() {
-  static bool done = false;
-  if (done) return;
-  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-  cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-  cudaGetLastError();
-  done = true;
+void k3_carveout_once(int device) {
+  static std::once_flag once[MAX_DEVICES];
+  if (device < 0 || device >= MAX_DEVICES) return;
+  std::call_once(once[device], [] {
+    cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaGetLastError();
+  });
 }
 
 // ---- K3: CDF scan + ancestor search (+ multinomial draw) ----------------------------------------
 template <typename real>
 int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   if (!cx.observed) return CSSM_OK;
-  k3_carveout_once<real>();
+  k3_carveout_once<real>(f->device);
   const Peers pr = make_peers(f, f->cur);
   const bool pdl = f->pdl && !cx.prof;
   const bool multi = f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL;
@@ -600,6 +636,10 @@ int step_consts(cssm_filter* f, double t_prev, double t, int has_obs, double y, 
     delta = std::pow(10, -m.lgcp_precision);
     n_sub = (dt == 0) ? 0 : (long long)(int)std::ceil(dt / delta);  // model/ParticleFilter.scala:190
     if (n_sub >= (1 << 22)) return fail(CSSM_ERR_UNSUPPORTED, "LGCP: more than 2^22 sub-steps in one increment");
+    // the Philox call counter of a step shares its word with the 8-bit purpose tag (RNG_STEP | call): n_sub * d / PER_CALL
+    // calls must stay below 2^24 or the stream would run into the resampling / sample-one streams of the same step
+    if (n_sub * (long long)m.d / (f->dtype == CSSM_F32 ? 4 : 2) >= (1ll << 24))
+      return fail(CSSM_ERR_UNSUPPORTED, "LGCP: sub-steps x latent dimension exceeds the 2^24 Philox calls of one step");
     transition_consts(m, delta, h);
     has_obs = 1;  // every datum is an event; FilterLgcp always weights and resamples (:217-225)
   } else {
@@ -638,15 +678,16 @@ int upload_ctab(cssm_filter* f, const std::vector<double>& host) {
     CU(cudaMalloc(&f->ctab, host.size() * esz));
     f->ctab_n = host.size();
   }
+  void* stage;
+  int rc = pin_reserve(f, host.size() * esz, &stage);
+  if (rc) return rc;
   if (f->dtype == CSSM_F32) {
-    std::vector<float> tmp(host.begin(), host.end());
-    CU(cudaMemcpyAsync(f->ctab, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, f->stream));
-    CU(cudaStreamSynchronize(f->stream));
+    float* o = (float*)stage;
+    for (size_t i = 0; i < host.size(); ++i) o[i] = (float)host[i];
   } else {
-    CU(cudaMemcpyAsync(f->ctab, host.data(), host.size() * 8, cudaMemcpyHostToDevice, f->stream));
-    CU(cudaStreamSynchronize(f->stream));
+    std::memcpy(stage, host.data(), host.size() * 8);
   }
-  return CSSM_OK;
+  return pin_send(f, f->ctab, host.size() * esz);
 }
 
 // constants (+ LGCP coefficient table) of one step taken outside a loaded series
@@ -786,26 +827,29 @@ bool series_eligible(cssm_filter* f, bool sample_states) {
 template <typename real>
 int upload_recs(cssm_filter* f) {
   const size_t T = f->series.size(), len = (size_t)4 * f->d + SERIES_REC_EXTRA;
-  std::vector<real> host(T * len);
+  const size_t bytes = T * len * sizeof(real);
+  void* stage;
+  int rc = pin_reserve(f, bytes, &stage);
+  if (rc) return rc;
+  real* host = (real*)stage;
   for (size_t s = 0; s < T; ++s) {
     StepArgs<real> a;
     to_args<real>(f->model, f->series[s].h, a);
-    real* r = host.data() + s * len;
+    real* r = host + s * len;
     for (int k = 0; k < f->d; ++k) {
       r[k] = a.A[k]; r[f->d + k] = a.D[k]; r[2 * f->d + k] = a.S[k]; r[3 * f->d + k] = a.C[k];
     }
     real* e = r + 4 * f->d;
     e[0] = a.y; e[1] = a.k0; e[2] = a.k1; e[3] = a.k2; e[4] = a.k3; e[5] = a.has_obs ? (real)1 : (real)0; e[6] = e[7] = (real)0;
   }
-  const size_t bytes = host.size() * sizeof(real);
   if (bytes > f->recs_cap) {
     if (f->recs) cudaFree(f->recs);
     f->recs = nullptr; f->recs_cap = 0;
     CU(cudaMalloc(&f->recs, bytes));
     f->recs_cap = bytes;
   }
-  CU(cudaMemcpyAsync(f->recs, host.data(), bytes, cudaMemcpyHostToDevice, f->stream));
-  CU(cudaStreamSynchronize(f->stream));  // `host` is pageable and goes out of scope
+  rc = pin_send(f, f->recs, bytes);
+  if (rc) return rc;
   f->recs_valid = true;
   return CSSM_OK;
 }
@@ -992,14 +1036,23 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   f->tb.nt = f->nt; f->tb.ns = f->ns;
   f->tb.tile_q = f->tile_q;
   if (const char* e = std::getenv("CSSM_FLAT_MAX_NT")) f->flat_max_nt = std::atoi(e);
-  cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz);
-  cudaMemset(f->x[1], 0, (size_t)f->d * f->Ns * esz);
-  cudaMemset(f->logw, 0, (size_t)(f->Ns + tile) * esz);
-  cudaMemset(f->sc, 0, sizeof(FilterScalars));
-  cudaMemset(f->xch, 0, sizeof(XchSlot) * MAXR);
-  cudaMemset(f->tb.super_sum, 0, (size_t)2 * f->ns * sizeof(u128));
-  cudaMemset(f->tb.super_q, 0, (size_t)2 * f->ns * sizeof(u128));
-  cudaMemset(f->tb.super_ticket, 0, (size_t)f->ns * sizeof(unsigned long long));
+  {
+    const cudaError_t em[] = {cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz),
+                              cudaMemset(f->x[1], 0, (size_t)f->d * f->Ns * esz),
+                              cudaMemset(f->logw, 0, (size_t)(f->Ns + tile) * esz),
+                              cudaMemset(f->anc, 0, (size_t)f->Ns * sizeof(int32_t)),
+                              cudaMemset(f->sc, 0, sizeof(FilterScalars)),
+                              cudaMemset(f->xch, 0, sizeof(XchSlot) * MAXR),
+                              cudaMemset(f->tb.super_sum, 0, (size_t)2 * f->ns * sizeof(u128)),
+                              cudaMemset(f->tb.super_q, 0, (size_t)2 * f->ns * sizeof(u128)),
+                              cudaMemset(f->tb.super_ticket, 0, (size_t)f->ns * sizeof(unsigned long long)),
+                              cudaMemset(f->series_ctl, 0, sizeof(SeriesCtl))};
+    for (cudaError_t e_ : em)
+      if (e_ != cudaSuccess) {
+        cssm_filter_destroy(f);
+        return fail(CSSM_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e_));
+      }
+  }
   if (cudaStreamCreateWithFlags(&f->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&f->ev0) != cudaSuccess ||
       cudaEventCreate(&f->ev1) != cudaSuccess) {
     cssm_filter_destroy(f);
@@ -1027,23 +1080,28 @@ int forecast_impl(cssm_filter* f, double t, double interval, int chain, bool sum
   f_coeffs(f->model, t, h.C);
   StepArgs<real> a;
   to_args<real>(f->model, h, a);
+  // getCredibleInterval ranks for the state, getOrderStatistic ranks for eta and the observations (see cssm_filter_intervals).
+  // Everything that can fail is checked BEFORE the forecast cloud is advanced: a rejected call leaves it (and the Philox
+  // counter of the forecast stream) untouched, so a retry does not double-step a chained forecast.
+  const long long idx = (long long)std::floor(interval * (double)n);
+  const long long lo_s = n - idx - 1, hi_s = idx - 1, lo_e = n - idx, hi_e = idx;
+  if (summarise) {
+    if (lo_s < 0 || lo_s >= n || hi_s < 0 || hi_s >= n || lo_e < 0 || lo_e >= n || hi_e < 0 || hi_e >= n)
+      return fail(CSSM_ERR_INVALID, "forecast: the order-statistic index is outside the cloud (the reference throws IndexOutOfBounds here)");
+    // scratch: mean[cols] | out[2*cols] | SelState[2*cols] | hist[cols*512 u32]
+    int rc = ensure_scratch(f, (size_t)cols + 2 * cols + 2 * (2 * cols) + (size_t)cols * 256 + 8);
+    if (rc) return rc;
+  }
   const Peers pr = make_peers(f, f->cur);
   const int32_t* anc = f->anc_valid ? f->anc : nullptr;
   ObsDraw od{f->model.obs_kind, f->model.obs_df, f->model.has_scale, f->model.scale};
-  k_forecast<real><<<nblk(n, 256), 256, 0, f->stream>>>(a, pr, anc, (real*)f->fc, chain, od, n, f->Ns, f->key0, f->key1, f->fc_ctr++);
+  k_forecast<real><<<nblk(n, 256), 256, 0, f->stream>>>(a, pr, anc, (real*)f->fc, chain, od, n, f->Ns, f->key0, f->key1, f->fc_ctr);
   f->launches++;
   CU(cudaGetLastError());
+  f->fc_ctr++;
   f->fc_valid = true;
   f->fc_t = t;
   if (!summarise) return CSSM_OK;
-  // getCredibleInterval ranks for the state, getOrderStatistic ranks for eta and the observations (see cssm_filter_intervals)
-  const long long idx = (long long)std::floor(interval * (double)n);
-  const long long lo_s = n - idx - 1, hi_s = idx - 1, lo_e = n - idx, hi_e = idx;
-  if (lo_s < 0 || lo_s >= n || hi_s < 0 || hi_s >= n || lo_e < 0 || lo_e >= n || hi_e < 0 || hi_e >= n)
-    return fail(CSSM_ERR_INVALID, "forecast: the order-statistic index is outside the cloud (the reference throws IndexOutOfBounds here)");
-  // scratch: mean[cols] | out[2*cols] | SelState[2*cols] | hist[cols*512 u32]
-  int rc = ensure_scratch(f, (size_t)cols + 2 * cols + 2 * (2 * cols) + (size_t)cols * 256 + 8);
-  if (rc) return rc;
   double* mean_dev = f->scratch;
   double* out_dev = mean_dev + cols;
   SelState* sel_dev = reinterpret_cast<SelState*>(out_dev + 2 * cols);
@@ -1227,6 +1285,8 @@ int cssm_filter_destroy(cssm_filter_t* f) {
     if (p) cudaFree(p);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
+  if (f->pin_ev) cudaEventDestroy(f->pin_ev);
+  if (f->pin) cudaFreeHost(f->pin);
   if (f->own_stream) cudaStreamDestroy(f->own_stream);
   delete f;
   return CSSM_OK;
@@ -1644,6 +1704,12 @@ int cssm_filter_ll_resident(cssm_filter_t* f, double* ll_out, double* ll_steps_o
       if (ess_out) ess_out[s] = pe;
     }
   }
+  return CSSM_OK;
+}
+
+int cssm_filter_series_len(const cssm_filter_t* f, int64_t* T_out) {
+  if (!f || !T_out) return fail(CSSM_ERR_INVALID, "null argument");
+  *T_out = (int64_t)f->series.size();
   return CSSM_OK;
 }
 

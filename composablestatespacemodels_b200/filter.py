@@ -65,34 +65,67 @@ class ObservationWithState:
         self.t, self.observation, self.eta, self.gamma, self.sdeState = t, observation, eta, gamma, sdeState
 
 
+class StaleStateError(RuntimeError):
+    """A PfState whose cloud the device handle no longer holds was read (see PfState)."""
+
+
 class PfState:
-    """model/ParticleFilter.scala:32-37.  `particles` is read from the device when asked for."""
+    """model/ParticleFilter.scala:32-37.  `t`, `observation`, `ll` and `ess` are plain values; the cloud stays in
+    device memory and `particles` copies it out when asked for.  The reference's PfState is an immutable value, the
+    handle's cloud is not: every init / step / whole-series call replaces it.  A state therefore remembers the
+    generation of the cloud it describes and reading the cloud of an older state (`particles`, getIntervals,
+    getForecast, paths) raises StaleStateError instead of silently returning the handle's CURRENT cloud.  Call
+    `materialise()` on a state that has to outlive the next step: it copies the cloud to the host once and the state
+    then behaves like the reference's value."""
 
     def __init__(self, t, observation, handle, ll, ess):
         self.t, self.observation, self.ll, self.ess = t, observation, ll, ess
         self._handle = handle
+        self._gen = handle.generation
+        self._host = None
+
+    def _live(self):
+        if self._gen != self._handle.generation:
+            raise StaleStateError(
+                f"this PfState (t = {self.t}) describes cloud generation {self._gen}, the filter handle has moved on to "
+                f"{self._handle.generation}: read a state before the next step, or keep it with materialise()")
+        return self._handle
+
+    def materialise(self):
+        """Copy the cloud to the host now; afterwards `particles` no longer depends on the handle."""
+        if self._host is None:
+            self._host = self._live().get_particles().T.copy()
+        return self
 
     @property
     def particles(self):
         """The resampled cloud as an array [N, d] (particle-major, like Vector[State])."""
-        return self._handle.get_particles().T.copy()
+        if self._host is not None:
+            return self._host
+        return self._live().get_particles().T.copy()
 
 
 class PfStateInterpolate:
     """model/ParticleFilter.scala:39-44: the particles are paths.  `particles` reads them from the device when asked
     for: an array [N, len, d] with the NEWEST state first (the reference's List[State] conses new states at the head)."""
 
-    def __init__(self, t, observation, handle, ll, ess, reverse=False):
+    def __init__(self, t, observation, handle, ll, ess, reverse=False, gen=None):
         self.t, self.observation, self.ll, self.ess = t, observation, ll, ess
         self._handle, self._reverse = handle, reverse
+        self._gen = handle.generation if gen is None else gen
+
+    def _live(self):
+        if self._gen != self._handle.generation:
+            raise StaleStateError(f"this PfStateInterpolate (t = {self.t}) is older than the handle's cloud; read it before the next step")
+        return self._handle
 
     def paths(self, indices=None):
         """Paths of the given particles (all by default), [n, len, d], OLDEST state first."""
-        return self._handle.get_paths(indices)
+        return self._live().get_paths(indices)
 
     @property
     def particles(self):
-        p = self._handle.get_paths()[:, ::-1, :]
+        p = self._live().get_paths()[:, ::-1, :]
         return p[::-1] if self._reverse else p
 
 
@@ -114,6 +147,7 @@ class GpuFilterHandle:
             _abi.check(self._lib.cssm_filter_create(C.byref(desc), self.n, resample_kind, dtype, device, seed, stream_id,
                                                     C.byref(self._h)))
         self.resample_kind, self.dtype = resample_kind, dtype
+        self.generation = 0  # bumped by every call that replaces the cloud (PfState staleness check)
 
     # ---- sharding ---------------------------------------------------------------------------
     def shard_export(self):
@@ -160,20 +194,24 @@ class GpuFilterHandle:
 
     # ---- stepping ---------------------------------------------------------------------------
     def init(self, t0):
+        self.generation += 1
         _abi.check(self._lib.cssm_filter_init(self._h, float(t0)))
 
     def init_state(self, t0, x0):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.generation += 1
         _abi.check(self._lib.cssm_filter_init_state(self._h, float(t0), _abi.dptr(x0)))
 
     def init_injected(self, t0, z0):
         z0 = np.ascontiguousarray(z0, dtype=np.float64)
         assert z0.shape == (self.d, self.n)
+        self.generation += 1
         _abi.check(self._lib.cssm_filter_init_injected(self._h, float(t0), _abi.dptr(z0)))
 
     def step(self, t, observation):
         ll, ess = C.c_double(), C.c_int32()
         has = 0 if observation is None else 1
+        self.generation += 1
         _abi.check(self._lib.cssm_filter_step(self._h, float(t), has, 0.0 if observation is None else float(observation),
                                               C.byref(ll), C.byref(ess)))
         return ll.value, ess.value
@@ -194,6 +232,7 @@ class GpuFilterHandle:
         w1 = np.empty(self.n) if "w1" in want else None
         anc = np.empty(self.n, dtype=np.int32) if "anc" in want else None
         ll, ess = C.c_double(), C.c_int32()
+        self.generation += 1
         _abi.check(self._lib.cssm_filter_step_injected(
             self._h, float(t), has, 0.0 if observation is None else float(observation), _abi.dptr(z), _abi.dptr(u),
             _abi.dptr(xp), _abi.dptr(lw), _abi.dptr(w1),
@@ -214,6 +253,7 @@ class GpuFilterHandle:
         y = np.ascontiguousarray(y, dtype=np.float64)
         h = None if has_obs is None else np.ascontiguousarray(has_obs, dtype=np.uint8)
         ll = C.c_double()
+        self.generation += 1
         _abi.check(self._lib.cssm_filter_ll(self._h, _abi.dptr(t), _abi.dptr(y),
                                             None if h is None else h.ctypes.data_as(_abi.c_uint8_p), t.size, C.byref(ll)))
         return ll.value
@@ -224,14 +264,24 @@ class GpuFilterHandle:
         h = None if has_obs is None else np.ascontiguousarray(has_obs, dtype=np.uint8)
         _abi.check(self._lib.cssm_filter_load_series(self._h, _abi.dptr(t), _abi.dptr(y),
                                                      None if h is None else h.ctypes.data_as(_abi.c_uint8_p), t.size))
-        self._T = t.size
+
+    def series_len(self):
+        """Length of the series the handle holds, as the C side counts it (load_series, ll_arrays, run_arrays and
+        set_params all (re)load one)."""
+        n = C.c_int64()
+        _abi.check(self._lib.cssm_filter_series_len(self._h, C.byref(n)))
+        return n.value
 
     def ll_resident(self, steps=False):
         ll = C.c_double()
+        self.generation += 1
         if not steps:
             _abi.check(self._lib.cssm_filter_ll_resident(self._h, C.byref(ll), None, None))
             return ll.value
-        lls, ess = np.empty(self._T), np.empty(self._T, dtype=np.int32)
+        T = self.series_len()  # the C side writes exactly this many entries
+        if T <= 0:
+            raise _abi.CssmError(-5, "no series loaded")
+        lls, ess = np.empty(T), np.empty(T, dtype=np.int32)
         _abi.check(self._lib.cssm_filter_ll_resident(self._h, C.byref(ll), _abi.dptr(lls), ess.ctypes.data_as(_abi.c_int32_p)))
         return ll.value, lls, ess
 
@@ -241,6 +291,7 @@ class GpuFilterHandle:
         h = None if has_obs is None else np.ascontiguousarray(has_obs, dtype=np.uint8)
         ll = C.c_double()
         states = np.empty((t.size + 1, self.d))
+        self.generation += 1
         _abi.check(self._lib.cssm_filter_run(self._h, _abi.dptr(t), _abi.dptr(y),
                                              None if h is None else h.ctypes.data_as(_abi.c_uint8_p), t.size, C.byref(ll),
                                              _abi.dptr(states)))
@@ -349,7 +400,13 @@ class ShardedGroup:
     """R shards of ONE filter inside one process, driven in lock-step by the cssm_group_* entry
     points: virtual ranks on one GPU (devices all equal) or one process over several GPUs.  This
     is how the sharded path is tested without a multi-process launch; the multi-process form is
-    one GpuFilterHandle(rank=r, world=R) per process plus shard_export / shard_connect."""
+    one GpuFilterHandle(rank=r, world=R) per process plus shard_export / shard_connect.
+
+    Virtual ranks (several shards on ONE device) are a test vehicle: the kernels of a sharded filter wait inside the
+    kernel for flags their peers write, and CUDA does not co-schedule kernels of different streams.  The group
+    drivers therefore put all shards of a device on ONE stream and launch every phase in rank order, so that each
+    wait is already satisfied when its kernel starts (cssm_api.cu, check_group); never drive same-device shards from
+    separate streams or threads.  One GPU per rank -- the production layout -- has no such restriction."""
 
     def __init__(self, mod, resample_kind, n_local, world, dtype=_abi.F32, devices=None, seed=0, stream_id=0):
         devices = [0] * world if devices is None else list(devices)
@@ -368,6 +425,7 @@ class ShardedGroup:
             s.close()
 
     def init(self, t0):
+        self.generation += 1
         _abi.check(self._lib.cssm_group_init(self._arr, self.world, float(t0)))
 
     def init_injected(self, t0, z0):
@@ -436,7 +494,7 @@ class _ParticleFilterBase:
     def stepFilter(self, s, y):
         """model/ParticleFilter.scala:116-132 (FilterLgcp :210-226).  The cloud lives in the
         handle, so states must be stepped in order (as foldLeft / scan do)."""
-        h = s._handle
+        h = s._live()  # the cloud lives in the handle: only its newest state can be stepped
         ll, ess = h.step(y.t, y.observation)
         return PfState(y.t, y.observation, h, ll, ess)
 
@@ -523,7 +581,7 @@ class FilterInterpolate:
 
     def stepInterpolate(self, s, y):
         """model/ParticleFilter.scala:281-298"""
-        h = s._handle
+        h = s._live()
         ll, ess = h.step(y.t, y.observation)
         if y.observation is None:
             ll, ess = s.ll, s.ess
@@ -566,7 +624,7 @@ class ParticleFilter:
         """model/ParticleFilter.scala:415-424: PfState -> PfOut (mean state, state intervals, eta = link(f(mean)),
         eta intervals).  The cloud stays on the device: mean and order statistics come from
         cssm_filter_intervals; the (monotone) link is applied here, in fp64, to the two order statistics of gamma."""
-        r = s._handle.intervals(s.t, interval)
+        r = s._live().intervals(s.t, interval)
         lo, up = model.link(r["gamma"][0]), model.link(r["gamma"][1])
         if lo > up:  # decreasing link (Beta: exp(-x)): ascending eta is descending gamma
             lo, up = model.link(r["gamma"][1]), model.link(r["gamma"][0])
@@ -579,14 +637,14 @@ class ParticleFilter:
         """model/ParticleFilter.scala:368-383: the particles of `s` advanced to `t` with eta and a drawn observation
         each, as ONE ObservationWithState whose fields are arrays over the particles (the reference returns a
         Vector of N of them)."""
-        s._handle.forecast(t, summarise=False)
+        s._live().forecast(t, summarise=False)
         c = s._handle.forecast_cloud()
         return ObservationWithState(t, c["obs"], c["eta"], c["gamma"], c["x"].T.copy())
 
     @staticmethod
     def getMeanForecast(s, mod, t, interval):
         """model/ParticleFilter.scala:394-412 -> ForecastOut; nothing but the 3(d + 2) summary numbers leaves the device."""
-        r = s._handle.forecast(t, interval)
+        r = s._live().forecast(t, interval)
         return ForecastOut(t, r["obs"][0], CredibleInterval(r["obs"][1], r["obs"][2]), r["eta"][0],
                            CredibleInterval(r["eta"][1], r["eta"][2]), r["mean"],
                            [CredibleInterval(a, b) for a, b in zip(r["lower"], r["upper"])])

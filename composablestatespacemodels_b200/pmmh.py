@@ -27,7 +27,11 @@ class GpuBootstrapFilter:
     (examples/DetermineParameters.scala:67-72).  Returns (ll, [last sampled state])."""
 
     def __init__(self, unparamModel, initParams, data, resample, n, dtype=_abi.F32, device=0, seed=0, stream_id=0,
-                 precision=None):
+                 precision=None, replicas=1):
+        """`replicas` > 1: that many handles (each with its own CUDA stream and Philox stream id) so that `many`
+        can evaluate several parameter values at once -- the two filter runs of an ApproxPMMH step, or the proposals of
+        several chains.  A small cloud leaves most of the GPU idle (a 2^16-particle filter is latency bound), so
+        concurrent evaluations cost little more than one."""
         from .resampling import Resampling
         self.unparamModel = unparamModel
         mod = unparamModel(initParams)
@@ -35,22 +39,51 @@ class GpuBootstrapFilter:
             from .model import Model
             mod = Model(mod.leaves, mod.step_mode, precision)
         self.precision = precision
-        self.handle = GpuFilterHandle(mod, Resampling.kind_of(resample), n, dtype, device, seed, stream_id)
         t, y, h = GpuFilterHandle._series(data)
         self.t_last = float(t[-1])
-        self.handle.load_series(t, y, h)
+        self.handles = []
+        for r in range(max(1, int(replicas))):
+            hd = GpuFilterHandle(mod, Resampling.kind_of(resample), n, dtype, device, seed, stream_id + r)
+            hd.load_series(t, y, h)
+            self.handles.append(hd)
+        self.handle = self.handles[0]
+        self._pool = None
 
-    def __call__(self, p):
+    def _model(self, p):
         mod = self.unparamModel(p)
         if self.precision is not None:
             from .model import Model
             mod = Model(mod.leaves, mod.step_mode, self.precision)
-        self.handle.set_params(mod)
-        ll = self.handle.ll_resident()
-        return ll, [StateSpace(self.t_last, self.handle.sample_one())]
+        return mod
+
+    def _eval(self, handle, p):
+        handle.set_params(self._model(p))
+        ll = handle.ll_resident()
+        return ll, [StateSpace(self.t_last, handle.sample_one())]
+
+    def __call__(self, p):
+        return self._eval(self.handle, p)
+
+    def many(self, ps):
+        """[pf(p) for p in ps], evaluated concurrently on the replica handles (one host thread each; the C calls
+        release the GIL and every handle has its own stream)."""
+        ps = list(ps)
+        if len(ps) > len(self.handles):
+            raise ValueError(f"{len(ps)} parameter values for {len(self.handles)} replica handle(s)")
+        if len(ps) == 1:
+            return [self._eval(self.handles[0], ps[0])]
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=len(self.handles))
+        futs = [self._pool.submit(self._eval, h, p) for h, p in zip(self.handles, ps)]
+        return [f.result() for f in futs]
 
     def close(self):
-        self.handle.close()
+        if self._pool is not None:
+            self._pool.shutdown()
+            self._pool = None
+        for h in self.handles:
+            h.close()
 
 
 class MetropolisHastings:
@@ -73,12 +106,20 @@ class MetropolisHastings:
             return MetropState(state[0], propParams, state[1][-1], s.accepted + 1)
         return s
 
-    def iters(self):
-        """model/PMMH.scala:95-98: the chain without its initial state (drop(1))."""
+    def markovIters(self):
+        """model/PMMH.scala:85-87 with model/MarkovChain.scala:7-17 and Breeze's Process.steps: the first element is
+        already ONE mhStep past `init` (MarkovChain.draw = resample(init).draw), every further one a step later."""
         s = self.init
         while True:
             s = self.mhStep(s)
             yield s
+
+    def iters(self):
+        """model/PMMH.scala:95-98: `markovIters.steps.drop(1)` -- the first state emitted is the result of the SECOND
+        mhStep (the first, always-accepted move away from the artificial ll = -1e99 start is dropped)."""
+        it = self.markovIters()
+        next(it)
+        return it
 
     def params(self):
         for s in self.iters():
@@ -100,8 +141,11 @@ class ApproxPMMH(MetropolisHastings):
 
     def mhStep(self, s):
         propParams = self.proposal(s.params)
-        state = self.pf(propParams)
-        oldState = self.pf(s.params)
+        if hasattr(self.pf, "many") and len(getattr(self.pf, "handles", ())) >= 2:
+            state, oldState = self.pf.many([propParams, s.params])  # the two filter runs of a step, side by side
+        else:
+            state = self.pf(propParams)
+            oldState = self.pf(s.params)
         a = (state[0] + self.logTransition(propParams, s.params) + self.prior(propParams)
              - self.logTransition(s.params, propParams) - oldState[0] - self.prior(s.params))
         u = self.rng.random()
@@ -124,6 +168,22 @@ def pmmhStep(pos, proposal, rng=None):
         ll = pos(prop)
         return (ll, prop) if math.log(rng.random()) < ll - s[0] else s
     return step
+
+
+def runChains(chains, n_iters, parallelism=2):
+    """examples/DetermineParameters.scala:68-80: `Source(1 to k).mapAsync(2) { chain => iters.take(n).runWith(sink) }` --
+    k independent chains, `parallelism` of them in flight at once (the reference's 2).  `chains`: iterators of MetropState
+    (MetropolisHastings.iters() over distinct GpuBootstrapFilters).  One host thread per running chain; the library calls
+    release the GIL, every handle owns its stream, and a 2^16-particle likelihood evaluation occupies a fraction of the
+    GPU, so chains on one device overlap.  Returns one list of n_iters states per chain, in input order."""
+    from concurrent.futures import ThreadPoolExecutor
+    chains = list(chains)
+
+    def run(it):
+        return [next(it) for _ in range(int(n_iters))]
+
+    with ThreadPoolExecutor(max_workers=max(1, min(int(parallelism), len(chains)))) as pool:
+        return list(pool.map(run, chains))
 
 
 MetropolisHastings.approxPmmh = staticmethod(approxPmmh)

@@ -231,6 +231,9 @@ int cssm_filter_load_series(cssm_filter_t* f, const double* t, const double* y,
                             const uint8_t* has_obs, int64_t T);
 int cssm_filter_ll_resident(cssm_filter_t* f, double* ll_out, double* ll_steps_out,
                             int32_t* ess_out);
+/* number of data of the series the handle holds (loaded by cssm_filter_load_series, _ll, _run or rebuilt by
+ * _set_params): the length cssm_filter_ll_resident writes to ll_steps_out / ess_out.  0: none loaded. */
+int cssm_filter_series_len(const cssm_filter_t* f, int64_t* T_out);
 
 /* filter, model/ParticleFilter.scala:152-158: as llFilter but also returns, for the initial
  * state and each of the T steps, ONE particle sampled uniformly from the cloud

@@ -77,9 +77,20 @@ def test_pmmh_chain_logic_with_a_fake_filter():
     pf = lambda p: (-0.5 * ((p.v - 1.0) / 0.5) ** 2, [("state", p.v)])
     prop = lambda p: FakeP(p.v + 0.8 * rng.standard_normal())
     mh = cs.ParticleMetropolisHastings(FakeP(5.0), prop, lambda a, b: 0.0, lambda p: 0.0, pf, rng)
-    it = mh.iters()
-    first = next(it)
+    first = next(mh.markovIters())
     assert first.accepted == 1                                            # init ll = -1e99: first proposal always accepted (:121)
+    # iters = markovIters.steps.drop(1) (model/PMMH.scala:95-98): the first emitted state is the SECOND mhStep
+    rng2 = np.random.default_rng(7)
+    a = cs.ParticleMetropolisHastings(FakeP(5.0), lambda p: FakeP(p.v + 0.8 * rng2.standard_normal()), lambda a, b: 0.0,
+                                      lambda p: 0.0, pf, rng2)
+    full = a.markovIters()
+    two = [next(full), next(full)]
+    rng2 = np.random.default_rng(7)
+    b = cs.ParticleMetropolisHastings(FakeP(5.0), lambda p: FakeP(p.v + 0.8 * rng2.standard_normal()), lambda a, b: 0.0,
+                                      lambda p: 0.0, pf, rng2)
+    emitted = next(b.iters())
+    assert emitted.params.v == two[1].params.v and emitted.accepted == two[1].accepted
+    it = mh.iters()
     xs = np.array([next(it).params.v for _ in range(20000)])[2000:]
     assert abs(xs.mean() - 1.0) < 0.05 and abs(xs.std() - 0.5) < 0.05
 
@@ -112,7 +123,7 @@ def test_approx_pmmh_reestimates_the_current_likelihood():
 
     rng = np.random.default_rng(3)
     mh = ApproxPMMH(0.0, lambda p: p + 5.0, lambda a, b: 0.0, lambda p: 0.0, pf, rng)
-    it = mh.iters()
+    it = mh.markovIters()
     s1 = next(it)
     assert len(calls) == 2 and calls == [5.0, 0.0]
     assert s1.accepted == 0 and s1.params == 0.0 and s1.ll == -10.0 - 0.002 and s1.state == ("state", 2)
