@@ -235,6 +235,8 @@ struct cssm_filter {
   // single-launch series kernel (small clouds, cssm_series.cuh)
   u128* tile_q = nullptr;          // [nt] exact tile sums of w1^2
   SeriesCtl* series_ctl = nullptr;
+  unsigned long long* series_ll = nullptr;  // flagged exchange slots of k_series_ll (LLW_WORDS x nt words)
+  int series_ll_on = 1;                     // CSSM_SERIES_LL=0: the grid-barrier kernel k_series_small instead
   void* recs = nullptr;            // per-observation records of the loaded series (filter dtype)
   size_t recs_cap = 0;             // bytes
   bool recs_valid = false;
@@ -780,7 +782,14 @@ void* series_kernel_ptr(int d, int kind) {
   if (d == 2) return strat ? (void*)k_series_small<real, 2, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 2, CSSM_RESAMPLE_SYSTEMATIC>;
   return strat ? (void*)k_series_small<real, 0, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 0, CSSM_RESAMPLE_SYSTEMATIC>;
 }
+template <typename real>
+void* series_ll_ptr(int d, int kind) {
+  const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
+  if (d == 2) return strat ? (void*)k_series_ll<real, 2, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_ll<real, 2, CSSM_RESAMPLE_SYSTEMATIC>;
+  return strat ? (void*)k_series_ll<real, 0, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_ll<real, 0, CSSM_RESAMPLE_SYSTEMATIC>;
+}
 void* series_kernel(const cssm_filter* f) {
+  if (f->series_ll_on) return (f->dtype == CSSM_F32) ? series_ll_ptr<float>(f->d, f->resample_kind) : series_ll_ptr<double>(f->d, f->resample_kind);
   return (f->dtype == CSSM_F32) ? series_kernel_ptr<float>(f->d, f->resample_kind) : series_kernel_ptr<double>(f->d, f->resample_kind);
 }
 // mid-size clouds: several tiles per block
@@ -863,8 +872,10 @@ int run_series_single_launch(cssm_filter* f) {
   rc = do_init(f, f->t0_series, nullptr, nullptr);
   if (rc) return rc;
   CU(cudaMemsetAsync(f->series_ctl, 0, sizeof(SeriesCtl), f->stream));
+  CU(cudaMemsetAsync(f->series_ll, 0, (size_t)LLW_WORDS * f->nt * sizeof(unsigned long long), f->stream));
   SeriesArgs sa;
   std::memset(&sa, 0, sizeof(sa));
+  sa.ll = f->series_ll;
   sa.x[0] = f->x[f->cur]; sa.x[1] = f->x[f->cur ^ 1];
   sa.logw = f->logw; sa.anc = f->anc; sa.sc = f->sc;
   sa.tile_sum = f->tb.tile_sum; sa.tile_q = f->tile_q; sa.tile_maxw = f->tb.tile_maxw;
@@ -1004,6 +1015,7 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   if (const char* e = std::getenv("CSSM_TILE_ITEMS")) { int v = std::atoi(e); if (v == 2 || v == 8) f->items = v; }
   if (const char* e = std::getenv("CSSM_PDL")) f->pdl = std::atoi(e) != 0;
   if (const char* e = std::getenv("CSSM_SERIES_MAX_N")) f->series_multi_max = std::atoll(e);
+  if (const char* e = std::getenv("CSSM_SERIES_LL")) f->series_ll_on = std::atoi(e) != 0;
   if (const char* e = std::getenv("CSSM_SERIES_KERNEL")) f->series_mode = std::atoi(e) ? CSSM_SERIES_AUTO : CSSM_SERIES_THREE_LAUNCH;
   const int tile = TILE_THREADS * f->items;
   f->nt = nblk(f->N, tile);
@@ -1032,6 +1044,7 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   if (resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ALLOC(f->cdf, (size_t)f->Ns * sizeof(double));
   ALLOC(f->tile_q, (size_t)(f->nt + 1) * sizeof(u128));
   ALLOC(f->series_ctl, sizeof(SeriesCtl));
+  ALLOC(f->series_ll, (size_t)LLW_WORDS * (f->nt + 1) * sizeof(unsigned long long));
 #undef ALLOC
   f->tb.nt = f->nt; f->tb.ns = f->ns;
   f->tb.tile_q = f->tile_q;
@@ -1279,7 +1292,7 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   if (f->own_stream) cudaStreamSynchronize(f->own_stream);
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
-                  f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl,
+                  f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl, f->series_ll,
                   f->recs, f->fc, f->px, f->panc, f->pres_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);

@@ -758,7 +758,12 @@ struct SumTables {
   u128* super_q;              // [2][ns]
   unsigned long long* super_ticket;  // [ns] monotone
   int nt, ns;
+  // single-launch series kernel with flagged exchange slots (cssm_series.cuh): the tile sums / maxima of the CURRENT step
+  // live in the slots every block has already polled, word k of tile q at ll[k * ll_stride + q], 32 payload bits per word
+  const unsigned long long* ll = nullptr;
+  int ll_stride = 0;
 };
+constexpr int LLW_MAX = 0, LLW_SUM = 2, LLW_DONE = 12, LLW_WORDS = 13;  // max key 2 words; tile_sum 4, tile_q 4, maxw 2; done 1
 
 __device__ __forceinline__ u128 block_sum128(u128 v, u128* s_warp) {  // result valid in thread 0
   v = warp_sum128(v);
@@ -771,6 +776,19 @@ __device__ __forceinline__ u128 block_sum128(u128 v, u128* s_warp) {  // result 
 }
 __device__ __forceinline__ u128 ld_gpu128(const u128* p) {
   return make_u128(ld_gpu(&p->lo), ld_gpu(&p->hi));
+}
+// exact sum / largest weight of tile tl of rank q, as another block published it (L2-coherent reads)
+__device__ __forceinline__ unsigned long long ll_pair(const SumTables& tb, int k, int tl) {
+  const unsigned long long a = ld_gpu(tb.ll + (size_t)k * tb.ll_stride + tl), b = ld_gpu(tb.ll + (size_t)(k + 1) * tb.ll_stride + tl);
+  return (a & 0xFFFFFFFFull) | (b << 32);
+}
+__device__ __forceinline__ u128 walk_tile_sum(const SumTables& tb, const Peers& pr, int q, int tl) {
+  if (tb.ll != nullptr) return make_u128(ll_pair(tb, LLW_SUM, tl), ll_pair(tb, LLW_SUM + 2, tl));
+  return ld_gpu128((q == pr.rank) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);
+}
+__device__ __forceinline__ double walk_tile_maxw(const SumTables& tb, const Peers& pr, int q, int tl) {
+  if (tb.ll != nullptr) return __longlong_as_double((long long)ll_pair(tb, LLW_SUM + 8, tl));
+  return __longlong_as_double((long long)ld_gpu((const unsigned long long*)((q == pr.rank) ? &tb.tile_maxw[tl] : &pr.tile_maxw[q][tl])));
 }
 
 // K2  w1 = exp(logw - max); exact sums of w1 and w1^2 per tile, per super tile and per rank.
@@ -1043,13 +1061,16 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128
 // does adding the next weight leave the cumulative value unchanged?  This is what makes a TreeMap
 // key repeat in the reference (model/Resampling.scala:55-57), tested in the reference's normalised
 // domain: C = fl(P/total), wn = fl(w/total).  A weight above 2^-52 * P cannot vanish (cheap filter).
+__device__ __noinline__ bool vanishes_exact(double P, double w, double total) {
+  const double c = __ddiv_rn(P, total);
+  return __dadd_rn(c, __ddiv_rn(w, total)) == c;
+}
 __device__ __forceinline__ bool vanishes(double P, double w, double total) {
   if (w > P * 2.220446049250313e-16) return false;
   // w <= 2^-55 P: fl(w/total) < 2^-54.9 fl(P/total) is below half an ulp of fl(P/total), the sum rounds
-  // back to it -- decided without the two divisions (only the three binades in between need them)
+  // back to it -- decided without the two divisions (only the three binades in between need them: out of line)
   if (w <= P * 2.7755575615628914e-17) return true;
-  const double c = __ddiv_rn(P, total);
-  return __dadd_rn(c, __ddiv_rn(w, total)) == c;
+  return vanishes_exact(P, w, total);
 }
 
 struct K3Ctl {
@@ -1065,11 +1086,14 @@ struct K3Ctl {
   long long step_slot;
 };
 
+// ---- block-wide scan + search: cumulative values and weights of the tile in shared memory, expansion by head scatter +
+//      block max-scan.  The kernel of the three-launch step (k_scan_search); measured faster there than the
+//      warp-synchronous variant below (0.144 vs 0.166 ms at 2^24 particles), which the single-launch series kernels use. ----
 // cdf_out == NULL: search (systematic / stratified), writes ancestors;
 // cdf_out != NULL: write the un-normalised CDF (multinomial), no search
 // shared memory of the scan + search of one tile
 template <int ITEMS>
-struct K3Smem {
+struct K3SmemBlk {
   static constexpr int TILE = TILE_THREADS * ITEMS;
   static constexpr int WIN = TILE + TILE_THREADS;  // outputs staged per pass (a tile has ~TILE offspring)
   double Ps[TileSmem<ITEMS>::SIZE];
@@ -1092,13 +1116,13 @@ struct K3Smem {
 // three-launch step (zeroes the accumulators of the next observed step); the single-launch series
 // kernel keeps its own.  All threads of the block call; returns whether a peer's memory was written.
 template <typename real, int ITEMS, int KIND, bool PROTO3>
-__device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restrict__ logw, const double* __restrict__ direct,
+__device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __restrict__ logw, const double* __restrict__ direct,
                                         long long N, FilterScalars* __restrict__ sc, const SumTables& tb, const Peers& pr,
                                         const K3Ctl& ctl, const double* __restrict__ uarr, double* __restrict__ cdf_out, int t,
                                         u128 tot, u128 qsum, unsigned long long key, u128 excl,
                                         const typename WeightSrc<real>::wt* wv_in = nullptr) {
   constexpr int TILE = TILE_THREADS * ITEMS;
-  constexpr int WIN = K3Smem<ITEMS>::WIN;
+  constexpr int WIN = K3SmemBlk<ITEMS>::WIN;
   double* Ps = sm.Ps;
   double* Ws = sm.Ws;
   int32_t* s_res = sm.s_res;
@@ -1387,8 +1411,488 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   return wrote_remote;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-synchronous scan + search.  A thread owns ITEMS consecutive particles, a warp 32*ITEMS, and
+// everything a particle needs -- its exact cumulative value, its offspring count, the end of the run
+// of repeated keys it starts -- lives in registers.  One block barrier publishes the warp totals;
+// from there on every warp expands ITS OWN particles into ITS OWN output range (the range is known
+// from the count at the warp's first cumulative value, no exchange of counts) through a private
+// shared-memory window: heads are scattered, each row of 32 outputs is filled by one ballot + one
+// indexed shuffle, and the row leaves as one coalesced store.  No cumulative values or weights in
+// shared memory (10 KB per block instead of 48), no block barrier in the expansion.
+// cdf_out == NULL: search (systematic / stratified), writes ancestors;
+// cdf_out != NULL: write the un-normalised CDF (multinomial), no search
+// ---------------------------------------------------------------------------------------------
+template <int ITEMS>
+struct K3Smem {
+  static constexpr int TILE = TILE_THREADS * ITEMS;
+  static constexpr int NW = TILE_THREADS / 32;
+  static constexpr int ROWS = ITEMS + (ITEMS >= 8 ? 2 : 1);  // rows of 32 outputs a warp stages per pass: its 32*ITEMS
+  static constexpr int WINW = 32 * ROWS;                      // particles have about 32*ITEMS offspring
+  int32_t s_res[NW][WINW];
+  u128 s_warp[NW];
+  u128 s_excl, s_tot, s_q, s_run;
+  unsigned long long s_key;
+  long long s_pend, s_jfinal;
+  double s_wnext, s_u, s_scale;
+  int s_tp, s_brk;
+  unsigned s_minw[NW];  // per-warp min weight of the tile (fp32 bits; non-negative floats order as integers)
+  int s_wbrk[NW];       // first particle of the warp that starts a new key (tiles with vanishing weights only)
+  static constexpr int HQ = 16;  // heavy particles (>= HEAVY offspring) of the tile: their ranges are filled by the whole block
+  int s_hq[HQ][3];      // first output, end, value
+  int s_hn;
+};
+
+// One tile in registers: the thread's weights and the cumulative values P_j = dbl128(exact prefix) of its ITEMS
+// consecutive particles, the value before the thread's / the warp's first particle, and the exact sum at the end of the
+// tile.  `excl` = exact sum of everything before the tile.  All threads call; LEAD: s_warp may still be read from an
+// earlier use (one more barrier).  The barrier inside also publishes what single threads of the caller wrote before.
+template <typename real, int ITEMS>
+struct TileRegs {
+  typename WeightSrc<real>::wt w[ITEMS];
+  double P[ITEMS];
+  double P_tstart, P_wstart;
+  u128 tile_end;
+};
+template <typename real, int ITEMS, bool LEAD>
+__device__ __forceinline__ void tile_scan_regs(const WeightSrc<real>& ws, int qb, u128 excl, long long tile0, long long N,
+                                               u128* s_warp, const typename WeightSrc<real>::wt* wv_in, TileRegs<real, ITEMS>& r) {
+  constexpr int NW = TILE_THREADS / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (wv_in != nullptr) {  // the caller already holds this thread's ITEMS weights (same values, same order)
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) r.w[j] = wv_in[j];
+  } else {
+    ws.template load<ITEMS>(tile0 + (long long)threadIdx.x * ITEMS, 1, N, r.w);
+  }
+  u128 e[ITEMS];
+  u128 run = make_u128(0, 0);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    run = add128(run, WeightSrc<real>::fix(r.w[j], qb));
+    e[j] = run;
+  }
+  u128 incl = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u128 o = shfl_up128(incl, d);
+    if (lane >= d) incl = add128(incl, o);
+  }
+  if (LEAD) __syncthreads();
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  u128 woff = excl, tend = excl;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const u128 v = s_warp[w];
+    tend = add128(tend, v);
+    woff = add128(woff, (w < wid) ? v : make_u128(0, 0));
+  }
+  u128 ex = shfl_up128(incl, 1);
+  if (lane == 0) ex = make_u128(0, 0);
+  const u128 off = add128(woff, ex);
+  r.P_wstart = dbl128(woff, qb);
+  r.P_tstart = dbl128(off, qb);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) r.P[j] = dbl128(add128(off, e[j]), qb);
+  r.tile_end = tend;
+}
+
+// Tile t of the scan + search once the exact sums are known: `tot` / `qsum` = sum of fix(w1) / of
+// fix(w1^2) over the whole filter, `key` = ordered key of the max log-weight, `excl` = exact sum of
+// everything before the tile.  Block 0 also updates ll and ESS.  PROTO3: called from the
+// three-launch step (zeroes the accumulators of the next observed step); the single-launch series
+// kernel keeps its own.  All threads of the block call; returns whether a peer's memory was written.
+template <typename real, int ITEMS, int KIND, bool PROTO3>
+__device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restrict__ logw, const double* __restrict__ direct,
+                                        long long N, FilterScalars* __restrict__ sc, const SumTables& tb, const Peers& pr,
+                                        const K3Ctl& ctl, const double* __restrict__ uarr, double* __restrict__ cdf_out, int t,
+                                        u128 tot, u128 qsum, unsigned long long key, u128 excl,
+                                        const typename WeightSrc<real>::wt* wv_in = nullptr) {
+  constexpr int TILE = TILE_THREADS * ITEMS;
+  constexpr int NW = K3Smem<ITEMS>::NW;
+  constexpr int ROWS = K3Smem<ITEMS>::ROWS;
+  constexpr int WINW = K3Smem<ITEMS>::WINW;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nt = tb.nt;
+  const long long Ng = (long long)pr.R * N;  // outputs of the whole (possibly sharded) filter
+  const PreScan ps = pre_scan(key, direct != nullptr);
+  const int qb = ps.qb;
+  const double total = dbl128(tot, qb);
+
+  // ---- thread 0: the resampling uniform and n / total; block 0: ll increment max + log(mean w1), ESS =
+  //      floor(1/sum wn^2); zero the accumulators of the next observed step.  Read after the barrier of the scan. ----
+  if (threadIdx.x == 0) {
+    double u;
+    if (ctl.use_u_inj) {
+      u = sc->u_inj;
+    } else {
+      uint4 v = philox4x32_10(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
+      u = u64_to_unit_double(v.x, v.y);
+    }
+    sm.s_u = u;
+    sm.s_scale = __ddiv_rn((double)Ng, total);
+    sm.s_pend = 0x7FFFFFFFFFFFFFFFll;
+    sm.s_hn = 0;
+  }
+  if (threadIdx.x == 64) {  // another warp than the one deriving the uniform: the two run side by side
+    if (t == 0) {
+      const double gmax = ps.gmax;
+      double incr = gmax + log(total / (double)Ng);
+      int flags = 0;
+      if (!(total > 0.0) || gmax != gmax || gmax - gmax != 0.0) {  // all weights zero / NaN / infinite max
+        incr = __longlong_as_double(0x7FF8000000000000ll);
+        flags |= FLAG_ZERO_TOTAL;
+      }
+      // sum (w/total)^2 = (exact sum w^2) / total^2; direct weights were pre-scaled by 2^-(96-qb)
+      const double tsc = __dmul_rn(total, __longlong_as_double((long long)(1023 - (96 - qb)) << 52));
+      const double s2 = __ddiv_rn(dbl128(qsum, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
+      const double inv = floor(1.0 / s2);
+      const int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
+      sc->gmax = gmax;
+      sc->total = total;
+      sc->qb = qb;
+      sc->ll_incr = incr;
+      if (ctl.add_ll) {
+        const double ll = sc->ll + incr;
+        sc->ll = ll;
+        sc->ess = ess;
+        if (ctl.ll_steps) ctl.ll_steps[ctl.step_slot] = ll;
+        if (ctl.ess_steps) ctl.ess_steps[ctl.step_slot] = ess;
+      }
+      if (flags) atomicOr(&sc->flags, flags);
+      if (PROTO3) {  // three-launch protocol: zero the accumulators of the next observed step
+        StepAcc* nx = &sc->acc[ctl.parity ^ 1];
+        nx->gmax_key = 0ull;
+        nx->tot = make_u128(0, 0);
+        nx->q = make_u128(0, 0);
+      }
+    }
+  }
+  if (PROTO3 && t < tb.ns && threadIdx.x == 1) {
+    tb.super_sum[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
+    tb.super_q[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
+  }
+
+  WeightSrc<real> ws{logw, direct, ps.gmax};
+  const long long tile0 = (long long)t * TILE;
+  const int tile_n = (int)min((long long)TILE, N - tile0);
+  const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
+  if (threadIdx.x == 32 && cdf_out == nullptr) {
+    // first weight after this tile (next tile, possibly the next rank's first particle); loaded here so
+    // that its latency hides behind the tile scan
+    double wn = 0.0;
+    if (t < nt - 1) wn = (double)ws(tile0 + TILE);
+    else if (pr.rank < pr.R - 1) wn = (double)WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[pr.rank + 1]), nullptr, ps.gmax}(0);
+    sm.s_wnext = wn;
+  }
+  TileRegs<real, ITEMS> r;
+  {
+    // the scan; before its barrier every warp leaves a lower bound (fp32, rounded down) of its smallest weight
+    typedef typename WeightSrc<real>::wt wt;
+    const long long base = tile0 + (long long)threadIdx.x * ITEMS;
+    wt wloc[ITEMS];
+    const wt* src = wv_in;
+    if (src == nullptr) {
+      ws.template load<ITEMS>(base, 1, N, wloc);
+      src = wloc;
+    }
+    float m = 3.4028234663852886e38f;
+    if (base + ITEMS <= N) {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) m = fminf(m, to_float_rd(src[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j)
+        if (base + j < N) m = fminf(m, to_float_rd(src[j]));
+    }
+    const unsigned mb = __reduce_min_sync(FULL, __float_as_uint(m));
+    if (lane == 0) sm.s_minw[wid] = mb;
+    tile_scan_regs<real, ITEMS, false>(ws, qb, excl, tile0, N, sm.s_warp, src, r);
+  }
+
+  if (cdf_out != nullptr) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const int idx = threadIdx.x * ITEMS + j;
+      if (idx < tile_n) cdf_out[tile0 + idx] = r.P[j];
+    }
+    return false;
+  }
+
+  bool wrote_remote = false;
+  // all weights zero / NaN (the reference divides by a zero total here and fails later): keep every
+  // particle as its own ancestor; FLAG_ZERO_TOTAL is already raised
+  const bool usable = (total > 0.0) && (total - total == 0.0);
+  if (!usable) {
+    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) pr.anc[pr.rank][tile0 + j] = (int32_t)((long long)pr.rank * N + tile0 + j);
+    return false;
+  }
+  // a tile whose weights are all zero owns no output: every cumulative value equals the one before the tile (a run that
+  // passes through it is resolved by the tile that holds its head).  Degenerate clouds consist mostly of such tiles.
+  if (!last_tile && r.tile_end.lo == excl.lo && r.tile_end.hi == excl.hi) return false;  // block-uniform
+  KFun<KIND> kf{sm.s_u, (double)Ng, ctl.inv_n, total, uarr, ctl.key0, ctl.key1, ctl.step};
+  const double c_end = dbl128(r.tile_end, qb);  // cumulative value of the tile's last particle (padding weighs nothing)
+  const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
+  // ---- offspring counts: c_j = #{outputs with key <= P_j}; particle j owns the outputs [c_{j-1}, c_j) ----
+  const double scale = sm.s_scale;
+  const long long lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_fast(dbl128(excl, qb), scale, Ng);
+  const double lo_d = (double)lo;
+  const int n_rel = (int)(Ng - lo);
+  int cr[ITEMS];  // counts relative to lo
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int idx = threadIdx.x * ITEMS + j;
+    cr[j] = (last_tile && idx >= tile_n - 1) ? n_rel : kf.count_rel(r.P[j], scale, Ng, lo, lo_d, n_rel);
+  }
+  // the count before the thread's first particle: the previous thread's last one; the warp's first thread evaluates
+  // the count at the warp's first cumulative value itself (the same integer the previous warp's last thread converts)
+  int cprev = __shfl_up_sync(FULL, cr[ITEMS - 1], 1);
+  {
+    const int idx_before = wid * 32 * ITEMS - 1;
+    const int c_w = (wid == 0) ? 0 : ((last_tile && idx_before >= tile_n - 1) ? n_rel : kf.count_rel(r.P_wstart, scale, Ng, lo, lo_d, n_rel));
+    if (lane == 0) cprev = c_w;
+  }
+  const int c0 = __shfl_sync(FULL, cprev, 0), c1 = __shfl_sync(FULL, cr[ITEMS - 1], 31);  // the warp's outputs [c0, c1)
+  const int n_out = last_tile ? n_rel : kf.count_rel(c_end, scale, Ng, lo, lo_d, n_rel);
+  const long long hi = lo + n_out;
+  // A key can only repeat where a weight is at most 2^-52 of the cumulative value before it (vanishes()).  If even the
+  // smallest weight of the tile is above 2^-52 of the tile's LAST cumulative value, no key of this tile repeats.
+  unsigned mm = sm.s_minw[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) mm = min(mm, sm.s_minw[w]);
+  const bool novanish = ctl.tie_first || (double)__uint_as_float(mm) > c_end * 2.220446049250313e-16;
+  // does the run of repeated keys at the end of this tile continue into the next tile?
+  const bool cont = !ctl.tie_first && !last_tile && vanishes(c_end, sm.s_wnext, total);
+  if (last_tile && threadIdx.x == 0 && kf(Ng - 1) > c_end) atomicOr(&sc->flags, FLAG_CLAMPED);  // reference would throw (m.head)
+
+  // ---- TreeMap: a duplicated key keeps the last particle inserted.  Particle p "breaks" when it starts a new key
+  //      (its weight does not vanish against the cumulative value before it); the offspring of j go to the particle
+  //      before the next break after j.  bmask: breaks among the thread's particles; nb_after: first break behind them.
+  unsigned bmask = (1u << ITEMS) - 1u;
+  int nb_after = 0;
+  if (!novanish) {  // block-uniform
+    bmask = 0u;
+    int first_brk = 0x7FFFFFFF;
+#pragma unroll
+    for (int j = ITEMS - 1; j >= 0; --j) {
+      const int idx = threadIdx.x * ITEMS + j;
+      const double before = j ? r.P[j - 1] : r.P_tstart;
+      const bool brk = (idx < tile_n) && !vanishes(before, (double)r.w[j], total);
+      if (brk) {
+        bmask |= 1u << j;
+        first_brk = idx;
+      }
+    }
+    int sfx = first_brk;  // first break in this thread or a later one of the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_down_sync(FULL, sfx, d);
+      if (lane + d < 32) sfx = min(sfx, o);
+    }
+    nb_after = __shfl_down_sync(FULL, sfx, 1);
+    if (lane == 31) nb_after = 0x7FFFFFFF;
+    if (lane == 0) sm.s_wbrk[wid] = sfx;
+    __syncthreads();
+    if (nb_after == 0x7FFFFFFF) {
+#pragma unroll
+      for (int w = 1; w < NW; ++w)
+        if (w > wid) nb_after = min(nb_after, sm.s_wbrk[w]);
+      if (nb_after == 0x7FFFFFFF) nb_after = tile_n;  // the run reaches the end of the tile
+    }
+  }
+  if (cont) {  // block-uniform: the first output whose run reaches the end of the tile
+    int nb = novanish ? 0 : nb_after;
+#pragma unroll
+    for (int j = ITEMS - 1; j >= 0; --j) {
+      const int idx = threadIdx.x * ITEMS + j;
+      const int prev = j ? cr[j - 1] : cprev;
+      const int val = novanish ? idx : nb - 1;
+      if (cr[j] > prev && val == tile_n - 1) atomicMin(&sm.s_pend, lo + prev);
+      if ((bmask >> j) & 1u) nb = idx;
+    }
+  }
+
+  // ---- expansion: the warp's particles into the warp's outputs [c0, c1), WINW per pass.  Every particle with
+  //      offspring drops its value at the head of its range; a row of 32 outputs takes, per lane, the nearest head at
+  //      or below it (ballot + indexed shuffle), else the value carried over from the row before.  A particle with many
+  //      offspring is not staged at all: its range is one value, written 32 outputs per store by the warp, or -- from
+  //      HEAVY offspring on -- queued for the whole block. -----------------------------------------------------------
+  constexpr int LONG_RUN = 64, HEAVY = 1024;
+  auto store_out = [&](int o, int val) {
+    const int32_t v = (int32_t)(gbase + val);
+    if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+      const long long i = lo + o;
+      const unsigned q = owner_of(pr, (unsigned)i);
+      pr.anc[q][i - (long long)q * N] = v;
+      wrote_remote |= (q != pr.rank);
+    } else {
+      (pr.anc[0] + lo)[o] = v;
+    }
+  };
+  {
+    int32_t* const res = sm.s_res[wid];
+    bool has_long = false;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) has_long |= (cr[j] - (j ? cr[j - 1] : cprev)) >= LONG_RUN;
+    has_long = __any_sync(FULL, has_long);
+    int carry = 0;
+    for (int w0 = c0; w0 < c1;) {  // warp-uniform
+      if (has_long) {
+        // the particle that owns output w0 (exactly one in the warp): does its range run on for LONG_RUN outputs?
+        int own_end = 0, own_val = 0;
+        bool mine = false;
+        int nb = nb_after;
+#pragma unroll
+        for (int j = ITEMS - 1; j >= 0; --j) {
+          const int idx = threadIdx.x * ITEMS + j;
+          const int prev = j ? cr[j - 1] : cprev;
+          if (prev <= w0 && w0 < cr[j]) {
+            mine = true;
+            own_end = cr[j];
+            own_val = novanish ? idx : nb - 1;
+          }
+          if ((bmask >> j) & 1u) nb = idx;
+        }
+        const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
+        own_end = __shfl_sync(FULL, own_end, src & 31);
+        own_val = __shfl_sync(FULL, own_val, src & 31);
+        if (src >= 0 && own_end - w0 >= LONG_RUN) {
+          bool queued = false;
+          if (own_end - w0 >= HEAVY) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&sm.s_hn, 1);
+            slot = __shfl_sync(FULL, slot, 0);
+            if (slot < K3Smem<ITEMS>::HQ) {
+              if (lane == 0) { sm.s_hq[slot][0] = w0; sm.s_hq[slot][1] = own_end; sm.s_hq[slot][2] = own_val; }
+              queued = true;
+            }
+          }
+          if (!queued)
+            for (int o = w0 + lane; o < own_end; o += 32) store_out(o, own_val);
+          w0 = own_end;
+          continue;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) res[k * 32 + lane] = -1;
+      __syncwarp();
+      {
+        int nb = nb_after;
+#pragma unroll
+        for (int j = ITEMS - 1; j >= 0; --j) {
+          const int idx = threadIdx.x * ITEMS + j;
+          const int prev = j ? cr[j - 1] : cprev;
+          const unsigned rel = (unsigned)(prev - w0);
+          if (cr[j] > prev && rel < (unsigned)WINW) res[rel] = novanish ? idx : nb - 1;
+          if ((bmask >> j) & 1u) nb = idx;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) {
+        const int o = w0 + k * 32 + lane;
+        if (w0 + k * 32 < c1) {  // warp-uniform
+          const int v = res[k * 32 + lane];
+          const unsigned below = __ballot_sync(FULL, v >= 0) & (0xFFFFFFFFu >> (31 - lane));
+          int got = __shfl_sync(FULL, v, (31 - __clz((int)below)) & 31);
+          got = below ? got : carry;
+          carry = __shfl_sync(FULL, got, 31);
+          if (o < c1) store_out(o, got);
+        }
+      }
+      __syncwarp();
+      w0 += WINW;
+    }
+  }
+  __syncthreads();  // the heavy queue is complete (and s_pend final)
+  {
+    const int hn = min(sm.s_hn, K3Smem<ITEMS>::HQ);
+    for (int h = 0; h < hn; ++h) {
+      const int a0 = sm.s_hq[h][0], a1 = sm.s_hq[h][1], val = sm.s_hq[h][2];
+      for (int o = a0 + threadIdx.x; o < a1; o += TILE_THREADS) store_out(o, val);
+    }
+  }
+  if (!cont) return wrote_remote;  // block-uniform
+  const long long pend = sm.s_pend;
+  if (pend < hi) {
+    // The selected run of repeated keys continues past this tile; its last element is the ancestor.
+    // Walk forward over the GLOBAL tile sequence (rank-major): whole tiles are skipped from the
+    // tables when every weight in them is strictly below half an ulp of the running (normalised)
+    // value and the value stays in its binade, otherwise the tile is recomputed.
+    const long long gnt = (long long)pr.R * nt;
+    if (tb.ll != nullptr) __threadfence();  // flagged slots were polled with relaxed loads: acquire before reading the peers' log-weights
+    if (threadIdx.x == 0) { sm.s_tp = pr.rank * nt + t + 1; sm.s_run = r.tile_end; sm.s_jfinal = -1; }
+    __syncthreads();
+    for (;;) {
+      if (threadIdx.x == 0) {
+        long long tp = sm.s_tp;
+        u128 run = sm.s_run;
+        while (tp < gnt) {
+          const int q = (int)(tp / nt), tl = (int)(tp % nt);
+          const u128 tsum = walk_tile_sum(tb, pr, q, tl);  // L2: another block wrote it
+          const double mxw = walk_tile_maxw(tb, pr, q, tl);
+          const u128 nrun = add128(run, tsum);
+          const double c = __ddiv_rn(dbl128(run, qb), total), ce = __ddiv_rn(dbl128(nrun, qb), total);
+          const long long cb = __double_as_longlong(c), eb = __double_as_longlong(ce);
+          const bool same_binade = (cb >> 52) == (eb >> 52) && ((cb >> 52) & 0x7ff) > 54;
+          const double half_ulp = same_binade ? __longlong_as_double((((cb >> 52) & 0x7ff) - 53) << 52) : 0.0;
+          if (same_binade && __ddiv_rn(mxw, total) < half_ulp) { run = nrun; ++tp; } else break;
+        }
+        sm.s_tp = (int)tp;
+        sm.s_run = run;
+        sm.s_brk = TILE;
+        if (tp >= gnt) sm.s_jfinal = Ng - 1;
+      }
+      __syncthreads();
+      if (sm.s_jfinal >= 0) break;
+      const int tp = sm.s_tp;
+      const int q = tp / nt, tl = tp % nt;
+      const u128 run0 = sm.s_run;
+      WeightSrc<real> wq{(q == pr.rank) ? logw : reinterpret_cast<const real*>(pr.logw[q]), direct, ps.gmax};
+      TileRegs<real, ITEMS> rq;
+      tile_scan_regs<real, ITEMS, true>(wq, qb, run0, (long long)tl * TILE, N, sm.s_warp, nullptr, rq);
+      const int tn = (int)min((long long)TILE, N - (long long)tl * TILE);
+      // first element of tile tp that does NOT vanish against its predecessor's value
+#pragma unroll
+      for (int j = ITEMS - 1; j >= 0; --j) {
+        const int idx = threadIdx.x * ITEMS + j;
+        const double before = j ? rq.P[j - 1] : rq.P_tstart;
+        if (idx < tn && !vanishes(before, (double)rq.w[j], total)) atomicMin(&sm.s_brk, idx);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (sm.s_brk < tn) sm.s_jfinal = (long long)q * N + (long long)tl * TILE + sm.s_brk - 1;
+        else if (tp == gnt - 1) sm.s_jfinal = Ng - 1;
+        else {
+          sm.s_run = rq.tile_end;  // thread 0 holds the exact sum at the end of tile tp
+          sm.s_tp = tp + 1;
+        }
+      }
+      __syncthreads();
+      if (sm.s_jfinal >= 0) break;
+    }
+    const long long jfinal = sm.s_jfinal;
+    for (long long i = pend + threadIdx.x; i < hi; i += TILE_THREADS) {
+      if (pr.R > 1) {
+        const unsigned q = owner_of(pr, (unsigned)i);
+        pr.anc[q][i - (long long)q * N] = (int32_t)jfinal;
+        wrote_remote |= (q != pr.rank);
+      } else {
+        pr.anc[0][i] = (int32_t)jfinal;
+      }
+    }
+  }
+  return wrote_remote;
+}
+
 #ifndef CSSM_K3_MINBLOCKS
+#ifdef CSSM_K3_WS
+#define CSSM_K3_MINBLOCKS 3
+#else
 #define CSSM_K3_MINBLOCKS 4
+#endif
 #endif
 // FLAT: the sum tables have no super tiles (SumTables::ns == 0, single rank) -- a separate instantiation, so that the
 // two-level kernel of the large clouds keeps its register allocation
@@ -1397,7 +1901,11 @@ __global__ void __launch_bounds__(TILE_THREADS, CSSM_K3_MINBLOCKS)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
               double* __restrict__ cdf_out) {
+#ifdef CSSM_K3_WS
   __shared__ K3Smem<ITEMS> sm;
+#else
+  __shared__ K3SmemBlk<ITEMS> sm;
+#endif
   u128& s_excl = sm.s_excl;
   u128& s_tot = sm.s_tot;
   u128& s_q = sm.s_q;
@@ -1476,8 +1984,13 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
     if (threadIdx.x == 0) s_excl = add128(s_excl, local);
   }
   __syncthreads();
+#ifdef CSSM_K3_WS
   const bool wrote_remote = k3_tile<real, ITEMS, KIND, true>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
                                                              s_key, s_excl);
+#else
+  const bool wrote_remote = k3_tile_blk<real, ITEMS, KIND, true>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
+                                                                 s_key, s_excl);
+#endif
   if (cdf_out != nullptr) return;
   if (pr.R > 1) {  // "resampling done": the last block tells the peers this step is complete
     if (wrote_remote) __threadfence_system();

@@ -1,4 +1,6 @@
-// CssmNative.scala -- @native declarations bound by jvm/cssm_jni.c.  NOT COMPILED IN THIS IMAGE.
+// CssmNative.scala -- @native declarations bound by jvm/cssm_jni.c.  NOT COMPILED IN THIS IMAGE (no JVM); the C side is
+// compiled and exercised through a fake JNIEnv by tests/test_jni_shim.py, which also checks that every @native method
+// below has its Java_com_github_jonnylaw_gpu_CssmNative_00024_<name> entry point and vice versa.
 package com.github.jonnylaw.gpu
 
 object CssmNative {
@@ -14,6 +16,13 @@ object CssmNative {
   @native def filterStep(h: Long, t: Double, hasObs: Boolean, y: Double, essOut: Array[Int]): Double
   @native def filterLl(h: Long, t: Array[Double], y: Array[Double], hasObs: Array[Byte]): Double
   @native def filterRun(h: Long, t: Array[Double], y: Array[Double], hasObs: Array[Byte], statesOut: Array[Double]): Double
+  /** the resident-series form PMMH uses: load once, then filterSetParams + filterLlResident per proposal */
+  @native def filterLoadSeries(h: Long, t: Array[Double], y: Array[Double], hasObs: Array[Byte]): Unit
+  @native def filterLlResident(h: Long): Double
+  @native def filterSeriesLen(h: Long): Long
+  /** 0 = the reference's TreeMap rule (default), 1 = first index (include/cssm.h, cssm_tie_rule) */
+  @native def filterSetTieRule(h: Long, rule: Int): Unit
+  @native def filterReseed(h: Long, seed: Long, streamId: Long): Unit
   @native def filterGetParticles(h: Long, out: Array[Double]): Unit
   @native def filterSeriesMode(h: Long, mode: Int): Unit
   /** out = mean[d] | lower[d] | upper[d] | gammaLower, gammaUpper (ParticleFilter.getIntervals on the device) */

@@ -166,12 +166,44 @@ final case class GpuResample(kind: Int, device: Int = 0) {
 }
 
 object FilterGpu {
-  /** BootstrapFilter for PMMH (model/PMMH.scala:58): one handle, re-parameterised per proposal.
-    * `build` turns Parameters into (list of un-composed models, composed model). */
-  def bootstrap(build: Parameters => (List[Model], Model), data: Vector[Data], resampleKind: Int, n: Int)
-      : BootstrapFilter[Parameters, StateSpace[State]] = Reader { p =>
-    val (ms, m) = build(p)
-    val f = FilterGpu(ms, m, resampleKind)
-    try f.filter(data, n) finally f.close()
+  /** BootstrapFilter for PMMH (model/PMMH.scala:58, examples/DetermineParameters.scala:67-72) over ONE device handle
+    * for the life of the chain: the observations are uploaded once (filterLoadSeries), every proposal re-parameterises
+    * the handle (filterSetParams: same shapes, no reallocation, the per-observation constants are rebuilt and sent
+    * asynchronously from pinned memory) and runs the resident series (filterLlResident); `state._2.last`, all that
+    * mhStep reads of the filtered states (model/PMMH.scala:76), is one particle of the final cloud (filterSampleOne).
+    * `build` turns Parameters into (list of un-composed models, composed model).  Close it when the chain is done. */
+  final class Bootstrap(build: Parameters => (List[Model], Model), data: Vector[Data], resampleKind: Int, n: Int,
+      precision: Int = 0, dtype: Int = 0, device: Int = 0, seed: Long = 0L, streamId: Long = 0L) extends AutoCloseable {
+    private var handle: Long = 0L
+    private val t = data.map(_.t).toArray
+    private val y = data.map(_.observation.getOrElse(0.0)).toArray
+    private val ho = data.map(d => (if (d.observation.isDefined) 1 else 0).toByte).toArray
+    private val tLast = data.last.t
+
+    private def eval(p: Parameters): (LogLikelihood, Vector[StateSpace[State]]) = {
+      val (ms, _) = build(p)
+      val desc = GpuDesc(ms, precision)
+      if (handle == 0L) {
+        handle = CssmNative.filterCreate(desc.kinds, desc.params, desc.obsKind, desc.scale.isDefined, desc.scale.getOrElse(0.0),
+          desc.stepMode, desc.precision, desc.obsDf, n.toLong, resampleKind, dtype, device, seed, streamId)
+        CssmNative.filterLoadSeries(handle, t, y, ho)
+      } else {
+        CssmNative.filterSetParams(handle, desc.kinds, desc.params, desc.obsKind, desc.scale.isDefined,
+          desc.scale.getOrElse(0.0), desc.stepMode, desc.precision, desc.obsDf)
+      }
+      val ll = CssmNative.filterLlResident(handle)
+      val dims = ms.map(_.sde.dimension)
+      val x = new Array[Double](dims.sum)
+      CssmNative.filterSampleOne(handle, x)
+      var off = 0
+      val state = dims.map { dim => val v = DenseVector(x.slice(off, off + dim)); off += dim; Tree.leaf(v): State }.reduceLeft(_ +++ _)
+      (ll, Vector(StateSpace(tLast, state)))
+    }
+    /** what MetropolisHastings.pf expects */
+    val reader: BootstrapFilter[Parameters, StateSpace[State]] = Reader(eval)
+    def close(): Unit = if (handle != 0L) { CssmNative.filterDestroy(handle); handle = 0L }
   }
+  def bootstrap(build: Parameters => (List[Model], Model), data: Vector[Data], resampleKind: Int, n: Int,
+      precision: Int = 0, dtype: Int = 0, device: Int = 0, seed: Long = 0L, streamId: Long = 0L): Bootstrap =
+    new Bootstrap(build, data, resampleKind, n, precision, dtype, device, seed, streamId)
 }

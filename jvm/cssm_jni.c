@@ -1,8 +1,11 @@
 /* cssm_jni.c -- JNI shim, one-to-one over include/cssm.h.
  *
- * NOT COMPILED IN THIS IMAGE: there is no JDK here (no jni.h).  On a machine with a JDK:
+ * On a machine with a JDK:
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../include \
  *       cssm_jni.c -L../composablestatespacemodels_b200/csrc -lcssm_gpu -o libcssm_jni.so
+ * This image has no JDK: tests/test_jni_shim.py compiles this file with -Wall -Werror against the stand-in header
+ * jvm/jni_stub/jni.h (same names and signatures as the JDK's), links it against libcssm_gpu.so and drives the
+ * Java_... entry points through a fake JNIEnv (tests/jni_harness.c).
  * Java side: jvm/CssmNative.scala (`@native` methods of object CssmNative).
  * Every non-zero status is rethrown as RuntimeException(cssm_last_error()), which is how the
  * reference reports errors (thrown exceptions, model/Sde.scala:183, model/Model.scala:46).
@@ -71,7 +74,44 @@ JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterSetPa
 }
 
 JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterDestroy(JNIEnv* env, jobject self, jlong h) {
+  (void)env; (void)self;
   cssm_filter_destroy((cssm_filter_t*)(intptr_t)h);
+}
+/* the resident-series form PMMH uses (model/PMMH.scala:71 evaluates the same data at every proposal):
+ * filterLoadSeries once, then filterSetParams + filterLlResident per proposal */
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterLoadSeries(
+    JNIEnv* env, jobject self, jlong h, jdoubleArray t, jdoubleArray y, jbyteArray hasObs) {
+  (void)self;
+  jsize T = (*env)->GetArrayLength(env, t);
+  jdouble* tp = (*env)->GetDoubleArrayElements(env, t, NULL);
+  jdouble* yp = (*env)->GetDoubleArrayElements(env, y, NULL);
+  jbyte* hp = (*env)->GetByteArrayElements(env, hasObs, NULL);
+  int rc = cssm_filter_load_series((cssm_filter_t*)(intptr_t)h, tp, yp, (const uint8_t*)hp, T);
+  (*env)->ReleaseDoubleArrayElements(env, t, tp, JNI_ABORT);
+  (*env)->ReleaseDoubleArrayElements(env, y, yp, JNI_ABORT);
+  (*env)->ReleaseByteArrayElements(env, hasObs, hp, JNI_ABORT);
+  check(env, rc);
+}
+JNIEXPORT jdouble JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterLlResident(JNIEnv* env, jobject self, jlong h) {
+  (void)self;
+  double ll = 0;
+  check(env, cssm_filter_ll_resident((cssm_filter_t*)(intptr_t)h, &ll, NULL, NULL));
+  return ll;
+}
+JNIEXPORT jlong JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterSeriesLen(JNIEnv* env, jobject self, jlong h) {
+  (void)self;
+  int64_t n = 0;
+  check(env, cssm_filter_series_len((const cssm_filter_t*)(intptr_t)h, &n));
+  return n;
+}
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterSetTieRule(JNIEnv* env, jobject self, jlong h, jint rule) {
+  (void)self;
+  check(env, cssm_filter_set_tie_rule((cssm_filter_t*)(intptr_t)h, rule));
+}
+JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterReseed(JNIEnv* env, jobject self, jlong h, jlong seed,
+                                                                                   jlong streamId) {
+  (void)self;
+  check(env, cssm_filter_reseed((cssm_filter_t*)(intptr_t)h, (uint64_t)seed, (uint64_t)streamId));
 }
 JNIEXPORT void JNICALL Java_com_github_jonnylaw_gpu_CssmNative_00024_filterInit(JNIEnv* env, jobject self, jlong h, jdouble t0) {
   check(env, cssm_filter_init((cssm_filter_t*)(intptr_t)h, t0));

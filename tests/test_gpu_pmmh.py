@@ -304,7 +304,9 @@ def test_filter_stream_is_the_scan_of_step_filter():
     assert states[8].ll == states[7].ll and states[8].ess == states[7].ess           # None observation (:121)
     g = Filter(mod, Resampling.systematicResampling, dtype=_abi.F64, seed=13)
     assert g.llFilter(data, N) == states[-1].ll
+    g._handle.reseed(13, 0)                            # the same Philox streams once more, now with the per-step values
     ll, lls, ess = g._handle.ll_resident(steps=True)
+    assert ll == states[-1].ll
     np.testing.assert_array_equal(lls, [s.ll for s in states[1:]])
     np.testing.assert_array_equal(ess, [s.ess for s in states[1:]])
     assert states[-1].particles.shape == (N, 1)        # the newest state owns the handle's cloud
