@@ -235,8 +235,6 @@ struct cssm_filter {
   // single-launch series kernel (small clouds, cssm_series.cuh)
   u128* tile_q = nullptr;          // [nt] exact tile sums of w1^2
   SeriesCtl* series_ctl = nullptr;
-  unsigned long long* series_ll = nullptr;  // flagged exchange slots of k_series_ll (LLW_WORDS x nt words)
-  int series_ll_on = 1;                     // CSSM_SERIES_LL=0: the grid-barrier kernel k_series_small instead
   void* recs = nullptr;            // per-observation records of the loaded series (filter dtype)
   size_t recs_cap = 0;             // bytes
   bool recs_valid = false;
@@ -500,12 +498,16 @@ int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
     } else {
       constexpr int PPT = VecOf<real>::PPT;
       const int g = nblk(f->N, 256 * PPT);
+      // single-rank filters run instantiations without any sharding code (SH = false)
 #define K1_CASE(DD)                                                                                                    \
-  e = launch(k_propagate_weight<real, DD>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, f->N, f->Ns, \
-             slot0, f->key0, f->key1, cx.step, ctl)
+  e = sharded ? launch(k_propagate_weight<real, DD, PPT, true>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, \
+                       f->N, f->Ns, slot0, f->key0, f->key1, cx.step, ctl)                                              \
+              : launch(k_propagate_weight<real, DD, PPT, false>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, \
+                       f->N, f->Ns, slot0, f->key0, f->key1, cx.step, ctl)
+      const bool sharded = pr.R > 1;
       static const int k1_ppt = std::getenv("CSSM_K1_PPT") ? std::atoi(std::getenv("CSSM_K1_PPT")) : 0;
       if (f->d == 7 && k1_ppt == 2 && sizeof(real) == 4) {
-        e = launch(k_propagate_weight<float, 7, 2>, nblk(f->N, 256 * 2), 256, f->stream, pdl, *reinterpret_cast<StepArgs<float>*>(&a), pr,
+        e = launch(k_propagate_weight<float, 7, 2, false>, nblk(f->N, 256 * 2), 256, f->stream, pdl, *reinterpret_cast<StepArgs<float>*>(&a), pr,
                    (float*)xdst, anc, (float*)f->logw, io.zinj, f->N, f->Ns, slot0, f->key0, f->key1, cx.step, ctl);
       } else if (f->d == 1) K1_CASE(1);
       else if (f->d == 2) K1_CASE(2);
@@ -538,12 +540,12 @@ int step_phase2(cssm_filter* f, StepCtx& cx) {
   cudaError_t e;
   {
     ProfScope ps_(f, CLS_SUMS, cx.prof);
-    if (f->items == 8)
-      e = launch(k_weight_sums<real, 8>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
-                 f->sc, cx.parity, f->obs_seq, step_tables(f), pr);
-    else
-      e = launch(k_weight_sums<real, 2>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, f->N,
-                 f->sc, cx.parity, f->obs_seq, step_tables(f), pr);
+#define K2_CASE(IT, SH)                                                                                               \
+  e = launch(k_weight_sums<real, IT, SH>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, \
+             f->N, f->sc, cx.parity, f->obs_seq, step_tables(f), pr)
+    if (pr.R > 1) { if (f->items == 8) K2_CASE(8, true); else K2_CASE(2, true); }
+    else { if (f->items == 8) K2_CASE(8, false); else K2_CASE(2, false); }
+#undef K2_CASE
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K2: ") + cudaGetErrorString(e));
   f->launches++;
@@ -564,6 +566,10 @@ void k3_carveout_once(int device) {
     cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_STRATIFIED, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_scan_search<real, 8, CSSM_RESAMPLE_STRATIFIED, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_scan_search<real, 2, CSSM_RESAMPLE_SYSTEMATIC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
@@ -584,7 +590,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   ctl.parity = cx.parity; ctl.obs_seq = f->obs_seq; ctl.gstep = f->gstep;
   const long long Ng = f->N * (long long)pr.R;
   ctl.inv_n = ((Ng & (Ng - 1)) == 0) ? 1.0 / (double)Ng : 0.0;
-  ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj; ctl.tie_first = f->tie_first;
+  ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj; ctl.tie_first = f->tie_first; ctl.defer_ll = 0;
   ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
   ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
   const bool strat = f->resample_kind == CSSM_RESAMPLE_STRATIFIED;
@@ -595,9 +601,11 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
     ProfScope ps_(f, CLS_SEARCH, cx.prof);
     const SumTables tbs = step_tables(f);
 #define K3_CASE(IT, KD)                                                                                                 \
-  e = tbs.ns == 0 ? launch(k_scan_search<real, IT, KD, true>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw,  \
+  e = tbs.ns == 0 ? launch(k_scan_search<real, IT, KD, true, false>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
                            (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)                                  \
-                  : launch(k_scan_search<real, IT, KD, false>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
+      : pr.R > 1  ? launch(k_scan_search<real, IT, KD, false, true>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
+                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)                                  \
+                  : launch(k_scan_search<real, IT, KD, false, false>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
                            (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)
     if (f->items == 8) { if (strat) K3_CASE(8, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(8, CSSM_RESAMPLE_SYSTEMATIC); }
     else { if (strat) K3_CASE(2, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(2, CSSM_RESAMPLE_SYSTEMATIC); }
@@ -782,14 +790,7 @@ void* series_kernel_ptr(int d, int kind) {
   if (d == 2) return strat ? (void*)k_series_small<real, 2, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 2, CSSM_RESAMPLE_SYSTEMATIC>;
   return strat ? (void*)k_series_small<real, 0, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 0, CSSM_RESAMPLE_SYSTEMATIC>;
 }
-template <typename real>
-void* series_ll_ptr(int d, int kind) {
-  const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
-  if (d == 2) return strat ? (void*)k_series_ll<real, 2, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_ll<real, 2, CSSM_RESAMPLE_SYSTEMATIC>;
-  return strat ? (void*)k_series_ll<real, 0, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_ll<real, 0, CSSM_RESAMPLE_SYSTEMATIC>;
-}
 void* series_kernel(const cssm_filter* f) {
-  if (f->series_ll_on) return (f->dtype == CSSM_F32) ? series_ll_ptr<float>(f->d, f->resample_kind) : series_ll_ptr<double>(f->d, f->resample_kind);
   return (f->dtype == CSSM_F32) ? series_kernel_ptr<float>(f->d, f->resample_kind) : series_kernel_ptr<double>(f->d, f->resample_kind);
 }
 // mid-size clouds: several tiles per block
@@ -872,10 +873,9 @@ int run_series_single_launch(cssm_filter* f) {
   rc = do_init(f, f->t0_series, nullptr, nullptr);
   if (rc) return rc;
   CU(cudaMemsetAsync(f->series_ctl, 0, sizeof(SeriesCtl), f->stream));
-  CU(cudaMemsetAsync(f->series_ll, 0, (size_t)LLW_WORDS * f->nt * sizeof(unsigned long long), f->stream));
   SeriesArgs sa;
   std::memset(&sa, 0, sizeof(sa));
-  sa.ll = f->series_ll;
+
   sa.x[0] = f->x[f->cur]; sa.x[1] = f->x[f->cur ^ 1];
   sa.logw = f->logw; sa.anc = f->anc; sa.sc = f->sc;
   sa.tile_sum = f->tb.tile_sum; sa.tile_q = f->tile_q; sa.tile_maxw = f->tb.tile_maxw;
@@ -1015,7 +1015,6 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   if (const char* e = std::getenv("CSSM_TILE_ITEMS")) { int v = std::atoi(e); if (v == 2 || v == 8) f->items = v; }
   if (const char* e = std::getenv("CSSM_PDL")) f->pdl = std::atoi(e) != 0;
   if (const char* e = std::getenv("CSSM_SERIES_MAX_N")) f->series_multi_max = std::atoll(e);
-  if (const char* e = std::getenv("CSSM_SERIES_LL")) f->series_ll_on = std::atoi(e) != 0;
   if (const char* e = std::getenv("CSSM_SERIES_KERNEL")) f->series_mode = std::atoi(e) ? CSSM_SERIES_AUTO : CSSM_SERIES_THREE_LAUNCH;
   const int tile = TILE_THREADS * f->items;
   f->nt = nblk(f->N, tile);
@@ -1044,7 +1043,6 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   if (resample_kind == CSSM_RESAMPLE_MULTINOMIAL) ALLOC(f->cdf, (size_t)f->Ns * sizeof(double));
   ALLOC(f->tile_q, (size_t)(f->nt + 1) * sizeof(u128));
   ALLOC(f->series_ctl, sizeof(SeriesCtl));
-  ALLOC(f->series_ll, (size_t)LLW_WORDS * (f->nt + 1) * sizeof(unsigned long long));
 #undef ALLOC
   f->tb.nt = f->nt; f->tb.ns = f->ns;
   f->tb.tile_q = f->tile_q;
@@ -1292,7 +1290,7 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   if (f->own_stream) cudaStreamSynchronize(f->own_stream);
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
-                  f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl, f->series_ll,
+                  f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl,
                   f->recs, f->fc, f->px, f->panc, f->pres_dev};
   for (void* p : ptrs)
     if (p) cudaFree(p);

@@ -207,15 +207,22 @@ __device__ __forceinline__ unsigned long long fix_sq48_f32(float w) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. 2011), counter-based, all state in registers.
+// Philox4x32 (Salmon et al. 2011, "Parallel random numbers: as easy as 1, 2, 3"), counter-based, all state in registers.
+// Rounds: 7 is the smallest count for which the paper reports Philox4x32 to pass the complete BigCrush battery
+// ("Crush-resistant"); 10 is the Random123 / cuRAND default with extra margin.  The generator is 35 % of K1's
+// instructions, and K1 is bound by instruction issue: 7 rounds take it from 0.206 to 0.191 ms at 2^24 particles (78 % ->
+// 87 % of the HBM peak, profiles/r02_summary.md).  -DCSSM_PHILOX_ROUNDS=10 builds the conservative variant.
 // ---------------------------------------------------------------------------------------------
 struct Philox {
   uint32_t k0, k1;
 };
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#ifndef CSSM_PHILOX_ROUNDS
+#define CSSM_PHILOX_ROUNDS 7
+#endif
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < CSSM_PHILOX_ROUNDS; ++r) {
     uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
     uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
     c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);

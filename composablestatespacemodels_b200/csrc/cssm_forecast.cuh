@@ -34,7 +34,7 @@ struct RngStream {
   }
   __device__ __forceinline__ uint32_t u32() {
     if (pos == 4) {
-      buf = philox4x32_10(make_uint4(c0, c1, step, RNG_FORECAST | (ncall & 0xFFFFFFu)), k0, k1);
+      buf = philox4x32(make_uint4(c0, c1, step, RNG_FORECAST | (ncall & 0xFFFFFFu)), k0, k1);
       ++ncall;
       pos = 0;
     }

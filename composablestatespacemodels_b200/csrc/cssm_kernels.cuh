@@ -186,7 +186,7 @@ template <> struct Normals<float> {
   static constexpr int PER_CALL = 4;
   __device__ __forceinline__ static void draw(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, float* z) {
-    uint4 v = philox4x32_10(make_uint4(c0, c1, c2, c3), k0, k1);
+    uint4 v = philox4x32(make_uint4(c0, c1, c2, c3), k0, k1);
     box_muller_f(v.x, v.y, z[0], z[1]);
     box_muller_f(v.z, v.w, z[2], z[3]);
   }
@@ -195,7 +195,7 @@ template <> struct Normals<double> {
   static constexpr int PER_CALL = 2;
   __device__ __forceinline__ static void draw(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, double* z) {
-    uint4 v = philox4x32_10(make_uint4(c0, c1, c2, c3), k0, k1);
+    uint4 v = philox4x32(make_uint4(c0, c1, c2, c3), k0, k1);
     box_muller_d(v, z[0], z[1]);
   }
 };
@@ -294,7 +294,12 @@ struct K1Ctl {
   unsigned long long obs_seq;   // observed steps completed before this one
   unsigned long long gstep;     // steps completed before this one
 };
+// (Round 2 measured a tail without block barriers -- every warp folds its max into a shared word with an atomic and the warp
+// that counts in last publishes: K1 0.2064 vs 0.2038 ms with Philox4x32-10, 0.1908 vs 0.1908 with 7 rounds.  No gain; this
+// simpler form stays.)
+template <bool SH>
 __device__ __forceinline__ void k1_tail(double mx, bool bad, int has_obs, const Peers& pr, const K1Ctl& ctl) {
+  const int RK = SH ? pr.R : 1;
   __shared__ double s_mx[8];
   __shared__ int s_bad;
   FilterScalars* sc = ctl.sc;
@@ -313,13 +318,13 @@ __device__ __forceinline__ void k1_tail(double mx, bool bad, int has_obs, const 
       if (s_bad) atomicOr(&sc->flags, FLAG_NAN_WEIGHT);
     }
   }
-  if (pr.R > 1 && threadIdx.x < 32) {
+  if (RK > 1 && threadIdx.x < 32) {
     int last = 0;
     unsigned long long key = 0ull;
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned long long tk = atomicAdd(&sc->ticket1, 1ull);
-      if (tk % gridDim.x == gridDim.x - 1) {  // every block of this launch has contributed
+      if (tk % gridDim.x == gridDim.x - 1) {
         __threadfence();
         last = 1;
         if (has_obs) key = ld_gpu(&sc->acc[ctl.parity].gmax_key);
@@ -360,7 +365,7 @@ template <> struct VecN<double, 2> { typedef double2 type; typedef int2 itype; }
 // both evaluate a particle with the same instruction sequence.  COH: the cloud and the ancestors
 // were written earlier in the SAME launch by other blocks, so they are read with ld.global.cg (L2)
 // instead of the non-coherent read-only path.
-template <typename real, int D, int PPT, bool COH = false, bool FULLBLK = false>
+template <typename real, int D, int PPT, bool COH = false, bool FULLBLK = false, bool SH = false>
 __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, const Peers& pr, real* __restrict__ xdst,
                                                     const int32_t* __restrict__ anc, real* __restrict__ logw,
                                                     const double* __restrict__ zinj, long long N, long long Ns,
@@ -393,15 +398,28 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
           if (valid[p]) s[p] = COH ? __ldcg(anc + i0 + p) : anc[i0 + p];
       }
     }
+    if (SH && pr.R > 1 && anc != nullptr) {
+      // ancestors are GLOBAL particle indices.  With exchangeable particles nearly every parent lives on this rank (only
+      // the offspring around the rank borders migrate): one range test per particle decides, and only a thread with a
+      // remote parent pays for the owner lookup and the peer pointer.
+      const long long own0 = (long long)pr.rank * pr.Nl, own1 = own0 + pr.Nl;
+      bool all_local = true;
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-      if (pr.R > 1 && anc != nullptr) {  // ancestors are GLOBAL particle indices: owner rank + local index
-        const unsigned g = (unsigned)s[p];
-        const unsigned q = owner_of(pr, g);
-        src[p] = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+      for (int p = 0; p < PPT; ++p) all_local &= !valid[p] || (s[p] >= own0 && s[p] < own1);
+      if (all_local) {
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) src[p] = xloc + (valid[p] ? s[p] - own0 : 0);
       } else {
-        src[p] = xloc + s[p];
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+          const unsigned g = (unsigned)s[p];
+          const unsigned q = owner_of(pr, g);
+          src[p] = reinterpret_cast<const real*>(pr.x[q]) + (g - q * (unsigned)pr.Nl);
+        }
       }
+    } else {
+#pragma unroll
+      for (int p = 0; p < PPT; ++p) src[p] = xloc + s[p];
     }
   }
   real g[PPT];
@@ -505,7 +523,7 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
 #ifndef CSSM_K1_MINBLOCKS
 #define CSSM_K1_MINBLOCKS 4
 #endif
-template <typename real, int D, int PPT = VecOf<real>::PPT>
+template <typename real, int D, int PPT = VecOf<real>::PPT, bool SH = false>
 __global__ void __launch_bounds__(256, PPT == 4 ? CSSM_K1_MINBLOCKS : 6)
 k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
                    const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
@@ -513,7 +531,7 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
                    K1Ctl ctl) {
   griddep_wait();
   griddep_launch();
-  if (pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
+  if (SH && pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
     const XchSlot* mine = pr.xch[pr.rank];
     gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
   }
@@ -521,11 +539,11 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
   double mx;
   bool bad;
   if ((long long)(blockIdx.x + 1) * blockDim.x * PPT <= N)  // all but the last block: no per-particle bounds predicates
-    propagate_particles<real, D, PPT, false, true>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+    propagate_particles<real, D, PPT, false, true, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
   else
-    propagate_particles<real, D, PPT, false, false>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
-  if (!a.has_obs && pr.R == 1) return;
-  k1_tail(mx, bad, a.has_obs, pr, ctl);
+    propagate_particles<real, D, PPT, false, false, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+  if (!a.has_obs && !(SH && pr.R > 1)) return;
+  k1_tail<SH>(mx, bad, a.has_obs, pr, ctl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -632,7 +650,7 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
     if (lw != lw) bad = true;
     else mx = (double)lw;
   }
-  k1_tail(mx, bad, 1, pr, ctl);
+  k1_tail<true>(mx, bad, 1, pr, ctl);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -758,12 +776,7 @@ struct SumTables {
   u128* super_q;              // [2][ns]
   unsigned long long* super_ticket;  // [ns] monotone
   int nt, ns;
-  // single-launch series kernel with flagged exchange slots (cssm_series.cuh): the tile sums / maxima of the CURRENT step
-  // live in the slots every block has already polled, word k of tile q at ll[k * ll_stride + q], 32 payload bits per word
-  const unsigned long long* ll = nullptr;
-  int ll_stride = 0;
 };
-constexpr int LLW_MAX = 0, LLW_SUM = 2, LLW_DONE = 12, LLW_WORDS = 13;  // max key 2 words; tile_sum 4, tile_q 4, maxw 2; done 1
 
 __device__ __forceinline__ u128 block_sum128(u128 v, u128* s_warp) {  // result valid in thread 0
   v = warp_sum128(v);
@@ -778,22 +791,16 @@ __device__ __forceinline__ u128 ld_gpu128(const u128* p) {
   return make_u128(ld_gpu(&p->lo), ld_gpu(&p->hi));
 }
 // exact sum / largest weight of tile tl of rank q, as another block published it (L2-coherent reads)
-__device__ __forceinline__ unsigned long long ll_pair(const SumTables& tb, int k, int tl) {
-  const unsigned long long a = ld_gpu(tb.ll + (size_t)k * tb.ll_stride + tl), b = ld_gpu(tb.ll + (size_t)(k + 1) * tb.ll_stride + tl);
-  return (a & 0xFFFFFFFFull) | (b << 32);
-}
 __device__ __forceinline__ u128 walk_tile_sum(const SumTables& tb, const Peers& pr, int q, int tl) {
-  if (tb.ll != nullptr) return make_u128(ll_pair(tb, LLW_SUM, tl), ll_pair(tb, LLW_SUM + 2, tl));
   return ld_gpu128((q == pr.rank) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);
 }
 __device__ __forceinline__ double walk_tile_maxw(const SumTables& tb, const Peers& pr, int q, int tl) {
-  if (tb.ll != nullptr) return __longlong_as_double((long long)ll_pair(tb, LLW_SUM + 8, tl));
   return __longlong_as_double((long long)ld_gpu((const unsigned long long*)((q == pr.rank) ? &tb.tile_maxw[tl] : &pr.tile_maxw[q][tl])));
 }
 
 // K2  w1 = exp(logw - max); exact sums of w1 and w1^2 per tile, per super tile and per rank.
 //     Strided access inside the tile: the order is irrelevant for an exact sum.
-template <typename real, int ITEMS>
+template <typename real, int ITEMS, bool SH = false>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               int parity, unsigned long long obs_seq, SumTables tb, const __grid_constant__ Peers pr) {
@@ -803,12 +810,13 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
   __shared__ unsigned long long s_key;
   griddep_wait();
   griddep_launch();
+  const int RK = SH ? pr.R : 1;
   StepAcc* A = &sc->acc[parity];
-  if (pr.R > 1) {  // all-gather of the per-rank maxima: every rank pushed its own into our slots
+  if (RK > 1) {  // all-gather of the per-rank maxima: every rank pushed its own into our slots
     const XchSlot* mine = pr.xch[pr.rank];
     gate_wait(&sc->gate2, obs_seq + 1, pr, sc, [&](int q) { return &mine[q].max_seq[parity]; });
     if (threadIdx.x < 32) {
-      unsigned long long key = ((int)threadIdx.x < pr.R) ? ld_relaxed_sys(&mine[threadIdx.x].max_key[parity]) : 0ull;
+      unsigned long long key = ((int)threadIdx.x < RK) ? ld_relaxed_sys(&mine[threadIdx.x].max_key[parity]) : 0ull;
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
         const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
@@ -873,7 +881,7 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
       atomic_add128(&A->q, ld_gpu128(ssq));
       __threadfence();
       const unsigned long long tk2 = atomicAdd(&sc->ticket2, 1ull);
-      if (pr.R > 1 && tk2 % (unsigned long long)tb.ns == (unsigned long long)tb.ns - 1) {
+      if (RK > 1 && tk2 % (unsigned long long)tb.ns == (unsigned long long)tb.ns - 1) {
         // last block of the grid: all-gather of (sum w, sum w^2) by direct stores into the peers
         __threadfence();
         pub_tot = ld_gpu128(&A->tot);
@@ -882,14 +890,14 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
       }
     }
   }
-  if (pr.R > 1 && threadIdx.x < 32 && warp_is_last(pub)) {  // lane q -> rank q, see push_progress_warp
+  if (RK > 1 && threadIdx.x < 32 && warp_is_last(pub)) {  // lane q -> rank q, see push_progress_warp
     pub_tot.lo = __shfl_sync(0xffffffffu, pub_tot.lo, 0);
     pub_tot.hi = __shfl_sync(0xffffffffu, pub_tot.hi, 0);
     pub_q.lo = __shfl_sync(0xffffffffu, pub_q.lo, 0);
     pub_q.hi = __shfl_sync(0xffffffffu, pub_q.hi, 0);
     __threadfence_system();
     const int q = threadIdx.x;
-    if (q < pr.R) {
+    if (q < RK) {
       XchSlot* s = &pr.xch[q][pr.rank];
       st_relaxed_sys(&s->tot_lo[parity], pub_tot.lo);
       st_relaxed_sys(&s->tot_hi[parity], pub_tot.hi);
@@ -913,7 +921,7 @@ struct KFun {
   uint32_t key0, key1, step;
   __device__ __forceinline__ double ui(long long i) const {
     if (uarr) return uarr[i];
-    uint4 v = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), step, RNG_RESAMPLE | 1u), key0, key1);
+    uint4 v = philox4x32(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), step, RNG_RESAMPLE | 1u), key0, key1);
     return u64_to_unit_double(v.x, v.y);
   }
   __device__ __forceinline__ double k(long long i) const {
@@ -1080,11 +1088,52 @@ struct K3Ctl {
   int direct;           // cssm_resample: caller weights, no ll update
   int add_ll, use_u_inj;
   int tie_first;        // CSSM_TIE_FIRST: plain inverse CDF (first index with C_j >= k), no TreeMap duplicate-key rule
+  int defer_ll;         // the caller updates ll / ESS itself (ll_ess_update), off the critical path of the search
   uint32_t key0, key1, step;
   double* ll_steps;
   int* ess_steps;
   long long step_slot;
 };
+
+// ONE thread of the whole filter, once per observed step: ll += max + log(mean w1) (model/ParticleFilter.scala:127), ESS =
+// floor(1 / sum wn^2) (:431-434) from the exact sums; PROTO3: also zero the accumulators of the next observed step.
+template <typename real, bool PROTO3>
+__device__ __noinline__ void ll_ess_update(FilterScalars* __restrict__ sc, const K3Ctl& ctl, u128 tot, u128 qsum, unsigned long long key,
+                                           long long Ng, bool direct) {
+  const PreScan ps = pre_scan(key, direct);
+  const int qb = ps.qb;
+  const double total = dbl128(tot, qb);
+  const double gmax = ps.gmax;
+  double incr = gmax + log(total / (double)Ng);
+  int flags = 0;
+  if (!(total > 0.0) || gmax != gmax || gmax - gmax != 0.0) {  // all weights zero / NaN / infinite max
+    incr = __longlong_as_double(0x7FF8000000000000ll);
+    flags |= FLAG_ZERO_TOTAL;
+  }
+  // sum (w/total)^2 = (exact sum w^2) / total^2; direct weights were pre-scaled by 2^-(96-qb)
+  const double tsc = __dmul_rn(total, __longlong_as_double((long long)(1023 - (96 - qb)) << 52));
+  const double s2 = __ddiv_rn(dbl128(qsum, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
+  const double inv = floor(1.0 / s2);
+  const int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
+  sc->gmax = gmax;
+  sc->total = total;
+  sc->qb = qb;
+  sc->ll_incr = incr;
+  if (ctl.add_ll) {
+    const double ll = sc->ll + incr;
+    sc->ll = ll;
+    sc->ess = ess;
+    if (ctl.ll_steps) ctl.ll_steps[ctl.step_slot] = ll;
+    if (ctl.ess_steps) ctl.ess_steps[ctl.step_slot] = ess;
+  }
+  if (flags) atomicOr(&sc->flags, flags);
+  if (PROTO3) {  // three-launch protocol: zero the accumulators of the next observed step
+    StepAcc* nx = &sc->acc[ctl.parity ^ 1];
+    nx->gmax_key = 0ull;
+    nx->tot = make_u128(0, 0);
+    nx->q = make_u128(0, 0);
+  }
+}
 
 // ---- block-wide scan + search: cumulative values and weights of the tile in shared memory, expansion by head scatter +
 //      block max-scan.  The kernel of the three-launch step (k_scan_search); measured faster there than the
@@ -1115,13 +1164,14 @@ struct K3SmemBlk {
 // everything before the tile.  Block 0 also updates ll and ESS.  PROTO3: called from the
 // three-launch step (zeroes the accumulators of the next observed step); the single-launch series
 // kernel keeps its own.  All threads of the block call; returns whether a peer's memory was written.
-template <typename real, int ITEMS, int KIND, bool PROTO3>
+template <typename real, int ITEMS, int KIND, bool PROTO3, bool SH = false>
 __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __restrict__ logw, const double* __restrict__ direct,
                                         long long N, FilterScalars* __restrict__ sc, const SumTables& tb, const Peers& pr,
                                         const K3Ctl& ctl, const double* __restrict__ uarr, double* __restrict__ cdf_out, int t,
                                         u128 tot, u128 qsum, unsigned long long key, u128 excl,
                                         const typename WeightSrc<real>::wt* wv_in = nullptr) {
   constexpr int TILE = TILE_THREADS * ITEMS;
+  const int RK = SH ? pr.R : 1, RNK = SH ? pr.rank : 0;  // single-rank instantiations carry no sharding code
   constexpr int WIN = K3SmemBlk<ITEMS>::WIN;
   double* Ps = sm.Ps;
   double* Ws = sm.Ws;
@@ -1138,7 +1188,7 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
   int& s_tp = sm.s_tp;
   int& s_brk = sm.s_brk;
   const int nt = tb.nt;
-  const long long Ng = (long long)pr.R * N;  // outputs of the whole (possibly sharded) filter
+  const long long Ng = (long long)RK * N;  // outputs of the whole (possibly sharded) filter
   const PreScan ps = pre_scan(key, direct != nullptr);
   const int qb = ps.qb;
   const double total = dbl128(tot, qb);
@@ -1150,47 +1200,15 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
     if (ctl.use_u_inj) {
       u = sc->u_inj;
     } else {
-      uint4 v = philox4x32_10(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
+      uint4 v = philox4x32(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
       u = u64_to_unit_double(v.x, v.y);
     }
     s_u = u;
     s_scale = __ddiv_rn((double)Ng, total);
     s_pend = 0x7FFFFFFFFFFFFFFFll;
   }
-  if (threadIdx.x == 64) {  // another warp than the one deriving the uniform: the two run side by side
-    if (t == 0) {
-      const double gmax = ps.gmax;
-      double incr = gmax + log(total / (double)Ng);
-      int flags = 0;
-      if (!(total > 0.0) || gmax != gmax || gmax - gmax != 0.0) {  // all weights zero / NaN / infinite max
-        incr = __longlong_as_double(0x7FF8000000000000ll);
-        flags |= FLAG_ZERO_TOTAL;
-      }
-      // sum (w/total)^2 = (exact sum w^2) / total^2; direct weights were pre-scaled by 2^-(96-qb)
-      const double tsc = __dmul_rn(total, __longlong_as_double((long long)(1023 - (96 - qb)) << 52));
-      const double s2 = __ddiv_rn(dbl128(qsum, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
-      const double inv = floor(1.0 / s2);
-      const int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
-      sc->gmax = gmax;
-      sc->total = total;
-      sc->qb = qb;
-      sc->ll_incr = incr;
-      if (ctl.add_ll) {
-        const double ll = sc->ll + incr;
-        sc->ll = ll;
-        sc->ess = ess;
-        if (ctl.ll_steps) ctl.ll_steps[ctl.step_slot] = ll;
-        if (ctl.ess_steps) ctl.ess_steps[ctl.step_slot] = ess;
-      }
-      if (flags) atomicOr(&sc->flags, flags);
-      if (PROTO3) {  // three-launch protocol: zero the accumulators of the next observed step
-        StepAcc* nx = &sc->acc[ctl.parity ^ 1];
-        nx->gmax_key = 0ull;
-        nx->tot = make_u128(0, 0);
-        nx->q = make_u128(0, 0);
-      }
-    }
-  }
+  if (threadIdx.x == 64 && t == 0 && !ctl.defer_ll)  // another warp than the one deriving the uniform: the two run side by side
+    ll_ess_update<real, PROTO3>(sc, ctl, tot, qsum, key, Ng, direct != nullptr);
   if (PROTO3 && t < tb.ns && threadIdx.x == 1) {
     tb.super_sum[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
     tb.super_q[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
@@ -1204,7 +1222,7 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
     // that its latency hides behind the tile scan
     double wn = 0.0;
     if (t < nt - 1) wn = (double)ws(tile0 + TILE);
-    else if (pr.rank < pr.R - 1) wn = (double)WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[pr.rank + 1]), nullptr, ps.gmax}(0);
+    else if (RNK < RK - 1) wn = (double)WeightSrc<real>{reinterpret_cast<const real*>(pr.logw[RNK + 1]), nullptr, ps.gmax}(0);
     s_wnext = wn;
   }
   double Pv[ITEMS];
@@ -1225,15 +1243,15 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
   // particle as its own ancestor; FLAG_ZERO_TOTAL is already raised
   const bool usable = (total > 0.0) && (total - total == 0.0);
   if (!usable) {
-    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) pr.anc[pr.rank][tile0 + j] = (int32_t)((long long)pr.rank * N + tile0 + j);
+    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) pr.anc[RNK][tile0 + j] = (int32_t)((long long)RNK * N + tile0 + j);
   } else {
   KFun<KIND> kf{s_u, (double)Ng, ctl.inv_n, total, uarr, ctl.key0, ctl.key1, ctl.step};
   const double c_end = Ps[phys<ITEMS>(tile_n - 1)];
-  const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
-  const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
+  const bool last_tile = (t == nt - 1) && (RNK == RK - 1);
+  const long long gbase = (long long)RNK * N + tile0;  // global index of the tile's first particle
   // ---- offspring counts: c_j = #{outputs with key <= P_j}; particle j owns the outputs [c_{j-1}, c_j) ----
   const double scale = s_scale;
-  const long long lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_fast(dbl128(excl, qb), scale, Ng);
+  const long long lo = (t == 0 && RNK == 0) ? 0 : kf.count_fast(dbl128(excl, qb), scale, Ng);
   const double lo_d = (double)lo;
   const int n_rel = (int)(Ng - lo);
   int cr[ITEMS];  // counts relative to lo
@@ -1319,7 +1337,10 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
           while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
         jts[k] = jt;
       }
-      int32_t* const out_local = pr.anc[pr.rank] + (lo + w0 - (long long)pr.rank * N);  // R == 1: plain coalesced stores
+      int32_t* const out_local = pr.anc[RNK] + (lo + w0 - (long long)RNK * N);  // R == 1: plain coalesced stores
+      // sharded: the outputs of a pass are consecutive slots; unless the pass straddles a rank border they all belong to
+      // this rank (the common case: offspring stay near their parents) and take the same plain stores
+      const bool pass_local = !SH || RK == 1 || (lo + w0 >= (long long)RNK * N && lo + w0 + n_w <= (long long)(RNK + 1) * N);
 #pragma unroll
       for (int k = 0; k < PER; ++k) {
         const int o = threadIdx.x + k * TILE_THREADS;
@@ -1328,10 +1349,10 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
           const long long i = lo + w0 + o;
           if (cont && jt == tile_n - 1) atomicMin(&s_pend, i);
           const int32_t val = (int32_t)(gbase + jt);
-          if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+          if (!pass_local) {  // offspring slot i belongs to rank i / N: scatter over NVLink
             const unsigned q = owner_of(pr, (unsigned)i);
             pr.anc[q][i - (long long)q * N] = val;
-            wrote_remote |= (q != pr.rank);
+            wrote_remote |= (q != RNK);
           } else {
             out_local[o] = val;
           }
@@ -1347,8 +1368,8 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
     // Walk forward over the GLOBAL tile sequence (rank-major): whole tiles are skipped from the
     // tables when every weight in them is strictly below half an ulp of the running (normalised)
     // value and the value stays in its binade, otherwise the tile is recomputed.
-    const long long gnt = (long long)pr.R * nt;
-    if (threadIdx.x == 0) { s_tp = pr.rank * nt + t + 1; s_run = add128(excl, tb.tile_sum[t]); s_jfinal = -1; }
+    const long long gnt = (long long)RK * nt;
+    if (threadIdx.x == 0) { s_tp = RNK * nt + t + 1; s_run = add128(excl, tb.tile_sum[t]); s_jfinal = -1; }
     __syncthreads();
     for (;;) {
       if (threadIdx.x == 0) {
@@ -1356,8 +1377,8 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
         u128 run = s_run;
         while (tp < gnt) {
           const int q = (int)(tp / nt), tl = (int)(tp % nt);
-          const u128 tsum = ld_gpu128((q == pr.rank) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);  // L2: another block wrote it
-          const double mxw = __longlong_as_double((long long)ld_gpu((const unsigned long long*)((q == pr.rank) ? &tb.tile_maxw[tl] : &pr.tile_maxw[q][tl])));
+          const u128 tsum = ld_gpu128((q == RNK) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);  // L2: another block wrote it
+          const double mxw = __longlong_as_double((long long)ld_gpu((const unsigned long long*)((q == RNK) ? &tb.tile_maxw[tl] : &pr.tile_maxw[q][tl])));
           const u128 nrun = add128(run, tsum);
           const double c = __ddiv_rn(dbl128(run, qb), total), ce = __ddiv_rn(dbl128(nrun, qb), total);
           const long long cb = __double_as_longlong(c), eb = __double_as_longlong(ce);
@@ -1375,7 +1396,7 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
       const int tp = s_tp;
       const int q = tp / nt, tl = tp % nt;
       const double c = dbl128(s_run, qb);
-      WeightSrc<real> wq{(q == pr.rank) ? logw : reinterpret_cast<const real*>(pr.logw[q]), direct, ps.gmax};
+      WeightSrc<real> wq{(q == RNK) ? logw : reinterpret_cast<const real*>(pr.logw[q]), direct, ps.gmax};
       tile_cdf<real, ITEMS>(wq, qb, s_run, (long long)tl * TILE, N, Ps, Ws, s_warp);
       const int tn = (int)min((long long)TILE, N - (long long)tl * TILE);
       // first element of tile tp that does NOT vanish against its predecessor's value
@@ -1388,7 +1409,7 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
         if (s_brk < tn) s_jfinal = (long long)q * N + (long long)tl * TILE + s_brk - 1;
         else if (tp == gnt - 1) s_jfinal = Ng - 1;
         else {
-          const u128 tsum = ld_gpu128((q == pr.rank) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);  // L2: another block wrote it
+          const u128 tsum = ld_gpu128((q == RNK) ? &tb.tile_sum[tl] : &pr.tile_sum[q][tl]);  // L2: another block wrote it
           s_run = add128(s_run, tsum);
           s_tp = tp + 1;
         }
@@ -1398,10 +1419,10 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
     }
     const long long jfinal = s_jfinal;
     for (long long i = pend + threadIdx.x; i < hi; i += TILE_THREADS) {
-      if (pr.R > 1) {
+      if (RK > 1) {
         const unsigned q = owner_of(pr, (unsigned)i);
         pr.anc[q][i - (long long)q * N] = (int32_t)jfinal;
-        wrote_remote |= (q != pr.rank);
+        wrote_remote |= (q != RNK);
       } else {
         pr.anc[0][i] = (int32_t)jfinal;
       }
@@ -1434,7 +1455,7 @@ struct K3Smem {
   u128 s_excl, s_tot, s_q, s_run;
   unsigned long long s_key;
   long long s_pend, s_jfinal;
-  double s_wnext, s_u, s_scale;
+  double s_wnext, s_u;
   int s_tp, s_brk;
   unsigned s_minw[NW];  // per-warp min weight of the tile (fp32 bits; non-negative floats order as integers)
   int s_wbrk[NW];       // first particle of the warp that starts a new key (tiles with vanishing weights only)
@@ -1443,34 +1464,48 @@ struct K3Smem {
   int s_hn;
 };
 
-// One tile in registers: the thread's weights and the cumulative values P_j = dbl128(exact prefix) of its ITEMS
-// consecutive particles, the value before the thread's / the warp's first particle, and the exact sum at the end of the
-// tile.  `excl` = exact sum of everything before the tile.  All threads call; LEAD: s_warp may still be read from an
-// earlier use (one more barrier).  The barrier inside also publishes what single threads of the caller wrote before.
+// One tile in registers.  The scan has a LOCAL part that needs nothing but the weights -- the thread's running exact sums,
+// the warp-inclusive scan of the thread totals, the warp totals in shared memory, the warp's smallest weight -- and a
+// FINISH that needs the exact sum of everything before the tile: the cumulative values P_j = dbl128(exact prefix) of the
+// thread's ITEMS consecutive particles, the value before the thread's / the warp's first particle, and the exact sum at
+// the end of the tile.  Between the two the block must synchronise once (s_warp, s_minw).  The single-launch series
+// kernel runs the local part BEFORE the grid-wide exchange of the tile sums (the tile sum is its by-product) and only
+// the finish after it.
+template <typename real, int ITEMS>
+struct TileScan {
+  typename WeightSrc<real>::wt w[ITEMS];
+  u128 e[ITEMS];  // inclusive exact sums within the thread
+  u128 incl;      // inclusive scan of the thread totals within the warp
+};
 template <typename real, int ITEMS>
 struct TileRegs {
-  typename WeightSrc<real>::wt w[ITEMS];
   double P[ITEMS];
   double P_tstart, P_wstart;
   u128 tile_end;
 };
-template <typename real, int ITEMS, bool LEAD>
-__device__ __forceinline__ void tile_scan_regs(const WeightSrc<real>& ws, int qb, u128 excl, long long tile0, long long N,
-                                               u128* s_warp, const typename WeightSrc<real>::wt* wv_in, TileRegs<real, ITEMS>& r) {
-  constexpr int NW = TILE_THREADS / 32;
+// weights in sc.w; base = global index of the thread's first particle; all threads call.  No barrier inside.
+template <typename real, int ITEMS>
+__device__ __forceinline__ void tile_scan_local(int qb, long long base, long long N, u128* s_warp, unsigned* s_minw,
+                                                TileScan<real, ITEMS>& sc) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (wv_in != nullptr) {  // the caller already holds this thread's ITEMS weights (same values, same order)
+  if (s_minw != nullptr) {  // a lower bound (fp32, rounded down) of the warp's smallest weight
+    float m = 3.4028234663852886e38f;
+    if (base + ITEMS <= N) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) r.w[j] = wv_in[j];
-  } else {
-    ws.template load<ITEMS>(tile0 + (long long)threadIdx.x * ITEMS, 1, N, r.w);
+      for (int j = 0; j < ITEMS; ++j) m = fminf(m, to_float_rd(sc.w[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j)
+        if (base + j < N) m = fminf(m, to_float_rd(sc.w[j]));
+    }
+    const unsigned mb = __reduce_min_sync(0xffffffffu, __float_as_uint(m));
+    if (lane == 0) s_minw[wid] = mb;
   }
-  u128 e[ITEMS];
   u128 run = make_u128(0, 0);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
-    run = add128(run, WeightSrc<real>::fix(r.w[j], qb));
-    e[j] = run;
+    run = add128(run, WeightSrc<real>::fix(sc.w[j], qb));
+    sc.e[j] = run;
   }
   u128 incl = run;
 #pragma unroll
@@ -1478,9 +1513,15 @@ __device__ __forceinline__ void tile_scan_regs(const WeightSrc<real>& ws, int qb
     const u128 o = shfl_up128(incl, d);
     if (lane >= d) incl = add128(incl, o);
   }
-  if (LEAD) __syncthreads();
+  sc.incl = incl;
   if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
+}
+// after the barrier that follows tile_scan_local
+template <typename real, int ITEMS>
+__device__ __forceinline__ void tile_scan_finish(int qb, u128 excl, const u128* s_warp, const TileScan<real, ITEMS>& sc,
+                                                 TileRegs<real, ITEMS>& r) {
+  constexpr int NW = TILE_THREADS / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u128 woff = excl, tend = excl;
 #pragma unroll
   for (int w = 0; w < NW; ++w) {
@@ -1488,14 +1529,30 @@ __device__ __forceinline__ void tile_scan_regs(const WeightSrc<real>& ws, int qb
     tend = add128(tend, v);
     woff = add128(woff, (w < wid) ? v : make_u128(0, 0));
   }
-  u128 ex = shfl_up128(incl, 1);
+  u128 ex = shfl_up128(sc.incl, 1);
   if (lane == 0) ex = make_u128(0, 0);
   const u128 off = add128(woff, ex);
   r.P_wstart = dbl128(woff, qb);
   r.P_tstart = dbl128(off, qb);
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) r.P[j] = dbl128(add128(off, e[j]), qb);
+  for (int j = 0; j < ITEMS; ++j) r.P[j] = dbl128(add128(off, sc.e[j]), qb);
   r.tile_end = tend;
+}
+
+// ONE thread, before the barrier that precedes the search: the resampling uniform (model/Resampling.scala:66) and the
+// per-tile bookkeeping
+template <int ITEMS>
+__device__ __forceinline__ void k3_prepare(K3Smem<ITEMS>& sm, const FilterScalars* sc, const K3Ctl& ctl) {
+  double u;
+  if (ctl.use_u_inj) {
+    u = sc->u_inj;
+  } else {
+    uint4 v = philox4x32(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
+    u = u64_to_unit_double(v.x, v.y);
+  }
+  sm.s_u = u;
+  sm.s_pend = 0x7FFFFFFFFFFFFFFFll;
+  sm.s_hn = 0;
 }
 
 // Tile t of the scan + search once the exact sums are known: `tot` / `qsum` = sum of fix(w1) / of
@@ -1503,12 +1560,14 @@ __device__ __forceinline__ void tile_scan_regs(const WeightSrc<real>& ws, int qb
 // everything before the tile.  Block 0 also updates ll and ESS.  PROTO3: called from the
 // three-launch step (zeroes the accumulators of the next observed step); the single-launch series
 // kernel keeps its own.  All threads of the block call; returns whether a peer's memory was written.
+// `pre` != NULL: the caller has already run tile_scan_local for this tile (the series kernel does it before the exchange of
+// the tile sums), called k3_prepare and stored sm.s_wnext, all followed by a block barrier: no barrier is needed here.
 template <typename real, int ITEMS, int KIND, bool PROTO3>
 __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restrict__ logw, const double* __restrict__ direct,
                                         long long N, FilterScalars* __restrict__ sc, const SumTables& tb, const Peers& pr,
                                         const K3Ctl& ctl, const double* __restrict__ uarr, double* __restrict__ cdf_out, int t,
                                         u128 tot, u128 qsum, unsigned long long key, u128 excl,
-                                        const typename WeightSrc<real>::wt* wv_in = nullptr) {
+                                        const TileScan<real, ITEMS>* pre = nullptr) {
   constexpr int TILE = TILE_THREADS * ITEMS;
   constexpr int NW = K3Smem<ITEMS>::NW;
   constexpr int ROWS = K3Smem<ITEMS>::ROWS;
@@ -1521,55 +1580,11 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   const int qb = ps.qb;
   const double total = dbl128(tot, qb);
 
-  // ---- thread 0: the resampling uniform and n / total; block 0: ll increment max + log(mean w1), ESS =
-  //      floor(1/sum wn^2); zero the accumulators of the next observed step.  Read after the barrier of the scan. ----
-  if (threadIdx.x == 0) {
-    double u;
-    if (ctl.use_u_inj) {
-      u = sc->u_inj;
-    } else {
-      uint4 v = philox4x32_10(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
-      u = u64_to_unit_double(v.x, v.y);
-    }
-    sm.s_u = u;
-    sm.s_scale = __ddiv_rn((double)Ng, total);
-    sm.s_pend = 0x7FFFFFFFFFFFFFFFll;
-    sm.s_hn = 0;
-  }
-  if (threadIdx.x == 64) {  // another warp than the one deriving the uniform: the two run side by side
-    if (t == 0) {
-      const double gmax = ps.gmax;
-      double incr = gmax + log(total / (double)Ng);
-      int flags = 0;
-      if (!(total > 0.0) || gmax != gmax || gmax - gmax != 0.0) {  // all weights zero / NaN / infinite max
-        incr = __longlong_as_double(0x7FF8000000000000ll);
-        flags |= FLAG_ZERO_TOTAL;
-      }
-      // sum (w/total)^2 = (exact sum w^2) / total^2; direct weights were pre-scaled by 2^-(96-qb)
-      const double tsc = __dmul_rn(total, __longlong_as_double((long long)(1023 - (96 - qb)) << 52));
-      const double s2 = __ddiv_rn(dbl128(qsum, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
-      const double inv = floor(1.0 / s2);
-      const int ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);  // Scala .toInt saturates, NaN -> 0
-      sc->gmax = gmax;
-      sc->total = total;
-      sc->qb = qb;
-      sc->ll_incr = incr;
-      if (ctl.add_ll) {
-        const double ll = sc->ll + incr;
-        sc->ll = ll;
-        sc->ess = ess;
-        if (ctl.ll_steps) ctl.ll_steps[ctl.step_slot] = ll;
-        if (ctl.ess_steps) ctl.ess_steps[ctl.step_slot] = ess;
-      }
-      if (flags) atomicOr(&sc->flags, flags);
-      if (PROTO3) {  // three-launch protocol: zero the accumulators of the next observed step
-        StepAcc* nx = &sc->acc[ctl.parity ^ 1];
-        nx->gmax_key = 0ull;
-        nx->tot = make_u128(0, 0);
-        nx->q = make_u128(0, 0);
-      }
-    }
-  }
+  // ---- thread 0: the resampling uniform; block 0: ll increment max + log(mean w1), ESS = floor(1/sum wn^2); zero the
+  //      accumulators of the next observed step.  Read after the barrier of the scan (pre: the caller did it). ----
+  if (threadIdx.x == 0 && pre == nullptr) k3_prepare<ITEMS>(sm, sc, ctl);
+  if (threadIdx.x == 64 && t == 0 && !ctl.defer_ll)  // another warp than the one deriving the uniform: the two run side by side
+    ll_ess_update<real, PROTO3>(sc, ctl, tot, qsum, key, Ng, direct != nullptr);
   if (PROTO3 && t < tb.ns && threadIdx.x == 1) {
     tb.super_sum[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
     tb.super_q[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
@@ -1579,7 +1594,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   const long long tile0 = (long long)t * TILE;
   const int tile_n = (int)min((long long)TILE, N - tile0);
   const bool last_tile = (t == nt - 1) && (pr.rank == pr.R - 1);
-  if (threadIdx.x == 32 && cdf_out == nullptr) {
+  if (threadIdx.x == 32 && cdf_out == nullptr && pre == nullptr) {
     // first weight after this tile (next tile, possibly the next rank's first particle); loaded here so
     // that its latency hides behind the tile scan
     double wn = 0.0;
@@ -1588,29 +1603,16 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     sm.s_wnext = wn;
   }
   TileRegs<real, ITEMS> r;
-  {
-    // the scan; before its barrier every warp leaves a lower bound (fp32, rounded down) of its smallest weight
-    typedef typename WeightSrc<real>::wt wt;
+  TileScan<real, ITEMS> own;
+  const TileScan<real, ITEMS>* scan = pre;
+  if (pre == nullptr) {
     const long long base = tile0 + (long long)threadIdx.x * ITEMS;
-    wt wloc[ITEMS];
-    const wt* src = wv_in;
-    if (src == nullptr) {
-      ws.template load<ITEMS>(base, 1, N, wloc);
-      src = wloc;
-    }
-    float m = 3.4028234663852886e38f;
-    if (base + ITEMS <= N) {
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j) m = fminf(m, to_float_rd(src[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j)
-        if (base + j < N) m = fminf(m, to_float_rd(src[j]));
-    }
-    const unsigned mb = __reduce_min_sync(FULL, __float_as_uint(m));
-    if (lane == 0) sm.s_minw[wid] = mb;
-    tile_scan_regs<real, ITEMS, false>(ws, qb, excl, tile0, N, sm.s_warp, src, r);
+    ws.template load<ITEMS>(base, 1, N, own.w);
+    tile_scan_local<real, ITEMS>(qb, base, N, sm.s_warp, sm.s_minw, own);
+    __syncthreads();
+    scan = &own;
   }
+  tile_scan_finish<real, ITEMS>(qb, excl, sm.s_warp, *scan, r);
 
   if (cdf_out != nullptr) {
 #pragma unroll
@@ -1636,7 +1638,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   const double c_end = dbl128(r.tile_end, qb);  // cumulative value of the tile's last particle (padding weighs nothing)
   const long long gbase = (long long)pr.rank * N + tile0;  // global index of the tile's first particle
   // ---- offspring counts: c_j = #{outputs with key <= P_j}; particle j owns the outputs [c_{j-1}, c_j) ----
-  const double scale = sm.s_scale;
+  const double scale = __ddiv_rn((double)Ng, total);  // every thread: one division instead of a broadcast through shared memory
   const long long lo = (t == 0 && pr.rank == 0) ? 0 : kf.count_fast(dbl128(excl, qb), scale, Ng);
   const double lo_d = (double)lo;
   const int n_rel = (int)(Ng - lo);
@@ -1679,7 +1681,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     for (int j = ITEMS - 1; j >= 0; --j) {
       const int idx = threadIdx.x * ITEMS + j;
       const double before = j ? r.P[j - 1] : r.P_tstart;
-      const bool brk = (idx < tile_n) && !vanishes(before, (double)r.w[j], total);
+      const bool brk = (idx < tile_n) && !vanishes(before, (double)scan->w[j], total);
       if (brk) {
         bmask |= 1u << j;
         first_brk = idx;
@@ -1822,7 +1824,6 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     // tables when every weight in them is strictly below half an ulp of the running (normalised)
     // value and the value stays in its binade, otherwise the tile is recomputed.
     const long long gnt = (long long)pr.R * nt;
-    if (tb.ll != nullptr) __threadfence();  // flagged slots were polled with relaxed loads: acquire before reading the peers' log-weights
     if (threadIdx.x == 0) { sm.s_tp = pr.rank * nt + t + 1; sm.s_run = r.tile_end; sm.s_jfinal = -1; }
     __syncthreads();
     for (;;) {
@@ -1852,14 +1853,19 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
       const u128 run0 = sm.s_run;
       WeightSrc<real> wq{(q == pr.rank) ? logw : reinterpret_cast<const real*>(pr.logw[q]), direct, ps.gmax};
       TileRegs<real, ITEMS> rq;
-      tile_scan_regs<real, ITEMS, true>(wq, qb, run0, (long long)tl * TILE, N, sm.s_warp, nullptr, rq);
+      TileScan<real, ITEMS> sq;
+      wq.template load<ITEMS>((long long)tl * TILE + (long long)threadIdx.x * ITEMS, 1, N, sq.w);
+      __syncthreads();  // s_warp may still be read from its previous use
+      tile_scan_local<real, ITEMS>(qb, 0, N, sm.s_warp, nullptr, sq);
+      __syncthreads();
+      tile_scan_finish<real, ITEMS>(qb, run0, sm.s_warp, sq, rq);
       const int tn = (int)min((long long)TILE, N - (long long)tl * TILE);
       // first element of tile tp that does NOT vanish against its predecessor's value
 #pragma unroll
       for (int j = ITEMS - 1; j >= 0; --j) {
         const int idx = threadIdx.x * ITEMS + j;
         const double before = j ? rq.P[j - 1] : rq.P_tstart;
-        if (idx < tn && !vanishes(before, (double)rq.w[j], total)) atomicMin(&sm.s_brk, idx);
+        if (idx < tn && !vanishes(before, (double)sq.w[j], total)) atomicMin(&sm.s_brk, idx);
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -1896,7 +1902,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
 #endif
 // FLAT: the sum tables have no super tiles (SumTables::ns == 0, single rank) -- a separate instantiation, so that the
 // two-level kernel of the large clouds keeps its register allocation
-template <typename real, int ITEMS, int KIND, bool FLAT = false>
+template <typename real, int ITEMS, int KIND, bool FLAT = false, bool SH = false>
 __global__ void __launch_bounds__(TILE_THREADS, CSSM_K3_MINBLOCKS)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
@@ -1915,15 +1921,16 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   griddep_wait();
   griddep_launch();
   const int t = blockIdx.x, p = ctl.parity;
+  const int RK = SH ? pr.R : 1;
   StepAcc* A = &sc->acc[p];
 
   // ---- totals: this rank's from the accumulators, the other ranks' from the exchange slots ------
-  if (pr.R > 1) {
+  if (RK > 1) {
     const XchSlot* mine = pr.xch[pr.rank];
     gate_wait(&sc->gate3, ctl.obs_seq + 1, pr, sc, [&](int q) { return &mine[q].sum_seq[p]; });
     if (threadIdx.x < 32) {  // lane q reads rank q's slot; sums by shuffles
       const int q = threadIdx.x;
-      const bool on = q < pr.R;
+      const bool on = q < RK;
       u128 tq = on ? make_u128(ld_relaxed_sys(&mine[q].tot_lo[p]), ld_relaxed_sys(&mine[q].tot_hi[p])) : make_u128(0, 0);
       u128 qq = on ? make_u128(ld_relaxed_sys(&mine[q].q_lo[p]), ld_relaxed_sys(&mine[q].q_hi[p])) : make_u128(0, 0);
       unsigned long long key = on ? ld_relaxed_sys(&mine[q].max_key[p]) : 0ull;
@@ -1988,11 +1995,11 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const bool wrote_remote = k3_tile<real, ITEMS, KIND, true>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
                                                              s_key, s_excl);
 #else
-  const bool wrote_remote = k3_tile_blk<real, ITEMS, KIND, true>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
+  const bool wrote_remote = k3_tile_blk<real, ITEMS, KIND, true, SH>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
                                                                  s_key, s_excl);
 #endif
   if (cdf_out != nullptr) return;
-  if (pr.R > 1) {  // "resampling done": the last block tells the peers this step is complete
+  if (RK > 1) {  // "resampling done": the last block tells the peers this step is complete
     if (wrote_remote) __threadfence_system();
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -2017,7 +2024,7 @@ k_multinomial_search(const double* __restrict__ cdf, long long N, const double* 
   double u;
   if (uarr) u = uarr[i];
   else {
-    uint4 v = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), step, RNG_RESAMPLE | 1u), key0, key1);
+    uint4 v = philox4x32(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), step, RNG_RESAMPLE | 1u), key0, key1);
     u = u64_to_unit_double(v.x, v.y);
   }
   const double target = __dmul_rn(u, cdf[N - 1]);
@@ -2068,7 +2075,7 @@ template <typename real>
 __global__ void k_sample_one(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc, double* __restrict__ out,
                              int d, long long N, long long Ns, uint32_t key0, uint32_t key1, uint32_t step) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint4 v = philox4x32_10(make_uint4(0u, 0u, step, RNG_SAMPLE_ONE), key0, key1);
+  uint4 v = philox4x32(make_uint4(0u, 0u, step, RNG_SAMPLE_ONE), key0, key1);
   unsigned long long r = ((unsigned long long)v.x << 32) | v.y;
   long long i = (long long)(r % (unsigned long long)N);
   const real* src = reinterpret_cast<const real*>(pr.x[pr.rank]) + i;

@@ -32,11 +32,16 @@ namespace cssm {
 //   A[d] D[d] S[d] C[d]  y k0 k1 k2 k3 has_obs pad pad          (StepArgs without the padding)
 constexpr int SERIES_REC_EXTRA = 8;
 
-struct SeriesCtl {
+struct __align__(16) SeriesCtl {
   unsigned long long bar;       // grid barrier arrivals (zero at launch)
-  unsigned long long gkey[2];   // ordered key of max(logw) by step parity (zero at launch)
+  unsigned long long gkey[2];   // k_series_multi: ordered key of max(logw) by step parity (zero at launch)
   unsigned long long pad;
+  // k_series_small: arrivals and the running max key side by side, read by ONE 16-byte load: a snapshot whose counter is
+  // complete carries the complete max (every block's RED.MAX precedes its releasing arrival), so the consumer needs no
+  // second round trip to fetch the key after the barrier
+  unsigned long long bar2, key2;
 };
+static_assert(sizeof(SeriesCtl) == 48, "SeriesCtl layout");
 
 struct SeriesArgs {
   void* x[2];               // ping-pong clouds; x[0] is the current one at entry
@@ -56,7 +61,6 @@ struct SeriesArgs {
   double inv_n;                 // 1/N when N is a power of two, else 0
   int tie_first;                // K3Ctl::tie_first
   unsigned long long* dbg;      // NULL, or 8 cycle counters of block 0 (CSSM_SERIES_DEBUG): P1 B1 P2 B2 P3 B3 head
-  unsigned long long* ll;       // flagged exchange slots of k_series_ll: LLW_WORDS x nt words, zero at launch
   Peers pr[2];                  // the (single-rank) topology with x[0] = the cloud read in even / odd steps: kept in
                                 // the kernel's constant bank instead of a 400-byte struct in local memory
 };
@@ -101,6 +105,43 @@ __device__ __forceinline__ void grid_barrier(SeriesCtl* c, FilterScalars* sc, un
   __syncthreads();
 }
 
+__device__ __forceinline__ void ld_acquire_gpu_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// The same barrier on the (bar2, key2) pair: *key_out = the max key every block folded into key2 BEFORE arriving (thread 0
+// only; the caller broadcasts it).  `idle`: work thread 0 does between its arrival and its first poll -- the barrier
+// takes ~2.7 k cycles whatever it does meanwhile, so up to that much serial work is free there.
+template <typename Idle>
+__device__ __forceinline__ void grid_barrier_key(SeriesCtl* c, FilterScalars* sc, unsigned long long& target, unsigned G,
+                                                 unsigned long long* key_out, Idle idle) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += G;
+    red_release_gpu_add(&c->bar2, 1ull);
+    idle();
+    unsigned long long n, k;
+    ld_acquire_gpu_pair(&c->bar2, n, k);
+    if (n < target && !(*(volatile int*)&sc->flags & FLAG_COMM_TIMEOUT)) {
+      unsigned long long t0 = 0;
+      unsigned spins = 0;
+      for (;;) {
+        ld_acquire_gpu_pair(&c->bar2, n, k);
+        if (n >= target) break;
+        if ((++spins & 1023u) == 0u) {
+          const unsigned long long now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 2000000000ull) {
+            atomicOr(&sc->flags, FLAG_COMM_TIMEOUT);
+            break;
+          }
+        }
+      }
+    }
+    if (key_out != nullptr) *key_out = k;
+  }
+  __syncthreads();
+}
+
 #define CSSM_STAMP(slot)                                              \
   if (sa.dbg != nullptr && t == 0 && threadIdx.x == 0) {              \
     const long long now_ = clock64();                                 \
@@ -108,16 +149,35 @@ __device__ __forceinline__ void grid_barrier(SeriesCtl* c, FilterScalars* sc, un
     stamp_ = now_;                                                    \
   }
 
+// the record of one observation -> the StepArgs in shared memory (one element per thread, rec_len <= TILE_THREADS)
+template <typename real>
+__device__ __forceinline__ void rec_to_args(StepArgs<real>& a, real rec_v, int d, int obs_kind) {
+  const int i = threadIdx.x, e = i - 4 * d;
+  if (i < 4 * d) {
+    const int which = i / d, k = i - which * d;
+    real* dst = (which == 0) ? a.A : (which == 1) ? a.D : (which == 2) ? a.S : a.C;
+    dst[k] = rec_v;
+  } else if (e == 0) a.y = rec_v;
+  else if (e == 1) a.k0 = rec_v;
+  else if (e == 2) a.k1 = rec_v;
+  else if (e == 3) a.k2 = rec_v;
+  else if (e == 4) a.k3 = rec_v;
+  else if (e == 5) a.has_obs = (rec_v != (real)0) ? 1 : 0;
+  else if (e == 6) { a.d = d; a.obs_kind = obs_kind; }
+}
+
 template <typename real, int D, int KIND>
-__global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_constant__ SeriesArgs sa) {
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_constant__ SeriesArgs sa) {
   constexpr int ITEMS = 2;
   constexpr int TILE = TILE_THREADS * ITEMS;
+  constexpr int NW = TILE_THREADS / 32;
   typedef typename WeightSrc<real>::wt wt;
   __shared__ K3Smem<ITEMS> sm;
-  __shared__ StepArgs<real> a;
-  __shared__ double s_mx[TILE_THREADS / 32], s_mxw[TILE_THREADS / 32];
-  __shared__ u128 s_r[3][TILE_THREADS / 32];
+  __shared__ StepArgs<real> abuf[2];  // the constants of step s in abuf[s & 1]; the next step's are written a step ahead
+  __shared__ double s_mx[NW], s_mxw[NW];
+  __shared__ u128 s_r[3][NW], s_q2[NW];
   __shared__ int s_bad;
+  __shared__ unsigned long long s_key;
 
   const int t = blockIdx.x;  // one tile per block, gridDim.x == nt
   const unsigned G = gridDim.x;
@@ -138,31 +198,23 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
   tb.nt = sa.nt;
   tb.ns = 0;
 
-  int cur = 0, n_obs = 0;
+  int cur = 0;
   bool anc_valid = false;
   const int rec_len = 4 * d + SERIES_REC_EXTRA;  // <= 136 <= TILE_THREADS: one element per thread
-  // the record of the NEXT step is fetched into a register before the last barrier of a step
-  real rec_v = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
+  {
+    const real r0 = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
+    rec_to_args<real>(abuf[0], r0, d, sa.obs_kind);
+    if (threadIdx.x == 0) s_bad = 0;
+  }
+  // the record of step s + 1 travels in a register during step s and is stored into the other buffer at the top of it
+  real rec_v = (sa.T > 1 && (int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + rec_len + threadIdx.x) : (real)0;
+  __syncthreads();
   for (int s = 0; s < sa.T; ++s) {
-    // ---- the step's constants: record -> shared StepArgs (read-only for the whole launch) ----------
-    {
-      const int i = threadIdx.x, e = i - 4 * d;
-      if (i < 4 * d) {
-        const int which = i / d, k = i - which * d;
-        real* dst = (which == 0) ? a.A : (which == 1) ? a.D : (which == 2) ? a.S : a.C;
-        dst[k] = rec_v;
-      } else if (e == 0) a.y = rec_v;
-      else if (e == 1) a.k0 = rec_v;
-      else if (e == 2) a.k1 = rec_v;
-      else if (e == 3) a.k2 = rec_v;
-      else if (e == 4) a.k3 = rec_v;
-      else if (e == 5) a.has_obs = (rec_v != (real)0) ? 1 : 0;
-      else if (e == 6) { a.d = d; a.obs_kind = sa.obs_kind; s_bad = 0; }
-      if (s + 1 < sa.T && i < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 1) * rec_len + i);
-    }
-    __syncthreads();
+    const StepArgs<real>& a = abuf[s & 1];
+    // abuf[(s + 1) & 1] was last read in step s - 1 (a grid barrier ago); it is published by the barriers of this step
+    if (s + 1 < sa.T) rec_to_args<real>(abuf[(s + 1) & 1], rec_v, d, sa.obs_kind);
+    if (s + 2 < sa.T && (int)threadIdx.x < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 2) * rec_len + threadIdx.x);
     const int has_obs = a.has_obs;
-    const int par = n_obs & 1;  // parity of the OBSERVED-step count: consecutive users of a key slot alternate
     const uint32_t step = sa.step0 + (uint32_t)s;
 
     CSSM_STAMP(6)
@@ -177,272 +229,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_series_small(const __grid_cons
     cur ^= 1;
     anc_valid = false;
     if (!has_obs) {  // propagated only (:121); the next gather may read any slot of this cloud
-      grid_barrier(sa.ctl, sa.sc, target, G);
-      continue;
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-    if (lane == 0) s_mx[wid] = mx;
-    if (bad) s_bad = 1;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double m2 = s_mx[0];
-      for (int w = 1; w < TILE_THREADS / 32; ++w) m2 = fmax(m2, s_mx[w]);
-      atomicMax(&sa.ctl->gkey[par], ord_key(m2));
-      if (s_bad) atomicOr(&sa.sc->flags, FLAG_NAN_WEIGHT);
-    }
-    CSSM_STAMP(0)
-    grid_barrier(sa.ctl, sa.sc, target, G);
-    CSSM_STAMP(1)
-
-    // ---- P2 ------------------------------------------------------------------------------------
-    const unsigned long long key = ld_gpu(&sa.ctl->gkey[par]);
-    const PreScan ps = pre_scan(key, false);
-    const int qb = ps.qb;
-    WeightSrc<real> ws{logw, nullptr, ps.gmax};
-    wt wv[ITEMS];  // this thread's weights, from the log-weights it still holds in registers
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) wv[j] = (i0 + j < N) ? ws.weight(lw[j]) : (wt)0;
-    {
-      if (t == 0 && threadIdx.x == 0) sa.ctl->gkey[par ^ 1] = 0ull;  // last read before the previous barrier
-      u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
-      wt mxv = (wt)0;
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j) {
-        acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
-        WeightSrc<real>::acc_sq(acc2, wv[j], 1.0);
-        mxv = wv[j] > mxv ? wv[j] : mxv;
-      }
-      const double mxw = WeightSrc<real>::warp_max(mxv);
-      acc = warp_sum128(acc);
-      acc2 = WeightSrc<real>::warp_sum_sq(acc2);
-      if (lane == 0) { s_r[0][wid] = acc; s_r[1][wid] = acc2; s_mxw[wid] = mxw; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        u128 t1 = s_r[0][0], t2 = s_r[1][0];
-        double m2 = s_mxw[0];
-        for (int w = 1; w < TILE_THREADS / 32; ++w) {
-          t1 = add128(t1, s_r[0][w]);
-          t2 = add128(t2, s_r[1][w]);
-          m2 = fmax(m2, s_mxw[w]);
-        }
-        sa.tile_sum[t] = t1;
-        sa.tile_q[t] = t2;
-        sa.tile_maxw[t] = m2;
-      }
-    }
-    CSSM_STAMP(2)
-    grid_barrier(sa.ctl, sa.sc, target, G);
-    CSSM_STAMP(3)
-
-    // ---- P3 ------------------------------------------------------------------------------------
-    {
-      u128 at = make_u128(0, 0), aq = make_u128(0, 0), ae = make_u128(0, 0);
-      for (int tt = threadIdx.x; tt < sa.nt; tt += TILE_THREADS) {
-        const u128 v = ld_gpu128(&sa.tile_sum[tt]);
-        at = add128(at, v);
-        if (tt < t) ae = add128(ae, v);
-        aq = add128(aq, ld_gpu128(&sa.tile_q[tt]));
-      }
-      at = warp_sum128(at);
-      aq = warp_sum128(aq);
-      ae = warp_sum128(ae);
-      if (lane == 0) { s_r[0][wid] = at; s_r[1][wid] = aq; s_r[2][wid] = ae; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        u128 r0 = s_r[0][0], r1 = s_r[1][0], r2 = s_r[2][0];
-        for (int w = 1; w < TILE_THREADS / 32; ++w) {
-          r0 = add128(r0, s_r[0][w]);
-          r1 = add128(r1, s_r[1][w]);
-          r2 = add128(r2, s_r[2][w]);
-        }
-        sm.s_tot = r0;
-        sm.s_q = r1;
-        sm.s_excl = r2;
-      }
-      __syncthreads();
-      K3Ctl kc;
-      kc.parity = 0;
-      kc.obs_seq = 0;
-      kc.gstep = 0;
-      kc.inv_n = sa.inv_n;
-      kc.direct = 0;
-      kc.add_ll = 1;
-      kc.use_u_inj = 0;
-      kc.tie_first = sa.tie_first;
-      kc.key0 = sa.key0;
-      kc.key1 = sa.key1;
-      kc.step = step;
-      kc.ll_steps = sa.ll_steps;
-      kc.ess_steps = sa.ess_steps;
-      kc.step_slot = s;
-      k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, sm.s_tot, sm.s_q, key,
-                                        sm.s_excl, wv);
-      anc_valid = true;
-      ++n_obs;
-    }
-    CSSM_STAMP(4)
-    grid_barrier(sa.ctl, sa.sc, target, G);
-    CSSM_STAMP(5)
-  }
-}
-#undef CSSM_STAMP
-
-// ---------------------------------------------------------------------------------------------
-// k_series_ll: the same one-tile-per-block schedule with FLAGGED EXCHANGE SLOTS instead of grid barriers.
-//
-// What a stage hands to the next one across blocks is tiny: the block's max log-weight after P1, its exact tile sums
-// after P2, "my ancestors are written" after P3.  Every block owns one slot per quantity; a 64-bit word of a slot carries
-// 32 payload bits and the 32-bit number of the step it belongs to, so a consumer polls the DATA words themselves (thread q
-// reads the slot of block q, all in flight at once) and needs no counter, no second round trip and -- for the max and the
-// sums, whose payload is the whole message -- no fence.  One release fence per step remains where bulk data changes hands:
-//   X2  fence + sums   publishes the cloud and the log-weights of P1 (issued an exchange earlier, so the fence finds them
-//                      acknowledged); the rare cross-tile walk of the search reads other tiles' log-weights
-//   X3  fence + flag   publishes the ancestors P3 scattered into other blocks' slots; awaited at the top of the next P1
-// The arrival counter of grid_barrier (MEMBAR + RED + acquire-polling, ~2.7 k cycles three times per observation) is gone.
-// Slots are reused without double buffering: nobody can publish step s+1 before everybody has consumed step s, because
-// each exchange is a full all-to-all.  Same per-particle code, same exact sums, same bits as the other schedules.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void ll_put2(unsigned long long* w, int stride, int k, int q, uint32_t seq, unsigned long long v) {
-  st_relaxed_gpu(w + (size_t)k * stride + q, ((unsigned long long)seq << 32) | (v & 0xFFFFFFFFull));
-  st_relaxed_gpu(w + (size_t)(k + 1) * stride + q, ((unsigned long long)seq << 32) | (v >> 32));
-}
-// wait until the K words k0 .. k0+K-1 of block q carry `seq`; out[k] = the words.  Bounded like grid_barrier.
-// ACQ: the last word is read with ld.acquire.gpu -- every word of a slot follows the producer's fence in program order, so
-// observing any of them with an acquire orders the consumer's later reads (and drops the SM's L1 lines, as the acquire
-// polling of grid_barrier does) behind everything the producer published.
-#ifndef CSSM_LL_POLL_THREADS
-#define CSSM_LL_POLL_THREADS 32   // threads of a block that poll the slots (thread p takes the blocks p, p + POLL, ...)
-#endif
-#ifndef CSSM_LL_SLEEP_NS
-#define CSSM_LL_SLEEP_NS 0        // back-off between two polls of a slot that is not ready
-#endif
-template <int K, bool ACQ>
-__device__ __forceinline__ void ll_wait(const unsigned long long* w, int stride, int k0, int q, uint32_t seq, unsigned long long* out,
-                                        FilterScalars* sc) {
-  unsigned spins = 0;
-  unsigned long long t0 = 0;
-  for (;;) {
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-      out[k] = (ACQ && k == K - 1) ? ld_acquire_gpu(w + (size_t)(k0 + k) * stride + q) : ld_gpu(w + (size_t)(k0 + k) * stride + q);
-#pragma unroll
-    for (int k = 0; k < K; ++k) ok &= (uint32_t)(out[k] >> 32) == seq;
-    if (ok) return;
-    if (CSSM_LL_SLEEP_NS > 0) __nanosleep(CSSM_LL_SLEEP_NS);
-    if ((++spins & 255u) == 0u) {
-      if (*(volatile int*)&sc->flags & FLAG_COMM_TIMEOUT) return;
-      const unsigned long long now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) {
-        atomicOr(&sc->flags, FLAG_COMM_TIMEOUT);
-        return;
-      }
-    }
-  }
-}
-__device__ __forceinline__ unsigned long long ll_join(unsigned long long lo_word, unsigned long long hi_word) {
-  return (lo_word & 0xFFFFFFFFull) | (hi_word << 32);
-}
-
-#define CSSM_STAMP(slot)                                              \
-  if (sa.dbg != nullptr && t == 0 && threadIdx.x == 0) {              \
-    const long long now_ = clock64();                                 \
-    atomicAdd(&sa.dbg[slot], (unsigned long long)(now_ - stamp_));    \
-    stamp_ = now_;                                                    \
-  }
-
-template <typename real, int D, int KIND>
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_series_ll(const __grid_constant__ SeriesArgs sa) {
-  constexpr int ITEMS = 2;
-  constexpr int TILE = TILE_THREADS * ITEMS;
-  constexpr int NW = TILE_THREADS / 32;
-  typedef typename WeightSrc<real>::wt wt;
-  __shared__ K3Smem<ITEMS> sm;
-  __shared__ StepArgs<real> a;
-  __shared__ double s_mx[NW], s_mxw[NW];
-  __shared__ unsigned long long s_kmax[NW];
-  __shared__ u128 s_r[3][NW];
-  __shared__ int s_bad;
-
-  const int t = blockIdx.x;  // one tile per block, gridDim.x == nt
-  const int nt = sa.nt;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int d = (D > 0) ? D : sa.d;
-  const long long N = sa.N, Ns = sa.Ns;
-  real* const logw = reinterpret_cast<real*>(sa.logw);
-  unsigned long long* const llw = sa.ll;
-  long long stamp_ = clock64();
-
-  SumTables tb;
-  tb.tile_sum = sa.tile_sum;
-  tb.tile_maxw = sa.tile_maxw;
-  tb.tile_q = sa.tile_q;
-  tb.super_sum = nullptr;
-  tb.super_q = nullptr;
-  tb.super_ticket = nullptr;
-  tb.nt = nt;
-  tb.ns = 0;
-  tb.ll = llw;
-  tb.ll_stride = nt;
-
-  int cur = 0;
-  bool anc_valid = false;
-  uint32_t wait_done = 0;  // sequence number of the X3 exchange the next gather has to wait for (0: none)
-  const int rec_len = 4 * d + SERIES_REC_EXTRA;  // <= 136 <= TILE_THREADS: one element per thread
-  real rec_v = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
-  for (int s = 0; s < sa.T; ++s) {
-    const uint32_t seq = (uint32_t)s + 1u;
-    // ---- the step's constants: record -> shared StepArgs (read-only for the whole launch) ----------
-    {
-      const int i = threadIdx.x, e = i - 4 * d;
-      if (i < 4 * d) {
-        const int which = i / d, k = i - which * d;
-        real* dst = (which == 0) ? a.A : (which == 1) ? a.D : (which == 2) ? a.S : a.C;
-        dst[k] = rec_v;
-      } else if (e == 0) a.y = rec_v;
-      else if (e == 1) a.k0 = rec_v;
-      else if (e == 2) a.k1 = rec_v;
-      else if (e == 3) a.k2 = rec_v;
-      else if (e == 4) a.k3 = rec_v;
-      else if (e == 5) a.has_obs = (rec_v != (real)0) ? 1 : 0;
-      else if (e == 6) { a.d = d; a.obs_kind = sa.obs_kind; s_bad = 0; }
-      if (s + 1 < sa.T && i < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 1) * rec_len + i);
-    }
-    // ---- X3 of the previous step: every block has published its ancestors (and its cloud) -----------
-    if (wait_done != 0u) {
-      for (int q = threadIdx.x; q < nt && threadIdx.x < CSSM_LL_POLL_THREADS; q += CSSM_LL_POLL_THREADS) {
-        unsigned long long v;
-        ll_wait<1, true>(llw, nt, LLW_DONE, q, wait_done, &v, sa.sc);  // acquire: the gathers below follow what the flag published
-      }
-      wait_done = 0u;
-    }
-    __syncthreads();
-    const int has_obs = a.has_obs;
-    const uint32_t step = sa.step0 + (uint32_t)s;
-    CSSM_STAMP(6)
-
-    // ---- P1 ------------------------------------------------------------------------------------
-    const Peers& pr = sa.pr[cur];
-    double mx;
-    bool bad;
-    real lw[ITEMS];
-    const long long i0 = (long long)t * TILE + (long long)threadIdx.x * ITEMS;
-    propagate_particles<real, D, ITEMS, true>(a, pr, reinterpret_cast<real*>(sa.x[cur ^ 1]), anc_valid ? sa.anc : nullptr, logw,
-                                              nullptr, N, Ns, 0ull, sa.key0, sa.key1, step, i0, mx, bad, lw);
-    cur ^= 1;
-    anc_valid = false;
-    if (!has_obs) {  // propagated only (:121): publish the cloud; the next gather may read any slot of it
-      __syncthreads();
-      if (threadIdx.x == 0 && s + 1 < sa.T) {
-        __threadfence();
-        st_relaxed_gpu(llw + (size_t)LLW_DONE * nt + t, (unsigned long long)seq << 32);
-      }
-      wait_done = seq;
+      grid_barrier_key(sa.ctl, sa.sc, target, G, nullptr, [] {});
       continue;
     }
 #pragma unroll
@@ -454,124 +241,100 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_ll(const __grid_cons
       double m2 = s_mx[0];
 #pragma unroll
       for (int w = 1; w < NW; ++w) m2 = fmax(m2, s_mx[w]);
-      ll_put2(llw, nt, LLW_MAX, t, seq, ord_key(m2));  // X1: the payload is the whole message, no fence
-      if (s_bad) atomicOr(&sa.sc->flags, FLAG_NAN_WEIGHT);
+      atomicMax(&sa.ctl->key2, ord_key(m2));
+      if (s_bad) { atomicOr(&sa.sc->flags, FLAG_NAN_WEIGHT); s_bad = 0; }
     }
     CSSM_STAMP(0)
-    // ---- X1: all-gather of the block maxima ---------------------------------------------------------
-    unsigned long long key = 0ull;
-    for (int q = threadIdx.x; q < nt && threadIdx.x < CSSM_LL_POLL_THREADS; q += CSSM_LL_POLL_THREADS) {
-      unsigned long long v[2];
-      ll_wait<2, false>(llw, nt, LLW_MAX, q, seq, v, sa.sc);
-      const unsigned long long kq = ll_join(v[0], v[1]);
-      key = kq > key ? kq : key;
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, m);
-      key = o > key ? o : key;
-    }
-    if (lane == 0) s_kmax[wid] = key;
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < NW; ++w) key = s_kmax[w] > key ? s_kmax[w] : key;
+    grid_barrier_key(sa.ctl, sa.sc, target, G, &s_key, [] {});  // the max arrives with the barrier's own snapshot
     CSSM_STAMP(1)
 
-    // ---- P2 ------------------------------------------------------------------------------------
+    // ---- P2: weights, and the LOCAL part of the tile scan (its by-product is the exact tile sum) ------------
+    const unsigned long long key = s_key;
     const PreScan ps = pre_scan(key, false);
     const int qb = ps.qb;
     WeightSrc<real> ws{logw, nullptr, ps.gmax};
-    wt wv[ITEMS];  // this thread's weights, from the log-weights it still holds in registers
+    K3Ctl kc;
+    kc.parity = 0;
+    kc.obs_seq = 0;
+    kc.gstep = 0;
+    kc.inv_n = sa.inv_n;
+    kc.direct = 0;
+    kc.add_ll = 1;
+    kc.use_u_inj = 0;
+    kc.tie_first = sa.tie_first;
+    kc.defer_ll = 1;  // ll / ESS: block 0, inside the wait of the step's last barrier
+    kc.key0 = sa.key0;
+    kc.key1 = sa.key1;
+    kc.step = step;
+    kc.ll_steps = sa.ll_steps;
+    kc.ess_steps = sa.ess_steps;
+    kc.step_slot = s;
+    TileScan<real, ITEMS> scan;  // this thread's weights, from the log-weights it still holds in registers
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) wv[j] = (i0 + j < N) ? ws.weight(lw[j]) : (wt)0;
+    for (int j = 0; j < ITEMS; ++j) scan.w[j] = (i0 + j < N) ? ws.weight(lw[j]) : (wt)0;
     {
-      u128 acc = make_u128(0, 0), acc2 = make_u128(0, 0);
+      if (threadIdx.x == 64) k3_prepare<ITEMS>(sm, sa.sc, kc);       // the resampling uniform: Philox, off the critical path
+      if (threadIdx.x == 32) sm.s_wnext = (t < sa.nt - 1) ? (double)ws((long long)(t + 1) * TILE) : 0.0;  // first weight of the next tile
+      u128 acc2 = make_u128(0, 0);
       wt mxv = (wt)0;
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
-        acc = add128(acc, WeightSrc<real>::fix(wv[j], qb));
-        WeightSrc<real>::acc_sq(acc2, wv[j], 1.0);
-        mxv = wv[j] > mxv ? wv[j] : mxv;
+        WeightSrc<real>::acc_sq(acc2, scan.w[j], 1.0);
+        mxv = scan.w[j] > mxv ? scan.w[j] : mxv;
       }
       const double mxw = WeightSrc<real>::warp_max(mxv);
-      acc = warp_sum128(acc);
       acc2 = WeightSrc<real>::warp_sum_sq(acc2);
-      if (lane == 0) { s_r[0][wid] = acc; s_r[1][wid] = acc2; s_mxw[wid] = mxw; }
+      tile_scan_local<real, ITEMS>(qb, i0, N, sm.s_warp, sm.s_minw, scan);
+      if (lane == 0) { s_q2[wid] = acc2; s_mxw[wid] = mxw; }
       __syncthreads();
       if (threadIdx.x == 0) {
-        u128 t1 = s_r[0][0], t2 = s_r[1][0];
+        u128 t1 = sm.s_warp[0], t2 = s_q2[0];
         double m2 = s_mxw[0];
 #pragma unroll
         for (int w = 1; w < NW; ++w) {
-          t1 = add128(t1, s_r[0][w]);
-          t2 = add128(t2, s_r[1][w]);
+          t1 = add128(t1, sm.s_warp[w]);
+          t2 = add128(t2, s_q2[w]);
           m2 = fmax(m2, s_mxw[w]);
         }
-        __threadfence();  // X2 also publishes the cloud and the log-weights of P1 (see the header)
-        ll_put2(llw, nt, LLW_SUM, t, seq, t1.lo);
-        ll_put2(llw, nt, LLW_SUM + 2, t, seq, t1.hi);
-        ll_put2(llw, nt, LLW_SUM + 4, t, seq, t2.lo);
-        ll_put2(llw, nt, LLW_SUM + 6, t, seq, t2.hi);
-        ll_put2(llw, nt, LLW_SUM + 8, t, seq, (unsigned long long)__double_as_longlong(m2));
+        sa.tile_sum[t] = t1;
+        sa.tile_q[t] = t2;
+        sa.tile_maxw[t] = m2;
       }
     }
     CSSM_STAMP(2)
-    // ---- X2: all-gather of the exact tile sums: total, sum of squares, this tile's exclusive prefix ----
-    u128 tot, qsum, excl;
+    grid_barrier_key(sa.ctl, sa.sc, target, G, nullptr, [] {});
+    CSSM_STAMP(3)
+
+    // ---- P3: totals and this tile's exclusive prefix from the tile sums, then the FINISH of the scan + the search ----
     {
       u128 at = make_u128(0, 0), aq = make_u128(0, 0), ae = make_u128(0, 0);
-      for (int q = threadIdx.x; q < nt && threadIdx.x < CSSM_LL_POLL_THREADS; q += CSSM_LL_POLL_THREADS) {
-        unsigned long long v[10];  // the last two words (the tile's largest weight) are only read by the cross-tile walk,
-        ll_wait<10, true>(llw, nt, LLW_SUM, q, seq, v, sa.sc);  // from the slots; waiting for them here makes that read safe
-        const u128 ts = make_u128(ll_join(v[0], v[1]), ll_join(v[2], v[3]));
-        at = add128(at, ts);
-        if (q < t) ae = add128(ae, ts);
-        aq = add128(aq, make_u128(ll_join(v[4], v[5]), ll_join(v[6], v[7])));
+      for (int tt = threadIdx.x; tt < sa.nt; tt += TILE_THREADS) {
+        const u128 v = ld_gpu128(&sa.tile_sum[tt]);
+        at = add128(at, v);
+        if (tt < t) ae = add128(ae, v);
+        if (t == 0) aq = add128(aq, ld_gpu128(&sa.tile_q[tt]));  // the sum of squares only feeds the ESS, which block 0 computes
       }
       at = warp_sum128(at);
-      aq = warp_sum128(aq);
       ae = warp_sum128(ae);
-      __syncthreads();  // s_r of P2 has been read
+      if (t == 0) aq = warp_sum128(aq);
       if (lane == 0) { s_r[0][wid] = at; s_r[1][wid] = aq; s_r[2][wid] = ae; }
       __syncthreads();
-      tot = s_r[0][0]; qsum = s_r[1][0]; excl = s_r[2][0];
+      u128 tot = s_r[0][0], qsum = s_r[1][0], excl = s_r[2][0];
 #pragma unroll
       for (int w = 1; w < NW; ++w) {
         tot = add128(tot, s_r[0][w]);
         qsum = add128(qsum, s_r[1][w]);
         excl = add128(excl, s_r[2][w]);
       }
-    }
-    CSSM_STAMP(3)
-
-    // ---- P3 ------------------------------------------------------------------------------------
-    {
-      K3Ctl kc;
-      kc.parity = 0;
-      kc.obs_seq = 0;
-      kc.gstep = 0;
-      kc.inv_n = sa.inv_n;
-      kc.direct = 0;
-      kc.add_ll = 1;
-      kc.use_u_inj = 0;
-      kc.tie_first = sa.tie_first;
-      kc.key0 = sa.key0;
-      kc.key1 = sa.key1;
-      kc.step = step;
-      kc.ll_steps = sa.ll_steps;
-      kc.ess_steps = sa.ess_steps;
-      kc.step_slot = s;
-      k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, tot, qsum, key, excl, wv);
+      if (t == 0 && threadIdx.x == 0) sa.ctl->key2 = 0ull;  // every block took its snapshot at the first barrier of the step
+      k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, tot, qsum, key, excl, &scan);
       anc_valid = true;
+      CSSM_STAMP(4)
+      // ll += max + log(mean w1) and the ESS (three divisions and a logarithm, one thread) ride in the barrier's wait
+      grid_barrier_key(sa.ctl, sa.sc, target, G, nullptr, [&] {
+        if (t == 0) ll_ess_update<real, false>(sa.sc, kc, tot, qsum, key, (long long)N, false);
+      });
     }
-    CSSM_STAMP(4)
-    // ---- X3: publish the ancestors; awaited at the top of the next step --------------------------------
-    __syncthreads();
-    if (threadIdx.x == 0 && s + 1 < sa.T) {
-      __threadfence();
-      st_relaxed_gpu(llw + (size_t)LLW_DONE * nt + t, (unsigned long long)seq << 32);
-    }
-    wait_done = seq;
     CSSM_STAMP(5)
   }
 }
@@ -754,6 +517,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_series_multi(const __grid_c
       kc.add_ll = 1;
       kc.use_u_inj = 0;
       kc.tie_first = sa.tie_first;
+      kc.defer_ll = 0;
       kc.key0 = sa.key0;
       kc.key1 = sa.key1;
       kc.step = step;

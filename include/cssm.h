@@ -127,7 +127,7 @@ int cssm_device_count(int* n_out);
 
 /* Replaces constructing Filter(mod, resample) / FilterLgcp(mod, resample, precision)
  * (model/ParticleFilter.scala:169-172,233-235) for `n_particles` particles.
- * `seed`/`stream_id` key the in-register Philox4x32-10 generator; runs with the same
+ * `seed`/`stream_id` key the in-register Philox4x32-7 generator (-DCSSM_PHILOX_ROUNDS=10 for the cuRAND round count); runs with the same
  * (seed, stream_id) and the same call sequence are reproducible and independent of the
  * launch geometry. */
 int cssm_filter_create(const cssm_model_desc_t* model, int64_t n_particles, int resample_kind,

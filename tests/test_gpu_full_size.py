@@ -150,3 +150,19 @@ def test_bench_line_carries_the_contract_keys():
     assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0
     assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert math.isfinite(j["log_likelihood_mean"])
+
+
+def test_injected_noise_step_parity_at_the_baseline_cloud_size():
+    """BASELINE.json configs[1]: the composed Poisson + seasonal + OU model at 2^20 particles, fp32, systematic -- every
+    stage of two stepFilters against the oracle on identical injected noise (states / log-weights 1e-5, w1, ESS and
+    ancestors bit-exact), not only the resampler and the likelihood as the other full-size tests do."""
+    from test_gpu_parity import run_steps
+    run_steps(c2(), 1 << 20, 2, SYS, _abi.F32, seed=21)
+
+
+def test_sharded_eight_virtual_ranks_with_the_large_tiles():
+    """BASELINE.json configs[4]'s model on eight (virtual) ranks at the tile size large clouds use (2048 particles, two-level
+    sum tables): 8 x 2^19 particles, same bits as the unsharded filter of 2^22 and as the oracle's resampler."""
+    from test_gpu_sharded import run_pair
+    from configs import c5
+    run_pair(c5(), 1 << 19, 8, 2, SYS, _abi.F32, seed=33)

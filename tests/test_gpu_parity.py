@@ -181,7 +181,7 @@ def test_lgcp_step_parity():
             o = oracle.Oracle(mod); o.reset(N)
             r = o.step(x, tp, t, 1.0, z, u, STRAT, oracle.device_order(dtype))
             rel_close(g["x_prop"], r["x_prop"], TOL[dtype], "lgcp state")
-            np.testing.assert_allclose(g["logw"], r["logw"], rtol=TOL[dtype] * 10, atol=TOL[dtype] * 10)
+            rel_close(g["logw"], r["logw"], TOL[dtype], "lgcp log-weights")  # north_star: 1e-5 fp32 / 1e-12 fp64, as everywhere
             mx = float(np.max(g["logw"]))
             w1 = oracle.w1(g["logw"], mx, oracle.device_order(dtype))
             np.testing.assert_array_equal(g["anc"], oracle.resample(STRAT, w1, u))
