@@ -626,6 +626,10 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     prof = h.profile_read()
     h.profile(0)
+    try:
+        extra["scan_tiles_last_run"] = dict(zip(("certified_fp64", "exact_fallback"), h.scan_stats()))
+    except Exception:
+        pass
     value = n_total * T * args.steps / (ms * 1e-3)
     if not sharded and wl_model != "c3":
         # the step after the filter in the streaming examples (examples/Filtering.scala:29): getIntervals of the

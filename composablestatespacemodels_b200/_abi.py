@@ -19,6 +19,7 @@ RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_MULTINOMIAL = 0, 1, 2
 F32, F64 = 0, 1
 SERIES_AUTO, SERIES_THREE_LAUNCH, SERIES_SINGLE_LAUNCH = 0, 1, 2
 TIE_REFERENCE, TIE_FIRST = 0, 1
+SCAN_AUTO, SCAN_EXACT = 0, 1
 MAX_RANKS, SHARD_BLOB_BYTES = 8, 1024
 
 c_double_p = C.POINTER(C.c_double)
@@ -113,6 +114,8 @@ _SIGNATURES = {
                              c_double_p],
     "cssm_filter_forecast_cloud": [_FILTER, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p],
     "cssm_filter_set_tie_rule": [_FILTER, C.c_int],
+    "cssm_filter_scan_mode": [_FILTER, C.c_int],
+    "cssm_filter_scan_stats": [_FILTER, c_int64_p, c_int64_p],
     "cssm_filter_paths_enable": [_FILTER, C.c_int64],
     "cssm_filter_paths_len": [_FILTER, c_int64_p],
     "cssm_filter_get_paths": [_FILTER, c_int32_p, C.c_int64, c_double_p],

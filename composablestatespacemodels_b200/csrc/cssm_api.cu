@@ -247,6 +247,7 @@ struct cssm_filter {
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
   int flat_max_nt = 2048;  // clouds of at most this many tiles: K2 without atomics, K3 adds the tile sums itself (CSSM_FLAT_MAX_NT)
   int tie_first = 0;  // CSSM_TIE_FIRST instead of the reference's TreeMap rule (cssm_filter_set_tie_rule)
+  int scan_fast = 1;  // k_scan_search tries the certified fp64 path first (cssm_filter_scan_mode; CSSM_K3_FAST=0)
   // forecast cloud (cssm_forecast.cuh): d + 4 columns [x1 | gamma | eta | obs | obs2], filter dtype
   // path storage (FilterInterpolate): px = (paths_cap + 1) propagated clouds, panc = paths_cap ancestor vectors
   void* px = nullptr;
@@ -591,6 +592,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   const long long Ng = f->N * (long long)pr.R;
   ctl.inv_n = ((Ng & (Ng - 1)) == 0) ? 1.0 / (double)Ng : 0.0;
   ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj; ctl.tie_first = f->tie_first; ctl.defer_ll = 0;
+  ctl.fast_ok = f->scan_fast;
   ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
   ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
   const bool strat = f->resample_kind == CSSM_RESAMPLE_STRATIFIED;
@@ -1047,6 +1049,7 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   f->tb.nt = f->nt; f->tb.ns = f->ns;
   f->tb.tile_q = f->tile_q;
   if (const char* e = std::getenv("CSSM_FLAT_MAX_NT")) f->flat_max_nt = std::atoi(e);
+  if (const char* e = std::getenv("CSSM_K3_FAST")) f->scan_fast = std::atoi(e) != 0;
   {
     const cudaError_t em[] = {cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz),
                               cudaMemset(f->x[1], 0, (size_t)f->d * f->Ns * esz),
@@ -1953,6 +1956,24 @@ int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_ou
     CU(cudaMemcpyAsync(dst, f->scratch, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
     CU(cudaStreamSynchronize(f->stream));
   }
+  return CSSM_OK;
+}
+
+int cssm_filter_scan_mode(cssm_filter_t* f, int mode) {
+  if (!f) return fail(CSSM_ERR_INVALID, "null filter handle");
+  if (mode != CSSM_SCAN_AUTO && mode != CSSM_SCAN_EXACT) return fail(CSSM_ERR_INVALID, "unknown scan mode");
+  f->scan_fast = mode == CSSM_SCAN_AUTO ? 1 : 0;
+  return CSSM_OK;
+}
+
+int cssm_filter_scan_stats(cssm_filter_t* f, int64_t* fast_tiles_out, int64_t* exact_tiles_out) {
+  int rc = enter(f);
+  if (rc) return rc;
+  FilterScalars s;
+  CU(cudaMemcpyAsync(&s, f->sc, sizeof(s), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  if (fast_tiles_out) *fast_tiles_out = (int64_t)s.n_fast;
+  if (exact_tiles_out) *exact_tiles_out = (int64_t)s.n_exact;
   return CSSM_OK;
 }
 

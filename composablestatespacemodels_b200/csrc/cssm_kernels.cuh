@@ -28,10 +28,29 @@
 // the next K1 gathers the parent state from the rank that owns the parent: both are plain
 // st.global / ld.global on peer-mapped pointers.
 #pragma once
+#include <type_traits>
 #include "cssm_common.cuh"
 #include "../../include/cssm.h"
 
 namespace cssm {
+
+// Code placement.  The SAME kernel binary runs up to 20 % faster or slower depending on the address the module loader
+// gives it (measured in round 2 on byte-identical k_weight_sums code of differently laid out builds: 0.0416 .. 0.0499 ms
+// at 2^24 particles, reproducible per build; the scan + search kernel and the series kernel likewise).  A build is
+// deterministic, so the layout is too: CSSM_LAYOUT_PAD inserts that many KiB of never-launched code ahead of the
+// kernels, and scripts/gpu_layout.sh measures the candidates.  The default below is the one that measured best for
+// this tree (profiles/r02_summary.md).
+#ifndef CSSM_LAYOUT_PAD
+#define CSSM_LAYOUT_PAD 0
+#endif
+#if CSSM_LAYOUT_PAD > 0
+__global__ void k_layout_pad(float* p) {
+  float v = p[0];
+#pragma unroll
+  for (int i = 0; i < CSSM_LAYOUT_PAD * 64; ++i) v = fmaf(v, 1.0001f, 0.5f);  // 16 bytes of code each
+  p[0] = v;
+}
+#endif
 
 constexpr int MAXD = 32;          // by-value kernel argument budget (5*32*8 B = 1.25 KB)
 constexpr int MAXR = CSSM_MAX_RANKS;
@@ -71,6 +90,7 @@ struct FilterScalars {
   double ll, ll_incr, u_inj;
   double gmax, total;  // of the last observed step (read-back of w1, tests)
   int ess, flags, qb, pad;
+  unsigned long long n_fast, n_exact;  // tiles of k_scan_search settled by the certified fp64 path / handed to the exact path
 };
 enum : int { FLAG_NAN_WEIGHT = 1, FLAG_ZERO_TOTAL = 2, FLAG_CLAMPED = 4, FLAG_COMM_TIMEOUT = 8 };
 
@@ -1089,6 +1109,7 @@ struct K3Ctl {
   int add_ll, use_u_inj;
   int tie_first;        // CSSM_TIE_FIRST: plain inverse CDF (first index with C_j >= k), no TreeMap duplicate-key rule
   int defer_ll;         // the caller updates ll / ESS itself (ll_ess_update), off the critical path of the search
+  int fast_ok;          // k_scan_search may try the certified fp64 path (cssm_filter_scan_mode; 0: exact path only)
   uint32_t key0, key1, step;
   double* ll_steps;
   int* ess_steps;
@@ -1893,6 +1914,235 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   return wrote_remote;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3 fast path: the tile in fp64 with CERTIFIED counts, the exact path as the fallback.
+//
+// What makes the scan + search expensive is exactness per particle: a 128-bit fixed-point prefix, its conversion to
+// fp64, an offspring count that must be THE count of keys below that value.  But the count is floor(y) + 1 with
+// y = P_j n / total - u, and floor() is insensitive to errors in y unless y is near an integer.  So the tile is
+// scanned in plain fp64 -- prefix L_j of the weights inside the tile (relative error below 2.3e-13 after 2048 adds) on
+// top of the EXACT cumulative value before the tile -- and y'_j = fma(L_j, s, fma(P_b, s, -(u + lo))) differs from the
+// exact path's y_j by less than 1e-6 for every cloud the library accepts (n < 2^31).  The exact path takes the
+// arithmetic count when y_j is further than 1e-5 from an integer (KFun::count_rel, proven there); the fast path takes
+// it when y'_j is further than 1.2e-5 away -- then y_j is outside its own band, on the same side of the same integer,
+// and both paths return the same count.  Likewise the TreeMap duplicate-key test vanishes(P, w): decided from P' when
+// w is clearly above 2^-52 P' or clearly below 2^-55 P' (a relative margin of 1e-9 absorbs the 2.3e-13), undecided in
+// between.  One undecided particle (4 % of the tiles at 2^24) sends the WHOLE tile to the exact path, which recomputes
+// it from scratch; so do the last tile of the cloud (clamping rule, ragged end) and a tile whose trailing run of
+// repeated keys continues into the next tile.  Ancestors are therefore bit-identical to the exact path, always.
+// Applies to fp32 filters, 2048-particle tiles, systematic resampling, one rank -- the large-cloud configuration.
+// ---------------------------------------------------------------------------------------------
+// vanishes(P, w, total) decided from an APPROXIMATION Pa of P (relative error below 1e-12): 1 repeats, 0 does not,
+// -1 cannot be certified.  The exact test is fl(c + wn) == c with c = fl(P / total), wn = fl(w / total): true iff wn is
+// below half an ulp of c (or equal to it with an even c).  c and ca = fl(Pa / total) have the same ulp unless c sits
+// within 1e-11 of a power of two; wn is the same number on both paths; so wn at least 1e-9 away (relatively) from half
+// an ulp of ca settles the matter.  Only weights between 2^-55 P and 2^-52 P come here.
+__device__ __noinline__ int vanishes_certified(double Pa, double w, double total) {
+  const double ca = __ddiv_rn(Pa, total), wn = __ddiv_rn(w, total);
+  const long long cb = __double_as_longlong(ca);
+  const int e = (int)((cb >> 52) & 0x7ff);
+  const unsigned long long mant = (unsigned long long)cb & 0xFFFFFFFFFFFFFull;
+  if (e < 60 || e > 2000) return -1;
+  if (mant < (1ull << 14) || mant > 0xFFFFFFFFFFFFFull - (1ull << 14)) return -1;  // within 4e-12 of a binade border
+  const double half_ulp = __longlong_as_double((long long)(e - 53) << 52);
+  if (wn <= half_ulp * (1.0 - 1e-9)) return 1;
+  if (wn >= half_ulp * (1.0 + 1e-9)) return 0;
+  return -1;
+}
+
+struct K3FastSmem {
+  static constexpr int TILE = TILE_THREADS * 8;
+  static constexpr int WIN = TILE + TILE_THREADS;
+  int32_t s_res[WIN];
+  double s_wsum[TILE_THREADS / 32];
+  int s_cnt[TILE_THREADS], s_cnt2[TILE_THREADS / 32];
+  unsigned s_vbits[TILE / 32];  // bit p: particle p of the tile repeats the key of its predecessor
+  double s_u, s_scale;
+  long long s_lo;
+  int s_flag, s_anyv;
+};
+
+template <bool FLAT>
+__device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __restrict__ logw, long long N, FilterScalars* __restrict__ sc,
+                                             const SumTables& tb, const K3Ctl& ctl, int32_t* __restrict__ anc_out, int t, u128 tot,
+                                             u128 qsum, unsigned long long key, u128 excl) {
+  constexpr int ITEMS = 8, TILE = K3FastSmem::TILE, WIN = K3FastSmem::WIN, PER = WIN / TILE_THREADS, NW = TILE_THREADS / 32;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nt = tb.nt;
+  if (t >= nt - 1) return false;  // the last tile: clamping rule and ragged end are the exact path's
+  const PreScan ps = pre_scan(key, false);
+  const float gmaxf = (float)ps.gmax;
+  const double total = dbl128(tot, 96);
+  if (!((total > 0.0) && (total - total == 0.0))) return false;
+  const long long tile0 = (long long)t * TILE;
+  const double P_b = dbl128(excl, 96);
+  const double c_end = dbl128(add128(excl, tb.tile_sum[t]), 96);  // the exact cumulative value of the tile's last particle
+  if (!ctl.tie_first) {  // a run of repeated keys that leaves the tile is resolved by the exact path's walk
+    const float w_next = expf_det(__fsub_rn(__ldg(logw + tile0 + TILE), gmaxf));
+    if (vanishes(c_end, (double)w_next, total)) return false;
+  }
+  const long long Ng = N;
+  if (threadIdx.x == 0) {  // one thread: the resampling uniform, n / total and the number of outputs before the tile
+    double u;
+    if (ctl.use_u_inj) {
+      u = sc->u_inj;
+    } else {
+      uint4 v = philox4x32(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
+      u = u64_to_unit_double(v.x, v.y);
+    }
+    const double scale = __ddiv_rn((double)Ng, total);
+    KFun<CSSM_RESAMPLE_SYSTEMATIC> kf{u, (double)Ng, ctl.inv_n, total, nullptr, ctl.key0, ctl.key1, ctl.step};
+    fs.s_u = u;
+    fs.s_scale = scale;
+    fs.s_lo = (t == 0) ? 0 : kf.count_fast(P_b, scale, Ng);
+    fs.s_flag = 0;
+    fs.s_anyv = 0;
+  }
+  if (threadIdx.x < TILE / 32) fs.s_vbits[threadIdx.x] = 0u;
+
+  // ---- weights and their fp64 prefix inside the tile (fixed association: the same bits for every launch) ----
+  float w[ITEMS];
+  double L[ITEMS];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(logw + tile0 + threadIdx.x * ITEMS);
+    const float4 b = *reinterpret_cast<const float4*>(logw + tile0 + threadIdx.x * ITEMS + 4);
+    const float lw[ITEMS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    double run = 0.0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      w[j] = expf_det(__fsub_rn(lw[j], gmaxf));
+      run = __dadd_rn(run, (double)w[j]);
+      L[j] = run;
+    }
+  }
+  double incl = L[ITEMS - 1];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl = __dadd_rn(incl, o);
+  }
+  if (lane == 31) fs.s_wsum[wid] = incl;
+  __syncthreads();
+  double off = 0.0;
+#pragma unroll
+  for (int ww = 0; ww < NW - 1; ++ww)
+    if (ww < wid) off = __dadd_rn(off, fs.s_wsum[ww]);
+  {
+    const double ex = __shfl_up_sync(FULL, incl, 1);
+    if (lane > 0) off = __dadd_rn(off, ex);
+  }
+
+  // ---- offspring counts, certified ----
+  const double scale = fs.s_scale;
+  const long long lo = fs.s_lo;
+  const int n_rel = (int)(Ng - lo);
+  const double yb = __fma_rn(P_b, scale, -__dadd_rn(fs.s_u, (double)lo));
+  bool undecided = false;
+  unsigned vmask = 0u;
+  int cr[ITEMS];
+  // no weight of the thread can repeat a key if even the smallest is clearly above 2^-52 of the LARGEST cumulative value
+  // the thread sees: one test for eight particles in the common case
+  float wmin = w[0];
+#pragma unroll
+  for (int j = 1; j < ITEMS; ++j) wmin = fminf(wmin, w[j]);
+  const bool check_v = !ctl.tie_first && !((double)wmin > __dadd_rn(P_b, __dadd_rn(off, L[ITEMS - 1])) * 2.2204460514709114e-16);
+  double cum_prev = off;  // tile-local cumulative value of the previous particle
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const double cum = __dadd_rn(off, L[j]);
+    const double y = __fma_rn(cum, scale, yb);
+    const int a = __double2int_rd(__dadd_rn(y, -1.2e-5)), b = __double2int_rd(__dadd_rn(y, 1.2e-5));
+    undecided |= (a != b);
+    cr[j] = max(min(a, n_rel - 1) + 1, 0);
+    if (check_v && (threadIdx.x | j) != 0) {
+      const double wd = (double)w[j], before = __dadd_rn(P_b, cum_prev);
+      if (!(wd > before * 2.2204460514709114e-16)) {          // not clearly above 2^-52 P
+        if (wd <= before * 2.7755575587873340e-17) vmask |= 1u << j;  // clearly below 2^-55 P: the key repeats
+        else {
+          const int r = vanishes_certified(before, wd, total);
+          if (r > 0) vmask |= 1u << j;
+          undecided |= (r < 0);
+        }
+      }
+    }
+    cum_prev = cum;
+  }
+  if (undecided) fs.s_flag = 1;
+  if (vmask) {
+    atomicOr(&fs.s_vbits[threadIdx.x >> 2], vmask << ((threadIdx.x & 3) * 8));
+    fs.s_anyv = 1;
+  }
+  fs.s_cnt[threadIdx.x] = cr[ITEMS - 1];
+  __syncthreads();
+  if (fs.s_flag) {  // block-uniform; nothing has been written to global memory yet
+    if (threadIdx.x == 0) atomicAdd(&sc->n_exact, 1ull);
+    return false;
+  }
+  if (threadIdx.x == 0) atomicAdd(&sc->n_fast, 1ull);
+
+  // ---- expansion, WIN outputs per pass (head scatter + max-scan, as the exact path), coalesced stores ----
+  const int n_out = fs.s_cnt[TILE_THREADS - 1];
+  const bool anyv = fs.s_anyv != 0;
+  const int32_t gbase = (int32_t)tile0;
+  const int prev0 = threadIdx.x ? fs.s_cnt[threadIdx.x - 1] : 0;
+  int carry = 0;
+  for (int w0 = 0; w0 < n_out; w0 += WIN) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) fs.s_res[threadIdx.x * PER + k] = -1;
+    __syncthreads();
+    {
+      int prev = prev0;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        if (cr[j] > prev && (unsigned)(prev - w0) < (unsigned)WIN) {
+          int jt = threadIdx.x * ITEMS + j;
+          if (anyv)  // TreeMap: the offspring go to the last particle of the run of repeated keys that follows (rare)
+            while (jt + 1 < TILE && ((fs.s_vbits[(jt + 1) >> 5] >> ((jt + 1) & 31)) & 1u)) ++jt;
+          fs.s_res[prev - w0] = jt;
+        }
+        prev = cr[j];
+      }
+    }
+    __syncthreads();
+    int v[PER];
+    int run = -1;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { run = max(run, fs.s_res[threadIdx.x * PER + k]); v[k] = run; }
+    int inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc = max(inc, o); }
+    if (lane == 31) fs.s_cnt2[wid] = inc;
+    __syncthreads();
+    int before = carry;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) {
+      const int c2 = fs.s_cnt2[ww];
+      if (ww < wid) before = max(before, c2);
+      carry = max(carry, c2);
+    }
+    { const int o = __shfl_up_sync(FULL, inc, 1); if (lane > 0) before = max(before, o); }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) fs.s_res[threadIdx.x * PER + k] = max(v[k], before);
+    __syncthreads();
+    const int n_w = min(WIN, n_out - w0);
+    int32_t* const out = anc_out + (lo + w0);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int o = threadIdx.x + k * TILE_THREADS;
+      if (o < n_w) out[o] = gbase + fs.s_res[o];
+    }
+    __syncthreads();
+  }
+  // ---- what block 0 / the first blocks do besides their tile (the exact path does the same at its top) ----
+  if (threadIdx.x == 64 && t == 0) ll_ess_update<float, true>(sc, ctl, tot, qsum, key, Ng, false);
+  if (!FLAT && t < tb.ns && threadIdx.x == 1) {
+    tb.super_sum[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
+    tb.super_q[(size_t)(ctl.parity ^ 1) * tb.ns + t] = make_u128(0, 0);
+  }
+  return true;
+}
+
 #ifndef CSSM_K3_MINBLOCKS
 #ifdef CSSM_K3_WS
 #define CSSM_K3_MINBLOCKS 3
@@ -1910,7 +2160,14 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
 #ifdef CSSM_K3_WS
   __shared__ K3Smem<ITEMS> sm;
 #else
-  __shared__ K3SmemBlk<ITEMS> sm;
+  // the fast path's window and the exact path's tile never live at the same time; the few words both need
+  // (s_excl, s_tot, s_q, s_key) are kept outside the union
+  constexpr bool FAST = std::is_same<real, float>::value && ITEMS == 8 && KIND == CSSM_RESAMPLE_SYSTEMATIC && !SH;
+  __shared__ union SmemU {
+    K3SmemBlk<ITEMS> blk;
+    K3FastSmem fast;
+  } smem_u;
+  K3SmemBlk<ITEMS>& sm = smem_u.blk;
 #endif
   u128& s_excl = sm.s_excl;
   u128& s_tot = sm.s_tot;
@@ -1995,8 +2252,16 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
   const bool wrote_remote = k3_tile<real, ITEMS, KIND, true>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
                                                              s_key, s_excl);
 #else
-  const bool wrote_remote = k3_tile_blk<real, ITEMS, KIND, true, SH>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, s_tot, s_q,
-                                                                 s_key, s_excl);
+  const u128 v_tot = s_tot, v_q = s_q, v_excl = s_excl;  // to registers: the fast path reuses the shared memory they sit in
+  const unsigned long long v_key = s_key;
+  if (FAST && direct == nullptr && cdf_out == nullptr && uarr == nullptr && ctl.fast_ok) {
+    __syncthreads();  // everyone holds the four values
+    if (k3_tile_fast<FLAT>(smem_u.fast, reinterpret_cast<const float*>(logw), N, sc, tb, ctl, pr.anc[0], t, v_tot, v_q, v_key, v_excl))
+      return;
+    __syncthreads();  // undecided: the exact path recomputes the tile from scratch
+  }
+  const bool wrote_remote = k3_tile_blk<real, ITEMS, KIND, true, SH>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, v_tot, v_q,
+                                                                 v_key, v_excl);
 #endif
   if (cdf_out != nullptr) return;
   if (RK > 1) {  // "resampling done": the last block tells the peers this step is complete

@@ -189,6 +189,16 @@ class GpuFilterHandle:
         particle inserted) or _abi.TIE_FIRST (textbook inverse CDF; see include/cssm.h)."""
         _abi.check(self._lib.cssm_filter_set_tie_rule(self._h, int(rule)))
 
+    def scan_mode(self, mode):
+        """_abi.SCAN_AUTO (certified fp64 scan with the exact path as fallback) or _abi.SCAN_EXACT (include/cssm.h)."""
+        _abi.check(self._lib.cssm_filter_scan_mode(self._h, int(mode)))
+
+    def scan_stats(self):
+        """(tiles settled by the certified fp64 path, tiles handed to the exact path) since the last initialisation"""
+        a, b = C.c_int64(), C.c_int64()
+        _abi.check(self._lib.cssm_filter_scan_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_stream(self, cuda_stream):
         _abi.check(self._lib.cssm_filter_set_stream(self._h, cuda_stream))
 

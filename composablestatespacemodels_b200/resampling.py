@@ -53,6 +53,27 @@ class Resampling:
         return _take(particles, ancestors(_abi.RESAMPLE_MULTINOMIAL, weights, _rng.random(len(weights))))
 
     @staticmethod
+    def residualResampling(particles, weights, return_ancestors=False):
+        """model/Resampling.scala:130-146, CORRECTED.  `weights` are LOG-likelihoods (the reference normalises them with
+        expNormalise).  Particle i is copied k_i = floor(n w_i) times; the remaining m = n - sum k_i places are drawn with
+        probabilities proportional to the residuals n w_i - k_i.  The reference's last two lines do not run --
+        `multinomialResampling(Vector.range(1, m), residualWeights)` draws n indices over the n residual weights and looks
+        them up in a vector of m - 1 items, then indexes the particles with those items -- so there is no behaviour to be
+        faithful to; this is the algorithm its doc comment (and Liu & Chen 1998) describes: m multinomial draws over the
+        residual weights, as ancestors of the ORIGINAL particles.  The draws run on the device (cssm_resample, the same
+        Multinomial.draw inverse-CDF walk as multinomialResampling); the deterministic copies are host arithmetic."""
+        w = Resampling.expNormalise(weights)
+        n = w.size
+        ki = np.floor(w * n).astype(np.int64)
+        anc = np.repeat(np.arange(n, dtype=np.int32), ki)
+        m = n - anc.size
+        if m > 0:
+            residual = n * w - ki
+            draws = ancestors(_abi.RESAMPLE_MULTINOMIAL, residual, _rng.random(n))[:m]  # draw j uses uniform j
+            anc = np.concatenate([anc, draws])
+        return anc if return_ancestors else _take(particles, anc)
+
+    @staticmethod
     def kind_of(resample):
         """Map a Resample value (or a kind constant / name) to the device's resample kind."""
         table = {

@@ -305,6 +305,16 @@ int cssm_filter_forecast(cssm_filter_t* f, double t, double interval, int chain,
  * getMeanForecast summarises); NULL to skip */
 int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_out, double* eta_out,
                                double* obs_out, double* obs2_out);
+/* How the scan + search kernel of large fp32 clouds (2048-particle tiles, systematic resampling, one rank) works.
+ * AUTO: every tile is first scanned in fp64 with CERTIFIED offspring counts -- a count is taken only where the error
+ * bound of the fp64 prefix cannot change it, a repeated-key decision only where it cannot flip -- and a tile with one
+ * undecided particle is recomputed by the exact 128-bit fixed-point path; the ancestors are bit-identical to EXACT,
+ * which runs the exact path on every tile.  cssm_filter_scan_stats: tiles settled by either path since the last
+ * initialisation (diagnostics). */
+#define CSSM_SCAN_AUTO 0
+#define CSSM_SCAN_EXACT 1
+int cssm_filter_scan_mode(cssm_filter_t* f, int mode);
+int cssm_filter_scan_stats(cssm_filter_t* f, int64_t* fast_tiles_out, int64_t* exact_tiles_out);
 /* the rule for repeated cumulative weights in systematic / stratified resampling (cssm_tie_rule); for a sharded filter
  * set the same rule on every shard */
 int cssm_filter_set_tie_rule(cssm_filter_t* f, int rule);

@@ -166,3 +166,31 @@ def test_sharded_eight_virtual_ranks_with_the_large_tiles():
     from test_gpu_sharded import run_pair
     from configs import c5
     run_pair(c5(), 1 << 19, 8, 2, SYS, _abi.F32, seed=33)
+
+
+@pytest.mark.parametrize("name", ["c2", "c5"])
+def test_certified_scan_equals_the_exact_path(name):
+    """The scan + search of large fp32 clouds first runs in fp64 with certified counts and hands undecided tiles to the
+    exact 128-bit path (include/cssm.h, cssm_filter_scan_mode).  Same seeds through AUTO and through EXACT: the
+    log-likelihood, every per-step value and the final cloud have the same bits; the fast path settles most tiles and the
+    fallback is exercised too."""
+    from configs import c5
+    mod = c2() if name == "c2" else c5()
+    t, y, _ = oracle.Oracle(mod).simulate(25, 0.1, 3)
+    N = (1 << 21) + 4096 + 77
+    out = []
+    for mode in (_abi.SCAN_AUTO, _abi.SCAN_EXACT):
+        h = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F32, seed=6)
+        h.scan_mode(mode)
+        h.load_series(t, y)
+        ll, lls, ess = h.ll_resident(steps=True)
+        out.append((ll, lls, ess, h.get_particles(), h.scan_stats()))
+        h.close()
+    a, e = out
+    assert a[0] == e[0]
+    np.testing.assert_array_equal(a[1], e[1])
+    np.testing.assert_array_equal(a[2], e[2])
+    np.testing.assert_array_equal(a[3], e[3])
+    fast, exact = a[4]
+    assert e[4][0] == 0                                  # EXACT never takes the fast path
+    assert fast > 5 * exact > 0, (fast, exact)           # most tiles certified, some undecided

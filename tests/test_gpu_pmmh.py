@@ -335,3 +335,34 @@ def test_lgcp_call_counter_bound_is_enforced():
     assert e.value.status == -4 and "Philox" in str(e.value)
     h.step(0.001, 1.0)                                 # a short increment is fine
     h.close()
+
+
+def test_residual_resampling_corrected():
+    """Residual resampling (model/Resampling.scala:130-146; the reference's version cannot run, see the docstring): every
+    particle keeps its floor(n w_i) deterministic copies, the remaining places are the device's multinomial draws over
+    the residual weights -- bit-exact against the oracle's multinomial on the same uniforms -- and the output has n items."""
+    from composablestatespacemodels_b200 import resampling
+    rng = np.random.default_rng(4)
+    n = 5000
+    lw = rng.normal(0.0, 1.5, n)
+    w = Resampling.expNormalise(lw)
+    ki = np.floor(w * n).astype(int)
+    resampling.seed(77)
+    anc = Resampling.residualResampling(np.arange(n), lw, return_ancestors=True)
+    assert anc.size == n
+    m = n - ki.sum()
+    np.testing.assert_array_equal(anc[: n - m], np.repeat(np.arange(n), ki))
+    us = np.random.default_rng(77).random(n)           # the same host stream the mirror consumed
+    want = oracle.resample(2, n * w - ki, us)[:m]
+    np.testing.assert_array_equal(anc[n - m:], want)
+    counts = np.bincount(anc, minlength=n)
+    assert np.all(counts >= ki)
+    # expected offspring n w_i: the residual part makes the scheme unbiased
+    resampling.seed(5)
+    tot = np.zeros(n)
+    for _ in range(60):
+        tot += np.bincount(Resampling.residualResampling(np.arange(n), lw, return_ancestors=True), minlength=n)
+    heavy = np.argsort(w)[-50:]
+    assert np.all(np.abs(tot[heavy] / 60 - n * w[heavy]) < 0.5)
+    out = Resampling.residualResampling(list(range(n)), lw)
+    assert len(out) == n
