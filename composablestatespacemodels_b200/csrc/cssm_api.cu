@@ -785,28 +785,9 @@ void launch_gather(cssm_filter* f, const int32_t* anc, double* out_dev) {
   k_gather<real, double><<<nblk(f->N, 256), 256, 0, f->stream>>>(pr, anc, out_dev, f->d, f->N, f->Ns, f->N);
 }
 
-// ---- single-launch series kernel ------------------------------------------------------------------
-template <typename real>
-void* series_kernel_ptr(int d, int kind) {
-  const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
-  if (d == 2) return strat ? (void*)k_series_small<real, 2, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 2, CSSM_RESAMPLE_SYSTEMATIC>;
-  return strat ? (void*)k_series_small<real, 0, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_small<real, 0, CSSM_RESAMPLE_SYSTEMATIC>;
-}
-void* series_kernel(const cssm_filter* f) {
-  return (f->dtype == CSSM_F32) ? series_kernel_ptr<float>(f->d, f->resample_kind) : series_kernel_ptr<double>(f->d, f->resample_kind);
-}
-// mid-size clouds: several tiles per block
-template <typename real, int ITEMS>
-void* series_multi_ptr(int d, int kind) {
-  const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
-  if (d == 7) return strat ? (void*)k_series_multi<real, 7, CSSM_RESAMPLE_STRATIFIED, ITEMS> : (void*)k_series_multi<real, 7, CSSM_RESAMPLE_SYSTEMATIC, ITEMS>;
-  return strat ? (void*)k_series_multi<real, 0, CSSM_RESAMPLE_STRATIFIED, ITEMS> : (void*)k_series_multi<real, 0, CSSM_RESAMPLE_SYSTEMATIC, ITEMS>;
-}
-void* series_multi_kernel(const cssm_filter* f) {
-  if (f->dtype == CSSM_F32)
-    return f->items == 8 ? series_multi_ptr<float, 8>(f->d, f->resample_kind) : series_multi_ptr<float, 2>(f->d, f->resample_kind);
-  return f->items == 8 ? series_multi_ptr<double, 8>(f->d, f->resample_kind) : series_multi_ptr<double, 2>(f->d, f->resample_kind);
-}
+// ---- single-launch series kernels: instantiated in their own translation unit (cssm_series.cu) -------------------
+void* series_kernel(const cssm_filter* f) { return cssm::series_small_kernel(f->dtype, f->d, f->resample_kind); }
+void* series_multi_kernel(const cssm_filter* f) { return cssm::series_multi_kernel(f->dtype, f->items, f->d, f->resample_kind); }
 int resident_blocks(const cssm_filter* f, void* kern) {
   int per_sm = 0, sms = 0, coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, f->device);
@@ -1010,6 +991,9 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   cssm_filter* f = new cssm_filter();
   f->device = device; f->dtype = dtype; f->resample_kind = resample_kind;
   f->N = n_particles; f->Ns = (n_particles + 63) / 64 * 64;
+  // experiment knob: extra elements of leading dimension (a power-of-two stride between the coordinate arrays of a cloud
+  // puts the d streams of a thread on the same address bits)
+  if (const char* e = std::getenv("CSSM_NS_PAD")) f->Ns += (std::atoll(e) + 63) / 64 * 64;
   f->model = hm; f->d = hm.d;
   f->rank = rank; f->world = world;
   // small clouds: 512-particle tiles so that the weight passes still fill the machine

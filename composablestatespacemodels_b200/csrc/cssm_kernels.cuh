@@ -34,17 +34,18 @@
 
 namespace cssm {
 
-// Code placement.  The SAME kernel binary runs up to 20 % faster or slower depending on the address the module loader
-// gives it (measured in round 2 on byte-identical k_weight_sums code of differently laid out builds: 0.0416 .. 0.0499 ms
-// at 2^24 particles, reproducible per build; the scan + search kernel and the series kernel likewise).  A build is
-// deterministic, so the layout is too: CSSM_LAYOUT_PAD inserts that many KiB of never-launched code ahead of the
-// kernels, and scripts/gpu_layout.sh measures the candidates.  The default below is the one that measured best for
-// this tree (profiles/r02_summary.md).
+// Optimiser sensitivity.  For IDENTICAL source ptxas emits different code for the step kernels depending on what else the
+// translation unit contains (round 2: k_propagate_weight<float,7> 82 KB vs 101 KB of code, 0.209 vs 0.191 ms at 2^24
+// particles; k_weight_sums 0.042 vs 0.049 ms the other way round; the scan + search and the series kernel likewise --
+// reproducible per build and identical on different B200 boxes, profiles/r02_summary.md).  The build is deterministic,
+// so the choice can be pinned: CSSM_LAYOUT_PAD adds a never-launched kernel of that many KiB to the module, which is
+// enough to move the optimiser from one variant to the other, and scripts/gpu_layout.sh measures the candidates.  The
+// default is the one that measured best for this tree.
 #ifndef CSSM_LAYOUT_PAD
-#define CSSM_LAYOUT_PAD 0
+#define CSSM_LAYOUT_PAD 0  // the build passes -DCSSM_LAYOUT_PAD=<k> (__graft_entry__.LAYOUT_PAD)
 #endif
 #if CSSM_LAYOUT_PAD > 0
-__global__ void k_layout_pad(float* p) {
+static __global__ void k_layout_pad(float* p) {
   float v = p[0];
 #pragma unroll
   for (int i = 0; i < CSSM_LAYOUT_PAD * 64; ++i) v = fmaf(v, 1.0001f, 0.5f);  // 16 bytes of code each
@@ -761,7 +762,7 @@ template <> struct WeightSrc<double> {
 };
 
 // max of a caller-given weight array -> acc[0].gmax_key (cssm_resample only)
-__global__ void __launch_bounds__(256) k_max_direct(const double* __restrict__ w, long long N, FilterScalars* sc) {
+static __global__ void __launch_bounds__(256) k_max_direct(const double* __restrict__ w, long long N, FilterScalars* sc) {
   double mx = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) mx = fmax(mx, w[i]);
 #pragma unroll
@@ -1089,7 +1090,7 @@ __device__ __forceinline__ void tile_cdf(const WeightSrc<real>& ws, int qb, u128
 // does adding the next weight leave the cumulative value unchanged?  This is what makes a TreeMap
 // key repeat in the reference (model/Resampling.scala:55-57), tested in the reference's normalised
 // domain: C = fl(P/total), wn = fl(w/total).  A weight above 2^-52 * P cannot vanish (cheap filter).
-__device__ __noinline__ bool vanishes_exact(double P, double w, double total) {
+static __device__ __noinline__ bool vanishes_exact(double P, double w, double total) {
   const double c = __ddiv_rn(P, total);
   return __dadd_rn(c, __ddiv_rn(w, total)) == c;
 }
@@ -1937,7 +1938,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
 // below half an ulp of c (or equal to it with an even c).  c and ca = fl(Pa / total) have the same ulp unless c sits
 // within 1e-11 of a power of two; wn is the same number on both paths; so wn at least 1e-9 away (relatively) from half
 // an ulp of ca settles the matter.  Only weights between 2^-55 P and 2^-52 P come here.
-__device__ __noinline__ int vanishes_certified(double Pa, double w, double total) {
+static __device__ __noinline__ int vanishes_certified(double Pa, double w, double total) {
   const double ca = __ddiv_rn(Pa, total), wn = __ddiv_rn(w, total);
   const long long cb = __double_as_longlong(ca);
   const int e = (int)((cb >> 52) & 0x7ff);
@@ -2280,7 +2281,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
 }
 
 // K4'  multinomial: Breeze Multinomial.draw first-draw walk = first j with cumulative >= u*sum
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_multinomial_search(const double* __restrict__ cdf, long long N, const double* __restrict__ uarr, uint32_t key0,
                      uint32_t key1, uint32_t step, int32_t* __restrict__ anc, int* __restrict__ flags_out) {
   griddep_wait();
@@ -2447,7 +2448,7 @@ k_select_hist(const __grid_constant__ Peers pr, const int32_t* __restrict__ anc,
 }
 
 // one block of 32 threads per (column, target): the digit whose bin holds the target rank
-__global__ void __launch_bounds__(32) k_select_pick(SelState* __restrict__ sel, unsigned* __restrict__ hist) {
+static __global__ void __launch_bounds__(32) k_select_pick(SelState* __restrict__ sel, unsigned* __restrict__ hist) {
   const int ct = blockIdx.x;  // 2*c + target
   unsigned* hh = hist + (size_t)ct * 256;
   if (threadIdx.x == 0) {

@@ -142,6 +142,11 @@ __device__ __forceinline__ void grid_barrier_key(SeriesCtl* c, FilterScalars* sc
   __syncthreads();
 }
 
+// the kernels below are instantiated in cssm_series.cu only: the optimiser's choices for them and for the step kernels of
+// cssm_api.cu then do not depend on each other; the host side asks for them by these two functions
+void* series_small_kernel(int dtype, int d, int resample_kind);
+void* series_multi_kernel(int dtype, int items, int d, int resample_kind);
+
 #define CSSM_STAMP(slot)                                              \
   if (sa.dbg != nullptr && t == 0 && threadIdx.x == 0) {              \
     const long long now_ = clock64();                                 \
