@@ -235,6 +235,12 @@ struct cssm_filter {
   // single-launch series kernel (small clouds, cssm_series.cuh)
   u128* tile_q = nullptr;          // [nt] exact tile sums of w1^2
   SeriesCtl* series_ctl = nullptr;
+  unsigned long long* anc64 = nullptr;  // k_series_small: tagged ancestor words (allocated on first use)
+  void* logw2 = nullptr;                // k_series_small: second log-weight buffer
+  u128* ser_tile_sum = nullptr;         // k_series_small: tile tables for its own tile size (256 * series_items particles)
+  u128* ser_tile_q = nullptr;
+  double* ser_tile_maxw = nullptr;
+  int series_items = 0;                 // particles per thread of k_series_small: 1 or 2 (0: not eligible)
   void* recs = nullptr;            // per-observation records of the loaded series (filter dtype)
   size_t recs_cap = 0;             // bytes
   bool recs_valid = false;
@@ -593,6 +599,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   ctl.inv_n = ((Ng & (Ng - 1)) == 0) ? 1.0 / (double)Ng : 0.0;
   ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj; ctl.tie_first = f->tie_first; ctl.defer_ll = 0;
   ctl.fast_ok = f->scan_fast;
+  ctl.anc64 = nullptr; ctl.anc_tag = 0;
   ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
   ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
   const bool strat = f->resample_kind == CSSM_RESAMPLE_STRATIFIED;
@@ -786,7 +793,7 @@ void launch_gather(cssm_filter* f, const int32_t* anc, double* out_dev) {
 }
 
 // ---- single-launch series kernels: instantiated in their own translation unit (cssm_series.cu) -------------------
-void* series_kernel(const cssm_filter* f) { return cssm::series_small_kernel(f->dtype, f->d, f->resample_kind); }
+void* series_kernel(const cssm_filter* f, int items) { return cssm::series_small_kernel(f->dtype, items, f->d, f->resample_kind); }
 void* series_multi_kernel(const cssm_filter* f) { return cssm::series_multi_kernel(f->dtype, f->items, f->d, f->resample_kind); }
 int resident_blocks(const cssm_filter* f, void* kern) {
   int per_sm = 0, sms = 0, coop = 0;
@@ -803,11 +810,14 @@ bool series_eligible(cssm_filter* f, bool sample_states) {
   if (f->model.obs_kind == CSSM_OBS_LGCP || f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) return false;
   if (f->series.empty() || f->series.size() > 0x7fffffffull) return false;
   if (f->series_max_blocks < 0) {
-    f->series_max_blocks = resident_blocks(f, series_kernel(f));
+    f->series_max_blocks = resident_blocks(f, series_kernel(f, 2));
     f->series_multi_blocks = resident_blocks(f, series_multi_kernel(f));
   }
   f->series_use_multi = false;
-  if (f->items == 2 && f->nt <= f->series_max_blocks) return true;   // one tile per block, weights stay in registers
+  // one 512-particle tile per block, weights stay in registers
+  f->series_items = 0;
+  if (nblk(f->N, 2 * TILE_THREADS) <= f->series_max_blocks) f->series_items = 2;
+  if (f->series_items != 0) return true;
   // several tiles per block: pays while a stage is short against the launch gaps it removes
   if (f->series_multi_blocks > 0 && (f->N <= f->series_multi_max || f->series_mode == CSSM_SERIES_SINGLE_LAUNCH)) {
     f->series_use_multi = true;
@@ -858,22 +868,43 @@ int run_series_single_launch(cssm_filter* f) {
   CU(cudaMemsetAsync(f->series_ctl, 0, sizeof(SeriesCtl), f->stream));
   SeriesArgs sa;
   std::memset(&sa, 0, sizeof(sa));
+  if (!f->series_use_multi) {  // one tile per block: tagged ancestors instead of a third grid barrier (cssm_series.cuh)
+    const size_t esz = (f->dtype == CSSM_F32) ? 4 : 8;
+    if (f->anc64 == nullptr) {
+      if (cudaMalloc((void**)&f->anc64, (size_t)f->Ns * sizeof(unsigned long long)) != cudaSuccess ||
+          cudaMalloc(&f->logw2, (size_t)(f->Ns + TILE_THREADS * f->items) * esz) != cudaSuccess)
+        return fail(CSSM_ERR_NOMEM, "cudaMalloc: series kernel buffers");
+      CU(cudaMemsetAsync(f->logw2, 0, (size_t)(f->Ns + TILE_THREADS * f->items) * esz, f->stream));
+      const size_t snt = (size_t)nblk(f->N, TILE_THREADS) + 1;
+      if (cudaMalloc((void**)&f->ser_tile_sum, snt * sizeof(u128)) != cudaSuccess || cudaMalloc((void**)&f->ser_tile_q, snt * sizeof(u128)) != cudaSuccess ||
+          cudaMalloc((void**)&f->ser_tile_maxw, snt * sizeof(double)) != cudaSuccess)
+        return fail(CSSM_ERR_NOMEM, "cudaMalloc: series kernel tables");
+    }
+    CU(cudaMemsetAsync(f->anc64, 0, (size_t)f->Ns * sizeof(unsigned long long), f->stream));  // tags of earlier launches
+    sa.anc64 = f->anc64;
+    sa.logw2 = f->logw2;
+  }
 
   sa.x[0] = f->x[f->cur]; sa.x[1] = f->x[f->cur ^ 1];
   sa.logw = f->logw; sa.anc = f->anc; sa.sc = f->sc;
   sa.tile_sum = f->tb.tile_sum; sa.tile_q = f->tile_q; sa.tile_maxw = f->tb.tile_maxw;
+  sa.nt = f->nt;
+  if (!f->series_use_multi) {
+    sa.tile_sum = f->ser_tile_sum; sa.tile_q = f->ser_tile_q; sa.tile_maxw = f->ser_tile_maxw;
+    sa.nt = nblk(f->N, TILE_THREADS * f->series_items);
+  }
   sa.ctl = f->series_ctl; sa.recs = f->recs; sa.ll_steps = f->ll_steps; sa.ess_steps = f->ess_steps;
-  sa.N = f->N; sa.Ns = f->Ns; sa.T = (int)T; sa.d = f->d; sa.nt = f->nt; sa.obs_kind = f->model.obs_kind;
+  sa.N = f->N; sa.Ns = f->Ns; sa.T = (int)T; sa.d = f->d; sa.obs_kind = f->model.obs_kind;
   sa.key0 = f->key0; sa.key1 = f->key1; sa.step0 = f->step_ctr;
   sa.inv_n = ((f->N & (f->N - 1)) == 0) ? 1.0 / (double)f->N : 0.0;
   sa.tie_first = f->tie_first;
   sa.pr[0] = make_peers(f, f->cur);
   sa.pr[1] = make_peers(f, f->cur ^ 1);
   static const bool debug_stamps = std::getenv("CSSM_SERIES_DEBUG") != nullptr;
-  if (debug_stamps) {
-    int rc2 = ensure_scratch(f, 8);
+  if (debug_stamps && !f->series_use_multi) {
+    int rc2 = ensure_scratch(f, (size_t)8 * 512);
     if (rc2) return rc2;
-    CU(cudaMemsetAsync(f->scratch, 0, 64, f->stream));
+    CU(cudaMemsetAsync(f->scratch, 0, (size_t)8 * 512 * 8, f->stream));
     sa.dbg = (unsigned long long*)f->scratch;
   }
   void* args[] = {&sa};
@@ -885,7 +916,7 @@ int run_series_single_launch(cssm_filter* f) {
       e = cudaLaunchCooperativeKernel(series_multi_kernel(f), dim3((unsigned)std::min(f->nt, f->series_multi_blocks)), dim3(TILE_THREADS),
                                       args, 0, f->stream);
     else
-      e = cudaLaunchCooperativeKernel(series_kernel(f), dim3((unsigned)f->nt), dim3(TILE_THREADS), args, 0, f->stream);
+      e = cudaLaunchCooperativeKernel(series_kernel(f, f->series_items), dim3((unsigned)sa.nt), dim3(TILE_THREADS), args, 0, f->stream);
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch series kernel: ") + cudaGetErrorString(e));
   f->launches++;
@@ -895,13 +926,25 @@ int run_series_single_launch(cssm_filter* f) {
   f->anc_valid = f->series.back().h.has_obs != 0;
   f->t_cur = f->series.back().t;
   CU(cudaEventRecord(f->ev1, f->stream));
-  if (debug_stamps) {
-    unsigned long long c[8];
-    CU(cudaMemcpyAsync(c, f->scratch, 64, cudaMemcpyDeviceToHost, f->stream));
+  if (sa.dbg != nullptr && sa.nt <= 512) {  // per stage: thread 0's cycles per step, min / mean / max over the blocks (and who was slowest)
+    static unsigned long long c[8 * 512];
+    CU(cudaMemcpyAsync(c, f->scratch, sizeof(c), cudaMemcpyDeviceToHost, f->stream));
     CU(cudaStreamSynchronize(f->stream));
-    std::fprintf(stderr, "series kernel, block 0, cycles per step: head %.0f P1 %.0f B1 %.0f P2 %.0f B2 %.0f P3 %.0f B3 %.0f (T=%zu, blocks %d)\n",
-                 c[6] / (double)T, c[0] / (double)T, c[1] / (double)T, c[2] / (double)T, c[3] / (double)T, c[4] / (double)T,
-                 c[5] / (double)T, T, f->nt);
+    const char* name[8] = {"P1", "B1", "P2", "B2", "P3", "anc-wait", "head", "-"};
+    const int order[7] = {6, 5, 0, 1, 2, 3, 4};
+    std::fprintf(stderr, "series kernel, cycles per step (T=%zu, blocks %d): ", T, sa.nt);
+    for (int k : order) {
+      double mn = 1e30, mx = 0, sum = 0;
+      int who = 0;
+      for (int b = 0; b < sa.nt; ++b) {
+        const double v = c[(size_t)k * sa.nt + b] / (double)T;
+        sum += v;
+        if (v < mn) mn = v;
+        if (v > mx) { mx = v; who = b; }
+      }
+      std::fprintf(stderr, "%s %.0f/%.0f/%.0f(b%d) ", name[k], mn, sum / sa.nt, mx, who);
+    }
+    std::fprintf(stderr, "\n");
   }
   return CSSM_OK;
 }
@@ -1278,7 +1321,7 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
   void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
                   f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl,
-                  f->recs, f->fc, f->px, f->panc, f->pres_dev};
+                  f->recs, f->fc, f->px, f->panc, f->pres_dev, f->anc64, f->logw2, f->ser_tile_sum, f->ser_tile_q, f->ser_tile_maxw};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (f->ev0) cudaEventDestroy(f->ev0);

@@ -335,6 +335,14 @@ __device__ __forceinline__ unsigned long long ld_gpu(const unsigned long long* p
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// tagged 64-bit words (tag << 32 | payload) handed from a producer block to a consumer block of the same grid through L2:
+// an aligned 8-byte store is single-copy atomic, so a word whose tag matches carries its payload -- no fence, no flag
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ld_gpu_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -379,6 +379,8 @@ template <typename real, int PPT> struct VecN;
 template <> struct VecN<float, 4> { typedef float4 type; typedef int4 itype; };
 template <> struct VecN<float, 2> { typedef float2 type; typedef int2 itype; };
 template <> struct VecN<double, 2> { typedef double2 type; typedef int2 itype; };
+template <> struct VecN<float, 1> { typedef float type; typedef int itype; };
+template <> struct VecN<double, 1> { typedef double type; typedef int itype; };
 
 // the PPT consecutive particles i0 .. i0+PPT-1 of one thread: gather, transition, f, log-weight.
 // Returns the thread's max log-weight (mx, -inf without an observation) and whether one was NaN.
@@ -386,15 +388,40 @@ template <> struct VecN<double, 2> { typedef double2 type; typedef int2 itype; }
 // both evaluate a particle with the same instruction sequence.  COH: the cloud and the ancestors
 // were written earlier in the SAME launch by other blocks, so they are read with ld.global.cg (L2)
 // instead of the non-coherent read-only path.
+// the normals of the coordinates kk .. kk+3 of the thread's PPT particles: counter = (global slot, step, chunk)
+template <typename real, int PPT>
+__device__ __forceinline__ void chunk_noise(int d, int kk, unsigned long long slot0, long long i0, uint32_t step, uint32_t key0,
+                                            uint32_t key1, real (&z)[4][PPT]) {
+  constexpr int PC = Normals<real>::PER_CALL;
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    unsigned long long slot = slot0 + (unsigned long long)(i0 + p);
+    real zz[4];
+    if (PC == 4) {
+      Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)(kk >> 2), key0, key1, zz);
+    } else {
+      Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)(kk >> 1), key0, key1, zz);
+      if (kk + 2 < d)
+        Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)((kk >> 1) + 1), key0, key1, zz + 2);
+      else
+        zz[2] = zz[3] = (real)0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j][p] = zz[j];
+  }
+}
+
+// sidx != NULL: the PPT source slots, already resolved by the caller (series kernel: polled from tagged ancestor words);
+// zpre != NULL (D > 0 only): the step's normals, drawn ahead by chunk_noise into zpre[chunk][4][PPT]
 template <typename real, int D, int PPT, bool COH = false, bool FULLBLK = false, bool SH = false>
 __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, const Peers& pr, real* __restrict__ xdst,
                                                     const int32_t* __restrict__ anc, real* __restrict__ logw,
                                                     const double* __restrict__ zinj, long long N, long long Ns,
                                                     unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
-                                                    long long i0, double& mx, bool& bad, real* lw_out = nullptr) {
+                                                    long long i0, double& mx, bool& bad, real* lw_out = nullptr,
+                                                    const int* sidx = nullptr, const real (*zpre)[4][PPT] = nullptr) {
   typedef typename VecN<real, PPT>::type vec_t;
   typedef typename VecN<real, PPT>::itype ivec_t;
-  constexpr int PC = Normals<real>::PER_CALL;
   const int d = (D > 0) ? D : a.d;
   const bool full = FULLBLK || (i0 + PPT <= N);  // FULLBLK: the caller knows that every thread of the block is full
   const real* src[PPT];
@@ -407,7 +434,10 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
       valid[p] = FULLBLK || (i0 + p < N);
       s[p] = i0 + p;
     }
-    if (anc != nullptr) {
+    if (sidx != nullptr) {
+#pragma unroll
+      for (int p = 0; p < PPT; ++p) s[p] = valid[p] ? (long long)sidx[p] : i0 + p;
+    } else if (anc != nullptr) {
       if (full) {
         const ivec_t v = COH ? __ldcg(reinterpret_cast<const ivec_t*>(anc + i0)) : *reinterpret_cast<const ivec_t*>(anc + i0);
         const int* vp = reinterpret_cast<const int*>(&v);
@@ -459,23 +489,13 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
     }
     // noise: counter = (global slot, step, chunk)
     real z[4][PPT];
-    if (zinj == nullptr) {
+    if (D > 0 && zpre != nullptr) {
 #pragma unroll
-      for (int p = 0; p < PPT; ++p) {
-        unsigned long long slot = slot0 + (unsigned long long)(i0 + p);
-        real zz[4];
-        if (PC == 4) {
-          Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)(kk >> 2), key0, key1, zz);
-        } else {
-          Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)(kk >> 1), key0, key1, zz);
-          if (kk + 2 < d)
-            Normals<real>::draw((uint32_t)slot, (uint32_t)(slot >> 32), step, RNG_STEP | (uint32_t)((kk >> 1) + 1), key0, key1, zz + 2);
-          else
-            zz[2] = zz[3] = (real)0;
-        }
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) z[j][p] = zz[j];
-      }
+        for (int p = 0; p < PPT; ++p) z[j][p] = zpre[kk >> 2][j][p];
+    } else if (zinj == nullptr) {
+      chunk_noise<real, PPT>(d, kk, slot0, i0, step, key0, key1, z);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -1115,6 +1135,10 @@ struct K3Ctl {
   double* ll_steps;
   int* ess_steps;
   long long step_slot;
+  // single-launch series kernel (k_series_small): ancestors leave as 64-bit words (tag << 32 | index) that the consumer
+  // polls -- no grid barrier between the search and the next gather.  NULL: plain int32 ancestors.
+  unsigned long long* anc64;
+  unsigned anc_tag;
 };
 
 // ONE thread of the whole filter, once per observed step: ll += max + log(mean w1) (model/ParticleFilter.scala:127), ESS =
@@ -1541,15 +1565,20 @@ __device__ __forceinline__ void tile_scan_local(int qb, long long base, long lon
 // after the barrier that follows tile_scan_local
 template <typename real, int ITEMS>
 __device__ __forceinline__ void tile_scan_finish(int qb, u128 excl, const u128* s_warp, const TileScan<real, ITEMS>& sc,
-                                                 TileRegs<real, ITEMS>& r) {
+                                                 TileRegs<real, ITEMS>& r, const u128* s_woff = nullptr) {
   constexpr int NW = TILE_THREADS / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u128 woff = excl, tend = excl;
+  if (s_woff != nullptr) {  // the caller already holds the exclusive prefix of the warp totals ([NW]: their sum)
+    woff = add128(excl, s_woff[wid]);
+    tend = add128(excl, s_woff[NW]);
+  } else {
 #pragma unroll
-  for (int w = 0; w < NW; ++w) {
-    const u128 v = s_warp[w];
-    tend = add128(tend, v);
-    woff = add128(woff, (w < wid) ? v : make_u128(0, 0));
+    for (int w = 0; w < NW; ++w) {
+      const u128 v = s_warp[w];
+      tend = add128(tend, v);
+      woff = add128(woff, (w < wid) ? v : make_u128(0, 0));
+    }
   }
   u128 ex = shfl_up128(sc.incl, 1);
   if (lane == 0) ex = make_u128(0, 0);
@@ -1589,7 +1618,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
                                         long long N, FilterScalars* __restrict__ sc, const SumTables& tb, const Peers& pr,
                                         const K3Ctl& ctl, const double* __restrict__ uarr, double* __restrict__ cdf_out, int t,
                                         u128 tot, u128 qsum, unsigned long long key, u128 excl,
-                                        const TileScan<real, ITEMS>* pre = nullptr) {
+                                        const TileScan<real, ITEMS>* pre = nullptr, const u128* pre_woff = nullptr) {
   constexpr int TILE = TILE_THREADS * ITEMS;
   constexpr int NW = K3Smem<ITEMS>::NW;
   constexpr int ROWS = K3Smem<ITEMS>::ROWS;
@@ -1634,7 +1663,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     __syncthreads();
     scan = &own;
   }
-  tile_scan_finish<real, ITEMS>(qb, excl, sm.s_warp, *scan, r);
+  tile_scan_finish<real, ITEMS>(qb, excl, sm.s_warp, *scan, r, pre != nullptr ? pre_woff : nullptr);
 
   if (cdf_out != nullptr) {
 #pragma unroll
@@ -1649,8 +1678,13 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   // all weights zero / NaN (the reference divides by a zero total here and fails later): keep every
   // particle as its own ancestor; FLAG_ZERO_TOTAL is already raised
   const bool usable = (total > 0.0) && (total - total == 0.0);
+  unsigned long long* const anc64 = PROTO3 ? nullptr : ctl.anc64;  // tagged ancestors: single-rank series kernel only
+  const unsigned long long tagw = (unsigned long long)ctl.anc_tag << 32;
   if (!usable) {
-    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) pr.anc[pr.rank][tile0 + j] = (int32_t)((long long)pr.rank * N + tile0 + j);
+    for (int j = threadIdx.x; j < tile_n; j += TILE_THREADS) {
+      if (anc64 != nullptr) st_relaxed_gpu(&anc64[tile0 + j], tagw | (unsigned long long)(unsigned)(tile0 + j));
+      else pr.anc[pr.rank][tile0 + j] = (int32_t)((long long)pr.rank * N + tile0 + j);
+    }
     return false;
   }
   // a tile whose weights are all zero owns no output: every cumulative value equals the one before the tile (a run that
@@ -1736,7 +1770,11 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
       if (cr[j] > prev && val == tile_n - 1) atomicMin(&sm.s_pend, lo + prev);
       if ((bmask >> j) & 1u) nb = idx;
     }
+    if (anc64 != nullptr) __syncthreads();  // s_pend is final before any tagged word leaves (below)
   }
+  // tagged ancestors are final the moment they are stored: the outputs of a run that continues past the tile -- they are
+  // rewritten after the walk below -- are held back by the expansion
+  const int o_pend = (anc64 != nullptr && cont && sm.s_pend - lo < (long long)n_out) ? (int)(sm.s_pend - lo) : 0x7FFFFFFF;
 
   // ---- expansion: the warp's particles into the warp's outputs [c0, c1), WINW per pass.  Every particle with
   //      offspring drops its value at the head of its range; a row of 32 outputs takes, per lane, the nearest head at
@@ -1746,7 +1784,9 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   constexpr int LONG_RUN = 64, HEAVY = 1024;
   auto store_out = [&](int o, int val) {
     const int32_t v = (int32_t)(gbase + val);
-    if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
+    if (anc64 != nullptr) {
+      if (o < o_pend) st_relaxed_gpu(&anc64[lo + o], tagw | (unsigned long long)(unsigned)v);
+    } else if (pr.R > 1) {  // offspring slot i belongs to rank i / N: scatter over NVLink
       const long long i = lo + o;
       const unsigned q = owner_of(pr, (unsigned)i);
       pr.anc[q][i - (long long)q * N] = v;
@@ -1903,7 +1943,9 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     }
     const long long jfinal = sm.s_jfinal;
     for (long long i = pend + threadIdx.x; i < hi; i += TILE_THREADS) {
-      if (pr.R > 1) {
+      if (anc64 != nullptr) {
+        st_relaxed_gpu(&anc64[i], tagw | (unsigned long long)(unsigned)jfinal);
+      } else if (pr.R > 1) {
         const unsigned q = owner_of(pr, (unsigned)i);
         pr.anc[q][i - (long long)q * N] = (int32_t)jfinal;
         wrote_remote |= (q != pr.rank);

@@ -32,21 +32,27 @@ namespace cssm {
 //   A[d] D[d] S[d] C[d]  y k0 k1 k2 k3 has_obs pad pad          (StepArgs without the padding)
 constexpr int SERIES_REC_EXTRA = 8;
 
-struct __align__(16) SeriesCtl {
-  unsigned long long bar;       // grid barrier arrivals (zero at launch)
-  unsigned long long gkey[2];   // k_series_multi: ordered key of max(logw) by step parity (zero at launch)
-  unsigned long long pad;
-  // k_series_small: arrivals and the running max key side by side, read by ONE 16-byte load: a snapshot whose counter is
-  // complete carries the complete max (every block's RED.MAX precedes its releasing arrival), so the consumer needs no
-  // second round trip to fetch the key after the barrier
-  unsigned long long bar2, key2;
+// k_series_small: arrivals and the running max key side by side, read by ONE 16-byte load: a snapshot whose counter is
+// complete carries the complete max (every block's RED.MAX precedes its releasing arrival), so the consumer needs no
+// second round trip to fetch the key after the barrier.  Two pairs, by step parity.
+struct __align__(16) SeriesPair {
+  unsigned long long bar, key;
 };
-static_assert(sizeof(SeriesCtl) == 48, "SeriesCtl layout");
+struct __align__(128) SeriesCtl {
+  unsigned long long bar;       // k_series_multi: grid barrier arrivals (zero at launch)
+  unsigned long long gkey[2];   // k_series_multi: ordered key of max(logw) by step parity (zero at launch)
+  unsigned long long pad[13];
+  SeriesPair pk[2];             // k_series_small (zero at launch)
+  unsigned long long pad2[12];
+};
+static_assert(sizeof(SeriesCtl) == 256, "SeriesCtl layout");
 
 struct SeriesArgs {
   void* x[2];               // ping-pong clouds; x[0] is the current one at entry
   void* logw;
+  void* logw2;              // k_series_small: second log-weight buffer (steps alternate; the last step writes `logw`)
   int32_t* anc;
+  unsigned long long* anc64;  // k_series_small: tagged ancestor words [Ns], zero at launch
   FilterScalars* sc;
   u128* tile_sum;           // [nt]
   u128* tile_q;             // [nt]
@@ -60,7 +66,7 @@ struct SeriesArgs {
   uint32_t key0, key1, step0;   // Philox step counter of the first step
   double inv_n;                 // 1/N when N is a power of two, else 0
   int tie_first;                // K3Ctl::tie_first
-  unsigned long long* dbg;      // NULL, or 8 cycle counters of block 0 (CSSM_SERIES_DEBUG): P1 B1 P2 B2 P3 B3 head
+  unsigned long long* dbg;      // NULL, or 8 cycle counters per block [8][grid] (CSSM_SERIES_DEBUG): P1 B1 P2 B2 P3 anc-wait head
   Peers pr[2];                  // the (single-rank) topology with x[0] = the cloud read in even / odd steps: kept in
                                 // the kernel's constant bank instead of a 400-byte struct in local memory
 };
@@ -108,24 +114,28 @@ __device__ __forceinline__ void grid_barrier(SeriesCtl* c, FilterScalars* sc, un
 __device__ __forceinline__ void ld_acquire_gpu_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-// The same barrier on the (bar2, key2) pair: *key_out = the max key every block folded into key2 BEFORE arriving (thread 0
-// only; the caller broadcasts it).  `idle`: work thread 0 does between its arrival and its first poll -- the barrier
-// takes ~2.7 k cycles whatever it does meanwhile, so up to that much serial work is free there.
-template <typename Idle>
-__device__ __forceinline__ void grid_barrier_key(SeriesCtl* c, FilterScalars* sc, unsigned long long& target, unsigned G,
-                                                 unsigned long long* key_out, Idle idle) {
+// The same barrier on an (arrivals, key) pair: *key_out = the max key every block folded into the pair BEFORE arriving
+// (thread 0 only; the caller broadcasts it).  Between the arrival and the first poll -- the barrier takes ~2.7 k cycles
+// whatever the block does meanwhile -- every thread runs `idle_all` and thread 0 then `idle_t0`: work that does not
+// depend on what the barrier publishes is free there.
+template <typename IdleAll, typename IdleT0>
+__device__ __forceinline__ void grid_barrier_pair(SeriesPair* c, FilterScalars* sc, unsigned long long& target, unsigned G,
+                                                  unsigned long long* key_out, IdleAll idle_all, IdleT0 idle_t0) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += G;
-    red_release_gpu_add(&c->bar2, 1ull);
-    idle();
+    red_release_gpu_add(&c->bar, 1ull);
+  }
+  idle_all();
+  if (threadIdx.x == 0) {
+    idle_t0();
     unsigned long long n, k;
-    ld_acquire_gpu_pair(&c->bar2, n, k);
+    ld_acquire_gpu_pair(&c->bar, n, k);
     if (n < target && !(*(volatile int*)&sc->flags & FLAG_COMM_TIMEOUT)) {
       unsigned long long t0 = 0;
       unsigned spins = 0;
       for (;;) {
-        ld_acquire_gpu_pair(&c->bar2, n, k);
+        ld_acquire_gpu_pair(&c->bar, n, k);
         if (n >= target) break;
         if ((++spins & 1023u) == 0u) {
           const unsigned long long now = global_timer_ns();
@@ -144,15 +154,30 @@ __device__ __forceinline__ void grid_barrier_key(SeriesCtl* c, FilterScalars* sc
 
 // the kernels below are instantiated in cssm_series.cu only: the optimiser's choices for them and for the step kernels of
 // cssm_api.cu then do not depend on each other; the host side asks for them by these two functions
-void* series_small_kernel(int dtype, int d, int resample_kind);
+void* series_small_kernel(int dtype, int items, int d, int resample_kind);
 void* series_multi_kernel(int dtype, int items, int d, int resample_kind);
 
 #define CSSM_STAMP(slot)                                              \
-  if (sa.dbg != nullptr && t == 0 && threadIdx.x == 0) {              \
+  if (sa.dbg != nullptr && threadIdx.x == 0) {                        \
     const long long now_ = clock64();                                 \
-    atomicAdd(&sa.dbg[slot], (unsigned long long)(now_ - stamp_));    \
+    s_dbg[slot] += (unsigned long long)(now_ - stamp_);               \
     stamp_ = now_;                                                    \
   }
+
+// max over the warp of a thread's largest log-weight (a value of the filter dtype held in a double, never NaN): for fp32
+// one REDUX.MAX on the order-preserving integer image instead of five shuffle rounds in fp64
+template <typename real> __device__ __forceinline__ double warp_max_lw(double mx);
+template <> __device__ __forceinline__ double warp_max_lw<double>(double mx) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  return mx;
+}
+template <> __device__ __forceinline__ double warp_max_lw<float>(double mx) {
+  const unsigned b = __float_as_uint((float)mx);
+  const unsigned k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  const unsigned r = __reduce_max_sync(0xffffffffu, k);
+  return (double)__uint_as_float((r & 0x80000000u) ? (r & 0x7fffffffu) : ~r);
+}
 
 // the record of one observation -> the StepArgs in shared memory (one element per thread, rec_len <= TILE_THREADS)
 template <typename real>
@@ -171,27 +196,46 @@ __device__ __forceinline__ void rec_to_args(StepArgs<real>& a, real rec_v, int d
   else if (e == 6) { a.d = d; a.obs_kind = obs_kind; }
 }
 
-template <typename real, int D, int KIND>
+// k_series_small: TWO grid barriers per observed step.  The third one -- "every ancestor is written before the next
+// gather" -- is replaced by tagged ancestor words: the search stores (step tag << 32 | index) and the thread that owns an
+// output slot polls ITS OWN words until they carry the tag of the step.  What that removes from the hazards the barrier
+// used to cover, and what covers them now:
+//   * log-weights: the walk over a run of repeated keys (k3_tile) may read another tile's log-weights while that tile
+//     already writes those of the next step -> two buffers, by step parity (the last step always uses sa.logw);
+//   * the running max: (arrivals, key) pairs by step parity; block 0 clears the other pair between the two barriers of
+//     a step, when nobody reads or updates it;
+//   * ll / ESS of step s: block 0, inside the wait of the first barrier of step s + 1 (or after the loop);
+//   * tile tables: written after the first barrier of step s + 1, which every block reaches after its search of step s.
+// A step without an observation keeps one barrier (the clouds are ping-pong buffers).
+// The normals of step s + 1 depend on nothing: every thread draws them while it waits for the second barrier of step s.
+// ITEMS = 1 (256-particle tiles, two blocks per SM) while the cloud fits that way: the stages are chains of dependent
+// instructions, and sixteen warps per SM with one particle per thread run them faster than eight with two.
+template <typename real, int D, int KIND, int ITEMS>
 __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_constant__ SeriesArgs sa) {
-  constexpr int ITEMS = 2;
   constexpr int TILE = TILE_THREADS * ITEMS;
   constexpr int NW = TILE_THREADS / 32;
+  constexpr int NCH = (D > 0) ? (D + 3) / 4 : 1;  // chunks of four coordinates whose normals are drawn ahead
   typedef typename WeightSrc<real>::wt wt;
   __shared__ K3Smem<ITEMS> sm;
   __shared__ StepArgs<real> abuf[2];  // the constants of step s in abuf[s & 1]; the next step's are written a step ahead
   __shared__ double s_mx[NW], s_mxw[NW];
   __shared__ u128 s_r[3][NW], s_q2[NW];
+  __shared__ u128 s_woff[NW + 1];  // exclusive prefix of the warp totals inside the tile, [NW] = the tile sum
   __shared__ int s_bad;
   __shared__ unsigned long long s_key;
+  __shared__ u128 s_ll_tot, s_ll_q;   // block 0: what the deferred ll / ESS update of the last observed step needs
+  __shared__ unsigned long long s_ll_key;
+  __shared__ int s_ll_slot;
 
   const int t = blockIdx.x;  // one tile per block, gridDim.x == nt
   const unsigned G = gridDim.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int d = (D > 0) ? D : sa.d;
   const long long N = sa.N, Ns = sa.Ns;
-  real* const logw = reinterpret_cast<real*>(sa.logw);
-  unsigned long long target = 0;
+  unsigned long long target[2] = {0ull, 0ull};
   long long stamp_ = clock64();
+  __shared__ unsigned long long s_dbg[8];  // CSSM_SERIES_DEBUG: cycles of thread 0 per stage (every block reports)
+  if (threadIdx.x < 8) s_dbg[threadIdx.x] = 0ull;
 
   SumTables tb;
   tb.tile_sum = sa.tile_sum;
@@ -204,15 +248,42 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
   tb.ns = 0;
 
   int cur = 0;
-  bool anc_valid = false;
+  unsigned anc_tag = 0;  // != 0: the ancestors of the previous step, as tagged words
   const int rec_len = 4 * d + SERIES_REC_EXTRA;  // <= 136 <= TILE_THREADS: one element per thread
   {
     const real r0 = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
     rec_to_args<real>(abuf[0], r0, d, sa.obs_kind);
-    if (threadIdx.x == 0) s_bad = 0;
+    if (threadIdx.x == 0) { s_bad = 0; s_ll_slot = -1; }
   }
   // the record of step s + 1 travels in a register during step s and is stored into the other buffer at the top of it
   real rec_v = (sa.T > 1 && (int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + rec_len + threadIdx.x) : (real)0;
+  const long long i0 = (long long)t * TILE + (long long)threadIdx.x * ITEMS;
+  real zpre[NCH][4][ITEMS];
+  bool z_ready = false;
+  K3Ctl kc;
+  kc.parity = 0;
+  kc.obs_seq = 0;
+  kc.gstep = 0;
+  kc.inv_n = sa.inv_n;
+  kc.direct = 0;
+  kc.add_ll = 1;
+  kc.use_u_inj = 0;
+  kc.tie_first = sa.tie_first;
+  kc.defer_ll = 1;
+  kc.fast_ok = 0;
+  kc.key0 = sa.key0;
+  kc.key1 = sa.key1;
+  kc.ll_steps = sa.ll_steps;
+  kc.ess_steps = sa.ess_steps;
+  kc.anc64 = sa.anc64;
+  auto deferred_ll = [&]() {  // thread 0 of block 0
+    if (t == 0 && s_ll_slot >= 0) {
+      K3Ctl k2 = kc;
+      k2.step_slot = s_ll_slot;
+      ll_ess_update<real, false>(sa.sc, k2, s_ll_tot, s_ll_q, s_ll_key, (long long)N, false);
+      s_ll_slot = -1;
+    }
+  };
   __syncthreads();
   for (int s = 0; s < sa.T; ++s) {
     const StepArgs<real>& a = abuf[s & 1];
@@ -221,6 +292,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
     if (s + 2 < sa.T && (int)threadIdx.x < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 2) * rec_len + threadIdx.x);
     const int has_obs = a.has_obs;
     const uint32_t step = sa.step0 + (uint32_t)s;
+    const int pp = s & 1;
+    SeriesPair* const pk = &sa.ctl->pk[pp];
+    real* const logw = reinterpret_cast<real*>(((sa.T - 1 - s) & 1) ? sa.logw2 : sa.logw);
 
     CSSM_STAMP(6)
     // ---- P1 ------------------------------------------------------------------------------------
@@ -228,17 +302,54 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
     double mx;
     bool bad;
     real lw[ITEMS];
-    const long long i0 = (long long)t * TILE + (long long)threadIdx.x * ITEMS;
-    propagate_particles<real, D, ITEMS, true>(a, pr, reinterpret_cast<real*>(sa.x[cur ^ 1]), anc_valid ? sa.anc : nullptr, logw,
-                                              nullptr, N, Ns, 0ull, sa.key0, sa.key1, step, i0, mx, bad, lw);
+    int sidx[ITEMS];
+    if (anc_tag != 0u) {  // the ancestors of this thread's two slots: poll until both words carry the tag of the last search
+      unsigned long long w[ITEMS];
+      auto load = [&]() {
+        if (ITEMS == 2) ld_gpu_pair(&sa.anc64[i0], w[0], w[ITEMS - 1]);
+        else w[0] = ld_gpu(&sa.anc64[i0]);
+      };
+      auto complete = [&]() {  // slots past the end of a ragged cloud are never written
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) ok &= !(i0 + j < N) || (unsigned)(w[j] >> 32) == anc_tag;
+        return ok;
+      };
+      load();
+      if (!complete()) {
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+          load();
+          if (complete()) break;
+          if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull || (*(volatile int*)&sa.sc->flags & FLAG_COMM_TIMEOUT)) {
+              atomicOr(&sa.sc->flags, FLAG_COMM_TIMEOUT);
+#pragma unroll
+              for (int j = 0; j < ITEMS; ++j) w[j] = (unsigned long long)(i0 + j);  // indices inside the cloud; the run is reported as failed
+              break;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) sidx[j] = (int)(unsigned)w[j];
+    }
+    CSSM_STAMP(5)
+    propagate_particles<real, D, ITEMS, true>(a, pr, reinterpret_cast<real*>(sa.x[cur ^ 1]), nullptr, logw, nullptr, N, Ns, 0ull,
+                                              sa.key0, sa.key1, step, i0, mx, bad, lw, anc_tag != 0u ? sidx : nullptr,
+                                              (D > 0 && z_ready) ? zpre : nullptr);
     cur ^= 1;
-    anc_valid = false;
-    if (!has_obs) {  // propagated only (:121); the next gather may read any slot of this cloud
-      grid_barrier_key(sa.ctl, sa.sc, target, G, nullptr, [] {});
+    anc_tag = 0u;
+    z_ready = false;
+    if (!has_obs) {  // propagated only (:121); one barrier: the clouds are ping-pong buffers
+      if (t == 0 && threadIdx.x == 0) sa.ctl->pk[pp ^ 1].key = 0ull;
+      grid_barrier_pair(pk, sa.sc, target[pp], G, nullptr, [] {}, [] {});
       continue;
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    mx = warp_max_lw<real>(mx);
     if (lane == 0) s_mx[wid] = mx;
     if (bad) s_bad = 1;
     __syncthreads();
@@ -246,11 +357,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
       double m2 = s_mx[0];
 #pragma unroll
       for (int w = 1; w < NW; ++w) m2 = fmax(m2, s_mx[w]);
-      atomicMax(&sa.ctl->key2, ord_key(m2));
+      atomicMax(&pk->key, ord_key(m2));
       if (s_bad) { atomicOr(&sa.sc->flags, FLAG_NAN_WEIGHT); s_bad = 0; }
     }
     CSSM_STAMP(0)
-    grid_barrier_key(sa.ctl, sa.sc, target, G, &s_key, [] {});  // the max arrives with the barrier's own snapshot
+    kc.step = step;
+    kc.step_slot = s;
+    kc.anc_tag = (unsigned)s + 1u;
+    // the max arrives with the barrier's own snapshot; in its shadow: the resampling uniform (one thread), and ll / ESS of
+    // the previous observed step (thread 0 of block 0)
+    grid_barrier_pair(pk, sa.sc, target[pp], G, &s_key,
+                      [&] { if (threadIdx.x == 64) k3_prepare<ITEMS>(sm, sa.sc, kc); },
+                      [&] { deferred_ll(); });
     CSSM_STAMP(1)
 
     // ---- P2: weights, and the LOCAL part of the tile scan (its by-product is the exact tile sum) ------------
@@ -258,28 +376,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
     const PreScan ps = pre_scan(key, false);
     const int qb = ps.qb;
     WeightSrc<real> ws{logw, nullptr, ps.gmax};
-    K3Ctl kc;
-    kc.parity = 0;
-    kc.obs_seq = 0;
-    kc.gstep = 0;
-    kc.inv_n = sa.inv_n;
-    kc.direct = 0;
-    kc.add_ll = 1;
-    kc.use_u_inj = 0;
-    kc.tie_first = sa.tie_first;
-    kc.defer_ll = 1;  // ll / ESS: block 0, inside the wait of the step's last barrier
-    kc.key0 = sa.key0;
-    kc.key1 = sa.key1;
-    kc.step = step;
-    kc.ll_steps = sa.ll_steps;
-    kc.ess_steps = sa.ess_steps;
-    kc.step_slot = s;
     TileScan<real, ITEMS> scan;  // this thread's weights, from the log-weights it still holds in registers
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) scan.w[j] = (i0 + j < N) ? ws.weight(lw[j]) : (wt)0;
     {
-      if (threadIdx.x == 64) k3_prepare<ITEMS>(sm, sa.sc, kc);       // the resampling uniform: Philox, off the critical path
       if (threadIdx.x == 32) sm.s_wnext = (t < sa.nt - 1) ? (double)ws((long long)(t + 1) * TILE) : 0.0;  // first weight of the next tile
+      if (t == 0 && threadIdx.x == 0) sa.ctl->pk[pp ^ 1].key = 0ull;  // nobody reads or updates the other pair now
       u128 acc2 = make_u128(0, 0);
       wt mxv = (wt)0;
 #pragma unroll
@@ -295,52 +397,77 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
       if (threadIdx.x == 0) {
         u128 t1 = sm.s_warp[0], t2 = s_q2[0];
         double m2 = s_mxw[0];
+        s_woff[0] = make_u128(0, 0);
 #pragma unroll
         for (int w = 1; w < NW; ++w) {
+          s_woff[w] = t1;  // exact sum of the warps before warp w: the scan's finish reads one word instead of adding eight
           t1 = add128(t1, sm.s_warp[w]);
           t2 = add128(t2, s_q2[w]);
           m2 = fmax(m2, s_mxw[w]);
         }
+        s_woff[NW] = t1;
         sa.tile_sum[t] = t1;
         sa.tile_q[t] = t2;
         sa.tile_maxw[t] = m2;
       }
     }
     CSSM_STAMP(2)
-    grid_barrier_key(sa.ctl, sa.sc, target, G, nullptr, [] {});
+    // in the shadow of the second barrier: the normals of the next step (they depend on nothing but the slot and the step)
+    grid_barrier_pair(pk, sa.sc, target[pp], G, nullptr,
+                      [&] {
+                        if (D > 0 && s + 1 < sa.T) {
+#pragma unroll
+                          for (int c = 0; c < NCH; ++c) chunk_noise<real, ITEMS>(d, 4 * c, 0ull, i0, step + 1u, sa.key0, sa.key1, zpre[c]);
+                          z_ready = true;
+                        }
+                      },
+                      [] {});
     CSSM_STAMP(3)
 
     // ---- P3: totals and this tile's exclusive prefix from the tile sums, then the FINISH of the scan + the search ----
     {
-      u128 at = make_u128(0, 0), aq = make_u128(0, 0), ae = make_u128(0, 0);
-      for (int tt = threadIdx.x; tt < sa.nt; tt += TILE_THREADS) {
-        const u128 v = ld_gpu128(&sa.tile_sum[tt]);
-        at = add128(at, v);
-        if (tt < t) ae = add128(ae, v);
-        if (t == 0) aq = add128(aq, ld_gpu128(&sa.tile_q[tt]));  // the sum of squares only feeds the ESS, which block 0 computes
+      // warp 0: the total; warp 1: the sum of the tiles before this one; warp 2 of block 0: the sum of squares (it only
+      // feeds the ESS, which block 0 computes).  One warp-wide sum each instead of three per warp plus an eight-way add.
+      if (wid < 3 && (wid < 2 || t == 0)) {
+        const u128* const src = (wid == 2) ? sa.tile_q : sa.tile_sum;
+        const int lim = (wid == 1) ? t : sa.nt;
+        u128 a_ = make_u128(0, 0);
+        for (int tt = lane; tt < lim; tt += 32) a_ = add128(a_, ld_gpu128(&src[tt]));
+        a_ = warp_sum128(a_);
+        if (lane == 0) s_r[0][wid] = a_;
       }
-      at = warp_sum128(at);
-      ae = warp_sum128(ae);
-      if (t == 0) aq = warp_sum128(aq);
-      if (lane == 0) { s_r[0][wid] = at; s_r[1][wid] = aq; s_r[2][wid] = ae; }
       __syncthreads();
-      u128 tot = s_r[0][0], qsum = s_r[1][0], excl = s_r[2][0];
-#pragma unroll
-      for (int w = 1; w < NW; ++w) {
-        tot = add128(tot, s_r[0][w]);
-        qsum = add128(qsum, s_r[1][w]);
-        excl = add128(excl, s_r[2][w]);
-      }
-      if (t == 0 && threadIdx.x == 0) sa.ctl->key2 = 0ull;  // every block took its snapshot at the first barrier of the step
-      k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, tot, qsum, key, excl, &scan);
-      anc_valid = true;
+      const u128 tot = s_r[0][0], excl = s_r[0][1];
+      const u128 qsum = (t == 0) ? s_r[0][2] : make_u128(0, 0);
+      if (t == 0 && threadIdx.x == 0) { s_ll_tot = tot; s_ll_q = qsum; s_ll_key = key; s_ll_slot = s; }
+      k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, tot, qsum, key, excl, &scan, s_woff);
+      anc_tag = kc.anc_tag;
+      // no block barrier here: what the next step writes before its first barrier (abuf of step s + 2, s_mx) is not read
+      // by the search, and the search's own shared memory is next written behind that barrier
       CSSM_STAMP(4)
-      // ll += max + log(mean w1) and the ESS (three divisions and a logarithm, one thread) ride in the barrier's wait
-      grid_barrier_key(sa.ctl, sa.sc, target, G, nullptr, [&] {
-        if (t == 0) ll_ess_update<real, false>(sa.sc, kc, tot, qsum, key, (long long)N, false);
-      });
     }
-    CSSM_STAMP(5)
+  }
+  if (threadIdx.x == 0) deferred_ll();
+  if (sa.dbg != nullptr && threadIdx.x == 0)
+    for (int k = 0; k < 8; ++k) sa.dbg[(size_t)k * G + t] = s_dbg[k];
+  // the host's view: plain int32 ancestors of the last search
+  if (anc_tag != 0u) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      if (i0 + j >= N) continue;
+      unsigned long long w = ld_gpu(&sa.anc64[i0 + j]);
+      unsigned long long t0 = 0;
+      unsigned spins = 0;
+      while ((unsigned)(w >> 32) != anc_tag) {
+        w = ld_gpu(&sa.anc64[i0 + j]);
+        if ((++spins & 1023u) == 0u) {
+          const unsigned long long now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 2000000000ull) { atomicOr(&sa.sc->flags, FLAG_COMM_TIMEOUT); w = (unsigned long long)(i0 + j); break; }
+        }
+      }
+      sa.anc[i0 + j] = (int32_t)(unsigned)w;
+    }
   }
 }
 #undef CSSM_STAMP
@@ -514,6 +641,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_series_multi(const __grid_c
       __syncthreads();
       const u128 tot = sm.s_tot, qsum = sm.s_q;
       K3Ctl kc;
+      kc.anc64 = nullptr;
+      kc.anc_tag = 0;
+      kc.fast_ok = 0;
       kc.parity = 0;
       kc.obs_seq = 0;
       kc.gstep = 0;
