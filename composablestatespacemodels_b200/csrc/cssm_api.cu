@@ -599,7 +599,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   ctl.inv_n = ((Ng & (Ng - 1)) == 0) ? 1.0 / (double)Ng : 0.0;
   ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj; ctl.tie_first = f->tie_first; ctl.defer_ll = 0;
   ctl.fast_ok = f->scan_fast;
-  ctl.anc64 = nullptr; ctl.anc_tag = 0;
+  ctl.anc64 = nullptr; ctl.anc_tag = 0; ctl.dbg = nullptr;
   ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
   ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
   const bool strat = f->resample_kind == CSSM_RESAMPLE_STRATIFIED;
@@ -810,13 +810,13 @@ bool series_eligible(cssm_filter* f, bool sample_states) {
   if (f->model.obs_kind == CSSM_OBS_LGCP || f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL) return false;
   if (f->series.empty() || f->series.size() > 0x7fffffffull) return false;
   if (f->series_max_blocks < 0) {
-    f->series_max_blocks = resident_blocks(f, series_kernel(f, 2));
+    f->series_max_blocks = std::min(resident_blocks(f, series_kernel(f, 2)), SERIES_SMALL_MAX_TILES);
     f->series_multi_blocks = resident_blocks(f, series_multi_kernel(f));
   }
   f->series_use_multi = false;
   // one 512-particle tile per block, weights stay in registers
   f->series_items = 0;
-  if (nblk(f->N, 2 * TILE_THREADS) <= f->series_max_blocks) f->series_items = 2;
+  if (nblk(f->N, 2 * TILE_THREADS) + 1 <= f->series_max_blocks) f->series_items = 2;  // one block per tile + the accountant
   if (f->series_items != 0) return true;
   // several tiles per block: pays while a stage is short against the launch gaps it removes
   if (f->series_multi_blocks > 0 && (f->N <= f->series_multi_max || f->series_mode == CSSM_SERIES_SINGLE_LAUNCH)) {
@@ -902,9 +902,9 @@ int run_series_single_launch(cssm_filter* f) {
   sa.pr[1] = make_peers(f, f->cur ^ 1);
   static const bool debug_stamps = std::getenv("CSSM_SERIES_DEBUG") != nullptr;
   if (debug_stamps && !f->series_use_multi) {
-    int rc2 = ensure_scratch(f, (size_t)8 * 512);
+    int rc2 = ensure_scratch(f, (size_t)16 * 512);
     if (rc2) return rc2;
-    CU(cudaMemsetAsync(f->scratch, 0, (size_t)8 * 512 * 8, f->stream));
+    CU(cudaMemsetAsync(f->scratch, 0, (size_t)16 * 512 * 8, f->stream));
     sa.dbg = (unsigned long long*)f->scratch;
   }
   void* args[] = {&sa};
@@ -916,7 +916,7 @@ int run_series_single_launch(cssm_filter* f) {
       e = cudaLaunchCooperativeKernel(series_multi_kernel(f), dim3((unsigned)std::min(f->nt, f->series_multi_blocks)), dim3(TILE_THREADS),
                                       args, 0, f->stream);
     else
-      e = cudaLaunchCooperativeKernel(series_kernel(f, f->series_items), dim3((unsigned)sa.nt), dim3(TILE_THREADS), args, 0, f->stream);
+      e = cudaLaunchCooperativeKernel(series_kernel(f, f->series_items), dim3((unsigned)sa.nt + 1u), dim3(TILE_THREADS), args, 0, f->stream);  // + the accountant block
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch series kernel: ") + cudaGetErrorString(e));
   f->launches++;
@@ -927,11 +927,11 @@ int run_series_single_launch(cssm_filter* f) {
   f->t_cur = f->series.back().t;
   CU(cudaEventRecord(f->ev1, f->stream));
   if (sa.dbg != nullptr && sa.nt <= 512) {  // per stage: thread 0's cycles per step, min / mean / max over the blocks (and who was slowest)
-    static unsigned long long c[8 * 512];
+    static unsigned long long c[16 * 512];
     CU(cudaMemcpyAsync(c, f->scratch, sizeof(c), cudaMemcpyDeviceToHost, f->stream));
     CU(cudaStreamSynchronize(f->stream));
-    const char* name[8] = {"P1", "B1", "P2", "B2", "P3", "anc-wait", "head", "-"};
-    const int order[7] = {6, 5, 0, 1, 2, 3, 4};
+    const char* name[16] = {"P1", "B1", "P2", "B2", "P3", "anc-wait", "head", "-", "P3:sums", "P3:finish", "P3:counts", "P3:ties", "P3:expand", "P3:sync", "-", "-"};
+    const int order[13] = {6, 5, 0, 1, 2, 3, 4, 8, 9, 10, 11, 12, 13};
     std::fprintf(stderr, "series kernel, cycles per step (T=%zu, blocks %d): ", T, sa.nt);
     for (int k : order) {
       double mn = 1e30, mx = 0, sum = 0;

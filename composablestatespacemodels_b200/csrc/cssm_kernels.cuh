@@ -1139,7 +1139,14 @@ struct K3Ctl {
   // polls -- no grid barrier between the search and the next gather.  NULL: plain int32 ancestors.
   unsigned long long* anc64;
   unsigned anc_tag;
+  unsigned long long* dbg;  // CSSM_SERIES_DEBUG: shared-memory cycle counters of thread 0 ([7] = last stamp, [8..15] = stages of the search)
 };
+#define K3_STAMP(slot)                                                        \
+  if (!PROTO3 && ctl.dbg != nullptr && threadIdx.x == 0) {                    \
+    const unsigned long long now_ = (unsigned long long)clock64();            \
+    ctl.dbg[slot] += now_ - ctl.dbg[7];                                       \
+    ctl.dbg[7] = now_;                                                        \
+  }
 
 // ONE thread of the whole filter, once per observed step: ll += max + log(mean w1) (model/ParticleFilter.scala:127), ESS =
 // floor(1 / sum wn^2) (:431-434) from the exact sums; PROTO3: also zero the accumulators of the next observed step.
@@ -1663,7 +1670,9 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
     __syncthreads();
     scan = &own;
   }
+  K3_STAMP(8)
   tile_scan_finish<real, ITEMS>(qb, excl, sm.s_warp, *scan, r, pre != nullptr ? pre_woff : nullptr);
+  K3_STAMP(9)
 
   if (cdf_out != nullptr) {
 #pragma unroll
@@ -1715,6 +1724,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   const int c0 = __shfl_sync(FULL, cprev, 0), c1 = __shfl_sync(FULL, cr[ITEMS - 1], 31);  // the warp's outputs [c0, c1)
   const int n_out = last_tile ? n_rel : kf.count_rel(c_end, scale, Ng, lo, lo_d, n_rel);
   const long long hi = lo + n_out;
+  K3_STAMP(10)
   // A key can only repeat where a weight is at most 2^-52 of the cumulative value before it (vanishes()).  If even the
   // smallest weight of the tile is above 2^-52 of the tile's LAST cumulative value, no key of this tile repeats.
   unsigned mm = sm.s_minw[0];
@@ -1781,6 +1791,7 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
   //      or below it (ballot + indexed shuffle), else the value carried over from the row before.  A particle with many
   //      offspring is not staged at all: its range is one value, written 32 outputs per store by the warp, or -- from
   //      HEAVY offspring on -- queued for the whole block. -----------------------------------------------------------
+  K3_STAMP(11)
   constexpr int LONG_RUN = 64, HEAVY = 1024;
   auto store_out = [&](int o, int val) {
     const int32_t v = (int32_t)(gbase + val);
@@ -1870,7 +1881,9 @@ __device__ __forceinline__ bool k3_tile(K3Smem<ITEMS>& sm, const real* __restric
       w0 += WINW;
     }
   }
+  K3_STAMP(12)
   __syncthreads();  // the heavy queue is complete (and s_pend final)
+  K3_STAMP(13)
   {
     const int hn = min(sm.s_hn, K3Smem<ITEMS>::HQ);
     for (int h = 0; h < hn; ++h) {

@@ -31,6 +31,7 @@ namespace cssm {
 // per-observation record in device memory, in the filter dtype:
 //   A[d] D[d] S[d] C[d]  y k0 k1 k2 k3 has_obs pad pad          (StepArgs without the padding)
 constexpr int SERIES_REC_EXTRA = 8;
+constexpr int SERIES_SMALL_MAX_TILES = 384;  // k_series_small: one tile per block, at most this many blocks (a multiple of 128)
 
 // k_series_small: arrivals and the running max key side by side, read by ONE 16-byte load: a snapshot whose counter is
 // complete carries the complete max (every block's RED.MAX precedes its releasing arrival), so the consumer needs no
@@ -118,10 +119,12 @@ __device__ __forceinline__ void ld_acquire_gpu_pair(const unsigned long long* p,
 // (thread 0 only; the caller broadcasts it).  Between the arrival and the first poll -- the barrier takes ~2.7 k cycles
 // whatever the block does meanwhile -- every thread runs `idle_all` and thread 0 then `idle_t0`: work that does not
 // depend on what the barrier publishes is free there.
-template <typename IdleAll, typename IdleT0>
+// LEAD = false: the caller has already passed a block barrier behind the block's last global write of the stage (or
+// thread 0 alone wrote), so thread 0 arrives at once.
+template <bool LEAD = true, typename IdleAll, typename IdleT0>
 __device__ __forceinline__ void grid_barrier_pair(SeriesPair* c, FilterScalars* sc, unsigned long long& target, unsigned G,
                                                   unsigned long long* key_out, IdleAll idle_all, IdleT0 idle_t0) {
-  __syncthreads();
+  if (LEAD) __syncthreads();
   if (threadIdx.x == 0) {
     target += G;
     red_release_gpu_add(&c->bar, 1ull);
@@ -223,9 +226,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
   __shared__ u128 s_woff[NW + 1];  // exclusive prefix of the warp totals inside the tile, [NW] = the tile sum
   __shared__ int s_bad;
   __shared__ unsigned long long s_key;
-  __shared__ u128 s_ll_tot, s_ll_q;   // block 0: what the deferred ll / ESS update of the last observed step needs
-  __shared__ unsigned long long s_ll_key;
-  __shared__ int s_ll_slot;
 
   const int t = blockIdx.x;  // one tile per block, gridDim.x == nt
   const unsigned G = gridDim.x;
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
   const long long N = sa.N, Ns = sa.Ns;
   unsigned long long target[2] = {0ull, 0ull};
   long long stamp_ = clock64();
-  __shared__ unsigned long long s_dbg[8];  // CSSM_SERIES_DEBUG: cycles of thread 0 per stage (every block reports)
-  if (threadIdx.x < 8) s_dbg[threadIdx.x] = 0ull;
+  __shared__ unsigned long long s_dbg[16];  // CSSM_SERIES_DEBUG: cycles of thread 0 per stage (every block reports)
+  if (threadIdx.x < 16) s_dbg[threadIdx.x] = 0ull;
 
   SumTables tb;
   tb.tile_sum = sa.tile_sum;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
   {
     const real r0 = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
     rec_to_args<real>(abuf[0], r0, d, sa.obs_kind);
-    if (threadIdx.x == 0) { s_bad = 0; s_ll_slot = -1; }
+    if (threadIdx.x == 0) s_bad = 0;
   }
   // the record of step s + 1 travels in a register during step s and is stored into the other buffer at the top of it
   real rec_v = (sa.T > 1 && (int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + rec_len + threadIdx.x) : (real)0;
@@ -276,20 +276,60 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
   kc.ll_steps = sa.ll_steps;
   kc.ess_steps = sa.ess_steps;
   kc.anc64 = sa.anc64;
-  auto deferred_ll = [&]() {  // thread 0 of block 0
-    if (t == 0 && s_ll_slot >= 0) {
-      K3Ctl k2 = kc;
-      k2.step_slot = s_ll_slot;
-      ll_ess_update<real, false>(sa.sc, k2, s_ll_tot, s_ll_q, s_ll_key, (long long)N, false);
-      s_ll_slot = -1;
-    }
-  };
+  kc.dbg = sa.dbg != nullptr ? s_dbg : nullptr;
   __syncthreads();
+  // ---- the accountant: one extra block (the last of the grid) that owns no particles.  It takes part in every barrier
+  //      -- never as the last to arrive -- and does what one thread has to do once per step: ll += max + log(mean w1) and
+  //      the ESS from the exact sums (three divisions and a logarithm in fp64), the reset of the other parity's max.  In
+  //      a block that also carries a tile that serial work made the block late for the next barrier, and with it the grid.
+  if (t == sa.nt) {
+    for (int s = 0; s < sa.T; ++s) {
+      const int pp = s & 1;
+      SeriesPair* const pk = &sa.ctl->pk[pp];
+      const bool obs = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)s * rec_len + 4 * d + 5) != (real)0;
+      if (!obs) {
+        if (threadIdx.x == 0) sa.ctl->pk[pp ^ 1].key = 0ull;
+        grid_barrier_pair(pk, sa.sc, target[pp], G, nullptr, [] {}, [] {});
+        continue;
+      }
+      grid_barrier_pair(pk, sa.sc, target[pp], G, &s_key, [] {}, [] {});
+      const unsigned long long key = s_key;
+      if (threadIdx.x == 0) sa.ctl->pk[pp ^ 1].key = 0ull;  // nobody reads or updates the other pair between the two barriers
+      grid_barrier_pair(pk, sa.sc, target[pp], G, nullptr, [] {}, [] {});
+      u128 a1 = make_u128(0, 0), a2 = make_u128(0, 0);
+      for (int tt = threadIdx.x; tt < sa.nt; tt += TILE_THREADS) {
+        const ulonglong2 v1 = __ldcg(reinterpret_cast<const ulonglong2*>(&sa.tile_sum[tt]));
+        const ulonglong2 v2 = __ldcg(reinterpret_cast<const ulonglong2*>(&sa.tile_q[tt]));
+        a1 = add128(a1, make_u128(v1.x, v1.y));
+        a2 = add128(a2, make_u128(v2.x, v2.y));
+      }
+      a1 = warp_sum128(a1);
+      a2 = warp_sum128(a2);
+      if (lane == 0) { s_r[0][wid] = a1; s_r[1][wid] = a2; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u128 tot = s_r[0][0], qsum = s_r[1][0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+          tot = add128(tot, s_r[0][w]);
+          qsum = add128(qsum, s_r[1][w]);
+        }
+        kc.step = sa.step0 + (uint32_t)s;
+        kc.step_slot = s;
+        ll_ess_update<real, false>(sa.sc, kc, tot, qsum, key, (long long)N, false);
+      }
+      __syncthreads();  // s_r, s_key
+    }
+    return;
+  }
   for (int s = 0; s < sa.T; ++s) {
     const StepArgs<real>& a = abuf[s & 1];
-    // abuf[(s + 1) & 1] was last read in step s - 1 (a grid barrier ago); it is published by the barriers of this step
-    if (s + 1 < sa.T) rec_to_args<real>(abuf[(s + 1) & 1], rec_v, d, sa.obs_kind);
-    if (s + 2 < sa.T && (int)threadIdx.x < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 2) * rec_len + threadIdx.x);
+    // the constants of step s + 1 go into the other buffer -- last read in step s - 1 -- inside the wait of this step's
+    // first barrier, and the record of step s + 2 is requested there
+    auto next_consts = [&]() {
+      if (s + 1 < sa.T) rec_to_args<real>(abuf[(s + 1) & 1], rec_v, d, sa.obs_kind);
+      if (s + 2 < sa.T && (int)threadIdx.x < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 2) * rec_len + threadIdx.x);
+    };
     const int has_obs = a.has_obs;
     const uint32_t step = sa.step0 + (uint32_t)s;
     const int pp = s & 1;
@@ -345,8 +385,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
     anc_tag = 0u;
     z_ready = false;
     if (!has_obs) {  // propagated only (:121); one barrier: the clouds are ping-pong buffers
-      if (t == 0 && threadIdx.x == 0) sa.ctl->pk[pp ^ 1].key = 0ull;
-      grid_barrier_pair(pk, sa.sc, target[pp], G, nullptr, [] {}, [] {});
+      grid_barrier_pair(pk, sa.sc, target[pp], G, nullptr, next_consts, [] {});
       continue;
     }
     mx = warp_max_lw<real>(mx);
@@ -364,11 +403,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
     kc.step = step;
     kc.step_slot = s;
     kc.anc_tag = (unsigned)s + 1u;
-    // the max arrives with the barrier's own snapshot; in its shadow: the resampling uniform (one thread), and ll / ESS of
-    // the previous observed step (thread 0 of block 0)
+    // the max arrives with the barrier's own snapshot; in its shadow: the next step's constants, the resampling uniform
     grid_barrier_pair(pk, sa.sc, target[pp], G, &s_key,
-                      [&] { if (threadIdx.x == 64) k3_prepare<ITEMS>(sm, sa.sc, kc); },
-                      [&] { deferred_ll(); });
+                             [&] { next_consts(); if (threadIdx.x == 64) k3_prepare<ITEMS>(sm, sa.sc, kc); },
+                             [] {});
     CSSM_STAMP(1)
 
     // ---- P2: weights, and the LOCAL part of the tile scan (its by-product is the exact tile sum) ------------
@@ -381,7 +419,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
     for (int j = 0; j < ITEMS; ++j) scan.w[j] = (i0 + j < N) ? ws.weight(lw[j]) : (wt)0;
     {
       if (threadIdx.x == 32) sm.s_wnext = (t < sa.nt - 1) ? (double)ws((long long)(t + 1) * TILE) : 0.0;  // first weight of the next tile
-      if (t == 0 && threadIdx.x == 0) sa.ctl->pk[pp ^ 1].key = 0ull;  // nobody reads or updates the other pair now
       u128 acc2 = make_u128(0, 0);
       wt mxv = (wt)0;
 #pragma unroll
@@ -426,20 +463,27 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
 
     // ---- P3: totals and this tile's exclusive prefix from the tile sums, then the FINISH of the scan + the search ----
     {
-      // warp 0: the total; warp 1: the sum of the tiles before this one; warp 2 of block 0: the sum of squares (it only
-      // feeds the ESS, which block 0 computes).  One warp-wide sum each instead of three per warp plus an eight-way add.
-      if (wid < 3 && (wid < 2 || t == 0)) {
-        const u128* const src = (wid == 2) ? sa.tile_q : sa.tile_sum;
-        const int lim = (wid == 1) ? t : sa.nt;
+      if (sa.dbg != nullptr && threadIdx.x == 0) s_dbg[7] = (unsigned long long)clock64();
+      // warps 0-3: the total, 32 tiles of every 128 each; warps 4-7 likewise the tiles before this one.  One 16-byte L2
+      // load per lane and chunk, issued back to back; one warp-wide sum per warp; eight words through shared memory.
+      {
+        const int lim = (wid >= 4) ? t : sa.nt;
         u128 a_ = make_u128(0, 0);
-        for (int tt = lane; tt < lim; tt += 32) a_ = add128(a_, ld_gpu128(&src[tt]));
+#pragma unroll
+        for (int c = 0; c < SERIES_SMALL_MAX_TILES / 128; ++c) {
+          const int tt = c * 128 + (wid & 3) * 32 + lane;
+          if (tt < lim) {
+            const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(&sa.tile_sum[tt]));
+            a_ = add128(a_, make_u128(v.x, v.y));
+          }
+        }
         a_ = warp_sum128(a_);
         if (lane == 0) s_r[0][wid] = a_;
       }
       __syncthreads();
-      const u128 tot = s_r[0][0], excl = s_r[0][1];
-      const u128 qsum = (t == 0) ? s_r[0][2] : make_u128(0, 0);
-      if (t == 0 && threadIdx.x == 0) { s_ll_tot = tot; s_ll_q = qsum; s_ll_key = key; s_ll_slot = s; }
+      const u128 tot = add128(add128(s_r[0][0], s_r[0][1]), add128(s_r[0][2], s_r[0][3]));
+      const u128 excl = add128(add128(s_r[0][4], s_r[0][5]), add128(s_r[0][6], s_r[0][7]));
+      const u128 qsum = make_u128(0, 0);  // the sum of squares only feeds the ESS: the accountant's
       k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, t, tot, qsum, key, excl, &scan, s_woff);
       anc_tag = kc.anc_tag;
       // no block barrier here: what the next step writes before its first barrier (abuf of step s + 2, s_mx) is not read
@@ -447,9 +491,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
       CSSM_STAMP(4)
     }
   }
-  if (threadIdx.x == 0) deferred_ll();
   if (sa.dbg != nullptr && threadIdx.x == 0)
-    for (int k = 0; k < 8; ++k) sa.dbg[(size_t)k * G + t] = s_dbg[k];
+    for (int k = 0; k < 16; ++k) sa.dbg[(size_t)k * sa.nt + t] = s_dbg[k];
   // the host's view: plain int32 ancestors of the last search
   if (anc_tag != 0u) {
 #pragma unroll
@@ -643,6 +686,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_series_multi(const __grid_c
       K3Ctl kc;
       kc.anc64 = nullptr;
       kc.anc_tag = 0;
+      kc.dbg = nullptr;
       kc.fast_ok = 0;
       kc.parity = 0;
       kc.obs_seq = 0;
