@@ -205,7 +205,9 @@ struct cssm_filter {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void* x[2] = {nullptr, nullptr};  // ping-pong clouds; x[cur] is the current one
   int cur = 0;
-  void* logw = nullptr;
+  void* logw = nullptr;       // the log-weights of the last observed step
+  void* logw_base = nullptr;  // the allocation: one buffer, or two for a sharded filter (by observed-step parity: a peer's walk
+  size_t logw_stride = 0;     // over a run of repeated keys may read the previous step's while this rank writes the next)
   int32_t* anc = nullptr;  // GLOBAL particle indices of the last resampling (offspring slots of this rank)
   bool anc_valid = false, initialised = false;
   FilterScalars* sc = nullptr;
@@ -354,11 +356,11 @@ Peers make_peers(const cssm_filter* f, int src) {
   pr.inv_nl = 1.0f / (float)f->N;
   for (int q = 0; q < pr.R; ++q) {
     if (q == pr.rank) {
-      pr.x[q] = f->x[src]; pr.anc[q] = f->anc; pr.logw[q] = f->logw;
+      pr.x[q] = f->x[src]; pr.anc[q] = f->anc; pr.logw[q] = (const char*)f->logw_base + (size_t)(f->obs_seq & 1ull) * f->logw_stride;
       pr.tile_sum[q] = f->tb.tile_sum; pr.tile_maxw[q] = f->tb.tile_maxw; pr.xch[q] = f->xch;
     } else {
       const cssm_filter::PeerPtrs& pp = f->peer[q];
-      pr.x[q] = pp.x[src]; pr.anc[q] = pp.anc; pr.logw[q] = pp.logw;
+      pr.x[q] = pp.x[src]; pr.anc[q] = pp.anc; pr.logw[q] = (const char*)pp.logw + (size_t)(f->obs_seq & 1ull) * f->logw_stride;
       pr.tile_sum[q] = pp.tile_sum; pr.tile_maxw[q] = pp.tile_maxw; pr.xch[q] = pp.xch;
     }
   }
@@ -482,10 +484,12 @@ int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
   cx.prof = f->prof_stride > 0 && (f->prof_step++ % f->prof_stride) == 0;
   cx.observed = h.has_obs != 0;
   cx.parity = (int)(f->obs_seq & 1ull);
+  if (cx.observed) f->logw = (char*)f->logw_base + (size_t)cx.parity * f->logw_stride;
   const Peers pr = make_peers(f, f->cur);
   real* xdst = (real*)f->x[f->cur ^ 1];
   const unsigned long long slot0 = (unsigned long long)f->rank * (unsigned long long)f->N;
-  K1Ctl ctl{f->sc, cx.parity, f->obs_seq, f->gstep};
+  static const bool shard_local = !(std::getenv("CSSM_SHARD_LOCAL") && std::atoi(std::getenv("CSSM_SHARD_LOCAL")) == 0);
+  K1Ctl ctl{f->sc, cx.parity, f->obs_seq, f->gstep, shard_local ? 1 : 0};
   const bool pdl = f->pdl && !cx.prof;
   cudaError_t e;
   {
@@ -507,7 +511,7 @@ int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
       const int g = nblk(f->N, 256 * PPT);
       // single-rank filters run instantiations without any sharding code (SH = false)
 #define K1_CASE(DD)                                                                                                    \
-  e = sharded ? launch(k_propagate_weight<real, DD, PPT, true>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, \
+  e = sharded ? launch(k_propagate_weight_sh<real, DD, PPT>, nblk(f->N, 256 * PPT * K1_SH_CHUNKS), 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, \
                        f->N, f->Ns, slot0, f->key0, f->key1, cx.step, ctl)                                              \
               : launch(k_propagate_weight<real, DD, PPT, false>, g, 256, f->stream, pdl, a, pr, xdst, anc, (real*)f->logw, io.zinj, \
                        f->N, f->Ns, slot0, f->key0, f->key1, cx.step, ctl)
@@ -1060,7 +1064,9 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   } while (0)
   ALLOC(f->x[0], (size_t)f->d * f->Ns * esz);
   ALLOC(f->x[1], (size_t)f->d * f->Ns * esz);
-  ALLOC(f->logw, (size_t)(f->Ns + tile) * esz);
+  f->logw_stride = (world > 1) ? (((size_t)(f->Ns + tile) * esz + 255) / 256) * 256 : 0;
+  ALLOC(f->logw_base, (world > 1) ? 2 * f->logw_stride : (size_t)(f->Ns + tile) * esz);
+  f->logw = f->logw_base;
   ALLOC(f->anc, (size_t)f->Ns * sizeof(int32_t));
   ALLOC(f->sc, sizeof(FilterScalars));
   ALLOC(f->xch, sizeof(XchSlot) * MAXR);
@@ -1080,7 +1086,7 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   {
     const cudaError_t em[] = {cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz),
                               cudaMemset(f->x[1], 0, (size_t)f->d * f->Ns * esz),
-                              cudaMemset(f->logw, 0, (size_t)(f->Ns + tile) * esz),
+                              cudaMemset(f->logw_base, 0, (world > 1) ? 2 * f->logw_stride : (size_t)(f->Ns + tile) * esz),
                               cudaMemset(f->anc, 0, (size_t)f->Ns * sizeof(int32_t)),
                               cudaMemset(f->sc, 0, sizeof(FilterScalars)),
                               cudaMemset(f->xch, 0, sizeof(XchSlot) * MAXR),
@@ -1213,7 +1219,7 @@ int cssm_filter_shard_export(cssm_filter_t* f, void* blob_out) {
   b.magic = BLOB_MAGIC;
   b.rank = f->rank; b.world = f->world; b.device = f->device; b.dtype = f->dtype; b.nt = f->nt; b.d = f->d;
   b.N = f->N; b.Ns = f->Ns; b.pid = (int64_t)getpid();
-  void* ptrs[7] = {f->x[0], f->x[1], f->anc, f->logw, f->tb.tile_sum, f->tb.tile_maxw, f->xch};
+  void* ptrs[7] = {f->x[0], f->x[1], f->anc, f->logw_base, f->tb.tile_sum, f->tb.tile_maxw, f->xch};
   for (int i = 0; i < 7; ++i) {
     b.ptr[i] = ptrs[i];
     if (f->world > 1) {
@@ -1319,7 +1325,7 @@ int cssm_filter_destroy(cssm_filter_t* f) {
   cudaSetDevice(f->device);
   if (f->own_stream) cudaStreamSynchronize(f->own_stream);
   for (void* p : f->ipc_opened) cudaIpcCloseMemHandle(p);
-  void* ptrs[] = {f->x[0], f->x[1], f->logw, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
+  void* ptrs[] = {f->x[0], f->x[1], f->logw_base, f->anc, f->sc, f->xch, f->tb.tile_sum, f->tb.tile_maxw, f->tb.super_sum, f->tb.super_q,
                   f->tb.super_ticket, f->ubuf, f->cdf, f->scratch, f->ctab, f->ll_steps, f->ess_steps, f->states, f->tile_q, f->series_ctl,
                   f->recs, f->fc, f->px, f->panc, f->pres_dev, f->anc64, f->logw2, f->ser_tile_sum, f->ser_tile_q, f->ser_tile_maxw};
   for (void* p : ptrs)

@@ -92,6 +92,9 @@ struct FilterScalars {
   double gmax, total;  // of the last observed step (read-back of w1, tests)
   int ess, flags, qb, pad;
   unsigned long long n_fast, n_exact;  // tiles of k_scan_search settled by the certified fp64 path / handed to the exact path
+  // sharded: the global output slots [out_lo, out_hi) of the last resampling belong to THIS rank's particles, so this rank's
+  // own search wrote their ancestors (block 0 of K3 writes the pair, the next K1 reads it)
+  long long out_lo, out_hi;
 };
 enum : int { FLAG_NAN_WEIGHT = 1, FLAG_ZERO_TOTAL = 2, FLAG_CLAMPED = 4, FLAG_COMM_TIMEOUT = 8 };
 
@@ -314,6 +317,7 @@ struct K1Ctl {
   int parity;                   // observed-step parity
   unsigned long long obs_seq;   // observed steps completed before this one
   unsigned long long gstep;     // steps completed before this one
+  int local_ok;                 // sharded: blocks whose ancestors this rank's own search wrote may start without the peers
 };
 // (Round 2 measured a tail without block barriers -- every warp folds its max into a shared word with an atomic and the warp
 // that counts in last publishes: K1 0.2064 vs 0.2038 ms with Philox4x32-10, 0.1908 vs 0.1908 with 7 rounds.  No gain; this
@@ -564,6 +568,9 @@ __device__ __forceinline__ void propagate_particles(const StepArgs<real>& a, con
 #ifndef CSSM_K1_MINBLOCKS
 #define CSSM_K1_MINBLOCKS 4
 #endif
+// chunks of 256 * PPT particles per block of a sharded filter's K1 (the host sizes the grid).  Measured on two ranks of 2^26
+// particles: 1 chunk 0.841 ms, 4 chunks 0.796, 13 chunks (eight waves of blocks, run-time count) 0.817; unsharded 0.732
+constexpr int K1_SH_CHUNKS = 4;
 template <typename real, int D, int PPT = VecOf<real>::PPT, bool SH = false>
 __global__ void __launch_bounds__(256, PPT == 4 ? CSSM_K1_MINBLOCKS : 6)
 k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
@@ -572,7 +579,7 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
                    K1Ctl ctl) {
   griddep_wait();
   griddep_launch();
-  if (SH && pr.R > 1) {  // the peers have finished the previous step: ancestors complete, parents readable
+  if (SH && pr.R > 1) {  // (sharded filters run k_propagate_weight_sh below; kept so that the single-rank code is what it was)
     const XchSlot* mine = pr.xch[pr.rank];
     gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
   }
@@ -583,6 +590,67 @@ k_propagate_weight(const __grid_constant__ StepArgs<real> a, const __grid_consta
     propagate_particles<real, D, PPT, false, true, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
   else
     propagate_particles<real, D, PPT, false, false, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+  if (!a.has_obs && !(SH && pr.R > 1)) return;
+  k1_tail<SH>(mx, bad, a.has_obs, pr, ctl);
+}
+
+// K1 of a sharded filter (its own kernel: the single-rank one above keeps the code the optimiser gives it alone)
+template <typename real, int D, int PPT = VecOf<real>::PPT>
+__global__ void __launch_bounds__(256, PPT == 4 ? CSSM_K1_MINBLOCKS : 6)
+k_propagate_weight_sh(const __grid_constant__ StepArgs<real> a, const __grid_constant__ Peers pr, real* __restrict__ xdst,
+                   const int32_t* __restrict__ anc, real* __restrict__ logw, const double* __restrict__ zinj,
+                   long long N, long long Ns, unsigned long long slot0, uint32_t key0, uint32_t key1, uint32_t step,
+                   K1Ctl ctl) {
+  constexpr bool SH = true;
+  griddep_wait();
+  griddep_launch();
+  // Sharded: a block takes K1_SH_CHUNKS consecutive chunks of 256 * PPT particles.  What a block of a sharded filter does
+  // once -- the test below with its two loads, and at the end a fence and a ticket atomic whose answer it has to wait for
+  // -- costs about a microsecond, a sixth of the life of a one-chunk block.
+  constexpr int CH = SH ? K1_SH_CHUNKS : 1;
+  const long long blk0 = (long long)blockIdx.x * blockDim.x * PPT * CH;  // first particle of the block
+  if (SH && pr.R > 1) {
+    // The peers must have finished the previous step -- before a block reads ancestors a PEER's search wrote.  The
+    // output slots [out_lo, out_hi) of the last resampling were written by this rank's own search (complete: it is the
+    // preceding kernel of the stream), and with exchangeable particles that is all but the slots near the rank borders:
+    // a block inside the range starts at once, and the rendezvous with the peers hides behind the kernel instead of
+    // standing in front of it.  What else the rendezvous used to order is ordered without it: the cloud written here was
+    // last read by the peers' K1 of the previous step (finished before this rank's search could pass its own gate),
+    // log-weights are double-buffered by observed-step parity (a peer's walk over a run of repeated keys may still read
+    // the previous buffer).  local_ok == 0, or the previous step had no observation: every block waits.
+    const long long g0 = (long long)pr.rank * pr.Nl + blk0, g1 = g0 + (long long)blockDim.x * PPT * CH;
+    const bool interior = ctl.local_ok && anc != nullptr && g0 >= ctl.sc->out_lo && g1 <= ctl.sc->out_hi;  // block-uniform
+    if (!interior) {
+      const XchSlot* mine = pr.xch[pr.rank];
+      gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
+    }
+  }
+  double mx;
+  bool bad;
+  if (!SH) {
+    const long long i0 = blk0 + (long long)threadIdx.x * PPT;
+    if ((long long)(blockIdx.x + 1) * blockDim.x * PPT <= N)  // all but the last block: no per-particle bounds predicates
+      propagate_particles<real, D, PPT, false, true, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+    else
+      propagate_particles<real, D, PPT, false, false, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mx, bad);
+  } else {
+    mx = -__longlong_as_double(0x7FF0000000000000ll);
+    bad = false;
+#pragma unroll 1
+    for (int c = 0; c < CH; ++c) {
+      const long long c0 = blk0 + (long long)c * blockDim.x * PPT;
+      if (c0 >= N) break;
+      const long long i0 = c0 + (long long)threadIdx.x * PPT;
+      double mxc;
+      bool badc;
+      if (c0 + (long long)blockDim.x * PPT <= N)
+        propagate_particles<real, D, PPT, false, true, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mxc, badc);
+      else
+        propagate_particles<real, D, PPT, false, false, SH>(a, pr, xdst, anc, logw, zinj, N, Ns, slot0, key0, key1, step, i0, mxc, badc);
+      mx = fmax(mx, mxc);
+      bad |= badc;
+    }
+  }
   if (!a.has_obs && !(SH && pr.R > 1)) return;
   k1_tail<SH>(mx, bad, a.has_obs, pr, ctl);
 }
@@ -2018,10 +2086,13 @@ struct K3FastSmem {
   int s_flag, s_anyv;
 };
 
-template <bool FLAT>
+template <bool FLAT, bool SHD = false>
 __device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __restrict__ logw, long long N, FilterScalars* __restrict__ sc,
                                              const SumTables& tb, const K3Ctl& ctl, int32_t* __restrict__ anc_out, int t, u128 tot,
-                                             u128 qsum, unsigned long long key, u128 excl) {
+                                             u128 qsum, unsigned long long key, u128 excl, int R = 1, int rank = 0) {
+  // R > 1: rank `rank` of a sharded filter.  `excl` includes the ranks before, counts and ancestors are global, anc_out is
+  // this rank's buffer: a tile whose outputs all fall into this rank's own slots is settled here, any other -- and the
+  // last tile of every rank -- by the exact path, which scatters to the peers.
   constexpr int ITEMS = 8, TILE = K3FastSmem::TILE, WIN = K3FastSmem::WIN, PER = WIN / TILE_THREADS, NW = TILE_THREADS / 32;
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -2038,7 +2109,7 @@ __device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __rest
     const float w_next = expf_det(__fsub_rn(__ldg(logw + tile0 + TILE), gmaxf));
     if (vanishes(c_end, (double)w_next, total)) return false;
   }
-  const long long Ng = N;
+  const long long Ng = SHD ? (long long)R * N : N, own0 = SHD ? (long long)rank * N : 0;
   if (threadIdx.x == 0) {  // one thread: the resampling uniform, n / total and the number of outputs before the tile
     double u;
     if (ctl.use_u_inj) {
@@ -2051,7 +2122,7 @@ __device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __rest
     KFun<CSSM_RESAMPLE_SYSTEMATIC> kf{u, (double)Ng, ctl.inv_n, total, nullptr, ctl.key0, ctl.key1, ctl.step};
     fs.s_u = u;
     fs.s_scale = scale;
-    fs.s_lo = (t == 0) ? 0 : kf.count_fast(P_b, scale, Ng);
+    fs.s_lo = (t == 0 && (!SHD || rank == 0)) ? 0 : kf.count_fast(P_b, scale, Ng);
     fs.s_flag = 0;
     fs.s_anyv = 0;
   }
@@ -2131,7 +2202,8 @@ __device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __rest
   }
   fs.s_cnt[threadIdx.x] = cr[ITEMS - 1];
   __syncthreads();
-  if (fs.s_flag) {  // block-uniform; nothing has been written to global memory yet
+  // block-uniform; nothing has been written to global memory yet.  Sharded: outputs in a peer's slots are the exact path's.
+  if (fs.s_flag || (SHD && (lo < own0 || lo + fs.s_cnt[TILE_THREADS - 1] > own0 + N))) {
     if (threadIdx.x == 0) atomicAdd(&sc->n_exact, 1ull);
     return false;
   }
@@ -2140,7 +2212,7 @@ __device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __rest
   // ---- expansion, WIN outputs per pass (head scatter + max-scan, as the exact path), coalesced stores ----
   const int n_out = fs.s_cnt[TILE_THREADS - 1];
   const bool anyv = fs.s_anyv != 0;
-  const int32_t gbase = (int32_t)tile0;
+  const int32_t gbase = SHD ? (int32_t)(own0 + tile0) : (int32_t)tile0;
   const int prev0 = threadIdx.x ? fs.s_cnt[threadIdx.x - 1] : 0;
   int carry = 0;
   for (int w0 = 0; w0 < n_out; w0 += WIN) {
@@ -2182,7 +2254,7 @@ __device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __rest
     for (int k = 0; k < PER; ++k) fs.s_res[threadIdx.x * PER + k] = max(v[k], before);
     __syncthreads();
     const int n_w = min(WIN, n_out - w0);
-    int32_t* const out = anc_out + (lo + w0);
+    int32_t* const out = SHD ? anc_out + (lo - own0 + w0) : anc_out + (lo + w0);
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const int o = threadIdx.x + k * TILE_THREADS;
@@ -2218,7 +2290,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
 #else
   // the fast path's window and the exact path's tile never live at the same time; the few words both need
   // (s_excl, s_tot, s_q, s_key) are kept outside the union
-  constexpr bool FAST = std::is_same<real, float>::value && ITEMS == 8 && KIND == CSSM_RESAMPLE_SYSTEMATIC && !SH;
+  constexpr bool FAST = std::is_same<real, float>::value && ITEMS == 8 && KIND == CSSM_RESAMPLE_SYSTEMATIC;
   __shared__ union SmemU {
     K3SmemBlk<ITEMS> blk;
     K3FastSmem fast;
@@ -2310,14 +2382,46 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
 #else
   const u128 v_tot = s_tot, v_q = s_q, v_excl = s_excl;  // to registers: the fast path reuses the shared memory they sit in
   const unsigned long long v_key = s_key;
+  if (SH && RK > 1 && t == 0 && threadIdx.x == 96 && cdf_out == nullptr) {
+    // Which global output slots belong to THIS rank's particles: [count of keys <= the exact sum before the rank,
+    // count of keys <= the exact sum at its end) -- the same counts its first and last tile use.  The next K1 lets
+    // blocks inside that range start without waiting for the peers (their ancestors are this kernel's own work).
+    const PreScan ps = pre_scan(v_key, direct != nullptr);
+    const double total = dbl128(v_tot, ps.qb);
+    const long long Ng = (long long)RK * N;
+    long long lo = (long long)pr.rank * N, hi = lo + N;  // unusable total: every particle stays its own ancestor
+    if ((total > 0.0) && (total - total == 0.0)) {
+      double u;
+      if (ctl.use_u_inj) {
+        u = sc->u_inj;
+      } else {
+        uint4 v = philox4x32(make_uint4(0u, 0u, ctl.step, RNG_RESAMPLE), ctl.key0, ctl.key1);
+        u = u64_to_unit_double(v.x, v.y);
+      }
+      KFun<KIND> kf{u, (double)Ng, ctl.inv_n, total, uarr, ctl.key0, ctl.key1, ctl.step};
+      const double scale = __ddiv_rn((double)Ng, total);
+      lo = (pr.rank == 0) ? 0 : kf.count_fast(dbl128(v_excl, ps.qb), scale, Ng);
+      hi = (pr.rank == RK - 1) ? Ng : kf.count_fast(dbl128(add128(v_excl, A->tot), ps.qb), scale, Ng);
+    }
+    sc->out_lo = lo;
+    sc->out_hi = hi;
+  }
+  bool settled = false;  // sharded only: the certified path wrote the tile's ancestors (all of them in this rank's slots)
   if (FAST && direct == nullptr && cdf_out == nullptr && uarr == nullptr && ctl.fast_ok) {
     __syncthreads();  // everyone holds the four values
-    if (k3_tile_fast<FLAT>(smem_u.fast, reinterpret_cast<const float*>(logw), N, sc, tb, ctl, pr.anc[0], t, v_tot, v_q, v_key, v_excl))
-      return;
+    if (!SH) {
+      if (k3_tile_fast<FLAT>(smem_u.fast, reinterpret_cast<const float*>(logw), N, sc, tb, ctl, pr.anc[0], t, v_tot, v_q, v_key, v_excl))
+        return;
+    } else {
+      settled = k3_tile_fast<FLAT, true>(smem_u.fast, reinterpret_cast<const float*>(logw), N, sc, tb, ctl, pr.anc[pr.rank], t, v_tot, v_q,
+                                   v_key, v_excl, RK, pr.rank);
+    }
     __syncthreads();  // undecided: the exact path recomputes the tile from scratch
   }
-  const bool wrote_remote = k3_tile_blk<real, ITEMS, KIND, true, SH>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, v_tot, v_q,
-                                                                 v_key, v_excl);
+  bool wrote_remote = false;
+  if (!SH || !settled)
+    wrote_remote = k3_tile_blk<real, ITEMS, KIND, true, SH>(sm, logw, direct, N, sc, tb, pr, ctl, uarr, cdf_out, t, v_tot, v_q, v_key,
+                                                            v_excl);
 #endif
   if (cdf_out != nullptr) return;
   if (RK > 1) {  // "resampling done": the last block tells the peers this step is complete
