@@ -208,6 +208,7 @@ struct cssm_filter {
   void* logw = nullptr;       // the log-weights of the last observed step
   void* logw_base = nullptr;  // the allocation: one buffer, or two for a sharded filter (by observed-step parity: a peer's walk
   size_t logw_stride = 0;     // over a run of repeated keys may read the previous step's while this rank writes the next)
+  bool shared_device = false; // sharded: a peer rank lives on this device (one stream for all of them: k_publish behind each kernel)
   int32_t* anc = nullptr;  // GLOBAL particle indices of the last resampling (offspring slots of this rank)
   bool anc_valid = false, initialised = false;
   FilterScalars* sc = nullptr;
@@ -475,6 +476,17 @@ struct StepCtx {
 };
 
 // ---- K1: gather + propagate + weight ------------------------------------------------------------
+// Sharded filters whose ranks share a device (and therefore a stream): a one-warp kernel behind each producing kernel
+// publishes its result to the peers.  One GPU per rank: block 0 of the consuming kernel does it (pub_here).
+inline bool pub_here(const cssm_filter* f) { return f->world > 1 && !f->shared_device; }
+int publish_after(cssm_filter* f, const Peers& pr, int what, int parity, unsigned long long value) {
+  if (f->world == 1 || !f->shared_device) return CSSM_OK;
+  k_publish<<<1, 32, 0, f->stream>>>(pr, f->sc, what, parity, value);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch k_publish: ") + cudaGetErrorString(e));
+  return CSSM_OK;
+}
+
 template <typename real>
 int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* ctab, double delta, const StepIO& io, StepCtx& cx) {
   StepArgs<real> a;
@@ -489,8 +501,8 @@ int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
   real* xdst = (real*)f->x[f->cur ^ 1];
   const unsigned long long slot0 = (unsigned long long)f->rank * (unsigned long long)f->N;
   static const bool shard_local = !(std::getenv("CSSM_SHARD_LOCAL") && std::atoi(std::getenv("CSSM_SHARD_LOCAL")) == 0);
-  K1Ctl ctl{f->sc, cx.parity, f->obs_seq, f->gstep, shard_local ? 1 : 0};
-  const bool pdl = f->pdl && !cx.prof;
+  K1Ctl ctl{f->sc, cx.parity, f->obs_seq, f->gstep, shard_local ? 1 : 0, pub_here(f) ? 1 : 0};
+  const bool pdl = f->pdl && !cx.prof && f->world == 1;  // sharded: stream order (block 0 of a kernel publishes the one before)
   cudaError_t e;
   {
     ProfScope ps_(f, CLS_PROPAGATE, cx.prof);
@@ -529,6 +541,10 @@ int step_phase1(cssm_filter* f, const StepHost& h, long long n_sub, const void* 
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K1: ") + cudaGetErrorString(e));
   f->launches++;
+  {
+    const int rcp = cx.observed ? publish_after(f, pr, 1, cx.parity, f->obs_seq) : publish_after(f, pr, 0, 0, f->gstep + 1);
+    if (rcp) return rcp;
+  }
   f->cur ^= 1;
   f->anc_valid = false;
   if (!cx.observed) f->gstep++;
@@ -547,20 +563,20 @@ template <typename real>
 int step_phase2(cssm_filter* f, StepCtx& cx) {
   if (!cx.observed) return CSSM_OK;
   const Peers pr = make_peers(f, f->cur);
-  const bool pdl = f->pdl && !cx.prof;
+  const bool pdl = f->pdl && !cx.prof && f->world == 1;  // sharded: stream order (block 0 of a kernel publishes the one before)
   cudaError_t e;
   {
     ProfScope ps_(f, CLS_SUMS, cx.prof);
 #define K2_CASE(IT, SH)                                                                                               \
   e = launch(k_weight_sums<real, IT, SH>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, (const double*)nullptr, \
-             f->N, f->sc, cx.parity, f->obs_seq, step_tables(f), pr)
+             f->N, f->sc, cx.parity, f->obs_seq, step_tables(f), pr, pub_here(f) ? 1 : 0)
     if (pr.R > 1) { if (f->items == 8) K2_CASE(8, true); else K2_CASE(2, true); }
     else { if (f->items == 8) K2_CASE(8, false); else K2_CASE(2, false); }
 #undef K2_CASE
   }
   if (e != cudaSuccess) return fail(CSSM_ERR_CUDA, std::string("launch K2: ") + cudaGetErrorString(e));
   f->launches++;
-  return CSSM_OK;
+  return publish_after(f, pr, 2, cx.parity, f->obs_seq);
 }
 
 // K3 keeps two padded tiles of doubles in shared memory (37 KB per block with 2048-particle tiles):
@@ -595,7 +611,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   if (!cx.observed) return CSSM_OK;
   k3_carveout_once<real>(f->device);
   const Peers pr = make_peers(f, f->cur);
-  const bool pdl = f->pdl && !cx.prof;
+  const bool pdl = f->pdl && !cx.prof && f->world == 1;  // sharded: stream order (block 0 of a kernel publishes the one before)
   const bool multi = f->resample_kind == CSSM_RESAMPLE_MULTINOMIAL;
   K3Ctl ctl;
   ctl.parity = cx.parity; ctl.obs_seq = f->obs_seq; ctl.gstep = f->gstep;
@@ -615,11 +631,11 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
     const SumTables tbs = step_tables(f);
 #define K3_CASE(IT, KD)                                                                                                 \
   e = tbs.ns == 0 ? launch(k_scan_search<real, IT, KD, true, false>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
-                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)                                  \
+                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf, pub_here(f) ? 1 : 0)                                  \
       : pr.R > 1  ? launch(k_scan_search<real, IT, KD, false, true>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
-                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)                                  \
+                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf, pub_here(f) ? 1 : 0)                                  \
                   : launch(k_scan_search<real, IT, KD, false, false>, f->nt, TILE_THREADS, f->stream, pdl, (const real*)f->logw, \
-                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf)
+                           (const double*)nullptr, f->N, f->sc, tbs, pr, ctl, ua, cdf, pub_here(f) ? 1 : 0)
     if (f->items == 8) { if (strat) K3_CASE(8, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(8, CSSM_RESAMPLE_SYSTEMATIC); }
     else { if (strat) K3_CASE(2, CSSM_RESAMPLE_STRATIFIED); else K3_CASE(2, CSSM_RESAMPLE_SYSTEMATIC); }
 #undef K3_CASE
@@ -636,7 +652,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   f->anc_valid = true;
   f->obs_seq++;
   f->gstep++;
-  return CSSM_OK;
+  return publish_after(f, pr, 0, 0, f->gstep);  // "resampling done": the number of completed steps
 }
 
 // one stepFilter on the device; no host synchronisation
@@ -1251,6 +1267,7 @@ int cssm_filter_shard_connect(cssm_filter_t* f, const void* blobs, int world) {
     if (q == f->rank) continue;
     void* p[7];
     if (b.pid == mypid) {  // same process (one host thread driving several shards): plain pointers
+      if (b.device == f->device) f->shared_device = true;
       if (b.device != f->device) {
         int can = 0;
         CU(cudaDeviceCanAccessPeer(&can, f->device, b.device));

@@ -273,6 +273,46 @@ __device__ __forceinline__ void push_progress_warp(const Peers& pr, unsigned lon
   const int q = threadIdx.x & 31;
   if (q < pr.R) st_release_sys(&pr.xch[q][pr.rank].progress, gstep_done);
 }
+// Ranks that share one device also share one stream (their kernels spin on each other's flags and CUDA does not
+// co-schedule streams): there the consumer of rank 0 runs before the producer of rank 1 has published, so a one-warp
+// kernel behind each producing kernel publishes instead (k_publish, below the helpers).
+// Consumer-side publication (sharded filters; first warp of block 0 of the consuming kernel, before its own gate): the
+// producing kernel is complete -- the launches of a sharded filter are serialised by the stream -- so its result is final
+// in this rank's memory and one warp hands it to the peers.
+//   K1 of step s+1: "every kernel of the steps before is complete" (the peers' searches may have written our ancestors)
+//   K2: this rank's max log-weight;   K3: this rank's exact (sum w, sum w^2)
+__device__ __forceinline__ void publish_max_warp(const Peers& pr, FilterScalars* sc, int parity, unsigned long long obs_seq) {
+  const unsigned long long key = ld_gpu(&sc->acc[parity].gmax_key);
+  __threadfence_system();
+  const int q = threadIdx.x & 31;
+  if (q < pr.R) {
+    XchSlot* s = &pr.xch[q][pr.rank];
+    st_relaxed_sys(&s->max_key[parity], key);
+    st_release_sys(&s->max_seq[parity], obs_seq + 1);
+  }
+}
+__device__ __forceinline__ void publish_sums_warp(const Peers& pr, FilterScalars* sc, int parity, unsigned long long obs_seq) {
+  const StepAcc* A = &sc->acc[parity];
+  const unsigned long long tl = ld_gpu(&A->tot.lo), th = ld_gpu(&A->tot.hi), ql = ld_gpu(&A->q.lo), qh = ld_gpu(&A->q.hi);
+  __threadfence_system();
+  const int q = threadIdx.x & 31;
+  if (q < pr.R) {
+    XchSlot* s = &pr.xch[q][pr.rank];
+    st_relaxed_sys(&s->tot_lo[parity], tl);
+    st_relaxed_sys(&s->tot_hi[parity], th);
+    st_relaxed_sys(&s->q_lo[parity], ql);
+    st_relaxed_sys(&s->q_hi[parity], qh);
+    st_release_sys(&s->sum_seq[parity], obs_seq + 1);
+  }
+}
+
+// what: 0 = "steps complete" (value = their number), 1 = this rank's max log-weight, 2 = its exact sums
+static __global__ void __launch_bounds__(32) k_publish(const __grid_constant__ Peers pr, FilterScalars* sc, int what, int parity,
+                                                       unsigned long long value) {
+  if (what == 0) push_progress_warp(pr, value);
+  else if (what == 1) publish_max_warp(pr, sc, parity, value);
+  else publish_sums_warp(pr, sc, parity, value);
+}
 
 // ---------------------------------------------------------------------------------------------
 // K0  x0[k][i] = sqrt(c0_k) * z + m0_k        (a.S = sqrt(c0), a.M = m0)
@@ -318,6 +358,7 @@ struct K1Ctl {
   unsigned long long obs_seq;   // observed steps completed before this one
   unsigned long long gstep;     // steps completed before this one
   int local_ok;                 // sharded: blocks whose ancestors this rank's own search wrote may start without the peers
+  int pub_here;                 // sharded: block 0 of this kernel publishes what the kernel before it left (else k_publish did)
 };
 // (Round 2 measured a tail without block barriers -- every warp folds its max into a shared word with an atomic and the warp
 // that counts in last publishes: K1 0.2064 vs 0.2038 ms with Philox4x32-10, 0.1908 vs 0.1908 with 7 rounds.  No gain; this
@@ -343,33 +384,10 @@ __device__ __forceinline__ void k1_tail(double mx, bool bad, int has_obs, const 
       if (s_bad) atomicOr(&sc->flags, FLAG_NAN_WEIGHT);
     }
   }
-  if (RK > 1 && threadIdx.x < 32) {
-    int last = 0;
-    unsigned long long key = 0ull;
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned long long tk = atomicAdd(&sc->ticket1, 1ull);
-      if (tk % gridDim.x == gridDim.x - 1) {
-        __threadfence();
-        last = 1;
-        if (has_obs) key = ld_gpu(&sc->acc[ctl.parity].gmax_key);
-      }
-    }
-    if (warp_is_last(last)) {
-      if (has_obs) {
-        key = __shfl_sync(0xffffffffu, key, 0);
-        __threadfence_system();
-        const int q = threadIdx.x;
-        if (q < pr.R) {
-          XchSlot* s = &pr.xch[q][pr.rank];
-          st_relaxed_sys(&s->max_key[ctl.parity], key);
-          st_release_sys(&s->max_seq[ctl.parity], ctl.obs_seq + 1);
-        }
-      } else {
-        push_progress_warp(pr, ctl.gstep + 1);
-      }
-    }
-  }
+  // Sharded: nothing is published here.  The kernels of a sharded filter run in stream order, so block 0 of the NEXT
+  // kernel finds this one complete and publishes its result to the peers (publish_* below): no fence, no ticket atomic
+  // and no wait for its answer at the end of every block of this kernel.
+  (void)RK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -618,6 +636,7 @@ k_propagate_weight_sh(const __grid_constant__ StepArgs<real> a, const __grid_con
     // last read by the peers' K1 of the previous step (finished before this rank's search could pass its own gate),
     // log-weights are double-buffered by observed-step parity (a peer's walk over a run of repeated keys may still read
     // the previous buffer).  local_ok == 0, or the previous step had no observation: every block waits.
+    if (ctl.pub_here && blockIdx.x == 0 && threadIdx.x < 32) push_progress_warp(pr, ctl.gstep);  // our kernels of the steps before are complete
     const long long g0 = (long long)pr.rank * pr.Nl + blk0, g1 = g0 + (long long)blockDim.x * PPT * CH;
     const bool interior = ctl.local_ok && anc != nullptr && g0 >= ctl.sc->out_lo && g1 <= ctl.sc->out_hi;  // block-uniform
     if (!interior) {
@@ -672,6 +691,7 @@ k_lgcp_weight(const __grid_constant__ StepArgs<real> a, const __grid_constant__ 
   griddep_wait();
   griddep_launch();
   if (pr.R > 1) {
+    if (ctl.pub_here && blockIdx.x == 0 && threadIdx.x < 32) push_progress_warp(pr, ctl.gstep);  // our kernels of the steps before are complete
     const XchSlot* mine = pr.xch[pr.rank];
     gate_wait(&ctl.sc->gate1, ctl.gstep, pr, ctl.sc, [&](int q) { return &mine[q].progress; });
   }
@@ -912,7 +932,7 @@ __device__ __forceinline__ double walk_tile_maxw(const SumTables& tb, const Peer
 template <typename real, int ITEMS, bool SH = false>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
-              int parity, unsigned long long obs_seq, SumTables tb, const __grid_constant__ Peers pr) {
+              int parity, unsigned long long obs_seq, SumTables tb, const __grid_constant__ Peers pr, int pub_here = 0) {
   constexpr int TILE = TILE_THREADS * ITEMS;
   __shared__ u128 s_w[TILE_THREADS / 32];
   __shared__ double s_mxw[TILE_THREADS / 32];
@@ -921,7 +941,8 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
   griddep_launch();
   const int RK = SH ? pr.R : 1;
   StepAcc* A = &sc->acc[parity];
-  if (RK > 1) {  // all-gather of the per-rank maxima: every rank pushed its own into our slots
+  if (RK > 1) {  // all-gather of the per-rank maxima: every rank pushes its own into our slots (block 0 of this kernel)
+    if (pub_here && blockIdx.x == 0 && threadIdx.x < 32) publish_max_warp(pr, sc, parity, obs_seq);
     const XchSlot* mine = pr.xch[pr.rank];
     gate_wait(&sc->gate2, obs_seq + 1, pr, sc, [&](int q) { return &mine[q].max_seq[parity]; });
     if (threadIdx.x < 32) {
@@ -961,8 +982,6 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
     s_mxw[threadIdx.x >> 5] = mxw;
   }
   const u128 t = block_sum128(acc, s_w);  // contains the __syncthreads that publishes s_w2 / s_mxw
-  int pub = 0;
-  u128 pub_tot = make_u128(0, 0), pub_q = make_u128(0, 0);
   if (threadIdx.x == 0) {
     u128 t2 = s_w2[0];
     double m2 = s_mxw[0];
@@ -988,31 +1007,6 @@ k_weight_sums(const real* __restrict__ logw, const double* __restrict__ direct, 
       __threadfence();
       atomic_add128(&A->tot, ld_gpu128(ssum));
       atomic_add128(&A->q, ld_gpu128(ssq));
-      __threadfence();
-      const unsigned long long tk2 = atomicAdd(&sc->ticket2, 1ull);
-      if (RK > 1 && tk2 % (unsigned long long)tb.ns == (unsigned long long)tb.ns - 1) {
-        // last block of the grid: all-gather of (sum w, sum w^2) by direct stores into the peers
-        __threadfence();
-        pub_tot = ld_gpu128(&A->tot);
-        pub_q = ld_gpu128(&A->q);
-        pub = 1;
-      }
-    }
-  }
-  if (RK > 1 && threadIdx.x < 32 && warp_is_last(pub)) {  // lane q -> rank q, see push_progress_warp
-    pub_tot.lo = __shfl_sync(0xffffffffu, pub_tot.lo, 0);
-    pub_tot.hi = __shfl_sync(0xffffffffu, pub_tot.hi, 0);
-    pub_q.lo = __shfl_sync(0xffffffffu, pub_q.lo, 0);
-    pub_q.hi = __shfl_sync(0xffffffffu, pub_q.hi, 0);
-    __threadfence_system();
-    const int q = threadIdx.x;
-    if (q < RK) {
-      XchSlot* s = &pr.xch[q][pr.rank];
-      st_relaxed_sys(&s->tot_lo[parity], pub_tot.lo);
-      st_relaxed_sys(&s->tot_hi[parity], pub_tot.hi);
-      st_relaxed_sys(&s->q_lo[parity], pub_q.lo);
-      st_relaxed_sys(&s->q_hi[parity], pub_q.hi);
-      st_release_sys(&s->sum_seq[parity], obs_seq + 1);
     }
   }
 }
@@ -2284,7 +2278,7 @@ template <typename real, int ITEMS, int KIND, bool FLAT = false, bool SH = false
 __global__ void __launch_bounds__(TILE_THREADS, CSSM_K3_MINBLOCKS)
 k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, long long N, FilterScalars* __restrict__ sc,
               SumTables tb, const __grid_constant__ Peers pr, K3Ctl ctl, const double* __restrict__ uarr,
-              double* __restrict__ cdf_out) {
+              double* __restrict__ cdf_out, int pub_here = 0) {
 #ifdef CSSM_K3_WS
   __shared__ K3Smem<ITEMS> sm;
 #else
@@ -2311,6 +2305,7 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
 
   // ---- totals: this rank's from the accumulators, the other ranks' from the exchange slots ------
   if (RK > 1) {
+    if (pub_here && blockIdx.x == 0 && threadIdx.x < 32) publish_sums_warp(pr, sc, p, ctl.obs_seq);  // K2 is complete: this rank's exact sums
     const XchSlot* mine = pr.xch[pr.rank];
     gate_wait(&sc->gate3, ctl.obs_seq + 1, pr, sc, [&](int q) { return &mine[q].sum_seq[p]; });
     if (threadIdx.x < 32) {  // lane q reads rank q's slot; sums by shuffles
@@ -2424,19 +2419,8 @@ k_scan_search(const real* __restrict__ logw, const double* __restrict__ direct, 
                                                             v_excl);
 #endif
   if (cdf_out != nullptr) return;
-  if (RK > 1) {  // "resampling done": the last block tells the peers this step is complete
-    if (wrote_remote) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int last = 0;
-      if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long tk = atomicAdd(&sc->ticket3, 1ull);
-        last = (tk % gridDim.x == gridDim.x - 1) ? 1 : 0;
-      }
-      if (warp_is_last(last)) push_progress_warp(pr, ctl.gstep + 1);
-    }
-  }
+  // Sharded: "resampling done" is told to the peers by block 0 of the next K1 (stream order: this kernel is complete by then)
+  (void)wrote_remote;
 }
 
 // K4'  multinomial: Breeze Multinomial.draw first-draw walk = first j with cumulative >= u*sum
