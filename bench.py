@@ -724,7 +724,10 @@ def main():
                                    "achieved_gbs_fused": real_bpp * n_local / (tot * 1e-3) / 1e9 if tot else None,
                                    "frac_fused": real_bpp * n_local / (tot * 1e-3) / 1e9 / peak if tot else None,
                                    "bytes_per_particle_survey_8d": 4 * d * b + 5 * b + 8,
-                                   "frac_survey_8d": (4 * d * b + 5 * b + 8) * n_local / (tot * 1e-3) / 1e9 / peak if tot else None}}
+                                   "frac_survey_8d": (4 * d * b + 5 * b + 8) * n_local / (tot * 1e-3) / 1e9 / peak if tot else None,
+                                   "note": "frac_fused counts the bytes the three kernels move (the gather never materialises a cloud, no "
+                                           "CDF is written); frac_survey_8d rates the same step time with SURVEY 8(d)'s B_step, the bytes of "
+                                           "an unfused step -- it can exceed 1 and is a speed-up over that step at the roof, not a bandwidth"}}
         elif prof.get("series", (0, 0))[1]:
             # small cloud: the whole llFilter is ONE cooperative launch (cssm_series.cuh); per launch it moves
             # T x N x (K1 2db+b+4, K2 b, K3 b+4) bytes, all of it L2 resident: latency bound, not HBM bound

@@ -29,5 +29,8 @@ ncu -i /tmp/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_raw.csv
 ncu -i /tmp/${TAG}_prof.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${TAG}_source.csv 2>/dev/null
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_series" -s 1 -c 1 -f -o /tmp/${TAG}_prof_series python bench.py --workload c4 --steps 1 --warmup 1 --no-cpu --chains "" > gpurun_out/${TAG}_ncu_series.log 2>&1
 ncu -i /tmp/${TAG}_prof_series.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_series_raw.csv 2>/dev/null
+ncu -i /tmp/${TAG}_prof_series.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${TAG}_series_source.csv 2>/dev/null
+gzip -f gpurun_out/${TAG}_series_source.csv
+CSSM_SERIES_DEBUG=1 timeout 300 python bench.py --workload c4 --steps 5 --no-cpu --chains "" 2>gpurun_out/${TAG}_series_stamps.txt >/dev/null
 gzip -f gpurun_out/${TAG}_source.csv
 ls -la gpurun_out | grep ${TAG} | head -40

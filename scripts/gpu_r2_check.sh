@@ -1,11 +1,15 @@
 #!/bin/bash
-# round 2: GPU suite (new PMMH / driver tests first), default bench line with the pmmh sub-record, c4 line
-TAG=${1:-r02_a}
+# the GPU suite, the three bench lines that matter, the series stamps
+TAG=${1:-cur}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_pmmh.py -m gpu -q -x > gpurun_out/${TAG}_pytest_pmmh.log 2>&1; echo "pytest pmmh rc=$?" >> gpurun_out/${TAG}_pytest_pmmh.log
-tail -15 gpurun_out/${TAG}_pytest_pmmh.log
-timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_pmmh.py > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
-tail -5 gpurun_out/${TAG}_pytest.log
-timeout 600 python bench.py --no-cpu > gpurun_out/${TAG}_bench_target.json 2> gpurun_out/${TAG}_bench_target.err; tail -c 3000 gpurun_out/${TAG}_bench_target.json; tail -5 gpurun_out/${TAG}_bench_target.err
-CSSM_SERIES_DEBUG=1 timeout 600 python bench.py --workload c4 --steps 30 --no-cpu > gpurun_out/${TAG}_bench_c4.json 2> gpurun_out/${TAG}_bench_c4.err; tail -c 1500 gpurun_out/${TAG}_bench_c4.json; tail -3 gpurun_out/${TAG}_bench_c4.err
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
+grep -E "passed|failed|FAILED|^E  " gpurun_out/${TAG}_pytest.log | head -20
+for wl in target c2; do
+  timeout 300 python bench.py --workload $wl --no-cpu --no-extra --obs 300 2>gpurun_out/${TAG}_err.txt | python -c "
+import json,sys
+try:
+    j=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=j['roofline']['kernel_ms_per_launch']; print('$wl %.4g'%j['value'], {a:round(x,4) for a,x in k.items() if x}, 'll', j.get('log_likelihood_mean'))
+except Exception as e:
+    print('ERR', e, open('gpurun_out/${TAG}_err.txt').read()[-800:])"
+done
+bash scripts/gpu_series2.sh $TAG $2
