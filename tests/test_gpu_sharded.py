@@ -49,8 +49,10 @@ def run_pair(mod, n_local, R, T, kind, dtype, seed, ys=None, missing=()):
             mx = float(np.max(a["logw"]))
             np.testing.assert_array_equal(a["anc"], oracle.resample(kind, oracle.w1(a["logw"], mx, oracle.device_order(dtype)), u))
         np.testing.assert_array_equal(grp.get_particles(), one.get_particles())
+    stats = [sh.scan_stats() for sh in grp.shards]  # per rank: (tiles settled by the certified fp64 scan, by the exact path)
     one.close()
     grp.close()
+    return stats
 
 
 @pytest.mark.parametrize("R", [2, 4, 8])
