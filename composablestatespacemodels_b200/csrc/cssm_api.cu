@@ -257,6 +257,9 @@ struct cssm_filter {
   int flat_max_nt = 2048;  // clouds of at most this many tiles: K2 without atomics, K3 adds the tile sums itself (CSSM_FLAT_MAX_NT)
   int tie_first = 0;  // CSSM_TIE_FIRST instead of the reference's TreeMap rule (cssm_filter_set_tie_rule)
   int scan_fast = 1;  // k_scan_search tries the certified fp64 path first (cssm_filter_scan_mode; CSSM_K3_FAST=0)
+  int scan_fast_min_nt = 1024;  // ... on clouds of more tiles than this (CSSM_K3_FAST=1: always).  A cloud of one or two waves of
+                                // blocks lasts as long as its slowest block, and a tile the certified path hands to the exact
+                                // path costs both: 2^20 particles 2.81e10 (exact only) vs 2.66e10, 2^21 equal, 2^22 3.83e10 vs 3.76e10
   // forecast cloud (cssm_forecast.cuh): d + 4 columns [x1 | gamma | eta | obs | obs2], filter dtype
   // path storage (FilterInterpolate): px = (paths_cap + 1) propagated clouds, panc = paths_cap ancestor vectors
   void* px = nullptr;
@@ -618,7 +621,7 @@ int step_phase3(cssm_filter* f, const StepIO& io, StepCtx& cx) {
   const long long Ng = f->N * (long long)pr.R;
   ctl.inv_n = ((Ng & (Ng - 1)) == 0) ? 1.0 / (double)Ng : 0.0;
   ctl.direct = 0; ctl.add_ll = 1; ctl.use_u_inj = io.use_u_inj; ctl.tie_first = f->tie_first; ctl.defer_ll = 0;
-  ctl.fast_ok = f->scan_fast;
+  ctl.fast_ok = f->scan_fast && f->nt > f->scan_fast_min_nt;
   ctl.anc64 = nullptr; ctl.anc_tag = 0; ctl.dbg = nullptr;
   ctl.key0 = f->key0; ctl.key1 = f->key1; ctl.step = cx.step;
   ctl.ll_steps = io.ll_steps; ctl.ess_steps = io.ess_steps; ctl.step_slot = io.step_slot;
@@ -1098,7 +1101,7 @@ int create_impl(const cssm_model_desc_t* model, int64_t n_particles, int resampl
   f->tb.nt = f->nt; f->tb.ns = f->ns;
   f->tb.tile_q = f->tile_q;
   if (const char* e = std::getenv("CSSM_FLAT_MAX_NT")) f->flat_max_nt = std::atoi(e);
-  if (const char* e = std::getenv("CSSM_K3_FAST")) f->scan_fast = std::atoi(e) != 0;
+  if (const char* e = std::getenv("CSSM_K3_FAST")) { f->scan_fast = std::atoi(e) != 0; if (f->scan_fast) f->scan_fast_min_nt = 0; }
   {
     const cudaError_t em[] = {cudaMemset(f->x[0], 0, (size_t)f->d * f->Ns * esz),
                               cudaMemset(f->x[1], 0, (size_t)f->d * f->Ns * esz),

@@ -305,8 +305,11 @@ int cssm_filter_forecast(cssm_filter_t* f, double t, double interval, int chain,
  * getMeanForecast summarises); NULL to skip */
 int cssm_filter_forecast_cloud(cssm_filter_t* f, double* x_out, double* gamma_out, double* eta_out,
                                double* obs_out, double* obs2_out);
-/* How the scan + search kernel of large fp32 clouds (2048-particle tiles, systematic resampling, one rank) works.
- * AUTO: every tile is first scanned in fp64 with CERTIFIED offspring counts -- a count is taken only where the error
+/* How the scan + search kernel of large fp32 clouds (2048-particle tiles, systematic resampling; every rank of a sharded
+ * filter likewise) works.
+ * AUTO: on clouds of more than 1024 tiles per rank (smaller ones last as long as their slowest block, and a tile handed
+ * from one path to the other costs both; CSSM_K3_FAST=1 in the environment lifts the limit) every tile is first scanned
+ * in fp64 with CERTIFIED offspring counts -- a count is taken only where the error
  * bound of the fp64 prefix cannot change it, a repeated-key decision only where it cannot flip -- and a tile with one
  * undecided particle is recomputed by the exact 128-bit fixed-point path; the ancestors are bit-identical to EXACT,
  * which runs the exact path on every tile.  cssm_filter_scan_stats: tiles settled by either path since the last

@@ -160,11 +160,12 @@ def test_injected_noise_step_parity_at_the_baseline_cloud_size():
     run_steps(c2(), 1 << 20, 2, SYS, _abi.F32, seed=21)
 
 
-def test_sharded_eight_virtual_ranks_with_the_large_tiles():
+def test_sharded_eight_virtual_ranks_with_the_large_tiles(monkeypatch):
     """BASELINE.json configs[4]'s model on eight (virtual) ranks at the tile size large clouds use (2048 particles, two-level
     sum tables): 8 x 2^19 particles, same bits as the unsharded filter of 2^22 and as the oracle's resampler."""
     from test_gpu_sharded import run_pair
     from configs import c5
+    monkeypatch.setenv("CSSM_K3_FAST", "1")  # the certified scan also on clouds of 256 tiles per rank (default: more than 1024)
     stats = run_pair(c5(), 1 << 19, 8, 2, SYS, _abi.F32, seed=33)
     # round 2: the certified fp64 scan runs on every rank (tiles whose outputs fall into the rank's own slots); the last
     # tile of a rank and tiles that write into a peer's slots go to the exact path
