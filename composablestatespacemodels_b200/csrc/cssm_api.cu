@@ -252,6 +252,7 @@ struct cssm_filter {
   int series_multi_blocks = 0;     // ... of k_series_multi
   long long series_multi_max = 1ll << 19;  // largest cloud the multi-tile series kernel is used for (CSSM_SERIES_MAX_N)
   bool series_use_multi = false;
+  bool series_use_one = false;     // tiny cloud: the whole llFilter in one block (k_series_one)
   bool last_single_launch = false;
   int pdl = 1;  // programmatic dependent launch between the kernels of a step
   int flat_max_nt = 2048;  // clouds of at most this many tiles: K2 without atomics, K3 adds the tile sums itself (CSSM_FLAT_MAX_NT)
@@ -837,6 +838,12 @@ bool series_eligible(cssm_filter* f, bool sample_states) {
     f->series_multi_blocks = resident_blocks(f, series_multi_kernel(f));
   }
   f->series_use_multi = false;
+  f->series_use_one = false;
+  static const bool no_one = std::getenv("CSSM_SERIES_ONE") != nullptr && std::atoi(std::getenv("CSSM_SERIES_ONE")) == 0;
+  if (f->N <= SERIES_ONE_MAX_N && !no_one) {  // the reference's own particle counts: one block, no grid-wide exchange at all
+    f->series_use_one = true;
+    return true;
+  }
   // one 512-particle tile per block, weights stay in registers
   f->series_items = 0;
   if (nblk(f->N, 2 * TILE_THREADS) + 1 <= f->series_max_blocks) f->series_items = 2;  // one block per tile + the accountant
@@ -891,7 +898,7 @@ int run_series_single_launch(cssm_filter* f) {
   CU(cudaMemsetAsync(f->series_ctl, 0, sizeof(SeriesCtl), f->stream));
   SeriesArgs sa;
   std::memset(&sa, 0, sizeof(sa));
-  if (!f->series_use_multi) {  // one tile per block: tagged ancestors instead of a third grid barrier (cssm_series.cuh)
+  if (!f->series_use_multi && !f->series_use_one) {  // one tile per block: tagged ancestors instead of a third grid barrier (cssm_series.cuh)
     const size_t esz = (f->dtype == CSSM_F32) ? 4 : 8;
     if (f->anc64 == nullptr) {
       if (cudaMalloc((void**)&f->anc64, (size_t)f->Ns * sizeof(unsigned long long)) != cudaSuccess ||
@@ -912,7 +919,7 @@ int run_series_single_launch(cssm_filter* f) {
   sa.logw = f->logw; sa.anc = f->anc; sa.sc = f->sc;
   sa.tile_sum = f->tb.tile_sum; sa.tile_q = f->tile_q; sa.tile_maxw = f->tb.tile_maxw;
   sa.nt = f->nt;
-  if (!f->series_use_multi) {
+  if (!f->series_use_multi && !f->series_use_one) {
     sa.tile_sum = f->ser_tile_sum; sa.tile_q = f->ser_tile_q; sa.tile_maxw = f->ser_tile_maxw;
     sa.nt = nblk(f->N, TILE_THREADS * f->series_items);
   }
@@ -924,7 +931,13 @@ int run_series_single_launch(cssm_filter* f) {
   sa.pr[0] = make_peers(f, f->cur);
   sa.pr[1] = make_peers(f, f->cur ^ 1);
   static const bool debug_stamps = std::getenv("CSSM_SERIES_DEBUG") != nullptr;
-  if (debug_stamps && !f->series_use_multi) {
+  if (f->series_use_one) {  // per-step records of the exact sums: ll / ESS of all steps are evaluated at the end of the launch
+    int rc2 = ensure_scratch(f, T * 6);
+    if (rc2) return rc2;
+    CU(cudaMemsetAsync(f->scratch, 0, T * 6 * sizeof(unsigned long long), f->stream));
+    sa.ll_rec = (unsigned long long*)f->scratch;
+  }
+  if (debug_stamps && !f->series_use_multi && !f->series_use_one) {
     int rc2 = ensure_scratch(f, (size_t)16 * 512);
     if (rc2) return rc2;
     CU(cudaMemsetAsync(f->scratch, 0, (size_t)16 * 512 * 8, f->stream));
@@ -935,7 +948,9 @@ int run_series_single_launch(cssm_filter* f) {
   cudaError_t e;
   {
     ProfScope ps_(f, CLS_SERIES, prof);
-    if (f->series_use_multi)
+    if (f->series_use_one)
+      e = cudaLaunchKernel(cssm::series_one_kernel(f->dtype, f->d, f->resample_kind), dim3(1), dim3(TILE_THREADS), args, 0, f->stream);
+    else if (f->series_use_multi)
       e = cudaLaunchCooperativeKernel(series_multi_kernel(f), dim3((unsigned)std::min(f->nt, f->series_multi_blocks)), dim3(TILE_THREADS),
                                       args, 0, f->stream);
     else

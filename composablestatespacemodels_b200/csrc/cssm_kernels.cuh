@@ -1250,6 +1250,26 @@ __device__ __noinline__ void ll_ess_update(FilterScalars* __restrict__ sc, const
   }
 }
 
+// the terms of ll_ess_update for one observed step, without touching the filter's scalars (k_series_one evaluates all
+// steps at the end of its launch, one thread per step, and adds the increments in order): same expressions, same bits
+template <typename real>
+__device__ __forceinline__ void ll_ess_terms(u128 tot, u128 qsum, unsigned long long key, long long Ng, double& incr, int& ess, int& flags) {
+  const PreScan ps = pre_scan(key, false);
+  const int qb = ps.qb;
+  const double total = dbl128(tot, qb);
+  const double gmax = ps.gmax;
+  incr = gmax + log(total / (double)Ng);
+  flags = 0;
+  if (!(total > 0.0) || gmax != gmax || gmax - gmax != 0.0) {
+    incr = __longlong_as_double(0x7FF8000000000000ll);
+    flags |= FLAG_ZERO_TOTAL;
+  }
+  const double tsc = __dmul_rn(total, __longlong_as_double((long long)(1023 - (96 - qb)) << 52));
+  const double s2 = __ddiv_rn(dbl128(qsum, WeightSrc<real>::Q2), __dmul_rn(tsc, tsc));
+  const double inv = floor(1.0 / s2);
+  ess = (inv == inv && inv < 2147483647.0) ? (int)inv : (inv == inv ? 2147483647 : 0);
+}
+
 // ---- block-wide scan + search: cumulative values and weights of the tile in shared memory, expansion by head scatter +
 //      block max-scan.  The kernel of the three-launch step (k_scan_search); measured faster there than the
 //      warp-synchronous variant below (0.144 vs 0.166 ms at 2^24 particles), which the single-launch series kernels use. ----

@@ -22,6 +22,18 @@ void* series_small_kernel(int dtype, int items, int d, int resample_kind) {
   return dtype == CSSM_F32 ? small_ptr<float, 2>(d, resample_kind) : small_ptr<double, 2>(d, resample_kind);
 }
 
+// tiny clouds: one block
+template <typename real>
+static void* one_ptr(int d, int kind) {
+  const bool strat = kind == CSSM_RESAMPLE_STRATIFIED;
+  if (d == 1) return strat ? (void*)k_series_one<real, 1, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_one<real, 1, CSSM_RESAMPLE_SYSTEMATIC>;
+  if (d == 2) return strat ? (void*)k_series_one<real, 2, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_one<real, 2, CSSM_RESAMPLE_SYSTEMATIC>;
+  return strat ? (void*)k_series_one<real, 0, CSSM_RESAMPLE_STRATIFIED> : (void*)k_series_one<real, 0, CSSM_RESAMPLE_SYSTEMATIC>;
+}
+void* series_one_kernel(int dtype, int d, int resample_kind) {
+  return dtype == CSSM_F32 ? one_ptr<float>(d, resample_kind) : one_ptr<double>(d, resample_kind);
+}
+
 // mid-size clouds: several tiles per block
 template <typename real, int ITEMS>
 static void* multi_ptr(int d, int kind) {

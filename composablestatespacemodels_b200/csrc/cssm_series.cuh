@@ -1,4 +1,5 @@
-// cssm_series.cuh -- llFilter (model/ParticleFilter.scala:137-140) of a SMALL cloud as ONE launch.
+// cssm_series.cuh -- llFilter (model/ParticleFilter.scala:137-140) of a SMALL cloud as ONE launch: k_series_one (at most 1024
+// particles, one block), k_series_small (one block per 512-particle tile, all resident; described first), k_series_multi.
 //
 // A PMMH likelihood evaluation (model/PMMH.scala:71) filters a few tens of thousands of particles
 // over hundreds of observations: every stage of a step is a few microseconds of work and the
@@ -70,6 +71,7 @@ struct SeriesArgs {
   unsigned long long* dbg;      // NULL, or 8 cycle counters per block [8][grid] (CSSM_SERIES_DEBUG): P1 B1 P2 B2 P3 anc-wait head
   Peers pr[2];                  // the (single-rank) topology with x[0] = the cloud read in even / odd steps: kept in
                                 // the kernel's constant bank instead of a 400-byte struct in local memory
+  unsigned long long* ll_rec;   // k_series_one: [T][6] exact totals, sum of squares and max key of every observed step
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
@@ -514,6 +516,185 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_series_small(const __grid_c
   }
 }
 #undef CSSM_STAMP
+
+// ---------------------------------------------------------------------------------------------
+// TINY clouds -- the particle counts of the reference's own examples (100 .. 1000 particles,
+// examples/DetermineParameters.scala:70, examples/Filtering.scala:24): the whole llFilter in ONE BLOCK.  No grid-wide
+// exchange exists: the max is a block reduction, the tile sum IS the total, the exclusive prefix is zero, ancestors go
+// through L2 between two block barriers.  Same per-particle code (propagate_particles, WeightSrc, tile_scan_*, k3_tile),
+// same exact sums: bit-identical to the other schedules.  256 threads x 4 particles.
+// ---------------------------------------------------------------------------------------------
+template <> struct VecN<double, 4> { typedef double4 type; typedef int4 itype; };
+constexpr int SERIES_ONE_ITEMS = 4;
+constexpr int SERIES_ONE_MAX_N = TILE_THREADS * SERIES_ONE_ITEMS;
+void* series_one_kernel(int dtype, int d, int resample_kind);
+
+template <typename real, int D, int KIND>
+__global__ void __launch_bounds__(TILE_THREADS, 1) k_series_one(const __grid_constant__ SeriesArgs sa) {
+  constexpr int ITEMS = SERIES_ONE_ITEMS;
+  constexpr int NW = TILE_THREADS / 32;
+  typedef typename WeightSrc<real>::wt wt;
+  __shared__ K3Smem<ITEMS> sm;
+  __shared__ StepArgs<real> a;
+  __shared__ double s_mx[NW], s_mxw[NW];
+  __shared__ u128 s_q2[NW], s_woff[NW + 1], s_qsum;
+  __shared__ int s_bad;
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int d = (D > 0) ? D : sa.d;
+  const long long N = sa.N, Ns = sa.Ns;
+  real* const logw = reinterpret_cast<real*>(sa.logw);
+  SumTables tb;
+  tb.tile_sum = sa.tile_sum;
+  tb.tile_maxw = sa.tile_maxw;
+  tb.tile_q = sa.tile_q;
+  tb.super_sum = nullptr;
+  tb.super_q = nullptr;
+  tb.super_ticket = nullptr;
+  tb.nt = 1;
+  tb.ns = 0;
+  K3Ctl kc;
+  kc.parity = 0;
+  kc.obs_seq = 0;
+  kc.gstep = 0;
+  kc.inv_n = sa.inv_n;
+  kc.direct = 0;
+  kc.add_ll = 1;
+  kc.use_u_inj = 0;
+  kc.tie_first = sa.tie_first;
+  kc.defer_ll = 1;  // ll / ESS of all steps at the end of the kernel, in parallel over the steps (below)
+  kc.fast_ok = 0;
+  kc.key0 = sa.key0;
+  kc.key1 = sa.key1;
+  kc.ll_steps = sa.ll_steps;
+  kc.ess_steps = sa.ess_steps;
+  kc.anc64 = nullptr;
+  kc.anc_tag = 0;
+  kc.dbg = nullptr;
+
+  int cur = 0;
+  bool anc_valid = false;
+  const int rec_len = 4 * d + SERIES_REC_EXTRA;
+  const long long i0 = (long long)threadIdx.x * ITEMS;
+  if (threadIdx.x == 0) s_bad = 0;
+  for (int s = 0; s < sa.T; ++s) {
+    {
+      const real rv = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)s * rec_len + threadIdx.x) : (real)0;
+      __syncthreads();  // the constants of the step before are no longer read; its ancestors and cloud are complete
+      rec_to_args<real>(a, rv, d, sa.obs_kind);
+      __syncthreads();
+    }
+    const int has_obs = a.has_obs;
+    const uint32_t step = sa.step0 + (uint32_t)s;
+    // ---- P1 ----
+    const Peers& pr = sa.pr[cur];
+    double mx;
+    bool bad;
+    real lw[ITEMS];
+    propagate_particles<real, D, ITEMS, true>(a, pr, reinterpret_cast<real*>(sa.x[cur ^ 1]), anc_valid ? sa.anc : nullptr, logw, nullptr,
+                                              N, Ns, 0ull, sa.key0, sa.key1, step, i0, mx, bad, lw);
+    cur ^= 1;
+    anc_valid = false;
+    if (!has_obs) continue;  // the barrier at the top of the next step orders the clouds
+    mx = warp_max_lw<real>(mx);
+    if (lane == 0) s_mx[wid] = mx;
+    if (bad) s_bad = 1;
+    __syncthreads();
+    double m2 = s_mx[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m2 = fmax(m2, s_mx[w]);
+    const unsigned long long key = ord_key(m2);
+    if (threadIdx.x == 0 && s_bad) { atomicOr(&sa.sc->flags, FLAG_NAN_WEIGHT); s_bad = 0; }
+    // ---- P2 ----
+    const PreScan ps = pre_scan(key, false);
+    const int qb = ps.qb;
+    WeightSrc<real> ws{logw, nullptr, ps.gmax};
+    kc.step = step;
+    kc.step_slot = s;
+    TileScan<real, ITEMS> scan;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) scan.w[j] = (i0 + j < N) ? ws.weight(lw[j]) : (wt)0;
+    {
+      if (threadIdx.x == 64) k3_prepare<ITEMS>(sm, sa.sc, kc);
+      if (threadIdx.x == 32) sm.s_wnext = 0.0;  // no tile behind this one
+      u128 acc2 = make_u128(0, 0);
+      wt mxv = (wt)0;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        WeightSrc<real>::acc_sq(acc2, scan.w[j], 1.0);
+        mxv = scan.w[j] > mxv ? scan.w[j] : mxv;
+      }
+      const double mxw = WeightSrc<real>::warp_max(mxv);
+      acc2 = WeightSrc<real>::warp_sum_sq(acc2);
+      tile_scan_local<real, ITEMS>(qb, i0, N, sm.s_warp, sm.s_minw, scan);
+      if (lane == 0) { s_q2[wid] = acc2; s_mxw[wid] = mxw; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u128 t1 = sm.s_warp[0], t2 = s_q2[0];
+        double mw = s_mxw[0];
+        s_woff[0] = make_u128(0, 0);
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+          s_woff[w] = t1;
+          t1 = add128(t1, sm.s_warp[w]);
+          t2 = add128(t2, s_q2[w]);
+          mw = fmax(mw, s_mxw[w]);
+        }
+        s_woff[NW] = t1;
+        s_qsum = t2;
+        sa.tile_sum[0] = t1;  // the tables a walk over a run of repeated keys would read (it cannot leave the only tile)
+        sa.tile_q[0] = t2;
+        sa.tile_maxw[0] = mw;
+        unsigned long long* r = sa.ll_rec + (size_t)s * 6;
+        r[0] = t1.lo; r[1] = t1.hi; r[2] = t2.lo; r[3] = t2.hi; r[4] = key; r[5] = 1ull;
+      }
+      __syncthreads();
+    }
+    // ---- P3: the tile sum is the total, nothing lies before the tile ----
+    k3_tile<real, ITEMS, KIND, false>(sm, logw, nullptr, N, sa.sc, tb, pr, kc, nullptr, nullptr, 0, s_woff[NW], s_qsum, key,
+                                      make_u128(0, 0), &scan, s_woff);
+    anc_valid = true;
+  }
+  // ---- ll and ESS of every observed step.  One thread per step evaluates max + log(mean w1) and floor(1 / sum wn^2)
+  //      (three divisions and a logarithm in fp64: inside the loop they held one warp back by ~2 k cycles per step and
+  //      the block with it); thread 0 then adds the increments in order -- the same sums, the same bits. ----
+  __syncthreads();
+  for (int s = threadIdx.x; s < sa.T; s += TILE_THREADS) {
+    unsigned long long* r = sa.ll_rec + (size_t)s * 6;
+    if (r[5] == 0ull) continue;  // no observation
+    double incr;
+    int ess, flags;
+    ll_ess_terms<real>(make_u128(r[0], r[1]), make_u128(r[2], r[3]), r[4], (long long)N, incr, ess, flags);
+    r[2] = (unsigned long long)__double_as_longlong(incr);  // the sum of squares has been used
+    r[3] = ((unsigned long long)(unsigned)flags << 32) | (unsigned long long)(unsigned)ess;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ll = sa.sc->ll;
+    int ess = sa.sc->ess, flags = 0, last = -1;
+    for (int s = 0; s < sa.T; ++s) {
+      const unsigned long long* r = sa.ll_rec + (size_t)s * 6;
+      if (r[5] == 0ull) continue;
+      ll = ll + __longlong_as_double((long long)r[2]);
+      ess = (int)(unsigned)(r[3] & 0xffffffffull);
+      flags |= (int)(unsigned)(r[3] >> 32);
+      if (sa.ll_steps) sa.ll_steps[s] = ll;
+      if (sa.ess_steps) sa.ess_steps[s] = ess;
+      last = s;
+    }
+    if (last >= 0) {
+      const unsigned long long* r = sa.ll_rec + (size_t)last * 6;
+      const PreScan ps = pre_scan(r[4], false);
+      sa.sc->gmax = ps.gmax;
+      sa.sc->total = dbl128(make_u128(r[0], r[1]), ps.qb);
+      sa.sc->qb = ps.qb;
+      sa.sc->ll_incr = __longlong_as_double((long long)r[2]);
+      sa.sc->ll = ll;
+      sa.sc->ess = ess;
+      if (flags) atomicOr(&sa.sc->flags, flags);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // The same single-launch schedule for MID-SIZE clouds (up to a few million particles): more tiles

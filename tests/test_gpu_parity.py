@@ -260,6 +260,63 @@ def test_series_kernel_equals_three_launch_path(name, dtype, kind):
     assert np.isfinite(a[0]) and a[7] != a[0]
 
 
+@pytest.mark.parametrize("name", sorted(ALL))
+@pytest.mark.parametrize("N", [100, 777, 1000, 1024])
+@pytest.mark.parametrize("dtype,kind", [(_abi.F32, SYS), (_abi.F64, SYS), (_abi.F32, STRAT), (_abi.F64, STRAT)])
+def test_one_block_series_kernel_equals_three_launch_path(name, N, dtype, kind):
+    """Clouds of the reference's own examples (100 .. 1000 particles, examples/DetermineParameters.scala:70,
+    examples/Filtering.scala:24) run the whole llFilter in ONE block (k_series_one): no grid-wide exchange.  Same bits as
+    the three-launch step -- per-step log-likelihood and ESS, the final cloud, a further stepFilter on it -- on ragged
+    clouds, with missing observations, and with extreme observations that make almost every weight vanish."""
+    mod = ALL[name]()
+    orc = oracle.Oracle(mod)
+    T = 24
+    t, y, _ = orc.simulate(T, 0.1, 5)
+    has = np.ones(T, dtype=np.uint8)
+    has[[0, 7, 8]] = 0
+    out = []
+    for mode in (_abi.SERIES_THREE_LAUNCH, _abi.SERIES_SINGLE_LAUNCH):
+        h = cs.GpuFilterHandle(mod, kind, N, dtype=dtype, seed=3)
+        h.series_mode(mode)
+        h.load_series(t, y, has)
+        ll, lls, ess = h.ll_resident(steps=True)
+        n_launch = h.last_launches()
+        x = h.get_particles()
+        ll2, ess2 = h.step(t[-1] + 0.1, float(y[-1]))
+        x2 = h.get_particles()
+        out.append((ll, lls, ess, x, ll2, ess2, x2, n_launch))
+        h.close()
+    a, b = out
+    assert b[7] == 2 and a[7] > T
+    assert a[0] == b[0] and a[4] == b[4] and a[5] == b[5]
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[6], b[6])
+
+
+def test_one_block_series_kernel_degenerate_weights():
+    """Runs of repeated keys inside the single tile of the one-block kernel (extreme observations)."""
+    mod = c5()
+    N, T = 1000, 6
+    t = 0.1 * np.arange(T)
+    y = np.array([0.3, 75.0, -60.0, 0.0, 40.0, 0.1])
+    out = []
+    for mode in (_abi.SERIES_THREE_LAUNCH, _abi.SERIES_SINGLE_LAUNCH):
+        for dtype in (_abi.F32, _abi.F64):
+            h = cs.GpuFilterHandle(mod, SYS, N, dtype=dtype, seed=11)
+            h.series_mode(mode)
+            h.load_series(t, y)
+            ll, lls, ess = h.ll_resident(steps=True)
+            out.append((ll, lls, ess, h.get_particles()))
+            h.close()
+    for i in (0, 1):
+        assert out[i][0] == out[i + 2][0]
+        np.testing.assert_array_equal(out[i][1], out[i + 2][1])
+        np.testing.assert_array_equal(out[i][2], out[i + 2][2])
+        np.testing.assert_array_equal(out[i][3], out[i + 2][3])
+
+
 def test_series_kernel_degenerate_weights_and_large_grid():
     """Duplicate-key runs that cross tiles inside the series kernel (extreme observations make
     almost every weight vanish), on a cloud that needs more than one block per SM."""
