@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_series_one(const __grid_con
   constexpr int NW = TILE_THREADS / 32;
   typedef typename WeightSrc<real>::wt wt;
   __shared__ K3Smem<ITEMS> sm;
-  __shared__ StepArgs<real> a;
+  __shared__ StepArgs<real> abuf[2];  // the constants of step s in abuf[s & 1]; the next step's are written a step ahead
   __shared__ double s_mx[NW], s_mxw[NW];
   __shared__ u128 s_q2[NW], s_woff[NW + 1], s_qsum;
   __shared__ int s_bad;
@@ -577,13 +577,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) k_series_one(const __grid_con
   const int rec_len = 4 * d + SERIES_REC_EXTRA;
   const long long i0 = (long long)threadIdx.x * ITEMS;
   if (threadIdx.x == 0) s_bad = 0;
+  {
+    const real r0 = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + threadIdx.x) : (real)0;
+    rec_to_args<real>(abuf[0], r0, d, sa.obs_kind);
+  }
+  // the record of step s + 1 travels in a register during step s and is stored into the other buffer at the top of it
+  real rec_v = (sa.T > 1 && (int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + rec_len + threadIdx.x) : (real)0;
   for (int s = 0; s < sa.T; ++s) {
-    {
-      const real rv = ((int)threadIdx.x < rec_len) ? __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)s * rec_len + threadIdx.x) : (real)0;
-      __syncthreads();  // the constants of the step before are no longer read; its ancestors and cloud are complete
-      rec_to_args<real>(a, rv, d, sa.obs_kind);
-      __syncthreads();
-    }
+    __syncthreads();  // the step before is complete in every thread: its ancestors and cloud, and abuf[(s + 1) & 1] is free
+    const StepArgs<real>& a = abuf[s & 1];
+    if (s + 1 < sa.T) rec_to_args<real>(abuf[(s + 1) & 1], rec_v, d, sa.obs_kind);
+    if (s + 2 < sa.T && (int)threadIdx.x < rec_len) rec_v = __ldg(reinterpret_cast<const real*>(sa.recs) + (size_t)(s + 2) * rec_len + threadIdx.x);
     const int has_obs = a.has_obs;
     const uint32_t step = sa.step0 + (uint32_t)s;
     // ---- P1 ----
