@@ -52,6 +52,9 @@ WORKLOADS = {
            "GPUs of the job (BASELINE.json configs[4])", "c5", 1 << 27, 100, "systematic"),
     "c3": ("LGCP + Brownian motion, 2^22 particles x 200 events, stratified, sub-step 10^-3 (BASELINE.json configs[2])",
            "c3", 1 << 22, 200, "stratified"),
+    "resample": ("isolated resampling through the Resample[A] seam (cssm_resample, host vectors in and out): the sizes and unit "
+                 "weights of the reference's ResamplingBenchmark (src/bench/scala/Resampling.scala:11-17) and 2^20 / 2^24 "
+                 "weights of SURVEY 8(d): unit, exp(N(0, 2^2)), degenerate", "resample", 1 << 24, 1, "systematic"),
 }
 
 
@@ -188,6 +191,88 @@ def kernels_blob():
         data = open(os.path.join(ROOT, "composablestatespacemodels_b200", "csrc", f), "rb").read()
         h.update(hashlib.sha1(b"blob %d\0" % len(data) + data).hexdigest().encode())
     return h.hexdigest()[:16]
+
+
+def run_resample(args, wl):
+    """The reference's ResamplingBenchmark (src/bench/scala/Resampling.scala: sizes 100 .. 6400, unit weights, systematic and
+    multinomial) and the large-cloud cases of SURVEY 8(d), through the stand-alone seam S2: `Resample[A]` = host weights in,
+    host ancestors out (cssm_resample: allocation, upload, max + exact sums + scan + search, download -- everything is
+    inside the timed call).  The CPU restatement (oracle.resample, one core) is timed on the same inputs.  `--impl
+    reference` times the CPU side only.  One JSON line; `value` = resampled particles/s, systematic, exp(N(0,4)) weights,
+    largest size."""
+    import oracle
+    from composablestatespacemodels_b200 import _abi
+    gpu = args.impl != "reference"
+    if gpu:
+        import torch
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        from composablestatespacemodels_b200.resampling import ancestors
+    rng = np.random.default_rng(3)
+    kinds = (("systematic", _abi.RESAMPLE_SYSTEMATIC), ("stratified", _abi.RESAMPLE_STRATIFIED), ("multinomial", _abi.RESAMPLE_MULTINOMIAL))
+    big = wl[2]
+    sizes = [100, 200, 400, 800, 1600, 3200, 6400, 1 << 20] + ([big] if big > (1 << 20) else [])
+
+    def weights(which, n):
+        if which == "unit":
+            return np.ones(n)
+        if which == "lognormal":
+            return np.exp(rng.normal(0.0, 2.0, n))
+        w = np.full(n, 1e-30)
+        w[n // 3] = 1.0
+        return w
+
+    cases, head = [], None
+    for n in sizes:
+        for which in (("unit",) if n <= 6400 else ("unit", "lognormal", "degenerate")):
+            w = weights(which, n)
+            for kname, kind in kinds:
+                if kname == "multinomial" and n > (1 << 20):
+                    continue  # the reference's multinomial is O(n^2); the device's is a binary search per draw, the oracle's too slow here
+                u = rng.random(1 if kname == "systematic" else n)
+                rec = {"n": n, "weights": which, "kind": kname}
+                if gpu:
+                    for _ in range(max(1, args.warmup if n <= (1 << 20) else 1)):
+                        a = ancestors(kind, w, u)
+                    reps = 20 if n <= 6400 else (5 if n <= (1 << 20) else max(2, args.steps // 2))
+                    t0 = time.perf_counter()
+                    for _ in range(reps):
+                        a = ancestors(kind, w, u)
+                    dt = (time.perf_counter() - t0) / reps
+                    rec.update({"gpu_particles_per_s": n / dt, "gpu_ms": dt * 1e3})
+                # (the CPU restatement walks runs of repeated keys output by output: quadratic on the degenerate case)
+                if not args.no_cpu and n <= (1 << 20) and (which != "degenerate" or n <= 6400):
+                    t0 = time.perf_counter()
+                    ac = oracle.resample(kind, w, u)
+                    dtc = time.perf_counter() - t0
+                    rec.update({"cpu_particles_per_s": n / dtc, "cpu_ms": dtc * 1e3})
+                    if gpu:
+                        rec["same_ancestors"] = bool(np.array_equal(a, ac))
+                cases.append(rec)
+                if kname == "systematic" and which == "lognormal":
+                    head = rec
+    key = "gpu_particles_per_s" if gpu else "cpu_particles_per_s"
+    if head is None or key not in head:
+        head = next(c for c in reversed(cases) if key in c)
+    cpu_head = next((c for c in reversed(cases) if "cpu_particles_per_s" in c and c["kind"] == "systematic" and c["weights"] == "lognormal"), None)
+    n = head["n"]
+    peak, peak_src = measured_peak()
+    line = {"metric": "resampled-particles/sec", "value": head[key], "unit": "particles/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head.get("gpu_ms" if gpu else "cpu_ms"), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl[0], "headline_case": {k: head[k] for k in ("n", "weights", "kind")}},
+            "roofline": {"bound": "hbm", "achieved": (8 + 8 + 4) * n / (head["gpu_ms"] * 1e-3) / 1e9 if gpu else None, "peak": peak, "unit": "GB/s",
+                         "frac": ((8 + 8 + 4) * n / (head["gpu_ms"] * 1e-3) / 1e9 / peak) if gpu else None, "traffic": None, "peak_source": peak_src,
+                         "note": "end to end through host vectors (PCIe copies, allocation): not a kernel figure; the kernels' own rates "
+                                 "are roofline.resampling of the default line (K2 and K3 with weights resident in HBM)"},
+            "cpu_baseline": ({"value": cpu_head["cpu_particles_per_s"], "unit": "particles/s", "cores": 1, "kind": "port",
+                              "sample": f"oracle.resample, systematic, exp(N(0,4)) weights, n = {cpu_head['n']}"} if cpu_head else None),
+            "e2e": {"value": head[key], "unit": "particles/s", "h2d_bytes_per_step": 8 * n + 8, "d2h_bytes_per_step": 4 * n} if gpu else
+                   {"value": head[key], "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": (4 if gpu else 0), "cases": cases}
+    if not gpu:
+        line["impl"] = "reference"
+    print(json.dumps(line))
 
 
 def measured_peak():
@@ -513,6 +598,8 @@ def main():
         wl[3] = args.obs
     if not args.steps:
         args.steps = 100 if args.workload == "c4" else 5
+    if args.workload == "resample":
+        return run_resample(args, wl)
     if args.impl == "reference":
         return run_reference(args, wl, args.workload)
 

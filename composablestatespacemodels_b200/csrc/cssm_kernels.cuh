@@ -1419,6 +1419,10 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
     constexpr int PER = WIN / TILE_THREADS;  // outputs per thread and pass
     const int prev0 = threadIdx.x ? s_cnt[threadIdx.x - 1] : 0;
     int carry = 0;  // local index of the particle that owns the last output of the previous pass
+    // the end of the run of repeated keys behind particle memo_j, as this thread last walked it: a heavy particle owns
+    // every output of many passes, and each of them would otherwise walk the same run again (2^24 outputs x a run of a
+    // thousand particles x two divisions per test: seconds)
+    int memo_j = -1, memo_e = -1;
     for (int w0 = 0; w0 < n_out; w0 += WIN) {
 #pragma unroll
       for (int k = 0; k < PER; ++k) s_res[threadIdx.x * PER + k] = -1;
@@ -1468,8 +1472,15 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
           const int jn = min(jt + 1, tile_n - 1);
           mayv = (o < n_w) && (jt + 1 < tile_n) && !(Ws[phys<ITEMS>(jn)] > Ps[phys<ITEMS>(jt)] * 2.220446049250313e-16);
         }
-        if (mayv)
-          while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+        if (mayv) {
+          if (jt == memo_j) {
+            jt = memo_e;
+          } else {
+            memo_j = jt;
+            while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+            memo_e = jt;
+          }
+        }
         jts[k] = jt;
       }
       int32_t* const out_local = pr.anc[RNK] + (lo + w0 - (long long)RNK * N);  // R == 1: plain coalesced stores
