@@ -162,6 +162,24 @@ def test_resample_large_bit_exact():
         assert np.mean(ref != got) < 1e-3
 
 
+def test_resample_one_heavy_particle_and_a_long_run_of_repeated_keys():
+    """SURVEY 8(d)'s degenerate case: one weight 1, the rest 1e-30.  Under the TreeMap rule every output goes to the last
+    particle of the run of repeated keys behind the heavy one -- a run that crosses many tiles, owned by a particle whose
+    offspring fill many passes of the exact scan path (the per-thread memo of the last walk; before it 2^24 outputs took
+    seconds).  Ancestors equal the oracle's; a second heavy particle splits the run."""
+    rng = np.random.default_rng(4)
+    for n, heavy in ((1 << 14, (5000,)), ((1 << 14) + 333, (17, 9000)), (40000, (39999,))):
+        w = np.full(n, 1e-30)
+        for h in heavy:
+            w[h] = 1.0
+        for kind in (SYS, STRAT):
+            u = rng.random(1 if kind == SYS else n)
+            got = cs.resampling.ancestors(kind, w, u)
+            np.testing.assert_array_equal(got, oracle.resample(kind, w, u, oracle.ORDER_DEVICE))
+            if len(heavy) == 1 and heavy[0] < n - 1:
+                assert np.mean(got == n - 1) > 0.99  # the last particle of the cloud takes (nearly) everything
+
+
 def test_lgcp_step_parity():
     mod = c3(precision=2)
     for dtype in (_abi.F64, _abi.F32):
