@@ -1423,7 +1423,57 @@ __device__ __forceinline__ bool k3_tile_blk(K3SmemBlk<ITEMS>& sm, const real* __
     // every output of many passes, and each of them would otherwise walk the same run again (2^24 outputs x a run of a
     // thousand particles x two divisions per test: seconds)
     int memo_j = -1, memo_e = -1;
+    constexpr int HEAVY_SPAN = 8 * WIN;  // a stretch of outputs this long without a head is filled directly
     for (int w0 = 0; w0 < n_out; w0 += WIN) {
+      if (w0 > 0 && n_out - w0 >= HEAVY_SPAN) {  // block-uniform, and false for every tile of an ordinary cloud
+        // One particle with very many offspring: where does the next particle's range begin?  Up to there every output
+        // belongs to `carry`, the owner of the last output of the pass before -- no staging, no scan, plain stores.
+        // (Window by window the 2^24 offspring of a single particle took 33 ms.)
+        int nh = 0x7FFFFFFF;
+        {
+          int prev = prev0;
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            if (cr[j] > prev && prev >= w0) nh = min(nh, prev);
+            prev = cr[j];
+          }
+        }
+        nh = __reduce_min_sync(0xffffffffu, nh);
+        if ((threadIdx.x & 31) == 0) s_cnt2[threadIdx.x >> 5] = nh;
+        __syncthreads();
+#pragma unroll
+        for (int ww = 0; ww < TILE_THREADS / 32; ++ww) nh = min(nh, s_cnt2[ww]);
+        __syncthreads();  // s_cnt2 is used again by the pass below
+        const int span_end = min(nh, n_out);
+        if (span_end - w0 >= HEAVY_SPAN) {
+          int jt = carry;
+          if (sm.s_novanish == 0 && jt + 1 < tile_n && !(Ws[phys<ITEMS>(jt + 1)] > Ps[phys<ITEMS>(jt)] * 2.220446049250313e-16)) {
+            if (jt == memo_j) {
+              jt = memo_e;
+            } else {
+              memo_j = jt;
+              while (jt + 1 < tile_n && vanishes(Ps[phys<ITEMS>(jt)], Ws[phys<ITEMS>(jt + 1)], total)) ++jt;
+              memo_e = jt;
+            }
+          }
+          if (cont && jt == tile_n - 1 && threadIdx.x == 0) atomicMin(&s_pend, lo + w0);
+          const int32_t val = (int32_t)(gbase + jt);
+          const bool span_local = !SH || RK == 1 || (lo + w0 >= (long long)RNK * N && lo + span_end <= (long long)(RNK + 1) * N);
+          if (span_local) {
+            int32_t* const out = pr.anc[RNK] + (lo - (long long)RNK * N);
+            for (int o = w0 + (int)threadIdx.x; o < span_end; o += TILE_THREADS) out[o] = val;
+          } else {
+            for (int o = w0 + (int)threadIdx.x; o < span_end; o += TILE_THREADS) {
+              const long long i = lo + o;
+              const unsigned q = owner_of(pr, (unsigned)i);
+              pr.anc[q][i - (long long)q * N] = val;
+              wrote_remote |= (q != RNK);
+            }
+          }
+          w0 = span_end - WIN;  // the loop adds WIN: the next pass starts at the next particle's first output
+          continue;
+        }
+      }
 #pragma unroll
       for (int k = 0; k < PER; ++k) s_res[threadIdx.x * PER + k] = -1;
       __syncthreads();
