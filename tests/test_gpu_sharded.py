@@ -74,6 +74,9 @@ def test_sharded_degenerate_weights_cross_rank_runs(monkeypatch):
     run_pair(c5(), 1024, 4, 3, STRAT, _abi.F32, seed=22, ys=[70.0, 0.5, -90.0])
     monkeypatch.setenv("CSSM_TILE_ITEMS", "8")  # the 2048-particle tiles large clouds use
     run_pair(c5(), 6000, 2, 3, SYS, _abi.F64, seed=23, ys=[70.0, 0.5, -90.0])
+    monkeypatch.delenv("CSSM_TILE_ITEMS")
+    # one particle with tens of thousands of offspring: the direct fill of the exact scan path, into the peers' slots too
+    run_pair(c5(), 12000, 4, 3, SYS, _abi.F32, seed=24, ys=[70.0, 0.5, -90.0])
 
 
 def test_sharded_philox_run_is_partition_invariant():
