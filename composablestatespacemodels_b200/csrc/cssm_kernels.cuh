@@ -2290,7 +2290,36 @@ __device__ __forceinline__ bool k3_tile_fast(K3FastSmem& fs, const float* __rest
   const int32_t gbase = SHD ? (int32_t)(own0 + tile0) : (int32_t)tile0;
   const int prev0 = threadIdx.x ? fs.s_cnt[threadIdx.x - 1] : 0;
   int carry = 0;
+  constexpr int HEAVY_SPAN = 8 * WIN;  // as in the exact path: a stretch this long without a head is filled directly
   for (int w0 = 0; w0 < n_out; w0 += WIN) {
+    if (w0 > 0 && n_out - w0 >= HEAVY_SPAN) {  // block-uniform, and false for every tile of an ordinary cloud
+      int nh = 0x7FFFFFFF;  // the first head at or behind w0: up to there every output belongs to `carry`
+      {
+        int prev = prev0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          if (cr[j] > prev && prev >= w0) nh = min(nh, prev);
+          prev = cr[j];
+        }
+      }
+      nh = __reduce_min_sync(FULL, nh);
+      if (lane == 0) fs.s_cnt2[wid] = nh;
+      __syncthreads();
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) nh = min(nh, fs.s_cnt2[ww]);
+      __syncthreads();  // s_cnt2 is used again by the pass below
+      const int span_end = min(nh, n_out);
+      if (span_end - w0 >= HEAVY_SPAN) {
+        int jt = carry;
+        if (anyv)
+          while (jt + 1 < TILE && ((fs.s_vbits[(jt + 1) >> 5] >> ((jt + 1) & 31)) & 1u)) ++jt;
+        const int32_t val = gbase + jt;
+        int32_t* const out = anc_out + (lo - own0);
+        for (int o = w0 + (int)threadIdx.x; o < span_end; o += TILE_THREADS) out[o] = val;
+        w0 = span_end - WIN;  // the loop adds WIN: the next pass starts at the next particle's first output
+        continue;
+      }
+    }
 #pragma unroll
     for (int k = 0; k < PER; ++k) fs.s_res[threadIdx.x * PER + k] = -1;
     __syncthreads();

@@ -199,3 +199,44 @@ def test_certified_scan_equals_the_exact_path(name):
     fast, exact = a[4]
     assert e[4][0] == 0                                  # EXACT never takes the fast path
     assert fast > 5 * exact > 0, (fast, exact)           # most tiles certified, some undecided
+
+
+def test_certified_scan_with_one_particle_that_takes_nearly_everything():
+    """Observations far in the tail on a cloud large enough for the certified scan (more than 1024 tiles): one particle has
+    millions of offspring -- a stretch of outputs without a head that both paths fill directly instead of window by window.
+    AUTO and EXACT: same log-likelihood, ESS and final cloud, bit for bit; and the steps are not slower than ordinary ones
+    by more than the fill costs (a cliff here was 3 s per step at 2^24 before the fill existed)."""
+    import time
+    from configs import c5
+    mod = c5()
+    N = (1 << 21) + 4096 + 77
+    t = 0.1 * np.arange(6)
+    y = np.array([0.3, 75.0, -60.0, 0.0, 40.0, 0.1])
+    out = []
+    for mode in (_abi.SCAN_AUTO, _abi.SCAN_EXACT):
+        h = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F32, seed=12)
+        h.scan_mode(mode)
+        h.load_series(t, y)
+        h.ll_resident()
+        t0 = time.perf_counter()
+        ll, lls, ess = h.ll_resident(steps=True)
+        dt = time.perf_counter() - t0
+        out.append((ll, lls, ess, h.get_particles(), h.scan_stats(), dt))
+        h.close()
+    a, e = out
+    assert a[4][0] > 0 and e[4][0] == 0
+    np.testing.assert_array_equal(a[2], e[2])
+    assert min(a[2]) <= 3, a[2]          # the steps really are degenerate
+    assert a[5] < 0.5 and e[5] < 0.5, (a[5], e[5])
+    h1 = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F32, seed=12)
+    h1.scan_mode(_abi.SCAN_AUTO)
+    h1.load_series(t, y)
+    h2 = cs.GpuFilterHandle(mod, SYS, N, dtype=_abi.F32, seed=12)
+    h2.scan_mode(_abi.SCAN_EXACT)
+    h2.load_series(t, y)
+    r1, r2 = h1.ll_resident(steps=True), h2.ll_resident(steps=True)
+    assert r1[0] == r2[0]
+    np.testing.assert_array_equal(r1[1], r2[1])
+    np.testing.assert_array_equal(h1.get_particles(), h2.get_particles())
+    h1.close()
+    h2.close()
