@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the bootstrap particle filter hot path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload target|c2|c1|c3|c4|c5] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload target|c2|c1|c3|c4|c5|resample] [--impl reference]
 
 Workloads:
   target  Poisson + seasonal(24,3) + OU, 2^24 particles x 1000 observations, systematic   (default)
