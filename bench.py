@@ -867,7 +867,10 @@ def main():
                           "tie_rule": "first index (NOT the reference's rule)" if args.tie_first else "reference (TreeMap: last particle of a repeated key)",
                           "l2": "working set %.0f MB per GPU %s the 126 MB L2, no flush" % (
                               ws_bytes / 1e6, "exceeds" if ws_bytes > 126e6 else "is below"),
-                          "parallelism": par},
+                          "parallelism": par,
+                          "timing": "value: CUDA events around the K steps, with per-kernel events on every 10th observation inside "
+                                    "(those observations run without programmatic dependent launch: at 2^20 particles that costs "
+                                    "several per cent, at 2^24 nothing measurable); e2e: wall clock, no per-kernel events"},
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                "log_likelihood_mean": float(np.mean(lls))}
         out.update(extra)
